@@ -1,0 +1,255 @@
+/*
+ * amdp_b200.h — C ABI of the B200-native AnyMDP stepping engine (libamdp_b200.so).
+ *
+ * This is the drop-in boundary for the AnyMDP hot path of FutureAGI/Xenoverse.  The reference
+ * has no FFI (it is pure Python); each entry point below names the reference code it replaces
+ * (paths relative to the reference tree, xenoverse/anymdp/...).  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: opaque handle, raw pointers, sizes.  No torch / C++ types cross this boundary.
+ *   - every function returns AMDP_OK (0) or a negative AMDP_E* code; the message for the last
+ *     failure on a handle is available from amdp_last_error().  Nothing throws across the ABI.
+ *   - unless a parameter is documented as HOST, pointers are DEVICE pointers on the handle's GPU,
+ *     owned by the caller (e.g. torch tensors).  The handle owns only what create/upload allocated.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  All calls
+ *     are asynchronous enqueues on that stream unless documented as synchronising.
+ *   - one handle is bound to one device and is not thread-safe; different handles may be driven
+ *     from different threads / processes (one process per GPU is the intended deployment).
+ *   - per-env runtime faults (action out of range, stepping a terminated env with auto-reset
+ *     disabled, stepping before reset) set a sticky device-side flag read by amdp_poll_errors();
+ *     they never cost a synchronisation per step.
+ *
+ * Draw slots.  Every (env, tick) owns a fixed table of random draws ("slots"), so the amount of
+ * randomness consumed never depends on data:  slot = kind + 8 * token, with kind
+ *     0 transition uniform        (token k < da)     anymdp_env.py:100
+ *     1 reset (s_0) uniform       (token 0)          anymdp_env.py:89
+ *     2 observation uniform       (token k < do)     anymdp_env.py:153,157 under step()
+ *     3 reset-observation uniform (token k < do)     anymdp_env.py:153,157 under reset()
+ *     4 reward standard normal z  (token k < da)     anymdp_env.py:105
+ *     5 uniform-random-policy action (token k < da)  (caller side in the reference)
+ *     6,7 spare
+ * Slots come from Philox4x32-10 with counter (env_lo, block | env_hi << 16, tick_lo, tick_hi),
+ * key (seed_lo, seed_hi); block b yields slots 2b (words 0,1) and 2b+1 (words 2,3) as 53-bit
+ * doubles ((w0 >> 5) * 2^26 + (w1 >> 6)) / 2^53 — numpy's MT19937 double construction — except the
+ * block of kinds 4/5: z = Box-Muller of words 0,1 (fp32), action = (word2 * na) >> 32.
+ * `env` is the GLOBAL env id (env_id_base + local index), so trajectories do not depend on how
+ * envs are sharded over GPUs.  Each reset/step call consumes one tick; a rollout consumes K.
+ * Any call may instead be given an explicit draw matrix (`u_inject`, double [N][n_slots] per tick)
+ * — this is how the engine is compared with the reference "given identical uniforms".
+ */
+#ifndef AMDP_B200_H
+#define AMDP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMDP_ABI_VERSION 1
+
+/* status codes */
+#define AMDP_OK       0
+#define AMDP_EINVAL  (-1)   /* bad argument */
+#define AMDP_ECUDA   (-2)   /* a CUDA runtime call failed */
+#define AMDP_ESTATE  (-3)   /* call sequence error (e.g. step before upload/assign) */
+#define AMDP_ENOMEM  (-4)   /* device allocation failed */
+
+/* task_type (anymdp_env.py:35-46) */
+#define AMDP_MDP      0
+#define AMDP_POMDP    1
+#define AMDP_MTPOMDP  2
+
+/* auto-reset modes (no reference equivalent) */
+#define AMDP_AUTORESET_SAME_STEP 0
+#define AMDP_AUTORESET_NEXT_STEP 1
+#define AMDP_AUTORESET_DISABLED  2
+
+/* sticky per-engine runtime fault bits returned by amdp_poll_errors() */
+#define AMDP_FAULT_NEED_RESET     1  /* anymdp_env.py:93-94 'Must "set_task" and "reset" before doing any actions' */
+#define AMDP_FAULT_TERMINAL_STATE 2  /* anymdp_env.py:95-96 'Unexpected Error: given an terminated state' */
+#define AMDP_FAULT_BAD_ACTION     4  /* anymdp_env.py:97 assert action < na */
+
+/* per-task upload status written by amdp_upload_tasks() */
+#define AMDP_TASK_OK            0
+#define AMDP_TASK_BAD_ROW_SUM   1   /* anymdp_env.py:66-71 'Transition Matrix Sum != 1' ((sum-1)^2 >= 1e-6, non-terminal row) */
+#define AMDP_TASK_NOT_NORMALISED 2  /* numpy choice(): 'probabilities do not sum to 1' (|kahan_sum(p)-1| > sqrt(eps)) */
+#define AMDP_TASK_NEGATIVE_P    3   /* numpy choice(): 'probabilities are not non-negative' */
+#define AMDP_TASK_S0_IN_SE      4   /* anymdp_env.py:74-76 a start state is also terminal */
+
+#define AMDP_SLOTS_PER_TOKEN 8
+#define AMDP_SLOT_TRANS      0
+#define AMDP_SLOT_RESET      1
+#define AMDP_SLOT_OBS        2
+#define AMDP_SLOT_RESET_OBS  3
+#define AMDP_SLOT_Z          4
+#define AMDP_SLOT_ACTION     5
+
+typedef struct amdp amdp_t;
+
+/* Engine geometry.  Replaces the attribute soup AnyMDPEnv.set_task copies from the task dict
+ * (anymdp_env.py:32-46): one engine steps n_envs envs over n_tasks uploaded tasks that share
+ * task_type, na, da, do and the padded sizes. */
+typedef struct amdp_config {
+    int32_t  device;        /* CUDA device ordinal */
+    int32_t  task_type;     /* AMDP_MDP / AMDP_POMDP / AMDP_MTPOMDP */
+    int32_t  autoreset;     /* AMDP_AUTORESET_* */
+    int32_t  na;            /* actions per token (anymdp_env.py:52 asserts na > 1) */
+    int32_t  n_pad;         /* max n_real (= len(state_mapping)) over tasks, rounded up to a multiple of 4 */
+    int32_t  no_pad;        /* max `no` over tasks rounded up to a multiple of 4 (POMDP/MTPOMDP; else 0) */
+    int32_t  n_obs_tok;     /* `do` (1 unless MTPOMDP) */
+    int32_t  n_act_tok;     /* `da` (1 unless MTPOMDP) */
+    int32_t  s0_pad;        /* max len(s_0) over tasks */
+    int32_t  reserved0;
+    int64_t  n_envs;        /* envs owned by this handle (this GPU's shard) */
+    int64_t  n_tasks;       /* tasks resident on this handle */
+    uint64_t seed;          /* Philox key */
+    uint64_t env_id_base;   /* global id of local env 0 (multi-GPU shards: results independent of GPU count) */
+} amdp_config;
+
+int         amdp_abi_version(void);
+const char* amdp_strerror(int code);
+
+/* AnyMDPEnv.__init__ (anymdp_env.py:23-30): allocates per-env state and the (empty) task tables. */
+int         amdp_create(amdp_t** out, const amdp_config* cfg);
+int         amdp_destroy(amdp_t* h);
+/* Message of the last failure on this handle ("" if none).  HOST string owned by the handle. */
+const char* amdp_last_error(const amdp_t* h);
+/* Number of draw slots per (env, tick) = 8 * max(da, do, 1). */
+int         amdp_n_slots(const amdp_t* h);
+/* Bytes of device memory the handle owns (tables + per-env state). */
+int64_t     amdp_device_bytes(const amdp_t* h);
+
+/*
+ * AnyMDPEnv.set_task (anymdp_env.py:32-79) for tasks [t0, t0+cnt): validates and converts the
+ * task arrays into device tables.  Inputs are DEVICE arrays, zero-padded to the engine's sizes:
+ *   transition, reward, reward_noise  double [cnt][n_pad][na][n_pad]   (task["transition"], ...)
+ *   state_mapping                     int32  [cnt][n_pad]
+ *   n_real                            int32  [cnt]                     len(state_mapping)
+ *   is_terminal                       uint8  [cnt][n_pad]              1 where the state is in s_e
+ *   s0_idx / s0_prob / n_s0           int32 [cnt][s0_pad] / double [cnt][s0_pad] / int32 [cnt]
+ *   max_steps                         double [cnt]                     (float in the reference, :114)
+ *   ns                                int32  [cnt]                     task["ns"] (ns < 2 => always terminated, :108)
+ *   obs_transition                    double [cnt][do][n_pad][no_pad]  or NULL for MDP
+ *   status_out                        int32  [cnt]  AMDP_TASK_* per task (device; may be NULL)
+ * Builds, per (task, s, a) row, the float64 CDF numpy's choice() would build at every step
+ * (sequential left-to-right cumsum, then one IEEE divide by the last entry), the fp32
+ * (reward, reward_noise) payload, and the observation / start-state CDFs.
+ */
+int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt,
+                      const double* transition, const double* reward, const double* reward_noise,
+                      const int32_t* state_mapping, const int32_t* n_real, const uint8_t* is_terminal,
+                      const int32_t* s0_idx, const double* s0_prob, const int32_t* n_s0,
+                      const double* max_steps, const int32_t* ns,
+                      const double* obs_transition, int32_t* status_out, void* stream);
+
+/* Which task each env runs: env_task int32 [n_envs] (values in [0, n_tasks)).  Marks every env
+ * "needs reset" and clears its counters (set_task's `need_reset = True`, anymdp_env.py:79). */
+int amdp_assign(amdp_t* h, const int32_t* env_task, void* stream);
+
+/*
+ * AnyMDPEnv.reset (anymdp_env.py:81-90) for the envs with mask[i] != 0 (all when mask == NULL).
+ *   obs_out    int32 [n_envs][do]  observation after reset; -1 for envs not selected
+ *   u_inject   double [n_envs][n_slots] or NULL (engine Philox draws at the current tick)
+ * Consumes one tick.
+ */
+int amdp_reset(amdp_t* h, const uint8_t* mask, int32_t* obs_out, const double* u_inject, void* stream);
+
+/*
+ * AnyMDPEnv.step (anymdp_env.py:112-132) + single_step (:92-110) + get_observation (:145-159)
+ * for every env, plus the auto-reset the engine was created with.  Consumes one tick.
+ *   actions      int32 [n_envs][da], or NULL = built-in uniform random policy (slot 5)
+ *   obs          int32 [n_envs][do]   observation returned to the agent (after auto-reset, if any)
+ *   final_obs    int32 [n_envs][do]   observation of the step itself (== obs unless reset) or NULL
+ *   reward       float [n_envs]
+ *   reward_gt    float [n_envs] or NULL          info["reward_gt"] (:129)
+ *   terminated, truncated  uint8 [n_envs]
+ *   actions_out  int32 [n_envs][da] or NULL      the actions actually applied
+ *   u_inject     double [n_envs][n_slots] or NULL
+ */
+int amdp_step(amdp_t* h, const int32_t* actions, int32_t* obs, int32_t* final_obs,
+              float* reward, float* reward_gt, uint8_t* terminated, uint8_t* truncated,
+              int32_t* actions_out, const double* u_inject, void* stream);
+
+/*
+ * K consecutive steps in one launch (the data-collection loop around env.step(),
+ * test_utils.py:42-60, with same-step / next-step auto-reset).  Consumes K ticks.
+ *   actions   int32 [K][n_envs][da], or NULL = uniform random policy
+ * Trajectory outputs (each may be NULL) are addressed as base[k * step_stride + env * env_stride]
+ * in ELEMENTS (obs/actions_out additionally [.. + token]); pass (step_stride = n_envs * width,
+ * env_stride = width) for [K][N][width] or (width, K * width) for env-major [N][K][width].
+ *   u_inject  double [K][n_envs][n_slots] or NULL
+ */
+typedef struct amdp_traj {
+    int32_t* obs;           /* width do */
+    int32_t* actions_out;   /* width da */
+    float*   reward;        /* width 1 */
+    float*   reward_gt;     /* width 1 */
+    uint8_t* done;          /* width 1: bit0 terminated, bit1 truncated */
+    int64_t  step_stride;   /* in units of one record of width 1 (multiplied by the width internally) */
+    int64_t  env_stride;
+} amdp_traj;
+
+int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const amdp_traj* traj,
+                 const double* u_inject, void* stream);
+
+/*
+ * Episode statistics since the last amdp_assign()/amdp_clear_stats(), reduced over this handle's envs:
+ *   out8 double [8] (device): episodes, sum_return, sum_return_sq, sum_length, min_return,
+ *                             max_return, total_steps, reserved
+ * (caller side in the reference: numpy.mean(rewards), test_utils.py:60).  Sum-type entries are
+ * what a multi-GPU job all-reduces (ncclSum) once per iteration; min/max use ncclMin/ncclMax.
+ */
+int amdp_stats(amdp_t* h, double* out8, void* stream);
+int amdp_clear_stats(amdp_t* h, void* stream);
+
+/* info["transition_gt"] (anymdp_env.py:130): out double [n_envs][da][ns_out]: row of the
+ * observation-indexed transition table at (state_mapping[current state], action[k]).
+ * actions int32 [n_envs][da]; ns_out = width of the observable state space. */
+int amdp_gather_transition_gt(amdp_t* h, const int32_t* actions, int32_t ns_out, double* out, void* stream);
+
+/* The draw matrix the engine would use at ticks [tick0, tick0+K): out double [K][n_envs][n_slots]. */
+int amdp_dump_draws(amdp_t* h, uint64_t tick0, int32_t K, double* out, void* stream);
+
+/* Tick counter (number of reset/step/rollout ticks consumed so far). HOST values. */
+int amdp_get_tick(const amdp_t* h, uint64_t* tick);
+int amdp_set_tick(amdp_t* h, uint64_t tick);
+/* Replace the Philox key (honours reset(seed=...), which the reference ignores: anymdp_env.py:81,87). */
+int amdp_set_seed(amdp_t* h, uint64_t seed);
+
+/* Checkpoint / introspection of per-env state (AnyMDPEnv._state, .steps; anymdp_env.py:134-143).
+ * All DEVICE arrays of length n_envs; any pointer may be NULL.
+ *   state int32 (inner index), steps int32, flags uint8 (bit0 pending auto-reset, bit1 never reset),
+ *   ep_return double */
+int amdp_get_state(amdp_t* h, int32_t* state, int32_t* steps, uint8_t* flags, double* ep_return, void* stream);
+int amdp_set_state(amdp_t* h, const int32_t* state, const int32_t* steps, const uint8_t* flags,
+                   const double* ep_return, void* stream);
+/* mapped (observable) state of every env: state_mapping[_state] (anymdp_env.py:134-136) */
+int amdp_get_mapped_state(amdp_t* h, int32_t* out, void* stream);
+
+/* Synchronises `stream`, returns the OR of AMDP_FAULT_* bits raised since the last poll in
+ * *faults (HOST) and clears them. */
+int amdp_poll_errors(amdp_t* h, uint32_t* faults, void* stream);
+
+/* Debug/verification: copy the built CDF row of (task, s, a) to out double [n_pad] (device). */
+int amdp_debug_cdf_row(amdp_t* h, int64_t task, int32_t s, int32_t a, double* out, void* stream);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t amdp_launch_count(const amdp_t* h);
+
+/*
+ * Host-buffer convenience for end-to-end use from non-CUDA callers: K-step rollout with HOST
+ * (preferably pinned) action input and trajectory output; the library stages through device
+ * buffers it owns, in chunks, overlapping copies with the rollout kernel.  Synchronises.
+ *   actions_host  int32 [K][n_envs][da] or NULL (uniform policy)
+ *   obs_host int32 [K][n_envs][do], reward_host float [K][n_envs], done_host uint8 [K][n_envs]
+ *   (any output may be NULL)
+ */
+int amdp_rollout_host(amdp_t* h, int32_t K, int32_t chunk, const int32_t* actions_host,
+                      int32_t* obs_host, float* reward_host, uint8_t* done_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMDP_B200_H */

@@ -38,9 +38,9 @@ SLOT_RESET = 1       # uniform for the s_0 draw of an (auto-)reset              
 SLOT_OBS = 2         # uniform for observation token k after the step            (k < do)
 SLOT_RESET_OBS = 3   # uniform for observation token k after an (auto-)reset     (k < do)
 SLOT_Z = 4           # standard normal for the reward of action token k          (k < da)
-SLOT_Z_SPARE = 5
-SLOT_ACTION = 6      # action of token k under the built-in uniform random policy (k < da)
-SLOT_SPARE = 7
+SLOT_ACTION = 5      # action of token k under the built-in uniform random policy (k < da)
+SLOT_SPARE0 = 6
+SLOT_SPARE1 = 7
 SLOTS_PER_TOKEN = 8
 
 
@@ -387,9 +387,11 @@ def engine_draws(seed, env_ids, tick, da=1, do=1, na=2):
     """The draw matrix U[N, n_slots] the engine uses at `tick` for global env ids `env_ids`.
 
     Philox counter = (env_lo, block, tick_lo, tick_hi), key = (seed_lo, seed_hi);
-    block b yields slots 2b (words 0,1) and 2b+1 (words 2,3) — except:
-      kind 4 (z):      Box-Muller on words 0,1 of block (4 + 8k)/2, single precision
-      kind 6 (action): (word0 * na) >> 32 of block (6 + 8k)/2
+    block b yields slots 2b (words 0,1) and 2b+1 (words 2,3) — except block (4 + 8k)/2, which
+    carries both non-uniform draws of token k so that an MDP step costs two Philox calls:
+      kind 4 (z):      Box-Muller on words 0,1, single-precision uniforms ((w >> 8) + 0.5) * 2^-24
+      kind 5 (action): (word2 * na) >> 32
+    Blocks (6 + 8k)/2 are never generated (spare slots stay 0).
     """
     env_ids = numpy.asarray(env_ids, dtype=numpy.uint64)
     ns_ = n_slots(da, do)
@@ -403,10 +405,9 @@ def engine_draws(seed, env_ids, tick, da=1, do=1, na=2):
             u1 = ((w[0] >> numpy.uint32(8)).astype(numpy.float32) + numpy.float32(0.5)) * numpy.float32(2.0 ** -24)
             u2 = ((w[1] >> numpy.uint32(8)).astype(numpy.float32) + numpy.float32(0.5)) * numpy.float32(2.0 ** -24)
             U[:, 2 * b] = numpy.sqrt(-2.0 * numpy.log(u1.astype(numpy.float64))) * numpy.cos(2.0 * numpy.pi * u2.astype(numpy.float64))
-            U[:, 2 * b + 1] = 0.0
-        elif kind == SLOT_ACTION:
-            U[:, 2 * b] = ((w[0].astype(numpy.uint64) * numpy.uint64(na)) >> numpy.uint64(32)).astype(numpy.float64)
-            U[:, 2 * b + 1] = 0.0
+            U[:, 2 * b + 1] = ((w[2].astype(numpy.uint64) * numpy.uint64(na)) >> numpy.uint64(32)).astype(numpy.float64)
+        elif kind == SLOT_SPARE0:
+            pass
         else:
             U[:, 2 * b] = u53(w[0], w[1])
             U[:, 2 * b + 1] = u53(w[2], w[3])

@@ -1,0 +1,22 @@
+"""xenoverse_b200 — B200-native stepping engine for Xenoverse's AnyMDP environment family.
+
+Importing the package registers `anymdp-v0`, exactly as `import xenoverse.anymdp` does in the
+reference (xenoverse/anymdp/__init__.py:24-30).  The CUDA library is loaded eagerly: without
+`libamdp_b200.so` the import fails — there is no CPU fallback.
+"""
+from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
+from .gym_compat import register, make, spaces, HAVE_GYMNASIUM  # noqa: F401
+from .engine import Engine, AMDPError, task_geometry, pack_tasks  # noqa: F401
+from .anymdp_env import AnyMDPEnv  # noqa: F401
+from .vec_env import AnyMDPVecEnv  # noqa: F401
+from .synth import synth_task, synth_packed, synth_geometry, packed_to_task  # noqa: F401
+
+__version__ = "0.1.0"
+
+register(
+    id="anymdp-v0",
+    entry_point="xenoverse_b200:AnyMDPEnv",
+    order_enforce=False,
+    disable_env_checker=True,
+    kwargs={"max_steps": 5000},
+)

@@ -1,0 +1,1058 @@
+// amdp_b200.cu — B200 (sm_100a) AnyMDP stepping engine behind the C ABI of include/amdp_b200.h.
+//
+// What this replaces (reference = FutureAGI/Xenoverse, xenoverse/anymdp/anymdp_env.py):
+//   set_task :32-79   -> k_build_tables (CDF build = the cumsum + normalise numpy's choice() redoes
+//                        every step, hoisted to upload time; same float64 operation order)
+//   reset    :81-90   -> k_reset
+//   step     :112-132 + single_step :92-110 + get_observation :145-159 -> k_step / k_rollout
+// The path is gather + search on float64 tables: HBM/L2 bound, no tensor-core work.
+//
+// Execution model: G = 1..32 adjacent lanes own one env ("group"); a CDF row of n_pad doubles is
+// fetched with one coalesced pass (each lane 32 B = one DRAM sector per 4*G entries) and the
+// draw index #{i : cdf[i] <= u} is a compare + group reduction — one memory round trip per
+// transition instead of log2(n) dependent ones.  Everything else a step needs is either in the
+// per-task small tables (L1/L2 resident) or in the fp32 payload entry addressed by (s, a, s').
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+
+#include "amdp_b200.h"
+
+#define FLAG_PENDING 1   // next_step mode: the next step() performs the reset
+#define FLAG_VIRGIN  2   // never reset since assign (anymdp_env.py:79 need_reset = True)
+
+// ------------------------------------------------------------------------------------------------
+// device tables / state (passed to kernels by value)
+// ------------------------------------------------------------------------------------------------
+struct Tables {
+    const double*  cdf;       // [T][n_pad][na][n_pad] normalised CDF rows, pad = 1.0
+    const float2*  payload;   // [T][n_pad][na][n_pad] (reward, reward_noise) fp32
+    const int32_t* sinfo;     // [T][n_pad]  state_mapping | (is_terminal << 31)
+    const double*  s0_cdf;    // [T][s0_pad] pad = 2.0
+    const int32_t* s0_idx;    // [T][s0_pad]
+    const double*  obs_cdf;   // [T][do][n_pad][no_pad] pad = 1.0 (POMDP / MTPOMDP)
+    const int32_t* max_ceil;  // [T] ceil(max_steps)
+    const uint8_t* tflags;    // [T] bit0: ns < 2 (always terminated, anymdp_env.py:108)
+    const double*  raw_t;     // [T][n_pad][na][n_pad] raw transition (only if keep_transition) or null
+    const int32_t* n_real;    // [T]
+    int n_pad, na, no_pad, d_o, d_a, s0_pad, task_type, autoreset;
+};
+
+struct EnvArrays {
+    int32_t* state;      // inner state index
+    int32_t* steps;      // steps in the current episode
+    uint8_t* flags;      // FLAG_*
+    double*  ep_return;  // running return of the current episode (fp64: SURVEY §7.2)
+    const int32_t* task; // task of each env
+    // per-env episode statistics (closed episodes only)
+    unsigned long long* ep_count;
+    double* sum_ret;
+    double* sum_ret_sq;
+    unsigned long long* sum_len;
+    double* min_ret;
+    double* max_ret;
+    unsigned int* faults;  // single word, sticky
+    long long n_envs;
+    unsigned long long env_id_base;
+    uint2 key;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Random123; constants as curand_philox4x32_x.h:88-91) and the draw constructions
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// numpy MT19937 double: ((a >> 5) * 2^26 + (b >> 6)) / 2^53 — exact in fp64
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+    const unsigned long long v = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
+    return (double)(long long)v * 1.1102230246251565e-16;
+}
+
+__device__ __forceinline__ uint4 philox_block(unsigned long long env, uint32_t block, unsigned long long tick, uint2 key) {
+    const uint4 ctr = make_uint4((uint32_t)env, block + ((uint32_t)(env >> 32) << 16), (uint32_t)tick, (uint32_t)(tick >> 32));
+    return philox4x32_10(ctr, key);
+}
+
+__device__ __forceinline__ float box_muller(uint32_t w0, uint32_t w1) {
+    const float u1 = (__uint2float_rn(w0 >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float u2 = (__uint2float_rn(w1 >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// Source of the draws of one (env, tick): injected matrix row or Philox.
+struct Draws {
+    const double* row;          // injected row (n_slots doubles) or null
+    unsigned long long env, tick;
+    uint2 key;
+    __device__ __forceinline__ void pair(int block, double& a, double& b) const {   // slots 2b, 2b+1 as uniforms
+        if (row) { a = row[2 * block]; b = row[2 * block + 1]; return; }
+        const uint4 w = philox_block(env, (uint32_t)block, tick, key);
+        a = u53(w.x, w.y);
+        b = u53(w.z, w.w);
+    }
+    __device__ __forceinline__ void z_action(int tok, int na, double& z, int& act) const {  // slots 4,5 of token
+        const int s = AMDP_SLOT_Z + AMDP_SLOTS_PER_TOKEN * tok;
+        if (row) { z = row[s]; act = (int)row[s + 1]; return; }
+        const uint4 w = philox_block(env, (uint32_t)(s >> 1), tick, key);
+        z = (double)box_muller(w.x, w.y);
+        act = (int)__umulhi(w.z, (uint32_t)na);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// group primitives: G adjacent lanes own one env
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ int group_sum(int v) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double2 ld_f64x2(const double* p) {
+    return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+// #{i < len : row[i] <= u}, row 32-byte aligned, len a multiple of 4.  All lanes of the warp
+// must call (shuffles); lanes with pred == false issue no loads.
+template <int G>
+__device__ __forceinline__ int row_count(const double* __restrict__ row, int len, double u, int lane, bool pred) {
+    int c = 0;
+    if (pred) {
+        for (int i = lane * 4; i < len; i += G * 4) {
+            const double2 a = ld_f64x2(row + i);
+            const double2 b = ld_f64x2(row + i + 2);
+            c += (a.x <= u) + (a.y <= u) + (b.x <= u) + (b.y <= u);
+        }
+    }
+    return group_sum<G>(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one env, one tick (registers in / registers out)
+// ------------------------------------------------------------------------------------------------
+struct EnvRegs {
+    int state, steps, flags;
+    double ep_return;
+    // statistics of episodes closed so far (loaded lazily only by the rollout kernel)
+    unsigned long long ep_count, sum_len;
+    double sum_ret, sum_ret_sq, min_ret, max_ret;
+};
+
+struct TickOut {
+    float reward, reward_gt;
+    int term, trunc;
+    int finished;         // an episode was closed in this tick
+    double fin_return;    // its return
+    int fin_steps;        // its length
+};
+
+#define MAX_TOK 8
+
+// Observation of state s (anymdp_env.py:145-159).  MDP: mapping; POMDP/MTPOMDP: one draw per token.
+template <int G>
+__device__ __forceinline__ void observe(const Tables& T, long long t, int s, const Draws& D, int kind, int lane, bool pred,
+                                        int* obs /* [d_o] */) {
+    if (T.task_type == AMDP_MDP) {
+        obs[0] = pred ? (T.sinfo[t * T.n_pad + s] & 0x7fffffff) : 0;
+        return;
+    }
+    for (int k = 0; k < T.d_o; ++k) {
+        double u0, u1;
+        D.pair((kind + AMDP_SLOTS_PER_TOKEN * k) >> 1, u0, u1);
+        const double u = (kind & 1) ? u1 : u0;
+        const double* row = T.obs_cdf + ((t * T.d_o + k) * T.n_pad + s) * (long long)T.no_pad;
+        obs[k] = row_count<G>(row, T.no_pad, u, lane, pred);
+    }
+}
+
+// Mirrors oracle.anymdp_oracle.OracleVecEnv.step for one env (which mirrors anymdp_env.py:112-132
+// plus the auto-reset modes).  `active` false => no memory traffic, but the lane still takes
+// part in the group shuffles.
+template <int G>
+__device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, long long t, bool active, int lane,
+                                         const Draws& D, const int32_t* act_in /* [d_a] or null */,
+                                         EnvRegs& R, TickOut& O, int* obs, int* final_obs, int* act_used) {
+    O.reward = 0.f; O.reward_gt = 0.f; O.term = 0; O.trunc = 0; O.finished = 0; O.fin_return = 0.0; O.fin_steps = 0;
+    const int da = T.d_a;
+    // draws of block 0: transition (token 0) and reset uniforms
+    double u_trans0, u_reset;
+    D.pair(0, u_trans0, u_reset);
+
+    const bool pending = active && T.autoreset == AMDP_AUTORESET_NEXT_STEP && (R.flags & FLAG_PENDING);
+    const bool stepping = active && !pending;
+    const int always_term = active ? (T.tflags[t] & 1) : 0;
+    unsigned int fault = 0;
+    // actions and reward normals of every token (fixed slots: consumption never depends on data)
+    double zs[MAX_TOK];
+    for (int k = 0; k < da; ++k) {
+        int a_pol = 0;
+        zs[k] = 0.0;
+        if (!act_in || stepping) D.z_action(k, T.na, zs[k], a_pol);
+        const int a = act_in ? (active ? act_in[k] : 0) : a_pol;
+        act_used[k] = a;
+        if (stepping && (a < 0 || a >= T.na)) fault |= AMDP_FAULT_BAD_ACTION;          // anymdp_env.py:97
+    }
+    if (stepping) {
+        if (R.flags & FLAG_VIRGIN) fault |= AMDP_FAULT_NEED_RESET;                     // anymdp_env.py:93-94
+        else if ((T.sinfo[t * T.n_pad + R.state] < 0) && !always_term) fault |= AMDP_FAULT_TERMINAL_STATE;  // :95-96
+    }
+    const bool ok = stepping && fault == 0;     // faulted envs are left untouched
+    int s = R.state;
+    bool term = false;
+    double rew = 0.0, rew_gt = 0.0;
+    if (ok) {
+        R.steps += 1;                                                                   // anymdp_env.py:113-114
+        O.trunc = R.steps >= T.max_ceil[t];
+    }
+    for (int k = 0; k < da; ++k) {
+        const bool live = ok && !term;                                                  // :120-126 break on termination
+        double u;
+        if (k == 0) u = u_trans0; else { double u1; D.pair((AMDP_SLOT_TRANS + AMDP_SLOTS_PER_TOKEN * k) >> 1, u, u1); }
+        const long long rowi = ((t * T.n_pad + s) * T.na + (live ? act_used[k] : 0)) * (long long)T.n_pad;
+        const int nxt = row_count<G>(T.cdf + rowi, T.n_pad, u, lane, live);            // :99-100
+        if (live) {
+            const float2 pay = __ldg(T.payload + rowi + nxt);                           // :103-105
+            const double r_gt = (double)pay.x;
+            rew_gt += r_gt;
+            rew += r_gt + (double)pay.y * zs[k];
+            s = nxt;                                                                    // :107
+            if ((T.sinfo[t * T.n_pad + s] < 0) || always_term) term = true;             // :108
+        }
+    }
+    if (ok) {
+        R.state = s;
+        O.term = term;
+        O.reward = (float)rew;
+        O.reward_gt = (float)rew_gt;
+        R.ep_return += rew;
+    }
+    // observation of the step (drawn after the transition, from the new state; :132,145-159)
+    observe<G>(T, t, s, D, AMDP_SLOT_OBS, lane, ok, obs);
+    for (int k = 0; k < T.d_o; ++k) final_obs[k] = obs[k];
+
+    const bool done = ok && (O.term || O.trunc);
+    bool do_reset = pending;
+    if (done && T.autoreset != AMDP_AUTORESET_DISABLED) {
+        // close the episode
+        O.finished = 1; O.fin_return = R.ep_return; O.fin_steps = R.steps;
+        R.ep_count += 1; R.sum_len += (unsigned long long)R.steps;
+        R.sum_ret += R.ep_return; R.sum_ret_sq += R.ep_return * R.ep_return;
+        R.min_ret = fmin(R.min_ret, R.ep_return); R.max_ret = fmax(R.max_ret, R.ep_return);
+        R.ep_return = 0.0;
+        if (T.autoreset == AMDP_AUTORESET_SAME_STEP) do_reset = true; else R.flags |= FLAG_PENDING;
+    }
+    // reset (anymdp_env.py:81-90): s_0 draw, then observation
+    int s_new = R.state;
+    if (do_reset) {
+        int c = 0;
+        for (int i = 0; i < T.s0_pad; ++i) c += (T.s0_cdf[t * T.s0_pad + i] <= u_reset);
+        s_new = T.s0_idx[t * T.s0_pad + min(c, T.s0_pad - 1)];
+        R.state = s_new; R.steps = 0; R.flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
+    }
+    if (T.task_type == AMDP_MDP) {
+        if (do_reset) { obs[0] = T.sinfo[t * T.n_pad + s_new] & 0x7fffffff; if (pending) final_obs[0] = obs[0]; }
+    } else {
+        int robs[MAX_TOK];
+        observe<G>(T, t, s_new, D, AMDP_SLOT_RESET_OBS, lane, do_reset, robs);
+        if (do_reset) for (int k = 0; k < T.d_o; ++k) { obs[k] = robs[k]; if (pending) final_obs[k] = robs[k]; }
+    }
+    if (fault && lane == 0) atomicOr(E.faults, fault);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_regs(const EnvArrays& E, long long e, EnvRegs& R, bool with_stats) {
+    R.state = E.state[e]; R.steps = E.steps[e]; R.flags = E.flags[e]; R.ep_return = E.ep_return[e];
+    if (with_stats) {
+        R.ep_count = E.ep_count[e]; R.sum_len = E.sum_len[e]; R.sum_ret = E.sum_ret[e];
+        R.sum_ret_sq = E.sum_ret_sq[e]; R.min_ret = E.min_ret[e]; R.max_ret = E.max_ret[e];
+    } else {
+        R.ep_count = 0; R.sum_len = 0; R.sum_ret = 0; R.sum_ret_sq = 0; R.min_ret = INFINITY; R.max_ret = -INFINITY;
+    }
+}
+
+__device__ __forceinline__ void store_regs(const EnvArrays& E, long long e, const EnvRegs& R) {
+    E.state[e] = R.state; E.steps[e] = R.steps; E.flags[e] = (uint8_t)R.flags; E.ep_return[e] = R.ep_return;
+}
+
+__device__ __forceinline__ void store_stats(const EnvArrays& E, long long e, const EnvRegs& R) {
+    E.ep_count[e] = R.ep_count; E.sum_len[e] = R.sum_len; E.sum_ret[e] = R.sum_ret;
+    E.sum_ret_sq[e] = R.sum_ret_sq; E.min_ret[e] = R.min_ret; E.max_ret[e] = R.max_ret;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) k_step(Tables T, EnvArrays E, unsigned long long tick, int n_slots,
+                                              const int32_t* __restrict__ actions, int32_t* __restrict__ obs_out,
+                                              int32_t* __restrict__ final_obs_out, float* __restrict__ reward,
+                                              float* __restrict__ reward_gt, uint8_t* __restrict__ terminated,
+                                              uint8_t* __restrict__ truncated, int32_t* __restrict__ actions_out,
+                                              const double* __restrict__ u_inject) {
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e = gtid / G;
+    const int lane = (int)(gtid % G);
+    const bool active = e < E.n_envs;
+    const long long ec = active ? e : 0;
+    const long long t = E.task[ec];
+    EnvRegs R;
+    load_regs(E, ec, R, false);
+    Draws D;
+    D.row = u_inject ? u_inject + ec * n_slots : nullptr;
+    D.env = E.env_id_base + (unsigned long long)ec; D.tick = tick; D.key = E.key;
+    TickOut O;
+    int obs[MAX_TOK], fobs[MAX_TOK], act[MAX_TOK];
+    env_tick<G>(T, E, t, active, lane, D, actions ? actions + ec * T.d_a : nullptr, R, O, obs, fobs, act);
+    if (active && lane == 0) {
+        store_regs(E, e, R);
+        if (O.finished) {
+            // per-env accumulators are only touched when an episode closes
+            E.ep_count[e] += 1; E.sum_len[e] += (unsigned long long)O.fin_steps;
+            E.sum_ret[e] += O.fin_return; E.sum_ret_sq[e] += O.fin_return * O.fin_return;
+            E.min_ret[e] = fmin(E.min_ret[e], O.fin_return); E.max_ret[e] = fmax(E.max_ret[e], O.fin_return);
+        }
+        for (int k = 0; k < T.d_o; ++k) {
+            obs_out[e * T.d_o + k] = obs[k];
+            if (final_obs_out) final_obs_out[e * T.d_o + k] = fobs[k];
+        }
+        reward[e] = O.reward;
+        if (reward_gt) reward_gt[e] = O.reward_gt;
+        terminated[e] = (uint8_t)O.term;
+        truncated[e] = (uint8_t)O.trunc;
+        if (actions_out) for (int k = 0; k < T.d_a; ++k) actions_out[e * T.d_a + k] = act[k];
+    }
+}
+
+// K ticks per launch, env state and statistics in registers across ticks.
+template <int G>
+__global__ void __launch_bounds__(256) k_rollout(Tables T, EnvArrays E, unsigned long long tick0, int K, int n_slots,
+                                                 const int32_t* __restrict__ actions, amdp_traj J,
+                                                 const double* __restrict__ u_inject) {
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e = gtid / G;
+    const int lane = (int)(gtid % G);
+    const bool active = e < E.n_envs;
+    const long long ec = active ? e : 0;
+    const long long t = E.task[ec];
+    EnvRegs R;
+    load_regs(E, ec, R, true);
+    Draws D;
+    D.env = E.env_id_base + (unsigned long long)ec; D.key = E.key;
+    int obs[MAX_TOK], fobs[MAX_TOK], act[MAX_TOK];
+    for (int k = 0; k < K; ++k) {
+        D.tick = tick0 + (unsigned long long)k;
+        D.row = u_inject ? u_inject + ((long long)k * E.n_envs + ec) * n_slots : nullptr;
+        TickOut O;
+        env_tick<G>(T, E, t, active, lane, D, actions ? actions + ((long long)k * E.n_envs + ec) * T.d_a : nullptr,
+                    R, O, obs, fobs, act);
+        if (active && lane == 0) {
+            const long long o = (long long)k * J.step_stride + e * J.env_stride;
+            if (J.obs) for (int j = 0; j < T.d_o; ++j) J.obs[o * T.d_o + j] = obs[j];
+            if (J.actions_out) for (int j = 0; j < T.d_a; ++j) J.actions_out[o * T.d_a + j] = act[j];
+            if (J.reward) J.reward[o] = O.reward;
+            if (J.reward_gt) J.reward_gt[o] = O.reward_gt;
+            if (J.done) J.done[o] = (uint8_t)(O.term | (O.trunc << 1));
+        }
+    }
+    if (active && lane == 0) { store_regs(E, e, R); store_stats(E, e, R); }
+}
+
+__global__ void k_reset(Tables T, EnvArrays E, unsigned long long tick, int n_slots, const uint8_t* __restrict__ mask,
+                        int32_t* __restrict__ obs_out, const double* __restrict__ u_inject) {
+    // one thread per env (G = 1): reset is rare and touches only the small per-task tables
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E.n_envs) return;
+    const bool sel = mask ? (mask[e] != 0) : true;
+    if (!sel) { for (int k = 0; k < T.d_o; ++k) obs_out[e * T.d_o + k] = -1; return; }
+    const long long t = E.task[e];
+    Draws D;
+    D.row = u_inject ? u_inject + e * n_slots : nullptr;
+    D.env = E.env_id_base + (unsigned long long)e; D.tick = tick; D.key = E.key;
+    double u_trans0, u_reset;
+    D.pair(0, u_trans0, u_reset);
+    int c = 0;
+    for (int i = 0; i < T.s0_pad; ++i) c += (T.s0_cdf[t * T.s0_pad + i] <= u_reset);
+    const int s = T.s0_idx[t * T.s0_pad + min(c, T.s0_pad - 1)];
+    E.state[e] = s; E.steps[e] = 0; E.flags[e] = 0; E.ep_return[e] = 0.0;
+    int obs[MAX_TOK];
+    observe<1>(T, t, s, D, AMDP_SLOT_RESET_OBS, 0, true, obs);
+    for (int k = 0; k < T.d_o; ++k) obs_out[e * T.d_o + k] = obs[k];
+}
+
+// ---- task upload -------------------------------------------------------------------------------
+// One thread per (task, s, a) row: sequential float64 cumsum (numpy's 1-D cumsum order), one IEEE
+// divide per entry by the last partial sum (`cdf /= cdf[-1]`), pad with 1.0.  All-zero rows
+// (terminal states, task_sampler_utils.py:108,152) would be 0/0 = NaN: they are filled with 1.0
+// and are never sampled.  Also performs set_task's and numpy choice()'s validity checks.
+__global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __restrict__ transition,
+                             const double* __restrict__ reward, const double* __restrict__ noise,
+                             const int32_t* __restrict__ n_real, const uint8_t* __restrict__ is_terminal,
+                             double* __restrict__ cdf, float2* __restrict__ payload, int32_t* __restrict__ status) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long rows = cnt * n_pad * na;
+    if (r >= rows) return;
+    const long long t = r / ((long long)n_pad * na);
+    const int s = (int)((r / na) % n_pad);
+    const int n = n_real[t];
+    const double* p = transition + r * n_pad;
+    double* c = cdf + r * n_pad;
+    float2* pl = payload + r * n_pad;
+    for (int i = 0; i < n_pad; ++i) pl[i] = make_float2((float)reward[r * n_pad + i], (float)noise[r * n_pad + i]);
+    if (s >= n) { for (int i = 0; i < n_pad; ++i) c[i] = 1.0; return; }
+    double acc = 0.0, ksum = 0.0, kc = 0.0;
+    bool neg = false;
+    for (int i = 0; i < n; ++i) {
+        const double x = p[i];
+        neg |= (x < 0.0);
+        acc = __dadd_rn(acc, x);
+        c[i] = acc;
+        // Kahan sum as numpy's kahan_sum() in choice()
+        const double y = __dsub_rn(x, kc);
+        const double tt = __dadd_rn(ksum, y);
+        kc = __dsub_rn(__dsub_rn(tt, ksum), y);
+        ksum = tt;
+    }
+    const double last = acc;
+    const bool terminal = is_terminal[t * n_pad + s] != 0;
+    int st = AMDP_TASK_OK;
+    if (!terminal) {
+        const double d = last - 1.0;
+        if (d * d >= 1.0e-6) st = AMDP_TASK_BAD_ROW_SUM;
+        else if (fabs(ksum - 1.0) > 1.4901161193847656e-08) st = AMDP_TASK_NOT_NORMALISED;
+        else if (neg) st = AMDP_TASK_NEGATIVE_P;
+    }
+    if (st != AMDP_TASK_OK && status) atomicMax(status + t, st);
+    if (last > 0.0 && !(st == AMDP_TASK_BAD_ROW_SUM)) {
+        for (int i = 0; i < n; ++i) {
+            double v = __ddiv_rn(c[i], last);
+            c[i] = (v == 0.0) ? 0.0 : v;     // canonicalise -0.0
+        }
+    } else {
+        for (int i = 0; i < n; ++i) c[i] = 1.0;
+    }
+    for (int i = n; i < n_pad; ++i) c[i] = 1.0;
+}
+
+// per-task small tables; one thread per task
+__global__ void k_build_small(int64_t cnt, int n_pad, int s0_pad, const int32_t* __restrict__ state_mapping,
+                              const int32_t* __restrict__ n_real, const uint8_t* __restrict__ is_terminal,
+                              const int32_t* __restrict__ s0_idx, const double* __restrict__ s0_prob,
+                              const int32_t* __restrict__ n_s0, const double* __restrict__ max_steps,
+                              const int32_t* __restrict__ ns, int32_t* __restrict__ sinfo, double* __restrict__ s0_cdf,
+                              int32_t* __restrict__ s0_idx_out, int32_t* __restrict__ max_ceil,
+                              uint8_t* __restrict__ tflags, int32_t* __restrict__ n_real_out,
+                              int32_t* __restrict__ status) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    for (int i = 0; i < n_pad; ++i) {
+        const int m = state_mapping[t * n_pad + i] & 0x7fffffff;
+        sinfo[t * n_pad + i] = m | (is_terminal[t * n_pad + i] ? (int)0x80000000 : 0);
+    }
+    const int k = n_s0[t];
+    double acc = 0.0;
+    for (int i = 0; i < k; ++i) { acc = __dadd_rn(acc, s0_prob[t * s0_pad + i]); s0_cdf[t * s0_pad + i] = acc; }
+    for (int i = 0; i < s0_pad; ++i) {
+        s0_cdf[t * s0_pad + i] = (i < k) ? __ddiv_rn(s0_cdf[t * s0_pad + i], acc) : 2.0;
+        const int idx = (i < k) ? s0_idx[t * s0_pad + i] : s0_idx[t * s0_pad + (k > 0 ? k - 1 : 0)];
+        s0_idx_out[t * s0_pad + i] = idx;
+        if (i < k && is_terminal[t * n_pad + idx] && status) atomicMax(status + t, AMDP_TASK_S0_IN_SE);
+    }
+    const double ms = ceil(max_steps[t]);
+    max_ceil[t] = ms > 2147483647.0 ? 2147483647 : (ms < 0.0 ? 0 : (int32_t)ms);
+    tflags[t] = (uint8_t)(ns[t] < 2 ? 1 : 0);
+    n_real_out[t] = n_real[t];
+}
+
+// observation CDF rows: one thread per (task, token, state)
+__global__ void k_build_obs(int64_t rows, int n_pad, int no_pad, const double* __restrict__ obs_t, double* __restrict__ obs_cdf) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const double* p = obs_t + r * no_pad;
+    double* c = obs_cdf + r * no_pad;
+    double acc = 0.0;
+    for (int i = 0; i < no_pad; ++i) { acc = __dadd_rn(acc, p[i]); c[i] = acc; }
+    // zero padding leaves the tail at the final partial sum, i.e. 1.0 after the divide
+    if (acc > 0.0) for (int i = 0; i < no_pad; ++i) { double v = __ddiv_rn(c[i], acc); c[i] = (v == 0.0) ? 0.0 : v; }
+    else for (int i = 0; i < no_pad; ++i) c[i] = 1.0;
+}
+
+__global__ void k_assign(EnvArrays E, int32_t* task_dst, const int32_t* __restrict__ env_task) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E.n_envs) return;
+    task_dst[e] = env_task[e];
+    E.state[e] = 0; E.steps[e] = 0; E.flags[e] = FLAG_VIRGIN; E.ep_return[e] = 0.0;
+    E.ep_count[e] = 0; E.sum_len[e] = 0; E.sum_ret[e] = 0.0; E.sum_ret_sq[e] = 0.0;
+    E.min_ret[e] = INFINITY; E.max_ret[e] = -INFINITY;
+}
+
+__global__ void k_clear_stats(EnvArrays E) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E.n_envs) return;
+    E.ep_count[e] = 0; E.sum_len[e] = 0; E.sum_ret[e] = 0.0; E.sum_ret_sq[e] = 0.0;
+    E.min_ret[e] = INFINITY; E.max_ret[e] = -INFINITY;
+}
+
+// ---- statistics: deterministic two-stage reduction ---------------------------------------------
+#define STAT_BLOCKS 148
+#define STAT_THREADS 256
+struct Stat6 { double n, sr, sq, sl, mn, mx; };
+
+__device__ __forceinline__ Stat6 stat_merge(Stat6 a, Stat6 b) {
+    a.n += b.n; a.sr += b.sr; a.sq += b.sq; a.sl += b.sl; a.mn = fmin(a.mn, b.mn); a.mx = fmax(a.mx, b.mx);
+    return a;
+}
+
+__device__ __forceinline__ Stat6 stat_block_reduce(Stat6 v) {
+    __shared__ Stat6 sh[STAT_THREADS];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = STAT_THREADS / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] = stat_merge(sh[threadIdx.x], sh[threadIdx.x + o]);
+        __syncthreads();
+    }
+    return sh[0];
+}
+
+__global__ void __launch_bounds__(STAT_THREADS) k_stats_partial(EnvArrays E, Stat6* __restrict__ part) {
+    Stat6 v = {0, 0, 0, 0, INFINITY, -INFINITY};
+    for (long long e = (long long)blockIdx.x * STAT_THREADS + threadIdx.x; e < E.n_envs; e += (long long)STAT_BLOCKS * STAT_THREADS) {
+        Stat6 w = {(double)E.ep_count[e], E.sum_ret[e], E.sum_ret_sq[e], (double)E.sum_len[e], E.min_ret[e], E.max_ret[e]};
+        v = stat_merge(v, w);
+    }
+    v = stat_block_reduce(v);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
+__global__ void __launch_bounds__(STAT_THREADS) k_stats_final(const Stat6* __restrict__ part, double total_steps, double* __restrict__ out8) {
+    Stat6 v = {0, 0, 0, 0, INFINITY, -INFINITY};
+    if (threadIdx.x < STAT_BLOCKS) v = part[threadIdx.x];
+    v = stat_block_reduce(v);
+    if (threadIdx.x == 0) {
+        out8[0] = v.n; out8[1] = v.sr; out8[2] = v.sq; out8[3] = v.sl; out8[4] = v.mn; out8[5] = v.mx;
+        out8[6] = total_steps; out8[7] = 0.0;
+    }
+}
+
+// ---- introspection -----------------------------------------------------------------------------
+__global__ void k_dump_draws(EnvArrays E, unsigned long long tick0, int K, int n_slots, int na, double* __restrict__ out) {
+    // one thread per (tick, env, block)
+    const int blocks = n_slots / 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)K * E.n_envs * blocks;
+    if (i >= total) return;
+    const int b = (int)(i % blocks);
+    const long long e = (i / blocks) % E.n_envs;
+    const long long k = i / ((long long)blocks * E.n_envs);
+    double* o = out + (k * E.n_envs + e) * n_slots + 2 * b;
+    const int kind = (2 * b) % AMDP_SLOTS_PER_TOKEN;
+    if (kind == 6) { o[0] = 0.0; o[1] = 0.0; return; }
+    const uint4 w = philox_block(E.env_id_base + (unsigned long long)e, (uint32_t)b, tick0 + (unsigned long long)k, E.key);
+    if (kind == AMDP_SLOT_Z) { o[0] = (double)box_muller(w.x, w.y); o[1] = (double)__umulhi(w.z, (uint32_t)na); }
+    else { o[0] = u53(w.x, w.y); o[1] = u53(w.z, w.w); }
+}
+
+__global__ void k_mapped_state(Tables T, EnvArrays E, int32_t* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E.n_envs) return;
+    out[e] = T.sinfo[(long long)E.task[e] * T.n_pad + E.state[e]] & 0x7fffffff;
+}
+
+// info["transition_gt"] (anymdp_env.py:130): one block per (env, token)
+__global__ void k_transition_gt(Tables T, EnvArrays E, const int32_t* __restrict__ actions, int ns_out, double* __restrict__ out) {
+    const long long e = blockIdx.x / T.d_a;
+    const int k = blockIdx.x % T.d_a;
+    const long long t = E.task[e];
+    const int s = E.state[e];
+    const int a = actions[e * T.d_a + k];
+    double* o = out + (e * T.d_a + k) * (long long)ns_out;
+    for (int j = threadIdx.x; j < ns_out; j += blockDim.x) o[j] = 0.0;
+    __syncthreads();
+    if (a < 0 || a >= T.na) return;
+    const double* row = T.raw_t + ((t * T.n_pad + s) * T.na + a) * (long long)T.n_pad;
+    const int n = T.n_real[t];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int m = T.sinfo[t * T.n_pad + j] & 0x7fffffff;
+        if (m < ns_out) o[m] = row[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct amdp {
+    amdp_config cfg;
+    int n_slots;
+    int G;                 // lanes per env
+    Tables T;
+    EnvArrays E;
+    // owned device memory
+    double* cdf; float2* payload; int32_t* sinfo; double* s0_cdf; int32_t* s0_idx; double* obs_cdf;
+    int32_t* max_ceil; uint8_t* tflags; double* raw_t; int32_t* n_real;
+    int32_t* env_task;
+    Stat6* stat_part;
+    unsigned int* faults;
+    unsigned long long tick;
+    double total_steps;
+    int64_t bytes;
+    int64_t launches;
+    bool uploaded, assigned;
+    char err[512];
+    // rollout_host staging
+    int32_t* st_act[2]; int32_t* st_obs[2]; float* st_rew[2]; uint8_t* st_done[2];
+    int st_chunk;
+    cudaStream_t st_stream[3];
+    cudaEvent_t st_ev_in[2], st_ev_k[2], st_ev_out[2];
+    bool st_ready;
+};
+
+static int fail(amdp* h, int code, const char* fmt, const char* a = "") {
+    if (h) snprintf(h->err, sizeof(h->err), fmt, a);
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            snprintf(h->err, sizeof(h->err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                            \
+            return AMDP_ECUDA;                                                                       \
+        }                                                                                            \
+    } while (0)
+
+template <typename Tp>
+static int dalloc(amdp* h, Tp** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(Tp));
+    if (e != cudaSuccess) {
+        snprintf(h->err, sizeof(h->err), "cudaMalloc of %zu bytes failed: %s", count * sizeof(Tp), cudaGetErrorString(e));
+        cudaGetLastError();
+        return AMDP_ENOMEM;
+    }
+    h->bytes += (int64_t)(count * sizeof(Tp));
+    return AMDP_OK;
+}
+
+static inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
+
+extern "C" int amdp_abi_version(void) { return AMDP_ABI_VERSION; }
+
+extern "C" const char* amdp_strerror(int code) {
+    switch (code) {
+        case AMDP_OK: return "ok";
+        case AMDP_EINVAL: return "invalid argument";
+        case AMDP_ECUDA: return "CUDA error";
+        case AMDP_ESTATE: return "invalid call sequence";
+        case AMDP_ENOMEM: return "out of device memory";
+        default: return "unknown error";
+    }
+}
+
+extern "C" const char* amdp_last_error(const amdp_t* h) { return h ? h->err : "null handle"; }
+extern "C" int amdp_n_slots(const amdp_t* h) { return h ? h->n_slots : 0; }
+extern "C" int64_t amdp_device_bytes(const amdp_t* h) { return h ? h->bytes : 0; }
+extern "C" int64_t amdp_launch_count(const amdp_t* h) { return h ? h->launches : 0; }
+
+static int pick_group(int n_pad) {
+    int g = 1;
+    while (g < 32 && g * 4 < n_pad) g <<= 1;
+    return g;
+}
+
+extern "C" int amdp_destroy(amdp_t* h) {
+    if (!h) return AMDP_OK;
+    cudaSetDevice(h->cfg.device);
+    void* ptrs[] = {h->cdf, h->payload, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
+                    h->n_real, h->env_task, h->stat_part, h->faults, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
+                    h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
+                    h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
+                    h->st_done[0], h->st_done[1]};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->st_ready) {
+        for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->st_stream[i]);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->st_ev_in[i]); cudaEventDestroy(h->st_ev_k[i]); cudaEventDestroy(h->st_ev_out[i]); }
+    }
+    delete h;
+    return AMDP_OK;
+}
+
+extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
+    if (!out || !cfg) return AMDP_EINVAL;
+    *out = nullptr;
+    amdp* h = new (std::nothrow) amdp;
+    if (!h) return AMDP_ENOMEM;
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    const amdp_config& c = h->cfg;
+    const bool mdp = c.task_type == AMDP_MDP;
+    if (c.task_type < AMDP_MDP || c.task_type > AMDP_MTPOMDP || c.autoreset < 0 || c.autoreset > 2 || c.na < 1 ||
+        c.n_pad < 4 || (c.n_pad & 3) || c.n_envs < 1 || c.n_tasks < 1 || c.n_obs_tok < 1 || c.n_obs_tok > MAX_TOK ||
+        c.n_act_tok < 1 || c.n_act_tok > MAX_TOK || c.s0_pad < 1 || (!mdp && (c.no_pad < 4 || (c.no_pad & 3))) ||
+        (c.task_type != AMDP_MTPOMDP && (c.n_obs_tok != 1 || c.n_act_tok != 1))) {
+        delete h;
+        return AMDP_EINVAL;
+    }
+    *out = h;   // from here on errors are reported through the handle; the caller destroys it
+    CK(cudaSetDevice(c.device));
+    const int toks = c.n_obs_tok > c.n_act_tok ? c.n_obs_tok : c.n_act_tok;
+    h->n_slots = AMDP_SLOTS_PER_TOKEN * toks;
+    h->G = pick_group(c.n_pad);
+    const size_t rows = (size_t)c.n_tasks * c.n_pad * c.na;
+    int rc;
+    if ((rc = dalloc(h, &h->cdf, rows * c.n_pad))) return rc;
+    if ((rc = dalloc(h, &h->payload, rows * c.n_pad))) return rc;
+    if (c.reserved0 & 1) { if ((rc = dalloc(h, &h->raw_t, rows * c.n_pad))) return rc; }
+    if ((rc = dalloc(h, &h->sinfo, (size_t)c.n_tasks * c.n_pad))) return rc;
+    if ((rc = dalloc(h, &h->s0_cdf, (size_t)c.n_tasks * c.s0_pad))) return rc;
+    if ((rc = dalloc(h, &h->s0_idx, (size_t)c.n_tasks * c.s0_pad))) return rc;
+    if (!mdp) { if ((rc = dalloc(h, &h->obs_cdf, (size_t)c.n_tasks * c.n_obs_tok * c.n_pad * c.no_pad))) return rc; }
+    if ((rc = dalloc(h, &h->max_ceil, (size_t)c.n_tasks))) return rc;
+    if ((rc = dalloc(h, &h->tflags, (size_t)c.n_tasks))) return rc;
+    if ((rc = dalloc(h, &h->n_real, (size_t)c.n_tasks))) return rc;
+    if ((rc = dalloc(h, &h->env_task, (size_t)c.n_envs))) return rc;
+    if ((rc = dalloc(h, &h->stat_part, (size_t)STAT_BLOCKS))) return rc;
+    if ((rc = dalloc(h, &h->faults, 1))) return rc;
+    EnvArrays& E = h->E;
+    if ((rc = dalloc(h, &E.state, (size_t)c.n_envs))) return rc;
+    if ((rc = dalloc(h, &E.steps, (size_t)c.n_envs))) return rc;
+    if ((rc = dalloc(h, &E.flags, (size_t)c.n_envs))) return rc;
+    if ((rc = dalloc(h, &E.ep_return, (size_t)c.n_envs))) return rc;
+    if ((rc = dalloc(h, &E.ep_count, (size_t)c.n_envs))) return rc;
+    if ((rc = dalloc(h, &E.sum_ret, (size_t)c.n_envs))) return rc;
+    if ((rc = dalloc(h, &E.sum_ret_sq, (size_t)c.n_envs))) return rc;
+    if ((rc = dalloc(h, &E.sum_len, (size_t)c.n_envs))) return rc;
+    if ((rc = dalloc(h, &E.min_ret, (size_t)c.n_envs))) return rc;
+    if ((rc = dalloc(h, &E.max_ret, (size_t)c.n_envs))) return rc;
+    CK(cudaMemset(h->faults, 0, sizeof(unsigned int)));
+    E.task = h->env_task; E.faults = h->faults; E.n_envs = c.n_envs; E.env_id_base = c.env_id_base;
+    E.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
+    Tables& T = h->T;
+    T.cdf = h->cdf; T.payload = h->payload; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
+    T.obs_cdf = h->obs_cdf; T.max_ceil = h->max_ceil; T.tflags = h->tflags; T.raw_t = h->raw_t; T.n_real = h->n_real;
+    T.n_pad = c.n_pad; T.na = c.na; T.no_pad = c.no_pad; T.d_o = c.n_obs_tok; T.d_a = c.n_act_tok; T.s0_pad = c.s0_pad;
+    T.task_type = c.task_type; T.autoreset = c.autoreset;
+    return AMDP_OK;
+}
+
+extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const double* transition, const double* reward,
+                                 const double* reward_noise, const int32_t* state_mapping, const int32_t* n_real,
+                                 const uint8_t* is_terminal, const int32_t* s0_idx, const double* s0_prob,
+                                 const int32_t* n_s0, const double* max_steps, const int32_t* ns,
+                                 const double* obs_transition, int32_t* status_out, void* stream) {
+    if (!h) return AMDP_EINVAL;
+    const amdp_config& c = h->cfg;
+    if (t0 < 0 || cnt < 1 || t0 + cnt > c.n_tasks) return fail(h, AMDP_EINVAL, "upload: task range out of bounds");
+    if (!transition || !reward || !reward_noise || !state_mapping || !n_real || !is_terminal || !s0_idx || !s0_prob ||
+        !n_s0 || !max_steps || !ns)
+        return fail(h, AMDP_EINVAL, "upload: null task array");
+    if (c.task_type != AMDP_MDP && !obs_transition) return fail(h, AMDP_EINVAL, "upload: POMDP engine needs obs_transition");
+    CK(cudaSetDevice(c.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (status_out) CK(cudaMemsetAsync(status_out, 0, sizeof(int32_t) * cnt, st));
+    const size_t per_task = (size_t)c.n_pad * c.na * c.n_pad;
+    const long long rows = (long long)cnt * c.n_pad * c.na;
+    k_build_rows<<<nblk(rows, 128), 128, 0, st>>>(cnt, c.n_pad, c.na, transition, reward, reward_noise, n_real, is_terminal,
+                                                  h->cdf + t0 * per_task, h->payload + t0 * per_task, status_out);
+    k_build_small<<<nblk(cnt, 128), 128, 0, st>>>(cnt, c.n_pad, c.s0_pad, state_mapping, n_real, is_terminal, s0_idx, s0_prob,
+                                                  n_s0, max_steps, ns, h->sinfo + t0 * c.n_pad, h->s0_cdf + t0 * c.s0_pad,
+                                                  h->s0_idx + t0 * c.s0_pad, h->max_ceil + t0, h->tflags + t0,
+                                                  h->n_real + t0, status_out);
+    h->launches += 2;
+    if (c.task_type != AMDP_MDP) {
+        const long long orows = (long long)cnt * c.n_obs_tok * c.n_pad;
+        k_build_obs<<<nblk(orows, 128), 128, 0, st>>>(orows, c.n_pad, c.no_pad, obs_transition,
+                                                      h->obs_cdf + (size_t)t0 * c.n_obs_tok * c.n_pad * c.no_pad);
+        h->launches += 1;
+    }
+    if (h->raw_t) CK(cudaMemcpyAsync(h->raw_t + t0 * per_task, transition, per_task * cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(cudaGetLastError());
+    h->uploaded = true;
+    return AMDP_OK;
+}
+
+extern "C" int amdp_assign(amdp_t* h, const int32_t* env_task, void* stream) {
+    if (!h || !env_task) return AMDP_EINVAL;
+    if (!h->uploaded) return fail(h, AMDP_ESTATE, "assign before upload_tasks");
+    CK(cudaSetDevice(h->cfg.device));
+    k_assign<<<nblk(h->cfg.n_envs, 256), 256, 0, (cudaStream_t)stream>>>(h->E, h->env_task, env_task);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    h->assigned = true;
+    h->total_steps = 0;
+    return AMDP_OK;
+}
+
+extern "C" int amdp_reset(amdp_t* h, const uint8_t* mask, int32_t* obs_out, const double* u_inject, void* stream) {
+    if (!h || !obs_out) return AMDP_EINVAL;
+    if (!h->assigned) return fail(h, AMDP_ESTATE, "Must call \"set_task\" first");
+    CK(cudaSetDevice(h->cfg.device));
+    k_reset<<<nblk(h->cfg.n_envs, 128), 128, 0, (cudaStream_t)stream>>>(h->T, h->E, h->tick, h->n_slots, mask, obs_out, u_inject);
+    h->launches += 1;
+    h->tick += 1;
+    CK(cudaGetLastError());
+    return AMDP_OK;
+}
+
+template <int G>
+static void launch_step(amdp* h, const int32_t* actions, int32_t* obs, int32_t* final_obs, float* reward, float* reward_gt,
+                        uint8_t* terminated, uint8_t* truncated, int32_t* actions_out, const double* u, cudaStream_t st) {
+    const long long threads = h->cfg.n_envs * G;
+    k_step<G><<<nblk(threads, 256), 256, 0, st>>>(h->T, h->E, h->tick, h->n_slots, actions, obs, final_obs, reward, reward_gt,
+                                                  terminated, truncated, actions_out, u);
+}
+
+extern "C" int amdp_step(amdp_t* h, const int32_t* actions, int32_t* obs, int32_t* final_obs, float* reward,
+                         float* reward_gt, uint8_t* terminated, uint8_t* truncated, int32_t* actions_out,
+                         const double* u_inject, void* stream) {
+    if (!h || !obs || !reward || !terminated || !truncated) return AMDP_EINVAL;
+    if (!h->assigned) return fail(h, AMDP_ESTATE, "Must \"set_task\" and \"reset\" before doing any actions");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (h->G) {
+#define CASE(g) case g: launch_step<g>(h, actions, obs, final_obs, reward, reward_gt, terminated, truncated, actions_out, u_inject, st); break;
+        CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)
+#undef CASE
+        default: return fail(h, AMDP_EINVAL, "bad group size");
+    }
+    h->launches += 1;
+    h->tick += 1;
+    h->total_steps += (double)h->cfg.n_envs;
+    CK(cudaGetLastError());
+    return AMDP_OK;
+}
+
+template <int G>
+static void launch_rollout(amdp* h, int K, const int32_t* actions, const amdp_traj& J, const double* u, cudaStream_t st) {
+    const long long threads = h->cfg.n_envs * G;
+    k_rollout<G><<<nblk(threads, 256), 256, 0, st>>>(h->T, h->E, h->tick, K, h->n_slots, actions, J, u);
+}
+
+extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const amdp_traj* traj, const double* u_inject,
+                            void* stream) {
+    if (!h || K < 1) return AMDP_EINVAL;
+    if (!h->assigned) return fail(h, AMDP_ESTATE, "Must \"set_task\" and \"reset\" before doing any actions");
+    if (h->cfg.autoreset == AMDP_AUTORESET_DISABLED) return fail(h, AMDP_EINVAL, "rollout needs an auto-reset mode");
+    CK(cudaSetDevice(h->cfg.device));
+    amdp_traj J;
+    memset(&J, 0, sizeof(J));
+    if (traj) J = *traj;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (h->G) {
+#define CASE(g) case g: launch_rollout<g>(h, K, actions, J, u_inject, st); break;
+        CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)
+#undef CASE
+        default: return fail(h, AMDP_EINVAL, "bad group size");
+    }
+    h->launches += 1;
+    h->tick += (unsigned long long)K;
+    h->total_steps += (double)h->cfg.n_envs * K;
+    CK(cudaGetLastError());
+    return AMDP_OK;
+}
+
+extern "C" int amdp_stats(amdp_t* h, double* out8, void* stream) {
+    if (!h || !out8) return AMDP_EINVAL;
+    if (!h->assigned) return fail(h, AMDP_ESTATE, "stats before assign");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    k_stats_partial<<<STAT_BLOCKS, STAT_THREADS, 0, st>>>(h->E, h->stat_part);
+    k_stats_final<<<1, STAT_THREADS, 0, st>>>(h->stat_part, h->total_steps, out8);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return AMDP_OK;
+}
+
+extern "C" int amdp_clear_stats(amdp_t* h, void* stream) {
+    if (!h) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    k_clear_stats<<<nblk(h->cfg.n_envs, 256), 256, 0, (cudaStream_t)stream>>>(h->E);
+    h->launches += 1;
+    h->total_steps = 0;
+    CK(cudaGetLastError());
+    return AMDP_OK;
+}
+
+extern "C" int amdp_gather_transition_gt(amdp_t* h, const int32_t* actions, int32_t ns_out, double* out, void* stream) {
+    if (!h || !actions || !out || ns_out < 1) return AMDP_EINVAL;
+    if (!h->raw_t) return fail(h, AMDP_ESTATE, "engine was created without keep_transition");
+    if (!h->assigned) return fail(h, AMDP_ESTATE, "transition_gt before assign");
+    CK(cudaSetDevice(h->cfg.device));
+    k_transition_gt<<<(unsigned int)(h->cfg.n_envs * h->cfg.n_act_tok), 128, 0, (cudaStream_t)stream>>>(h->T, h->E, actions, ns_out, out);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return AMDP_OK;
+}
+
+extern "C" int amdp_dump_draws(amdp_t* h, uint64_t tick0, int32_t K, double* out, void* stream) {
+    if (!h || !out || K < 1) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    const long long total = (long long)K * h->cfg.n_envs * (h->n_slots / 2);
+    k_dump_draws<<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(h->E, tick0, K, h->n_slots, h->cfg.na, out);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return AMDP_OK;
+}
+
+extern "C" int amdp_get_tick(const amdp_t* h, uint64_t* tick) {
+    if (!h || !tick) return AMDP_EINVAL;
+    *tick = h->tick;
+    return AMDP_OK;
+}
+
+extern "C" int amdp_set_tick(amdp_t* h, uint64_t tick) {
+    if (!h) return AMDP_EINVAL;
+    h->tick = tick;
+    return AMDP_OK;
+}
+
+extern "C" int amdp_set_seed(amdp_t* h, uint64_t seed) {
+    if (!h) return AMDP_EINVAL;
+    h->cfg.seed = seed;
+    h->E.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    return AMDP_OK;
+}
+
+extern "C" int amdp_get_state(amdp_t* h, int32_t* state, int32_t* steps, uint8_t* flags, double* ep_return, void* stream) {
+    if (!h) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->cfg.n_envs;
+    if (state) CK(cudaMemcpyAsync(state, h->E.state, n * 4, cudaMemcpyDeviceToDevice, st));
+    if (steps) CK(cudaMemcpyAsync(steps, h->E.steps, n * 4, cudaMemcpyDeviceToDevice, st));
+    if (flags) CK(cudaMemcpyAsync(flags, h->E.flags, n, cudaMemcpyDeviceToDevice, st));
+    if (ep_return) CK(cudaMemcpyAsync(ep_return, h->E.ep_return, n * 8, cudaMemcpyDeviceToDevice, st));
+    return AMDP_OK;
+}
+
+extern "C" int amdp_set_state(amdp_t* h, const int32_t* state, const int32_t* steps, const uint8_t* flags,
+                              const double* ep_return, void* stream) {
+    if (!h) return AMDP_EINVAL;
+    if (!h->assigned) return fail(h, AMDP_ESTATE, "set_state before assign");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->cfg.n_envs;
+    if (state) CK(cudaMemcpyAsync(h->E.state, state, n * 4, cudaMemcpyDeviceToDevice, st));
+    if (steps) CK(cudaMemcpyAsync(h->E.steps, steps, n * 4, cudaMemcpyDeviceToDevice, st));
+    if (flags) CK(cudaMemcpyAsync(h->E.flags, flags, n, cudaMemcpyDeviceToDevice, st));
+    if (ep_return) CK(cudaMemcpyAsync(h->E.ep_return, ep_return, n * 8, cudaMemcpyDeviceToDevice, st));
+    return AMDP_OK;
+}
+
+extern "C" int amdp_get_mapped_state(amdp_t* h, int32_t* out, void* stream) {
+    if (!h || !out) return AMDP_EINVAL;
+    if (!h->assigned) return fail(h, AMDP_ESTATE, "mapped_state before assign");
+    CK(cudaSetDevice(h->cfg.device));
+    k_mapped_state<<<nblk(h->cfg.n_envs, 256), 256, 0, (cudaStream_t)stream>>>(h->T, h->E, out);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return AMDP_OK;
+}
+
+extern "C" int amdp_poll_errors(amdp_t* h, uint32_t* faults, void* stream) {
+    if (!h || !faults) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int v = 0;
+    CK(cudaMemcpyAsync(&v, h->faults, sizeof(v), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (v) CK(cudaMemsetAsync(h->faults, 0, sizeof(v), st));
+    *faults = v;
+    return AMDP_OK;
+}
+
+extern "C" int amdp_debug_cdf_row(amdp_t* h, int64_t task, int32_t s, int32_t a, double* out, void* stream) {
+    if (!h || !out) return AMDP_EINVAL;
+    const amdp_config& c = h->cfg;
+    if (task < 0 || task >= c.n_tasks || s < 0 || s >= c.n_pad || a < 0 || a >= c.na) return fail(h, AMDP_EINVAL, "cdf_row: index out of range");
+    CK(cudaSetDevice(c.device));
+    const size_t off = (((size_t)task * c.n_pad + s) * c.na + a) * c.n_pad;
+    CK(cudaMemcpyAsync(out, h->cdf + off, sizeof(double) * c.n_pad, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return AMDP_OK;
+}
+
+// ---- host-buffer rollout: chunked, double-buffered ---------------------------------------------
+static int staging_init(amdp* h, int chunk) {
+    const amdp_config& c = h->cfg;
+    if (h->st_ready && h->st_chunk >= chunk) return AMDP_OK;
+    if (h->st_ready) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(h->st_act[i]); cudaFree(h->st_obs[i]); cudaFree(h->st_rew[i]); cudaFree(h->st_done[i]);
+            h->st_act[i] = nullptr; h->st_obs[i] = nullptr; h->st_rew[i] = nullptr; h->st_done[i] = nullptr;
+        }
+    } else {
+        for (int i = 0; i < 3; ++i) CK(cudaStreamCreateWithFlags(&h->st_stream[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&h->st_ev_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->st_ev_k[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->st_ev_out[i], cudaEventDisableTiming));
+        }
+        h->st_ready = true;
+    }
+    const size_t per = (size_t)chunk * c.n_envs;
+    int rc;
+    for (int i = 0; i < 2; ++i) {
+        if ((rc = dalloc(h, &h->st_act[i], per * c.n_act_tok))) return rc;
+        if ((rc = dalloc(h, &h->st_obs[i], per * c.n_obs_tok))) return rc;
+        if ((rc = dalloc(h, &h->st_rew[i], per))) return rc;
+        if ((rc = dalloc(h, &h->st_done[i], per))) return rc;
+    }
+    h->st_chunk = chunk;
+    return AMDP_OK;
+}
+
+extern "C" int amdp_rollout_host(amdp_t* h, int32_t K, int32_t chunk, const int32_t* actions_host, int32_t* obs_host,
+                                 float* reward_host, uint8_t* done_host) {
+    if (!h || K < 1) return AMDP_EINVAL;
+    if (!h->assigned) return fail(h, AMDP_ESTATE, "Must \"set_task\" and \"reset\" before doing any actions");
+    const amdp_config& c = h->cfg;
+    CK(cudaSetDevice(c.device));
+    if (chunk < 1 || chunk > K) chunk = K;
+    int rc = staging_init(h, chunk);
+    if (rc) return rc;
+    cudaStream_t s_in = h->st_stream[0], s_k = h->st_stream[1], s_out = h->st_stream[2];
+    const size_t N = (size_t)c.n_envs;
+    int i = 0;
+    for (int k0 = 0; k0 < K; k0 += chunk, ++i) {
+        const int b = i & 1;
+        const int kc = (K - k0 < chunk) ? (K - k0) : chunk;
+        // buffer b is free once the copy-out of chunk i-2 has finished
+        if (i >= 2) { CK(cudaStreamWaitEvent(s_in, h->st_ev_out[b], 0)); CK(cudaStreamWaitEvent(s_k, h->st_ev_out[b], 0)); }
+        if (actions_host) {
+            CK(cudaMemcpyAsync(h->st_act[b], actions_host + (size_t)k0 * N * c.n_act_tok, sizeof(int32_t) * kc * N * c.n_act_tok,
+                               cudaMemcpyHostToDevice, s_in));
+            CK(cudaEventRecord(h->st_ev_in[b], s_in));
+            CK(cudaStreamWaitEvent(s_k, h->st_ev_in[b], 0));
+        }
+        amdp_traj J;
+        memset(&J, 0, sizeof(J));
+        J.obs = obs_host ? h->st_obs[b] : nullptr;
+        J.reward = reward_host ? h->st_rew[b] : nullptr;
+        J.done = done_host ? h->st_done[b] : nullptr;
+        J.step_stride = (int64_t)N; J.env_stride = 1;
+        rc = amdp_rollout(h, kc, actions_host ? h->st_act[b] : nullptr, &J, nullptr, s_k);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->st_ev_k[b], s_k));
+        CK(cudaStreamWaitEvent(s_out, h->st_ev_k[b], 0));
+        if (obs_host) CK(cudaMemcpyAsync(obs_host + (size_t)k0 * N * c.n_obs_tok, h->st_obs[b], sizeof(int32_t) * kc * N * c.n_obs_tok, cudaMemcpyDeviceToHost, s_out));
+        if (reward_host) CK(cudaMemcpyAsync(reward_host + (size_t)k0 * N, h->st_rew[b], sizeof(float) * kc * N, cudaMemcpyDeviceToHost, s_out));
+        if (done_host) CK(cudaMemcpyAsync(done_host + (size_t)k0 * N, h->st_done[b], (size_t)kc * N, cudaMemcpyDeviceToHost, s_out));
+        CK(cudaEventRecord(h->st_ev_out[b], s_out));
+    }
+    CK(cudaStreamSynchronize(s_out));
+    CK(cudaStreamSynchronize(s_k));
+    return AMDP_OK;
+}

@@ -1,0 +1,337 @@
+"""Host-side owner of one amdp_t handle: task packing, upload and the raw tensor-level calls.
+
+`Engine` is the thin Python face of the C ABI (include/amdp_b200.h).  I/O buffers are CUDA
+`torch.Tensor`s owned by the caller; torch is used only for device memory and streams.
+The reference code each call replaces is cited in the header file.
+"""
+import ctypes
+import math
+
+import numpy
+import torch
+
+from . import _lib
+from ._lib import lib
+
+
+class AMDPError(RuntimeError):
+    pass
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def round_up4(n):
+    return max(4, (int(n) + 3) // 4 * 4)
+
+
+# --------------------------------------------------------------------------------------------------
+# task packing: list of reference task dicts -> zero-padded arrays
+# --------------------------------------------------------------------------------------------------
+def task_geometry(tasks):
+    """Engine-wide sizes implied by a list of task dicts (all must share task_type / na / da / do)."""
+    t0 = tasks[0]
+    tt = t0["task_type"]
+    if tt not in _lib.TASK_TYPES:
+        raise NotImplementedError(f"Unknown task type: {tt}")            # anymdp_env.py:46
+    na = int(t0["na"])
+    da = int(t0.get("da", 1)) if tt == "MTPOMDP" else 1
+    do = int(t0.get("do", 1)) if tt == "MTPOMDP" else 1
+    n_max, no_max, s0_max = 1, 1, 1
+    for t in tasks:
+        if t["task_type"] != tt or int(t["na"]) != na:
+            raise ValueError("all tasks of one engine must share task_type and na")
+        if tt == "MTPOMDP" and (int(t["da"]) != da or int(t["do"]) != do):
+            raise ValueError("all MTPOMDP tasks of one engine must share da and do")
+        n_max = max(n_max, len(t["state_mapping"]))
+        s0_max = max(s0_max, len(numpy.atleast_1d(t["s_0"])))
+        if tt != "MDP":
+            no_max = max(no_max, int(t["no"]))
+    return {"task_type": tt, "na": na, "da": da, "do": do, "n_pad": round_up4(n_max),
+            "no_pad": round_up4(no_max) if tt != "MDP" else 0, "s0_pad": s0_max}
+
+
+def validate_task(task):
+    """The host-side asserts of AnyMDPEnv.set_task (anymdp_env.py:48-53); value checks run on the device."""
+    tr = numpy.asarray(task["transition"])
+    assert tr.shape == numpy.asarray(task["reward"]).shape
+    assert tr.shape[0] == len(task["state_mapping"]) and tr.shape[1] == task["na"]
+    assert task["ns"] > 0, "State space must be at least 1"
+    assert task["na"] > 1, "Action space must be at least 2"
+    if task["task_type"] != "MDP":
+        assert task["no"] > 0, "Observation space must be at least 1"
+
+
+def pack_tasks(tasks, geo, default_max_steps=5000):
+    """-> dict of numpy arrays in the layout amdp_upload_tasks expects."""
+    cnt, n, na, s0p = len(tasks), geo["n_pad"], geo["na"], geo["s0_pad"]
+    out = {
+        "transition": numpy.zeros((cnt, n, na, n)), "reward": numpy.zeros((cnt, n, na, n)),
+        "reward_noise": numpy.zeros((cnt, n, na, n)),
+        "state_mapping": numpy.zeros((cnt, n), dtype=numpy.int32), "n_real": numpy.zeros(cnt, dtype=numpy.int32),
+        "is_terminal": numpy.zeros((cnt, n), dtype=numpy.uint8),
+        "s0_idx": numpy.zeros((cnt, s0p), dtype=numpy.int32), "s0_prob": numpy.zeros((cnt, s0p)),
+        "n_s0": numpy.zeros(cnt, dtype=numpy.int32), "max_steps": numpy.zeros(cnt),
+        "ns": numpy.zeros(cnt, dtype=numpy.int32), "obs_transition": None,
+    }
+    if geo["task_type"] != "MDP":
+        out["obs_transition"] = numpy.zeros((cnt, geo["do"], n, geo["no_pad"]))
+    for i, t in enumerate(tasks):
+        validate_task(t)
+        k = len(t["state_mapping"])
+        out["transition"][i, :k, :, :k] = t["transition"]
+        out["reward"][i, :k, :, :k] = t["reward"]
+        out["reward_noise"][i, :k, :, :k] = t["reward_noise"]
+        out["state_mapping"][i, :k] = t["state_mapping"]
+        out["n_real"][i] = k
+        s_e = numpy.asarray(t["s_e"]).astype(numpy.int64)
+        out["is_terminal"][i, s_e] = 1
+        s0 = numpy.atleast_1d(numpy.asarray(t["s_0"])).astype(numpy.int64)
+        out["s0_idx"][i, :len(s0)] = s0
+        out["s0_prob"][i, :len(s0)] = numpy.atleast_1d(numpy.asarray(t["s_0_prob"], dtype=numpy.float64))
+        out["n_s0"][i] = len(s0)
+        out["max_steps"][i] = float(t.get("max_steps", default_max_steps))
+        out["ns"][i] = int(t["ns"])
+        if geo["task_type"] == "POMDP":
+            ot = numpy.asarray(t["observation_transition"], dtype=numpy.float64)
+            out["obs_transition"][i, 0, :k, :ot.shape[1]] = ot
+        elif geo["task_type"] == "MTPOMDP":
+            for j, m in enumerate(t["observation_transition"]):
+                m = numpy.asarray(m, dtype=numpy.float64)
+                out["obs_transition"][i, j, :k, :m.shape[1]] = m
+    return out
+
+
+_STATUS_MSG = {
+    _lib.TASK_BAD_ROW_SUM: "Transition Matrix Sum != 1",                       # anymdp_env.py:71
+    _lib.TASK_NOT_NORMALISED: "probabilities do not sum to 1",                # numpy choice(), raised at step time by the reference
+    _lib.TASK_NEGATIVE_P: "probabilities are not non-negative",               # numpy choice()
+    _lib.TASK_S0_IN_SE: "a state is both a start state and a terminal state",  # anymdp_env.py:76
+}
+
+
+class Engine:
+    def __init__(self, num_envs, num_tasks, geo, device=0, seed=0, autoreset="same_step", env_id_base=0,
+                 keep_transition=False):
+        if not torch.cuda.is_available():
+            raise AMDPError("xenoverse_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.geo = dict(geo)
+        self.N, self.T = int(num_envs), int(num_tasks)
+        self.da, self.do = geo["da"], geo["do"]
+        self.autoreset = autoreset
+        cfg = _lib.Config(device=self.device.index, task_type=_lib.TASK_TYPES[geo["task_type"]],
+                          autoreset=_lib.AUTORESET[autoreset], na=geo["na"], n_pad=geo["n_pad"], no_pad=geo["no_pad"],
+                          n_obs_tok=geo["do"], n_act_tok=geo["da"], s0_pad=geo["s0_pad"],
+                          reserved0=1 if keep_transition else 0, n_envs=self.N, n_tasks=self.T,
+                          seed=int(seed) & (2 ** 64 - 1), env_id_base=int(env_id_base))
+        h = ctypes.c_void_p()
+        rc = lib.amdp_create(ctypes.byref(h), ctypes.byref(cfg))
+        self._h = h
+        if rc != _lib.OK:
+            msg = lib.amdp_last_error(h).decode() if h else lib.amdp_strerror(rc).decode()
+            if h:
+                lib.amdp_destroy(h)
+                self._h = None
+            raise AMDPError(f"amdp_create failed ({rc}): {msg}")
+        self.n_slots = lib.amdp_n_slots(h)
+
+    # ---- plumbing -----------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != _lib.OK:
+            msg = lib.amdp_last_error(self._h).decode()
+            if rc == _lib.ESTATE:
+                raise Exception(msg)                 # the reference raises bare Exception for call-order errors
+            raise AMDPError(f"{lib.amdp_strerror(rc).decode()}: {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.amdp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev(self, a, dtype):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(numpy.ascontiguousarray(a), dtype=dtype).to(self.device)
+
+    @property
+    def device_bytes(self):
+        return int(lib.amdp_device_bytes(self._h))
+
+    @property
+    def launch_count(self):
+        return int(lib.amdp_launch_count(self._h))
+
+    @property
+    def tick(self):
+        v = ctypes.c_uint64()
+        self._ck(lib.amdp_get_tick(self._h, ctypes.byref(v)))
+        return int(v.value)
+
+    @tick.setter
+    def tick(self, v):
+        self._ck(lib.amdp_set_tick(self._h, int(v)))
+
+    def set_seed(self, seed):
+        self._ck(lib.amdp_set_seed(self._h, int(seed) & (2 ** 64 - 1)))
+
+    # ---- task upload (set_task) ---------------------------------------------------------------
+    def upload_packed(self, t0, p):
+        """p: dict of arrays/tensors in the amdp_upload_tasks layout (see `pack_tasks`). Returns status int32[cnt] (host)."""
+        with torch.cuda.device(self.device):
+            f64, i32, u8 = torch.float64, torch.int32, torch.uint8
+            tr = self._dev(p["transition"], f64)
+            cnt = tr.shape[0]
+            g = self.geo
+            assert tuple(tr.shape) == (cnt, g["n_pad"], g["na"], g["n_pad"]), tr.shape
+            bufs = [tr, self._dev(p["reward"], f64), self._dev(p["reward_noise"], f64),
+                    self._dev(p["state_mapping"], i32), self._dev(p["n_real"], i32), self._dev(p["is_terminal"], u8),
+                    self._dev(p["s0_idx"], i32), self._dev(p["s0_prob"], f64), self._dev(p["n_s0"], i32),
+                    self._dev(p["max_steps"], f64), self._dev(p["ns"], i32)]
+            obs = None
+            if g["task_type"] != "MDP":
+                obs = self._dev(p["obs_transition"], f64)
+                assert tuple(obs.shape) == (cnt, g["do"], g["n_pad"], g["no_pad"]), obs.shape
+            status = torch.zeros(cnt, dtype=i32, device=self.device)
+            self._ck(lib.amdp_upload_tasks(self._h, int(t0), int(cnt), *[_ptr(b) for b in bufs], _ptr(obs),
+                                           _ptr(status), _stream()))
+            st = status.cpu().numpy()           # synchronises: the staging tensors may now be freed
+        return st
+
+    def upload_tasks(self, tasks, t0=0, chunk_bytes=1 << 30, default_max_steps=5000):
+        """set_task for a list of task dicts, staged through the device in chunks."""
+        g = self.geo
+        per = 3 * 8 * g["n_pad"] * g["na"] * g["n_pad"]
+        step = max(1, int(chunk_bytes // per))
+        for i in range(0, len(tasks), step):
+            part = tasks[i:i + step]
+            st = self.upload_packed(t0 + i, pack_tasks(part, g, default_max_steps))
+            bad = numpy.nonzero(st)[0]
+            if len(bad):
+                code = int(st[bad[0]])
+                msg = _STATUS_MSG.get(code, f"task status {code}")
+                if code in (_lib.TASK_NOT_NORMALISED, _lib.TASK_NEGATIVE_P):
+                    raise ValueError(f"{msg} (task {t0 + i + int(bad[0])})")
+                raise Exception(f"{msg} at task {t0 + i + int(bad[0])}")
+
+    def assign(self, env_task):
+        with torch.cuda.device(self.device):
+            et = self._dev(env_task, torch.int32)
+            assert et.numel() == self.N
+            if self.N and (int(et.min()) < 0 or int(et.max()) >= self.T):
+                raise ValueError("env_task out of range")
+            self._ck(lib.amdp_assign(self._h, _ptr(et), _stream()))
+            torch.cuda.current_stream().synchronize()
+
+    # ---- stepping -----------------------------------------------------------------------------
+    def new_buffers(self):
+        d, N = self.device, self.N
+        return {"obs": torch.empty((N, self.do), dtype=torch.int32, device=d),
+                "final_obs": torch.empty((N, self.do), dtype=torch.int32, device=d),
+                "reward": torch.empty(N, dtype=torch.float32, device=d),
+                "reward_gt": torch.empty(N, dtype=torch.float32, device=d),
+                "terminated": torch.empty(N, dtype=torch.uint8, device=d),
+                "truncated": torch.empty(N, dtype=torch.uint8, device=d),
+                "action": torch.empty((N, self.da), dtype=torch.int32, device=d)}
+
+    def reset(self, obs_out, mask=None, u_inject=None):
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_reset(self._h, _ptr(mask), _ptr(obs_out), _ptr(u_inject), _stream()))
+
+    def step(self, actions, out, u_inject=None):
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_step(self._h, _ptr(actions), _ptr(out["obs"]), _ptr(out.get("final_obs")),
+                                   _ptr(out["reward"]), _ptr(out.get("reward_gt")), _ptr(out["terminated"]),
+                                   _ptr(out["truncated"]), _ptr(out.get("action")), _ptr(u_inject), _stream()))
+
+    def rollout(self, K, actions=None, traj=None, u_inject=None, env_major=False):
+        """traj: dict with optional tensors obs [K,N,do], action [K,N,da], reward, reward_gt, done [K,N]
+        (or [N,K,...] when env_major)."""
+        J = _lib.Traj()
+        traj = traj or {}
+        J.obs, J.actions_out = _ptr(traj.get("obs")), _ptr(traj.get("action"))
+        J.reward, J.reward_gt, J.done = _ptr(traj.get("reward")), _ptr(traj.get("reward_gt")), _ptr(traj.get("done"))
+        if env_major:
+            J.step_stride, J.env_stride = 1, int(K)
+        else:
+            J.step_stride, J.env_stride = self.N, 1
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_rollout(self._h, int(K), _ptr(actions), ctypes.byref(J), _ptr(u_inject), _stream()))
+
+    def rollout_host(self, K, chunk, actions=None, obs=None, reward=None, done=None):
+        """Host (pinned) buffers in / out; synchronous.  Tensors are CPU torch tensors."""
+        self._ck(lib.amdp_rollout_host(self._h, int(K), int(chunk), _ptr(actions), _ptr(obs), _ptr(reward), _ptr(done)))
+
+    # ---- statistics / introspection -----------------------------------------------------------
+    def stats_tensor(self, out=None):
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(8, dtype=torch.float64, device=self.device)
+            self._ck(lib.amdp_stats(self._h, _ptr(out), _stream()))
+        return out
+
+    def clear_stats(self):
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_clear_stats(self._h, _stream()))
+
+    def poll_errors(self):
+        v = ctypes.c_uint32()
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_poll_errors(self._h, ctypes.byref(v), _stream()))
+        return int(v.value)
+
+    def dump_draws(self, tick0, K):
+        out = torch.empty((K, self.N, self.n_slots), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_dump_draws(self._h, int(tick0), int(K), _ptr(out), _stream()))
+        return out
+
+    def get_state(self):
+        d, N = self.device, self.N
+        st = {"state": torch.empty(N, dtype=torch.int32, device=d), "steps": torch.empty(N, dtype=torch.int32, device=d),
+              "flags": torch.empty(N, dtype=torch.uint8, device=d), "ep_return": torch.empty(N, dtype=torch.float64, device=d)}
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_get_state(self._h, _ptr(st["state"]), _ptr(st["steps"]), _ptr(st["flags"]),
+                                        _ptr(st["ep_return"]), _stream()))
+        return st
+
+    def set_state(self, st):
+        with torch.cuda.device(self.device):
+            bufs = [self._dev(st["state"], torch.int32), self._dev(st["steps"], torch.int32),
+                    self._dev(st["flags"], torch.uint8), self._dev(st["ep_return"], torch.float64)]
+            self._ck(lib.amdp_set_state(self._h, *[_ptr(b) for b in bufs], _stream()))
+            torch.cuda.current_stream().synchronize()
+
+    def mapped_state(self):
+        out = torch.empty(self.N, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_get_mapped_state(self._h, _ptr(out), _stream()))
+        return out
+
+    def transition_gt(self, actions, ns_out):
+        a = self._dev(actions, torch.int32).reshape(self.N, self.da)
+        out = torch.empty((self.N, self.da, int(ns_out)), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_gather_transition_gt(self._h, _ptr(a), int(ns_out), _ptr(out), _stream()))
+        return out
+
+    def cdf_row(self, task, s, a):
+        out = torch.empty(self.geo["n_pad"], dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_debug_cdf_row(self._h, int(task), int(s), int(a), _ptr(out), _stream()))
+        return out
+
+
+def ceil_max_steps(x):
+    return int(math.ceil(float(x)))

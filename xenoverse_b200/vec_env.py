@@ -1,0 +1,206 @@
+"""AnyMDPVecEnv — N AnyMDP environments stepped by one fused CUDA kernel per tick.
+
+No reference equivalent exists (the closest in-repo use is SB3's DummyVecEnv over 4 reference
+envs, xenoverse/anymdp/test_ppo.py:34-38); the per-env semantics are exactly those of
+`AnyMDPEnv.reset/step` (xenoverse/anymdp/anymdp_env.py:81-159) plus an explicit auto-reset mode
+(SURVEY.md App. A.3).  All I/O are CUDA torch tensors.
+"""
+import numpy
+import torch
+
+from . import _lib
+from .engine import Engine, task_geometry
+
+_FAULT_MSG = (
+    (_lib.FAULT_NEED_RESET, Exception, "Must \"set_task\" and \"reset\" before doing any actions"),   # anymdp_env.py:94
+    (_lib.FAULT_TERMINAL_STATE, Exception, "Unexpected Error: given an terminated state"),             # anymdp_env.py:96
+    (_lib.FAULT_BAD_ACTION, AssertionError, "Action is out of range"),                                # anymdp_env.py:97
+)
+
+
+def raise_faults(bits):
+    for bit, exc, msg in _FAULT_MSG:
+        if bits & bit:
+            raise exc(msg)
+
+
+class AnyMDPVecEnv:
+    """
+    num_envs   envs owned by this process / GPU
+    device     CUDA device (int or torch.device)
+    seed       Philox key; trajectories are a pure function of (seed, global env id, tick)
+    autoreset  "same_step" (SB3 DummyVecEnv behaviour: the returned obs is the reset obs, the
+               terminal one is info["final_obs"]), "next_step" (the step after a done performs
+               the reset and ignores its action) or "disabled" (reference behaviour: stepping a
+               terminated env is an error)
+    env_id_base global id of local env 0 when envs are sharded over several GPUs
+    """
+
+    def __init__(self, num_envs, device=0, seed=0, autoreset="same_step", env_id_base=0, keep_transition=False):
+        if autoreset not in _lib.AUTORESET:
+            raise ValueError(f"autoreset must be one of {sorted(_lib.AUTORESET)}")
+        self.num_envs = int(num_envs)
+        self.device_arg, self.seed, self.autoreset = device, int(seed), autoreset
+        self.env_id_base, self.keep_transition = int(env_id_base), keep_transition
+        self.engine = None
+        self.task_set = False
+
+    # ---- set_task (anymdp_env.py:32-79) ---------------------------------------------------------
+    def set_task(self, tasks, env_task_ids=None, packed=None):
+        """tasks: one task dict or a list of them (the dicts AnyMDPTaskSampler & co. return).
+        env_task_ids: int array [num_envs]; default env i -> task i % len(tasks).
+        packed: alternatively (geometry dict, iterable of (t0, packed-batch)) with device tensors in
+        the amdp_upload_tasks layout, for tasks generated directly on the GPU."""
+        if packed is not None:
+            geo, n_tasks, batches = packed
+        else:
+            if isinstance(tasks, dict):
+                tasks = [tasks]
+            tasks = list(tasks)
+            geo, n_tasks = task_geometry(tasks), len(tasks)
+        if self.engine is not None:
+            self.engine.close()
+        self.engine = Engine(self.num_envs, n_tasks, geo, device=self.device_arg, seed=self.seed,
+                             autoreset=self.autoreset, env_id_base=self.env_id_base,
+                             keep_transition=self.keep_transition)
+        if packed is not None:
+            for t0, batch in batches:
+                st = self.engine.upload_packed(t0, batch)
+                if st.any():
+                    raise Exception(f"invalid task in packed batch at {t0}: status {st[st != 0][:4]}")
+        else:
+            self.engine.upload_tasks(tasks)
+        if env_task_ids is None:
+            env_task_ids = numpy.arange(self.num_envs, dtype=numpy.int64) % n_tasks
+        self.engine.assign(env_task_ids)
+        self.geo = geo
+        self.task_type, self.na, self.da, self.do = geo["task_type"], geo["na"], geo["da"], geo["do"]
+        self.device = self.engine.device
+        self._buf = self.engine.new_buffers()
+        self._stats = torch.empty(8, dtype=torch.float64, device=self.device)
+        self.task_set = True
+
+    def _require_task(self):
+        if not self.task_set:
+            raise Exception("Must call \"set_task\" first")                       # anymdp_env.py:83
+
+    def _squeeze(self, t):
+        return t[:, 0] if t.shape[-1] == 1 and self.task_type != "MTPOMDP" else t
+
+    # ---- reset (anymdp_env.py:81-90) ------------------------------------------------------------
+    def reset(self, mask=None, seed=None, u_inject=None):
+        """Reset the envs selected by `mask` (bool/uint8 tensor [N]; all if None).
+        Returns (obs int32 [N] or [N, do], {"steps": int32 zeros}); unselected envs report -1."""
+        self._require_task()
+        if seed is not None:
+            self.engine.set_seed(seed)
+        m = None if mask is None else self.engine._dev(mask, torch.uint8)
+        self.engine.reset(self._buf["obs"], mask=m, u_inject=u_inject)
+        return self._squeeze(self._buf["obs"]), {"steps": torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)}
+
+    # ---- step (anymdp_env.py:112-132) -----------------------------------------------------------
+    def step(self, actions=None, u_inject=None, check=False):
+        """actions: int tensor [N] (or [N, da] for MTPOMDP); None = built-in uniform random policy.
+        Returns (obs, reward f32[N], terminated bool[N], truncated bool[N], info).  The tensors are
+        the env's own output buffers and are overwritten by the next call."""
+        self._require_task()
+        a = None
+        if actions is not None:
+            a = self.engine._dev(actions, torch.int32).reshape(self.num_envs, self.da)
+        b = self._buf
+        self.engine.step(a, b, u_inject=u_inject)
+        if check:
+            raise_faults(self.engine.poll_errors())
+        info = {"reward_gt": b["reward_gt"], "final_obs": self._squeeze(b["final_obs"]), "action": self._squeeze(b["action"])}
+        return self._squeeze(b["obs"]), b["reward"], b["terminated"].bool(), b["truncated"].bool(), info
+
+    def check(self):
+        """Raise the reference's exception for any per-env fault recorded since the last check (synchronises)."""
+        raise_faults(self.engine.poll_errors())
+
+    # ---- K steps per launch ---------------------------------------------------------------------
+    def rollout(self, K, actions=None, policy="uniform", record=("obs", "action", "reward", "done"), u_inject=None,
+                out=None):
+        """The data-collection loop around env.step() (test_utils.py:42-60) as one kernel launch.
+        actions int tensor [K, N(, da)] or None with policy="uniform".  Returns a dict of [K, N(, w)]
+        tensors for the requested fields (`done`: bit0 terminated, bit1 truncated)."""
+        self._require_task()
+        if actions is None and policy != "uniform":
+            raise ValueError("policy must be 'uniform' when no actions are given")
+        a = None if actions is None else self.engine._dev(actions, torch.int32).reshape(K, self.num_envs, self.da)
+        N, d = self.num_envs, self.device
+        traj = out if out is not None else {}
+        if out is None:
+            if "obs" in record:
+                traj["obs"] = torch.empty((K, N, self.do), dtype=torch.int32, device=d)
+            if "action" in record:
+                traj["action"] = torch.empty((K, N, self.da), dtype=torch.int32, device=d)
+            if "reward" in record:
+                traj["reward"] = torch.empty((K, N), dtype=torch.float32, device=d)
+            if "reward_gt" in record:
+                traj["reward_gt"] = torch.empty((K, N), dtype=torch.float32, device=d)
+            if "done" in record:
+                traj["done"] = torch.empty((K, N), dtype=torch.uint8, device=d)
+        self.engine.rollout(K, actions=a, traj=traj, u_inject=u_inject)
+        return traj
+
+    # ---- statistics -----------------------------------------------------------------------------
+    def episode_stats_tensor(self):
+        """float64[8] on device: episodes, sum_return, sum_return_sq, sum_length, min, max, total_steps, 0."""
+        return self.engine.stats_tensor(self._stats)
+
+    def episode_stats(self, group=None):
+        """Closed-episode statistics; with a torch.distributed `group` (or the default group when
+        initialised and group=True) they are all-reduced over the ranks (one tiny NCCL call)."""
+        s = self.episode_stats_tensor().clone()
+        if group is not None:
+            import torch.distributed as dist
+            g = None if group is True else group
+            sums, mn, mx = s[[0, 1, 2, 3, 6]].clone(), s[4:5].clone(), s[5:6].clone()
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=g)
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=g)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=g)
+            s[[0, 1, 2, 3, 6]] = sums
+            s[4], s[5] = mn[0], mx[0]
+        v = s.cpu().numpy()
+        n = int(v[0])
+        return {"episodes": n, "sum_return": float(v[1]), "sum_return_sq": float(v[2]), "sum_length": int(v[3]),
+                "min_return": float(v[4]), "max_return": float(v[5]), "total_steps": int(v[6]),
+                "mean_return": float(v[1] / n) if n else float("nan"),
+                "mean_length": float(v[3] / n) if n else float("nan")}
+
+    def clear_episode_stats(self):
+        self.engine.clear_stats()
+
+    # ---- introspection (anymdp_env.py:134-143,161-165) ------------------------------------------
+    @property
+    def state(self):
+        return self.engine.mapped_state()
+
+    @property
+    def inner_state(self):
+        return self.engine.get_state()["state"]
+
+    def transition_gt(self, actions):
+        """info["transition_gt"] (anymdp_env.py:130) for every env: float64 [N, da, ns]; needs keep_transition=True."""
+        ns = max(int(x) for x in numpy.atleast_1d(self.geo.get("ns_out", self.geo["n_pad"])))
+        return self.engine.transition_gt(actions, ns)
+
+    # ---- checkpoint / resume (bit-exact: counter-based RNG) --------------------------------------
+    def state_dict(self):
+        st = {k: v.cpu() for k, v in self.engine.get_state().items()}
+        st["tick"] = self.engine.tick
+        st["seed"] = self.seed
+        return st
+
+    def load_state_dict(self, st):
+        self._require_task()
+        self.engine.set_state(st)
+        self.engine.tick = st["tick"]
+        self.seed = int(st["seed"])
+        self.engine.set_seed(self.seed)
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
