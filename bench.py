@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""AnyMDP env-steps/sec on B200 (BASELINE.json metric), with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A bench "step" is ONE rollout launch: `--ticks` (default 512) consecutive env.step() ticks for every
+env of the workload, uniform random policy from the engine's Philox stream, full trajectory
+(obs, action, reward, done) written to HBM, plus the per-iteration episode-statistics reduction
+(and its NCCL all-reduce when N > 1).  value = env-steps of all ranks / max-over-ranks device time.
+
+Workloads (BASELINE.json configs / SURVEY.md §8d); per-GPU sizes, weak scaling over ranks:
+  cfg2  4096 envs, 4096 distinct synthetic tasks ns=128 na=5 (5 GiB of tables >> L2)   [default]
+  cfg3  65536 envs, POMDP ns=64 na=8 no=64, 4096 tasks shared round-robin
+  cfg4  65536 envs, ns=1024 na=16, `--tasks` tasks (256 = 64 GiB of tables; sharded over ranks)
+  cfg5  131072 envs, ns=32 na=5, one distinct task per env
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    #        envs/GPU  tasks/GPU  ns    na  no
+    "cfg2": (4096,     4096,      128,  5,  None),
+    "cfg3": (65536,    4096,      64,   8,  64),
+    "cfg4": (65536,    256,       1024, 16, None),
+    "cfg5": (131072,   131072,    32,   5,  None),
+}
+
+
+def sectors(n):
+    """distinct 32-B sectors a bisection over n doubles touches."""
+    return max(1, math.ceil(math.log2(n)) - 2)
+
+
+def b_alg(ns, no):
+    """Algorithmic bytes per env-step — the fixed yardstick of roofline.achieved."""
+    if no is None:
+        return 38 + 32 * (sectors(ns) + 2)
+    return 38 + 32 * (sectors(ns) + 2 + sectors(no))
+
+
+def describe(name, envs, tasks, ns, na, no, ticks):
+    kind = "MDP" if no is None else f"POMDP no={no}"
+    return (f"{name}: AnyMDP {kind} batch {envs} envs x ns={ns} na={na}, {tasks} synthetic tasks per GPU, "
+            f"uniform random policy, {ticks} ticks per rollout launch")
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's numpy loop (oracle/reference_loop.py port) on host cores
+# --------------------------------------------------------------------------------------------------
+def run_reference(args, name, envs, tasks, ns, na, no):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import reference_loop as rl
+    cores = len(os.sched_getaffinity(0))
+    per_worker = args.ref_steps_per_worker
+    rounds = rl.timed_pool(ns, na, no, cores, per_worker, args.steps, warm=args.warmup)
+    total = sum(rounds)
+    value = cores * per_worker * args.steps / total
+    sample = (f"{cores} processes x 1 env each, own synthetic task (ns={ns} na={na}), {per_worker} env-steps per "
+              f"process per step, reset on done; numpy.random.choice/normal per step as anymdp_env.py:99-105")
+    line = {
+        "impl": "reference", "metric": "AnyMDP env-steps/sec", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": describe(name, envs, tasks, ns, na, no, args.ticks)},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(args):
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "6", "--warmup", "1",
+           "--workload", args.workload, "--ref-steps-per-worker", str(args.ref_steps_per_worker)]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env).stdout.strip().splitlines()
+        return json.loads(out[-1])["cpu_baseline"]
+    except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU measurement
+        return {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md recipe), sampled DURING the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# the B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args, name, envs, tasks, ns, na, no):
+    import torch
+    import torch.distributed as dist
+    from xenoverse_b200 import AnyMDPVecEnv, synth_packed, synth_geometry
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_subprocess(args)      # before the GPU is busy; separate process, host cores only
+
+    K, W, ticks = args.steps, args.warmup, args.ticks
+    if name == "cfg4" and world > 1:
+        tasks = max(1, tasks // world)                # cfg4 shards its 256 tasks over the ranks
+    geo = synth_geometry(ns, na, no)
+    env = AnyMDPVecEnv(envs, device=local, seed=0, env_id_base=rank * envs)
+    per_task = 3 * 8 * geo["n_pad"] * na * geo["n_pad"]
+    chunk = max(1, min(tasks, (768 << 20) // per_task))
+
+    def batches():
+        for t0 in range(0, tasks, chunk):
+            yield t0, synth_packed(ns, na, min(chunk, tasks - t0), seed=1000 + rank * tasks + t0, device=dev, no=no)
+
+    t_up = time.time()
+    env.set_task(None, packed=(geo, tasks, batches()))
+    torch.cuda.synchronize()
+    t_up = time.time() - t_up
+    env.reset()
+    N = envs
+    traj = {"obs": torch.empty((ticks, N, 1), dtype=torch.int32, device=dev),
+            "action": torch.empty((ticks, N, 1), dtype=torch.int32, device=dev),
+            "reward": torch.empty((ticks, N), dtype=torch.float32, device=dev),
+            "done": torch.empty((ticks, N), dtype=torch.uint8, device=dev)}
+    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+
+    def one_step(ev=None):
+        if ev:
+            ev[0].record()
+        env.rollout(ticks, out=traj)
+        if ev:
+            ev[1].record()
+        env.engine.stats_tensor(stats)               # per-iteration episode statistics
+        if world > 1:
+            dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM)
+
+    for _ in range(W):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = env.engine.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(K):
+        one_step(evs[i])
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clk = clocks.stop() if rank == 0 else None
+    launches = env.engine.launch_count - launches0
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    kern_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / K], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    ms, kern_ms = float(ms), float(kern_ms)
+    env.check()
+    ep = env.episode_stats(group=True if world > 1 else None)
+
+    # ---- end to end through the C ABI with HOST buffers (amdp_rollout_host) -----------------------
+    e2e = None
+    if not args.no_e2e:
+        eK = args.e2e_ticks
+        g = torch.Generator().manual_seed(rank)
+        acts_h = torch.randint(0, na, (eK, N, 1), dtype=torch.int32, generator=g).pin_memory()
+        obs_h = torch.empty((eK, N, 1), dtype=torch.int32).pin_memory()
+        rew_h = torch.empty((eK, N), dtype=torch.float32).pin_memory()
+        done_h = torch.empty((eK, N), dtype=torch.uint8).pin_memory()
+        reps = max(3, min(K, 10))
+        for _ in range(2):
+            env.engine.rollout_host(eK, args.e2e_chunk, acts_h, obs_h, rew_h, done_h)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        w0 = time.perf_counter()
+        for _ in range(reps):
+            env.engine.rollout_host(eK, args.e2e_chunk, acts_h, obs_h, rew_h, done_h)   # synchronous
+        w = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * N * eK * reps / float(w), "unit": "env-steps/s",
+               "h2d_bytes_per_step": int(acts_h.numel() * 4), "d2h_bytes_per_step": int(obs_h.numel() * 4 + rew_h.numel() * 4 + done_h.numel()),
+               "step": f"one amdp_rollout_host call = {eK} ticks x {N} envs, pinned host actions in, host obs/reward/done out, "
+                       f"chunks of {args.e2e_chunk} ticks double-buffered; wall clock around {reps} synchronous calls",
+               "ms_per_step": 1e3 * float(w) / reps}
+        env.check()
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.isfile(peaks_path):
+            peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, which = 6650.0, "fallback (B200_PROFILING.md)"
+        balg = b_alg(ns, no)
+        achieved = balg * N * ticks / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tpath):
+            traffic = json.load(open(tpath)).get(name)
+        value = world * N * ticks * K / (ms * 1e-3)
+        line = {
+            "metric": "AnyMDP env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": describe(name, envs, tasks, ns, na, no, ticks), "envs_per_gpu": N, "tasks_per_gpu": tasks,
+                       "ticks_per_step": ticks, "table_bytes_per_gpu": env.engine.device_bytes,
+                       "l2": "inputs larger than L2 (tables >> 126 MB; no flush needed)" if env.engine.device_bytes > (1 << 30)
+                             else "tables may be L2 resident", "parallelism": f"env-sharded dp{world}",
+                       "upload_s": round(t_up, 2)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": which, "kernel": "k_rollout",
+                         "algorithmic_bytes_per_env_step": balg, "kernel_ms_per_launch": kern_ms},
+            "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "episodes": ep["episodes"], "mean_return": ep["mean_return"], "mean_length": ep["mean_length"],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ticks", type=int, default=512)
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--tasks", type=int, default=0, help="override tasks per GPU")
+    ap.add_argument("--e2e-ticks", type=int, default=512)
+    ap.add_argument("--e2e-chunk", type=int, default=64)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-steps-per-worker", type=int, default=20000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    envs, tasks, ns, na, no = WORKLOADS[args.workload]
+    envs = args.envs or envs
+    tasks = args.tasks or tasks
+    if args.impl == "reference":
+        run_reference(args, args.workload, envs, tasks, ns, na, no)
+    else:
+        run_b200(args, args.workload, envs, tasks, ns, na, no)
+
+
+if __name__ == "__main__":
+    main()

@@ -166,11 +166,12 @@ int amdp_reset(amdp_t* h, const uint8_t* mask, int32_t* obs_out, const double* u
  *   reward_gt    float [n_envs] or NULL          info["reward_gt"] (:129)
  *   terminated, truncated  uint8 [n_envs]
  *   actions_out  int32 [n_envs][da] or NULL      the actions actually applied
+ *   steps_out    int32 [n_envs] or NULL          info["steps"] (:129): step count of the episode the tick belongs to
  *   u_inject     double [n_envs][n_slots] or NULL
  */
 int amdp_step(amdp_t* h, const int32_t* actions, int32_t* obs, int32_t* final_obs,
               float* reward, float* reward_gt, uint8_t* terminated, uint8_t* truncated,
-              int32_t* actions_out, const double* u_inject, void* stream);
+              int32_t* actions_out, int32_t* steps_out, const double* u_inject, void* stream);
 
 /*
  * K consecutive steps in one launch (the data-collection loop around env.step(),

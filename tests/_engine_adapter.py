@@ -36,11 +36,11 @@ class EngineVecEnv:
             a = torch.as_tensor(numpy.asarray(actions, dtype=numpy.int32).reshape(self.N, self.da)).to(self.eng.device)
         self.eng.step(a, self.buf, u_inject=self._u(U))
         st = self.eng.get_state()
-        out = {k: self.buf[k].cpu().numpy() for k in ("obs", "final_obs", "reward", "reward_gt", "terminated", "truncated", "action")}
+        out = {k: self.buf[k].cpu().numpy() for k in ("obs", "final_obs", "reward", "reward_gt", "terminated", "truncated", "action", "steps")}
         out["terminated"] = out["terminated"].astype(bool)
         out["truncated"] = out["truncated"].astype(bool)
         out["state"] = st["state"].cpu().numpy().astype(numpy.int64)
-        out["steps"] = st["steps"].cpu().numpy().astype(numpy.int64)
+        out["steps"] = out["steps"].astype(numpy.int64)
         return out
 
     def stats(self):

@@ -47,7 +47,7 @@ _SIGNATURES = {
     "amdp_upload_tasks": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int64] + [_P] * 14),
     "amdp_assign": (ctypes.c_int, [_P, _P, _P]),
     "amdp_reset": (ctypes.c_int, [_P, _P, _P, _P, _P]),
-    "amdp_step": (ctypes.c_int, [_P] * 11),
+    "amdp_step": (ctypes.c_int, [_P] * 12),
     "amdp_rollout": (ctypes.c_int, [_P, ctypes.c_int32, _P, ctypes.POINTER(Traj), _P, _P]),
     "amdp_stats": (ctypes.c_int, [_P, _P, _P]),
     "amdp_clear_stats": (ctypes.c_int, [_P, _P]),

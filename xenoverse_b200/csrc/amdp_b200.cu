@@ -155,6 +155,7 @@ struct EnvRegs {
 struct TickOut {
     float reward, reward_gt;
     int term, trunc;
+    int steps;            // info["steps"] of this tick (before any same-step reset)
     int finished;         // an episode was closed in this tick
     double fin_return;    // its return
     int fin_steps;        // its length
@@ -186,7 +187,7 @@ template <int G>
 __device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, long long t, bool active, int lane,
                                          const Draws& D, const int32_t* act_in /* [d_a] or null */,
                                          EnvRegs& R, TickOut& O, int* obs, int* final_obs, int* act_used) {
-    O.reward = 0.f; O.reward_gt = 0.f; O.term = 0; O.trunc = 0; O.finished = 0; O.fin_return = 0.0; O.fin_steps = 0;
+    O.reward = 0.f; O.reward_gt = 0.f; O.term = 0; O.trunc = 0; O.steps = 0; O.finished = 0; O.fin_return = 0.0; O.fin_steps = 0;
     const int da = T.d_a;
     // draws of block 0: transition (token 0) and reset uniforms
     double u_trans0, u_reset;
@@ -240,6 +241,7 @@ __device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, lo
         O.reward_gt = (float)rew_gt;
         R.ep_return += rew;
     }
+    O.steps = R.steps;
     // observation of the step (drawn after the transition, from the new state; :132,145-159)
     observe<G>(T, t, s, D, AMDP_SLOT_OBS, lane, ok, obs);
     for (int k = 0; k < T.d_o; ++k) final_obs[k] = obs[k];
@@ -262,6 +264,7 @@ __device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, lo
         for (int i = 0; i < T.s0_pad; ++i) c += (T.s0_cdf[t * T.s0_pad + i] <= u_reset);
         s_new = T.s0_idx[t * T.s0_pad + min(c, T.s0_pad - 1)];
         R.state = s_new; R.steps = 0; R.flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
+        if (pending) O.steps = 0;
     }
     if (T.task_type == AMDP_MDP) {
         if (do_reset) { obs[0] = T.sinfo[t * T.n_pad + s_new] & 0x7fffffff; if (pending) final_obs[0] = obs[0]; }
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(256) k_step(Tables T, EnvArrays E, unsigned lo
                                               int32_t* __restrict__ final_obs_out, float* __restrict__ reward,
                                               float* __restrict__ reward_gt, uint8_t* __restrict__ terminated,
                                               uint8_t* __restrict__ truncated, int32_t* __restrict__ actions_out,
-                                              const double* __restrict__ u_inject) {
+                                              int32_t* __restrict__ steps_out, const double* __restrict__ u_inject) {
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long e = gtid / G;
     const int lane = (int)(gtid % G);
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(256) k_step(Tables T, EnvArrays E, unsigned lo
         terminated[e] = (uint8_t)O.term;
         truncated[e] = (uint8_t)O.trunc;
         if (actions_out) for (int k = 0; k < T.d_a; ++k) actions_out[e * T.d_a + k] = act[k];
+        if (steps_out) steps_out[e] = O.steps;
     }
 }
 
@@ -809,21 +813,22 @@ extern "C" int amdp_reset(amdp_t* h, const uint8_t* mask, int32_t* obs_out, cons
 
 template <int G>
 static void launch_step(amdp* h, const int32_t* actions, int32_t* obs, int32_t* final_obs, float* reward, float* reward_gt,
-                        uint8_t* terminated, uint8_t* truncated, int32_t* actions_out, const double* u, cudaStream_t st) {
+                        uint8_t* terminated, uint8_t* truncated, int32_t* actions_out, int32_t* steps_out, const double* u,
+                        cudaStream_t st) {
     const long long threads = h->cfg.n_envs * G;
     k_step<G><<<nblk(threads, 256), 256, 0, st>>>(h->T, h->E, h->tick, h->n_slots, actions, obs, final_obs, reward, reward_gt,
-                                                  terminated, truncated, actions_out, u);
+                                                  terminated, truncated, actions_out, steps_out, u);
 }
 
 extern "C" int amdp_step(amdp_t* h, const int32_t* actions, int32_t* obs, int32_t* final_obs, float* reward,
                          float* reward_gt, uint8_t* terminated, uint8_t* truncated, int32_t* actions_out,
-                         const double* u_inject, void* stream) {
+                         int32_t* steps_out, const double* u_inject, void* stream) {
     if (!h || !obs || !reward || !terminated || !truncated) return AMDP_EINVAL;
     if (!h->assigned) return fail(h, AMDP_ESTATE, "Must \"set_task\" and \"reset\" before doing any actions");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     switch (h->G) {
-#define CASE(g) case g: launch_step<g>(h, actions, obs, final_obs, reward, reward_gt, terminated, truncated, actions_out, u_inject, st); break;
+#define CASE(g) case g: launch_step<g>(h, actions, obs, final_obs, reward, reward_gt, terminated, truncated, actions_out, steps_out, u_inject, st); break;
         CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)
 #undef CASE
         default: return fail(h, AMDP_EINVAL, "bad group size");

@@ -243,7 +243,8 @@ class Engine:
                 "reward_gt": torch.empty(N, dtype=torch.float32, device=d),
                 "terminated": torch.empty(N, dtype=torch.uint8, device=d),
                 "truncated": torch.empty(N, dtype=torch.uint8, device=d),
-                "action": torch.empty((N, self.da), dtype=torch.int32, device=d)}
+                "action": torch.empty((N, self.da), dtype=torch.int32, device=d),
+                "steps": torch.empty(N, dtype=torch.int32, device=d)}
 
     def reset(self, obs_out, mask=None, u_inject=None):
         with torch.cuda.device(self.device):
@@ -253,7 +254,8 @@ class Engine:
         with torch.cuda.device(self.device):
             self._ck(lib.amdp_step(self._h, _ptr(actions), _ptr(out["obs"]), _ptr(out.get("final_obs")),
                                    _ptr(out["reward"]), _ptr(out.get("reward_gt")), _ptr(out["terminated"]),
-                                   _ptr(out["truncated"]), _ptr(out.get("action")), _ptr(u_inject), _stream()))
+                                   _ptr(out["truncated"]), _ptr(out.get("action")), _ptr(out.get("steps")), _ptr(u_inject),
+                                   _stream()))
 
     def rollout(self, K, actions=None, traj=None, u_inject=None, env_major=False):
         """traj: dict with optional tensors obs [K,N,do], action [K,N,da], reward, reward_gt, done [K,N]

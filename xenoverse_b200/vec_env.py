@@ -111,7 +111,7 @@ class AnyMDPVecEnv:
         self.engine.step(a, b, u_inject=u_inject)
         if check:
             raise_faults(self.engine.poll_errors())
-        info = {"reward_gt": b["reward_gt"], "final_obs": self._squeeze(b["final_obs"]), "action": self._squeeze(b["action"])}
+        info = {"steps": b["steps"], "reward_gt": b["reward_gt"], "final_obs": self._squeeze(b["final_obs"]), "action": self._squeeze(b["action"])}
         return self._squeeze(b["obs"]), b["reward"], b["terminated"].bool(), b["truncated"].bool(), info
 
     def check(self):
