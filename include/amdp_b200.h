@@ -236,6 +236,9 @@ int amdp_poll_errors(amdp_t* h, uint32_t* faults, void* stream);
 /* Debug/verification: copy the built CDF row of (task, s, a) to out double [n_pad] (device). */
 int amdp_debug_cdf_row(amdp_t* h, int64_t task, int32_t s, int32_t a, double* out, void* stream);
 
+/* Debug/verification: route amdp_rollout through the generic per-tick kernel instead of the fast MDP kernel. */
+int amdp_debug_force_generic(amdp_t* h, int on);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t amdp_launch_count(const amdp_t* h);
 

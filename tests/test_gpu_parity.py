@@ -289,3 +289,52 @@ def test_checkpoint_resume_bit_exact():
     got = b.rollout(41)
     for key in ("obs", "reward", "done", "action"):
         assert torch.equal(want[key], got[key]), key
+
+
+@pytest.mark.parametrize("ns,na,N,mode,given", [
+    (16, 5, 100, "same_step", False), (16, 5, 100, "next_step", True), (32, 4, 77, "same_step", True),
+    (64, 8, 50, "next_step", False), (128, 5, 33, "same_step", False), (128, 5, 33, "next_step", True),
+    (256, 3, 9, "same_step", False), (200, 3, 7, "same_step", True), (12, 3, 40, "next_step", False),
+    (8, 2, 65, "same_step", False), (1024, 2, 3, "same_step", False)])
+def test_fast_rollout_kernel_equals_generic_kernel(ns, na, N, mode, given):
+    """The latency-optimised MDP rollout kernel and the generic per-tick kernel (itself checked against the
+    oracle above) must agree bit for bit — observations, actions, done flags, rewards, state, statistics."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    T = min(N, 6)
+    tasks = [synth_task(ns, na, 300 + t) for t in range(T)]
+    for t in tasks:
+        t["max_steps"] = 31.2
+    K = 130
+    acts = torch.randint(0, na, (K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(ns)).cuda() if given else None
+    outs = []
+    for generic in (False, True):
+        env = AnyMDPVecEnv(N, seed=17, autoreset=mode, env_id_base=1000)
+        env.set_task(tasks)
+        env.engine.force_generic(generic)
+        env.reset()
+        tr = env.rollout(K, actions=acts, record=("obs", "action", "reward", "reward_gt", "done"))
+        tr2 = env.rollout(7, actions=None if acts is None else acts[:7], record=("obs", "action", "reward", "reward_gt", "done"))
+        env.check()
+        outs.append((tr, tr2, env.engine.get_state(), env.episode_stats()))
+    (a, a2, sa, ea), (b, b2, sb, eb) = outs
+    for key in ("obs", "action", "done", "reward", "reward_gt"):
+        assert torch.equal(a[key], b[key]), key
+        assert torch.equal(a2[key], b2[key]), key + " (second launch)"
+    for key in ("state", "steps", "flags", "ep_return"):
+        assert torch.equal(sa[key], sb[key]), key
+    assert ea == eb and ea["episodes"] > 0
+
+
+def test_fast_rollout_faults():
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    env = AnyMDPVecEnv(8)
+    env.set_task(synth_task(16, 5, 1))
+    env.rollout(4)
+    with pytest.raises(Exception, match="reset"):
+        env.check()
+    env.reset()
+    bad = torch.zeros((4, 8), dtype=torch.int32)
+    bad[2, 3] = 9
+    env.rollout(4, actions=bad)
+    with pytest.raises(AssertionError):
+        env.check()

@@ -374,6 +374,228 @@ __global__ void __launch_bounds__(256) k_rollout(Tables T, EnvArrays E, unsigned
     if (active && lane == 0) { store_regs(E, e, R); store_stats(E, e, R); }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: MDP, one action token, engine Philox draws, auto-reset on (the benchmark / data-
+// collection configuration).  Same arithmetic as env_tick, restructured for issue slots and latency:
+//   * the G lanes of an env generate the draws of G consecutive ticks in ONE Philox pass (lane j
+//     computes tick k0 + j) and broadcast them tick by tick, so the RNG costs ~1/G of a
+//     per-lane evaluation per tick;
+//   * the (reward, noise) payload load is taken off the dependent chain: it is issued when s' is
+//     known and consumed one tick later, after the NEXT row load is already in flight.  The chain
+//     per tick is: CDF row (HBM) -> compare/ballot -> per-task state table (L1) -> next row address;
+//   * rows and payload are streamed past L1 (no reuse), keeping L1 for the per-task tables.
+// C = 4-double chunks per lane held in registers (n_pad == 4*G*C); C == 0: any n_pad, looped.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ldg_stream_f64x2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float2 ldg_stream_f32x2(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+template <int G, int C, bool GIVEN>
+__global__ void __launch_bounds__(128, 8) k_rollout_mdp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
+                                                     const int32_t* __restrict__ actions, const amdp_traj J) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int CR = C > 0 ? C : 1;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e_raw = gtid / G;
+    const int lane = threadIdx.x & (G - 1);
+    const int gbase = (threadIdx.x & 31) & ~(G - 1);           // first warp lane of this group
+    const bool active = e_raw < E.n_envs;
+    const long long e = active ? e_raw : E.n_envs - 1;         // spare groups shadow the last env, stores masked
+    const bool writer = active && lane == 0;
+    const int n_pad = T.n_pad, na = T.na;
+    const long long t = E.task[e];
+    const long long tsz = (long long)n_pad * na * n_pad;
+    const double* __restrict__ cdf_t = T.cdf + t * tsz;
+    const float2* __restrict__ pay_t = T.payload + t * tsz;
+    const int32_t* __restrict__ sinfo_t = T.sinfo + t * n_pad;
+    const int max_ceil = T.max_ceil[t];
+    const bool always_term = (T.tflags[t] & 1) != 0;
+    const bool next_mode = T.autoreset == AMDP_AUTORESET_NEXT_STEP;
+    const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
+
+    int s = E.state[e], steps = E.steps[e], flags = E.flags[e];
+    double ep_ret = E.ep_return[e];
+    unsigned long long ep_count = E.ep_count[e], sum_len = E.sum_len[e];
+    double sum_ret = E.sum_ret[e], sum_sq = E.sum_ret_sq[e], min_ret = E.min_ret[e], max_ret = E.max_ret[e];
+
+    unsigned fault = 0;
+    bool dead = false;                                         // faulted envs are left untouched (as in env_tick)
+    if (flags & FLAG_VIRGIN) { fault |= AMDP_FAULT_NEED_RESET; dead = true; }
+    else if (!(next_mode && (flags & FLAG_PENDING)) && sinfo_t[s] < 0 && !always_term) { fault |= AMDP_FAULT_TERMINAL_STATE; dead = true; }
+
+    // draws of the current batch of G ticks (lane j: tick k0 + j)
+    double b_ut = 0.0, b_ur = 0.0;
+    float b_z = 0.f;
+    int b_act = 0;
+    // deferred reward bookkeeping of the previous tick
+    float2 pay_p = make_float2(0.f, 0.f);
+    float z_p = 0.f;
+    int fin_p = 0;            // bit0: a step happened, bit1: it closed an episode
+    int steps_p = 0;
+    long long o_p = 0;
+
+    for (int k = 0; k < K; ++k) {
+        const int j = k & (G - 1);
+        if (j == 0) {
+            const unsigned long long tk = tick0 + (unsigned long long)(k + lane);
+            const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
+            b_ut = u53(w0.x, w0.y);
+            b_ur = u53(w0.z, w0.w);
+            const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
+            b_z = box_muller(w2.x, w2.y);
+            if (GIVEN) b_act = (k + lane < K) ? actions[(long long)(k + lane) * E.n_envs + e] : 0;
+            else b_act = (int)__umulhi(w2.z, (uint32_t)na);
+        }
+        const double u = __shfl_sync(FULL, b_ut, j, G);
+        const float z = __shfl_sync(FULL, b_z, j, G);
+        const int a = __shfl_sync(FULL, b_act, j, G);
+        const long long o = (long long)k * J.step_stride + e * J.env_stride;
+        const bool pending = next_mode && (flags & FLAG_PENDING);
+        bool valid = !dead && !pending;
+        if (GIVEN && valid && (unsigned)a >= (unsigned)na) { fault |= AMDP_FAULT_BAD_ACTION; valid = false; }
+
+        // (A) issue the CDF row load
+        const long long rowi = ((long long)s * na + (valid ? a : 0)) * n_pad;
+        double2 r[2 * CR];
+        int cnt_loop = 0;
+        if (C > 0) {
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < CR; ++c) {
+                    const double* q = cdf_t + rowi + (c * G + lane) * 4;
+                    r[2 * c] = ldg_stream_f64x2(q);
+                    r[2 * c + 1] = ldg_stream_f64x2(q + 2);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2 * CR; ++c) r[c] = make_double2(2.0, 2.0);
+            }
+        }
+
+        // (B) previous tick's reward, return and episode statistics — overlaps the row load
+        if (fin_p & 1) {
+            const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
+            ep_ret += rew;
+            if (writer) {
+                if (J.reward) J.reward[o_p] = (float)rew;
+                if (J.reward_gt) J.reward_gt[o_p] = pay_p.x;
+            }
+            if (fin_p & 2) {
+                ep_count += 1; sum_len += (unsigned long long)steps_p;
+                sum_ret += ep_ret; sum_sq += ep_ret * ep_ret;
+                min_ret = fmin(min_ret, ep_ret); max_ret = fmax(max_ret, ep_ret);
+                ep_ret = 0.0;
+            }
+        }
+        fin_p = 0;
+
+        // (C) next state = #{cdf <= u}
+        int nxt;
+        if (C > 0) {
+            // chunk m = c * G + lane holds entries [4m, 4m + 4).  The CDF is non-decreasing, so the chunks whose
+            // last entry is <= u form a prefix in m order; the draw index is 4 * (#full chunks) + the count
+            // inside the first non-full chunk.
+            int c4[CR];
+            int full_chunks = 0;
+#pragma unroll
+            for (int c = 0; c < CR; ++c) {
+                c4[c] = (r[2 * c].x <= u) + (r[2 * c].y <= u) + (r[2 * c + 1].x <= u) + (r[2 * c + 1].y <= u);
+                const unsigned b = __ballot_sync(FULL, c4[c] == 4);
+                full_chunks += __popc((b >> gbase) & (G == 32 ? FULL : ((1u << G) - 1u)));
+            }
+            int mine = c4[0];
+#pragma unroll
+            for (int c = 1; c < CR; ++c) if (full_chunks >= c * G) mine = c4[c];
+            nxt = 4 * full_chunks + __shfl_sync(FULL, mine, full_chunks & (G - 1), G);
+        } else {
+            if (valid) {
+                for (int i = lane * 4; i < n_pad; i += G * 4) {
+                    const double2 x = ldg_stream_f64x2(cdf_t + rowi + i);
+                    const double2 y = ldg_stream_f64x2(cdf_t + rowi + i + 2);
+                    cnt_loop += (x.x <= u) + (x.y <= u) + (y.x <= u) + (y.y <= u);
+                }
+            }
+            nxt = group_sum<G>(cnt_loop);
+        }
+
+        int obs_out = 0, done_bits = 0;
+        bool do_reset = pending;
+        if (valid) {
+            // (D) payload load for (s, a, s'): consumed next tick
+            pay_p = ldg_stream_f32x2(pay_t + rowi + nxt);
+            z_p = z; o_p = o;
+            // (E) state update, termination, truncation (anymdp_env.py:107-108,113-114)
+            const int si = __ldg(sinfo_t + nxt);
+            s = nxt;
+            steps += 1;
+            const bool term = (si < 0) || always_term;
+            const bool trunc = steps >= max_ceil;
+            obs_out = si & 0x7fffffff;
+            done_bits = (term ? 1 : 0) | (trunc ? 2 : 0);
+            steps_p = steps;
+            fin_p = 1;
+            if (done_bits) {
+                fin_p = 3;
+                if (next_mode) flags |= FLAG_PENDING; else do_reset = true;
+            }
+        } else if (writer && !pending) {
+            if (J.reward) J.reward[o] = 0.f;
+            if (J.reward_gt) J.reward_gt[o] = 0.f;
+        }
+        // reset (anymdp_env.py:81-90)
+        if (__any_sync(FULL, do_reset)) {
+            const double ur = __shfl_sync(FULL, b_ur, j, G);
+            if (do_reset) {
+                int c = 0;
+                for (int i = 0; i < T.s0_pad; ++i) c += (T.s0_cdf[t * T.s0_pad + i] <= ur);
+                s = T.s0_idx[t * T.s0_pad + min(c, T.s0_pad - 1)];
+                steps = 0;
+                flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
+                obs_out = __ldg(sinfo_t + s) & 0x7fffffff;
+                if (pending && writer) {
+                    if (J.reward) J.reward[o] = 0.f;
+                    if (J.reward_gt) J.reward_gt[o] = 0.f;
+                }
+            }
+        }
+        if (writer) {
+            if (J.obs) J.obs[o] = obs_out;
+            if (J.actions_out) J.actions_out[o] = a;
+            if (J.done) J.done[o] = (uint8_t)done_bits;
+        }
+    }
+    // flush the deferred bookkeeping of the last tick
+    if (fin_p & 1) {
+        const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
+        ep_ret += rew;
+        if (writer) {
+            if (J.reward) J.reward[o_p] = (float)rew;
+            if (J.reward_gt) J.reward_gt[o_p] = pay_p.x;
+        }
+        if (fin_p & 2) {
+            ep_count += 1; sum_len += (unsigned long long)steps_p;
+            sum_ret += ep_ret; sum_sq += ep_ret * ep_ret;
+            min_ret = fmin(min_ret, ep_ret); max_ret = fmax(max_ret, ep_ret);
+            ep_ret = 0.0;
+        }
+    }
+    if (writer) {
+        E.state[e] = s; E.steps[e] = steps; E.flags[e] = (uint8_t)flags; E.ep_return[e] = ep_ret;
+        E.ep_count[e] = ep_count; E.sum_len[e] = sum_len; E.sum_ret[e] = sum_ret; E.sum_ret_sq[e] = sum_sq;
+        E.min_ret[e] = min_ret; E.max_ret[e] = max_ret;
+        if (fault) atomicOr(E.faults, fault);
+    }
+}
+
 __global__ void k_reset(Tables T, EnvArrays E, unsigned long long tick, int n_slots, const uint8_t* __restrict__ mask,
                         int32_t* __restrict__ obs_out, const double* __restrict__ u_inject) {
     // one thread per env (G = 1): reset is rare and touches only the small per-task tables
@@ -613,6 +835,7 @@ struct amdp {
     int64_t bytes;
     int64_t launches;
     bool uploaded, assigned;
+    bool force_generic;    // debug: route rollouts through the generic kernel
     char err[512];
     // rollout_host staging
     int32_t* st_act[2]; int32_t* st_obs[2]; float* st_rew[2]; uint8_t* st_done[2];
@@ -846,6 +1069,28 @@ static void launch_rollout(amdp* h, int K, const int32_t* actions, const amdp_tr
     k_rollout<G><<<nblk(threads, 256), 256, 0, st>>>(h->T, h->E, h->tick, K, h->n_slots, actions, J, u);
 }
 
+template <int G, int C>
+static void launch_fast_gc(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
+    const long long threads = h->cfg.n_envs * G;
+    if (actions) k_rollout_mdp<G, C, true><<<nblk(threads, 128), 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
+    else k_rollout_mdp<G, C, false><<<nblk(threads, 128), 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
+}
+
+// lanes per env and register-resident chunks per lane for the fast kernel: n_pad == 4 * G * C
+static void launch_rollout_fast(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
+    const int n_pad = h->cfg.n_pad;
+    const int G = h->G;
+    const int C = (n_pad == 4 * G) ? 1 : (n_pad == 8 * G ? 2 : 0);
+    switch (G) {
+        case 1: if (C == 1) launch_fast_gc<1, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<1, 2>(h, K, actions, J, st); else launch_fast_gc<1, 0>(h, K, actions, J, st); break;
+        case 2: if (C == 1) launch_fast_gc<2, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<2, 2>(h, K, actions, J, st); else launch_fast_gc<2, 0>(h, K, actions, J, st); break;
+        case 4: if (C == 1) launch_fast_gc<4, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<4, 2>(h, K, actions, J, st); else launch_fast_gc<4, 0>(h, K, actions, J, st); break;
+        case 8: if (C == 1) launch_fast_gc<8, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<8, 2>(h, K, actions, J, st); else launch_fast_gc<8, 0>(h, K, actions, J, st); break;
+        case 16: if (C == 1) launch_fast_gc<16, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<16, 2>(h, K, actions, J, st); else launch_fast_gc<16, 0>(h, K, actions, J, st); break;
+        default: if (C == 1) launch_fast_gc<32, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<32, 2>(h, K, actions, J, st); else launch_fast_gc<32, 0>(h, K, actions, J, st); break;
+    }
+}
+
 extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const amdp_traj* traj, const double* u_inject,
                             void* stream) {
     if (!h || K < 1) return AMDP_EINVAL;
@@ -856,11 +1101,16 @@ extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const 
     memset(&J, 0, sizeof(J));
     if (traj) J = *traj;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (h->G) {
+    const bool fast = h->cfg.task_type == AMDP_MDP && !u_inject && !h->force_generic;
+    if (fast) {
+        launch_rollout_fast(h, K, actions, J, st);
+    } else {
+        switch (h->G) {
 #define CASE(g) case g: launch_rollout<g>(h, K, actions, J, u_inject, st); break;
-        CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)
+            CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)
 #undef CASE
-        default: return fail(h, AMDP_EINVAL, "bad group size");
+            default: return fail(h, AMDP_EINVAL, "bad group size");
+        }
     }
     h->launches += 1;
     h->tick += (unsigned long long)K;
@@ -928,6 +1178,12 @@ extern "C" int amdp_set_seed(amdp_t* h, uint64_t seed) {
     if (!h) return AMDP_EINVAL;
     h->cfg.seed = seed;
     h->E.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    return AMDP_OK;
+}
+
+extern "C" int amdp_debug_force_generic(amdp_t* h, int on) {
+    if (!h) return AMDP_EINVAL;
+    h->force_generic = on != 0;
     return AMDP_OK;
 }
 

@@ -183,6 +183,10 @@ class Engine:
     def tick(self, v):
         self._ck(lib.amdp_set_tick(self._h, int(v)))
 
+    def force_generic(self, on=True):
+        """Debug: run rollouts through the generic per-tick kernel (used to cross-check the fast kernel)."""
+        self._ck(lib.amdp_debug_force_generic(self._h, 1 if on else 0))
+
     def set_seed(self, seed):
         self._ck(lib.amdp_set_seed(self._h, int(seed) & (2 ** 64 - 1)))
 
