@@ -399,141 +399,209 @@ __device__ __forceinline__ float2 ldg_stream_f32x2(const float2* p) {
     return v;
 }
 
-template <int G, int C, bool GIVEN>
-__global__ void __launch_bounds__(128, 8) k_rollout_mdp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
-                                                     const int32_t* __restrict__ actions, const amdp_traj J) {
-    constexpr unsigned FULL = 0xffffffffu;
+template <int G, int C, bool GIVEN, bool NEXT>
+__global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
+                                                        const int32_t* __restrict__ actions, const amdp_traj J) {
     constexpr int CR = C > 0 ? C : 1;
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long e_raw = gtid / G;
-    const int lane = threadIdx.x & (G - 1);
-    const int gbase = (threadIdx.x & 31) & ~(G - 1);           // first warp lane of this group
-    const bool active = e_raw < E.n_envs;
-    const long long e = active ? e_raw : E.n_envs - 1;         // spare groups shadow the last env, stores masked
-    const bool writer = active && lane == 0;
+    constexpr int EPB = 128 / G;                                  // envs per block
+    constexpr bool MAYSKIP = GIVEN || NEXT;                       // a tick may not step (bad action / pending reset)
+    // closed-episode statistics live in shared memory (touched by lane 0 of the group only, ~10 % of ticks)
+    __shared__ double sh_stat[4][EPB];                            // sum_ret, sum_ret_sq, min_ret, max_ret
+    __shared__ unsigned long long sh_cnt[2][EPB];                 // ep_count, sum_len
+    const int wl = threadIdx.x & 31;
+    int lane = threadIdx.x & (G - 1);
+    const int gi = threadIdx.x / G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(G - 1)));
+    const int gshift = wl & ~(G - 1);
+    const long long e = (long long)blockIdx.x * EPB + gi;
+    if (e >= E.n_envs) return;                                    // groups are independent (group-local sync masks)
     const int n_pad = T.n_pad, na = T.na;
     const long long t = E.task[e];
     const long long tsz = (long long)n_pad * na * n_pad;
-    const double* __restrict__ cdf_t = T.cdf + t * tsz;
+    const double* __restrict__ cdf_lane = T.cdf + t * tsz + lane * 4;
     const float2* __restrict__ pay_t = T.payload + t * tsz;
     const int32_t* __restrict__ sinfo_t = T.sinfo + t * n_pad;
+    // keep these in registers (ptxas otherwise re-derives them from t / %tid every tick)
+    asm volatile("" : "+l"(cdf_lane));
+    asm volatile("" : "+l"(pay_t));
+    asm volatile("" : "+l"(sinfo_t));
+    asm volatile("" : "+r"(lane));
     const int max_ceil = T.max_ceil[t];
     const bool always_term = (T.tflags[t] & 1) != 0;
-    const bool next_mode = T.autoreset == AMDP_AUTORESET_NEXT_STEP;
     const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
+    const long long N = E.n_envs;
 
     int s = E.state[e], steps = E.steps[e], flags = E.flags[e];
     double ep_ret = E.ep_return[e];
-    unsigned long long ep_count = E.ep_count[e], sum_len = E.sum_len[e];
-    double sum_ret = E.sum_ret[e], sum_sq = E.sum_ret_sq[e], min_ret = E.min_ret[e], max_ret = E.max_ret[e];
+
+    // staged trajectory records.  Lane L holds obs/action/done of tick (batch start + L) and the reward of the most
+    // recently SETTLED tick whose index is L mod G (rewards settle one tick late, see below).
+    int st_obs = 0, st_ad = 0;                                    // st_ad = action | done_bits << 28
+    float st_rew = 0.f, st_rgt = 0.f;
+    auto flush_rec = [&](int kb, int cnt) {                       // obs / action / done of ticks [kb, kb + cnt)
+        if (lane < cnt) {
+            const long long o = (long long)(kb + lane) * J.step_stride + e * J.env_stride;
+            if (J.obs) J.obs[o] = st_obs;
+            if (J.actions_out) J.actions_out[o] = st_ad & 0x0fffffff;
+            if (J.done) J.done[o] = (uint8_t)((unsigned)st_ad >> 28);
+        }
+    };
+    auto flush_rew = [&](int kb, int cnt) {                       // rewards of ticks [kb, kb + cnt) and of tick kb - 1 (lane G - 1)
+        int k = -1;
+        if (lane < cnt) k = kb + lane;
+        else if (lane == G - 1 && kb > 0) k = kb - 1;
+        if (k >= 0) {
+            const long long o = (long long)k * J.step_stride + e * J.env_stride;
+            if (J.reward) J.reward[o] = st_rew;
+            if (J.reward_gt) J.reward_gt[o] = st_rgt;
+        }
+    };
 
     unsigned fault = 0;
-    bool dead = false;                                         // faulted envs are left untouched (as in env_tick)
-    if (flags & FLAG_VIRGIN) { fault |= AMDP_FAULT_NEED_RESET; dead = true; }
-    else if (!(next_mode && (flags & FLAG_PENDING)) && sinfo_t[s] < 0 && !always_term) { fault |= AMDP_FAULT_TERMINAL_STATE; dead = true; }
+    if (flags & FLAG_VIRGIN) fault = AMDP_FAULT_NEED_RESET;                                   // anymdp_env.py:93-94
+    else if (!(NEXT && (flags & FLAG_PENDING)) && sinfo_t[s] < 0 && !always_term) fault = AMDP_FAULT_TERMINAL_STATE;
+    if (fault) {
+        // faulted envs are left untouched (as in env_tick); their records are zero except the action
+        for (int kb = 0; kb < K; kb += G) {
+            const int k = kb + lane;
+            int a = 0;
+            if (k < K) {
+                if (GIVEN) a = actions[(long long)k * N + e];
+                else a = (int)__umulhi(philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key).z, (uint32_t)na);
+            }
+            st_ad = a & 0x0fffffff;
+            const int cnt = min(G, K - kb);
+            flush_rec(kb, cnt);
+            if (lane < cnt) {
+                const long long o = (long long)k * J.step_stride + e * J.env_stride;
+                if (J.reward) J.reward[o] = 0.f;
+                if (J.reward_gt) J.reward_gt[o] = 0.f;
+            }
+        }
+        if (lane == 0) atomicOr(E.faults, fault);
+        return;
+    }
+    if (lane == 0) {
+        sh_cnt[0][gi] = E.ep_count[e]; sh_cnt[1][gi] = E.sum_len[e];
+        sh_stat[0][gi] = E.sum_ret[e]; sh_stat[1][gi] = E.sum_ret_sq[e];
+        sh_stat[2][gi] = E.min_ret[e]; sh_stat[3][gi] = E.max_ret[e];
+    }
 
-    // draws of the current batch of G ticks (lane j: tick k0 + j)
+    // draws of the current batch of G ticks (lane L: tick batch start + L), one Philox pass per batch
     double b_ut = 0.0, b_ur = 0.0;
     float b_z = 0.f;
     int b_act = 0;
-    // deferred reward bookkeeping of the previous tick
-    float2 pay_p = make_float2(0.f, 0.f);
-    float z_p = 0.f;
-    int fin_p = 0;            // bit0: a step happened, bit1: it closed an episode
-    int steps_p = 0;
-    long long o_p = 0;
+    auto refill = [&](int kb) {
+        const unsigned long long tk = tick0 + (unsigned long long)(kb + lane);
+        const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
+        b_ut = u53(w0.x, w0.y);
+        b_ur = u53(w0.z, w0.w);
+        const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
+        b_z = box_muller(w2.x, w2.y);
+        if (GIVEN) b_act = (kb + lane < K) ? actions[(long long)(kb + lane) * N + e] : 0;
+        else b_act = (int)__umulhi(w2.z, (uint32_t)na);
+    };
 
-    for (int k = 0; k < K; ++k) {
-        const int j = k & (G - 1);
-        if (j == 0) {
-            const unsigned long long tk = tick0 + (unsigned long long)(k + lane);
-            const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
-            b_ut = u53(w0.x, w0.y);
-            b_ur = u53(w0.z, w0.w);
-            const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
-            b_z = box_muller(w2.x, w2.y);
-            if (GIVEN) b_act = (k + lane < K) ? actions[(long long)(k + lane) * E.n_envs + e] : 0;
-            else b_act = (int)__umulhi(w2.z, (uint32_t)na);
+    // inputs of the tick whose row load is in flight
+    double u = 0.0;
+    float z = 0.f;
+    int a = 0;
+    bool valid = true;
+    unsigned rowi = 0;
+    double2 r[2 * CR];
+    // fetch the draws of the tick in batch slot j and issue its CDF row load (anymdp_env.py:99)
+    auto prepare = [&](int j) {
+        u = __shfl_sync(gmask, b_ut, j, G);
+        z = __shfl_sync(gmask, b_z, j, G);
+        a = __shfl_sync(gmask, b_act, j, G);
+        if (MAYSKIP) {
+            valid = !(NEXT && (flags & FLAG_PENDING));
+            if (GIVEN && valid && (unsigned)a >= (unsigned)na) { fault |= AMDP_FAULT_BAD_ACTION; valid = false; }   // :97
         }
-        const double u = __shfl_sync(FULL, b_ut, j, G);
-        const float z = __shfl_sync(FULL, b_z, j, G);
-        const int a = __shfl_sync(FULL, b_act, j, G);
-        const long long o = (long long)k * J.step_stride + e * J.env_stride;
-        const bool pending = next_mode && (flags & FLAG_PENDING);
-        bool valid = !dead && !pending;
-        if (GIVEN && valid && (unsigned)a >= (unsigned)na) { fault |= AMDP_FAULT_BAD_ACTION; valid = false; }
-
-        // (A) issue the CDF row load
-        const long long rowi = ((long long)s * na + (valid ? a : 0)) * n_pad;
-        double2 r[2 * CR];
-        int cnt_loop = 0;
+        rowi = (unsigned)(s * na + ((!MAYSKIP || valid) ? a : 0)) * (unsigned)n_pad;
         if (C > 0) {
-            if (valid) {
-#pragma unroll
-                for (int c = 0; c < CR; ++c) {
-                    const double* q = cdf_t + rowi + (c * G + lane) * 4;
-                    r[2 * c] = ldg_stream_f64x2(q);
-                    r[2 * c + 1] = ldg_stream_f64x2(q + 2);
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 2 * CR; ++c) r[c] = make_double2(2.0, 2.0);
-            }
-        }
-
-        // (B) previous tick's reward, return and episode statistics — overlaps the row load
-        if (fin_p & 1) {
-            const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
-            ep_ret += rew;
-            if (writer) {
-                if (J.reward) J.reward[o_p] = (float)rew;
-                if (J.reward_gt) J.reward_gt[o_p] = pay_p.x;
-            }
-            if (fin_p & 2) {
-                ep_count += 1; sum_len += (unsigned long long)steps_p;
-                sum_ret += ep_ret; sum_sq += ep_ret * ep_ret;
-                min_ret = fmin(min_ret, ep_ret); max_ret = fmax(max_ret, ep_ret);
-                ep_ret = 0.0;
-            }
-        }
-        fin_p = 0;
-
-        // (C) next state = #{cdf <= u}
-        int nxt;
-        if (C > 0) {
-            // chunk m = c * G + lane holds entries [4m, 4m + 4).  The CDF is non-decreasing, so the chunks whose
-            // last entry is <= u form a prefix in m order; the draw index is 4 * (#full chunks) + the count
-            // inside the first non-full chunk.
-            int c4[CR];
-            int full_chunks = 0;
 #pragma unroll
             for (int c = 0; c < CR; ++c) {
-                c4[c] = (r[2 * c].x <= u) + (r[2 * c].y <= u) + (r[2 * c + 1].x <= u) + (r[2 * c + 1].y <= u);
-                const unsigned b = __ballot_sync(FULL, c4[c] == 4);
-                full_chunks += __popc((b >> gbase) & (G == 32 ? FULL : ((1u << G) - 1u)));
-            }
-            int mine = c4[0];
-#pragma unroll
-            for (int c = 1; c < CR; ++c) if (full_chunks >= c * G) mine = c4[c];
-            nxt = 4 * full_chunks + __shfl_sync(FULL, mine, full_chunks & (G - 1), G);
-        } else {
-            if (valid) {
-                for (int i = lane * 4; i < n_pad; i += G * 4) {
-                    const double2 x = ldg_stream_f64x2(cdf_t + rowi + i);
-                    const double2 y = ldg_stream_f64x2(cdf_t + rowi + i + 2);
-                    cnt_loop += (x.x <= u) + (x.y <= u) + (y.x <= u) + (y.y <= u);
+                const double* q = cdf_lane + rowi + c * (G * 4);
+                if (!MAYSKIP || valid) {
+                    r[2 * c] = ldg_stream_f64x2(q);
+                    r[2 * c + 1] = ldg_stream_f64x2(q + 2);
+                } else {
+                    r[2 * c] = make_double2(2.0, 2.0);
+                    r[2 * c + 1] = make_double2(2.0, 2.0);
                 }
             }
-            nxt = group_sum<G>(cnt_loop);
+        }
+    };
+
+    // deferred reward of the previous tick: payload (0, 0) when that tick did not step
+    float2 pay_p = make_float2(0.f, 0.f);
+    float z_p = 0.f;
+    bool close_p = false;     // the previous tick closed an episode ...
+    int steps_p = 0;          // ... of this length
+
+    refill(0);
+    prepare(0);
+    for (int k = 0; k < K; ++k) {
+        const int j = k & (G - 1);
+        // (B) settle the previous tick: reward = gt + noise * z (anymdp_env.py:103-105), return, statistics.
+        //     Its payload load was issued AFTER this tick's row load, so both HBM round trips overlap.
+        {
+            const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
+            ep_ret += rew;
+            if (lane == ((k - 1) & (G - 1))) { st_rew = (float)rew; st_rgt = pay_p.x; }
+            if (close_p) {
+                if (lane == 0) {
+                    sh_cnt[0][gi] += 1; sh_cnt[1][gi] += (unsigned long long)steps_p;
+                    sh_stat[0][gi] += ep_ret; sh_stat[1][gi] += ep_ret * ep_ret;
+                    sh_stat[2][gi] = fmin(sh_stat[2][gi], ep_ret); sh_stat[3][gi] = fmax(sh_stat[3][gi], ep_ret);
+                }
+                ep_ret = 0.0;
+                close_p = false;
+            }
         }
 
+        // (C) next state = #{cdf <= u}  (numpy choice: searchsorted(cdf, u, 'right'))
+        int nxt;
+        if (C > 0) {
+            // every lane holds 4 * C entries; a ballot per entry position and a population count of each ballot
+            nxt = 0;
+#pragma unroll
+            for (int c = 0; c < CR; ++c) {
+                const unsigned b0 = __ballot_sync(gmask, r[2 * c].x <= u);
+                const unsigned b1 = __ballot_sync(gmask, r[2 * c].y <= u);
+                const unsigned b2 = __ballot_sync(gmask, r[2 * c + 1].x <= u);
+                const unsigned b3 = __ballot_sync(gmask, r[2 * c + 1].y <= u);
+                if (G == 32) nxt += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+                else {
+                    const unsigned m = (1u << G) - 1u;
+                    nxt += __popc((b0 >> gshift) & m) + __popc((b1 >> gshift) & m) + __popc((b2 >> gshift) & m) + __popc((b3 >> gshift) & m);
+                }
+            }
+        } else {
+            int cnt = 0;
+            if (!MAYSKIP || valid) {
+                for (int i = 0; i < n_pad; i += G * 4) {
+                    if (i + lane * 4 < n_pad) {
+                        const double2 x = ldg_stream_f64x2(cdf_lane + rowi + i);
+                        const double2 y = ldg_stream_f64x2(cdf_lane + rowi + i + 2);
+                        cnt += (x.x <= u) + (x.y <= u) + (y.x <= u) + (y.y <= u);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = G >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
+            nxt = cnt;
+        }
+
+        // (E) state update, termination, truncation (anymdp_env.py:107-108,113-114), reset (:81-90)
         int obs_out = 0, done_bits = 0;
-        bool do_reset = pending;
-        if (valid) {
-            // (D) payload load for (s, a, s'): consumed next tick
-            pay_p = ldg_stream_f32x2(pay_t + rowi + nxt);
-            z_p = z; o_p = o;
-            // (E) state update, termination, truncation (anymdp_env.py:107-108,113-114)
+        bool do_reset = NEXT && !valid && (flags & FLAG_PENDING);
+        const bool stepped = !MAYSKIP || valid;
+        const unsigned pay_i = rowi + (unsigned)nxt;
+        const float z_k = z;
+        const int a_k = a;
+        if (stepped) {
             const int si = __ldg(sinfo_t + nxt);
             s = nxt;
             steps += 1;
@@ -541,57 +609,63 @@ __global__ void __launch_bounds__(128, 8) k_rollout_mdp(const Tables T, const En
             const bool trunc = steps >= max_ceil;
             obs_out = si & 0x7fffffff;
             done_bits = (term ? 1 : 0) | (trunc ? 2 : 0);
-            steps_p = steps;
-            fin_p = 1;
             if (done_bits) {
-                fin_p = 3;
-                if (next_mode) flags |= FLAG_PENDING; else do_reset = true;
-            }
-        } else if (writer && !pending) {
-            if (J.reward) J.reward[o] = 0.f;
-            if (J.reward_gt) J.reward_gt[o] = 0.f;
-        }
-        // reset (anymdp_env.py:81-90)
-        if (__any_sync(FULL, do_reset)) {
-            const double ur = __shfl_sync(FULL, b_ur, j, G);
-            if (do_reset) {
-                int c = 0;
-                for (int i = 0; i < T.s0_pad; ++i) c += (T.s0_cdf[t * T.s0_pad + i] <= ur);
-                s = T.s0_idx[t * T.s0_pad + min(c, T.s0_pad - 1)];
-                steps = 0;
-                flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
-                obs_out = __ldg(sinfo_t + s) & 0x7fffffff;
-                if (pending && writer) {
-                    if (J.reward) J.reward[o] = 0.f;
-                    if (J.reward_gt) J.reward_gt[o] = 0.f;
-                }
+                close_p = true;
+                steps_p = steps;
+                if (NEXT) flags |= FLAG_PENDING; else do_reset = true;
             }
         }
-        if (writer) {
-            if (J.obs) J.obs[o] = obs_out;
-            if (J.actions_out) J.actions_out[o] = a;
-            if (J.done) J.done[o] = (uint8_t)done_bits;
+        if (do_reset) {
+            const double ur = __shfl_sync(gmask, b_ur, j, G);
+            int c = 0;
+            for (int i = 0; i < T.s0_pad; ++i) c += (T.s0_cdf[t * T.s0_pad + i] <= ur);
+            s = T.s0_idx[t * T.s0_pad + min(c, T.s0_pad - 1)];
+            steps = 0;
+            flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
+            obs_out = __ldg(sinfo_t + s) & 0x7fffffff;
         }
+        if (lane == j) {
+            st_obs = obs_out;
+            st_ad = (a_k & 0x0fffffff) | (done_bits << 28);
+        }
+        // once per G ticks: write the batch's records (lane-parallel) and draw the next batch
+        if (j == G - 1) {
+            const int kb = k - (G - 1);
+            flush_rec(kb, G);
+            flush_rew(kb, G - 1);
+            refill(k + 1);
+        }
+        // (A) the NEXT tick's row load goes out before this tick's payload load: the dependent chain per tick is one
+        //     HBM round trip: row -> compare/ballot -> per-task state table (L1) -> next row address.  (After the
+        //     last tick this prefetches one row that is never used.)
+        prepare((k + 1) & (G - 1));
+        // (D) payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104): consumed at the top of the next tick
+        if (stepped) pay_p = ldg_stream_f32x2(pay_t + pay_i); else pay_p = make_float2(0.f, 0.f);
+        z_p = z_k;
     }
-    // flush the deferred bookkeeping of the last tick
-    if (fin_p & 1) {
+    // settle the last tick and write what is still staged
+    {
         const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
         ep_ret += rew;
-        if (writer) {
-            if (J.reward) J.reward[o_p] = (float)rew;
-            if (J.reward_gt) J.reward_gt[o_p] = pay_p.x;
-        }
-        if (fin_p & 2) {
-            ep_count += 1; sum_len += (unsigned long long)steps_p;
-            sum_ret += ep_ret; sum_sq += ep_ret * ep_ret;
-            min_ret = fmin(min_ret, ep_ret); max_ret = fmax(max_ret, ep_ret);
+        if (lane == ((K - 1) & (G - 1))) { st_rew = (float)rew; st_rgt = pay_p.x; }
+        if (close_p) {
+            if (lane == 0) {
+                sh_cnt[0][gi] += 1; sh_cnt[1][gi] += (unsigned long long)steps_p;
+                sh_stat[0][gi] += ep_ret; sh_stat[1][gi] += ep_ret * ep_ret;
+                sh_stat[2][gi] = fmin(sh_stat[2][gi], ep_ret); sh_stat[3][gi] = fmax(sh_stat[3][gi], ep_ret);
+            }
             ep_ret = 0.0;
         }
+        const int kb = (K / G) * G;
+        flush_rec(kb, K - kb);
+        flush_rew(kb, K - kb);
     }
-    if (writer) {
+    // a pending-reset flag raised by prepare() of the never-executed tick K must not leak: flags only change in (E)
+    if (lane == 0) {
         E.state[e] = s; E.steps[e] = steps; E.flags[e] = (uint8_t)flags; E.ep_return[e] = ep_ret;
-        E.ep_count[e] = ep_count; E.sum_len[e] = sum_len; E.sum_ret[e] = sum_ret; E.sum_ret_sq[e] = sum_sq;
-        E.min_ret[e] = min_ret; E.max_ret[e] = max_ret;
+        E.ep_count[e] = sh_cnt[0][gi]; E.sum_len[e] = sh_cnt[1][gi];
+        E.sum_ret[e] = sh_stat[0][gi]; E.sum_ret_sq[e] = sh_stat[1][gi];
+        E.min_ret[e] = sh_stat[2][gi]; E.max_ret[e] = sh_stat[3][gi];
         if (fault) atomicOr(E.faults, fault);
     }
 }
@@ -1071,9 +1145,15 @@ static void launch_rollout(amdp* h, int K, const int32_t* actions, const amdp_tr
 
 template <int G, int C>
 static void launch_fast_gc(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
-    const long long threads = h->cfg.n_envs * G;
-    if (actions) k_rollout_mdp<G, C, true><<<nblk(threads, 128), 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
-    else k_rollout_mdp<G, C, false><<<nblk(threads, 128), 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
+    const unsigned int blocks = nblk(h->cfg.n_envs * G, 128);
+    const bool next = h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP;
+    if (actions) {
+        if (next) k_rollout_mdp<G, C, true, true><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
+        else k_rollout_mdp<G, C, true, false><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
+    } else {
+        if (next) k_rollout_mdp<G, C, false, true><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
+        else k_rollout_mdp<G, C, false, false><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
+    }
 }
 
 // lanes per env and register-resident chunks per lane for the fast kernel: n_pad == 4 * G * C
