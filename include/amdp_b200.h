@@ -236,6 +236,10 @@ int amdp_poll_errors(amdp_t* h, uint32_t* faults, void* stream);
 /* Debug/verification: copy the built CDF row of (task, s, a) to out double [n_pad] (device). */
 int amdp_debug_cdf_row(amdp_t* h, int64_t task, int32_t s, int32_t a, double* out, void* stream);
 
+/* Debug/verification (synchronises): out4 HOST uint64[4]; [0] = ticks on which the fast kernel's 16-bit CDF filter was
+ * undecided and the exact float64 row was read instead. */
+int amdp_debug_counters(amdp_t* h, uint64_t* out4);
+
 /* Debug/verification: route amdp_rollout through the generic per-tick kernel instead of the fast MDP kernel. */
 int amdp_debug_force_generic(amdp_t* h, int on);
 

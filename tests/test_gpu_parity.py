@@ -338,3 +338,26 @@ def test_fast_rollout_faults():
     env.rollout(4, actions=bad)
     with pytest.raises(AssertionError):
         env.check()
+
+
+@pytest.mark.parametrize("ns,na,mode", [(128, 5, "same_step"), (16, 5, "next_step"), (40, 3, "same_step")])
+def test_filter_fallback_is_exercised_and_exact(ns, na, mode):
+    """Enough env-steps that the 16-bit CDF filter of the fast kernel is undecided many times (u and a CDF entry in
+    the same 2^-16 cell): those ticks must read the float64 row and still agree bit for bit with the generic kernel."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    tasks = [synth_task(ns, na, 500 + t) for t in range(8)]
+    N, K = 3000, 200
+    outs = []
+    for generic in (False, True):
+        env = AnyMDPVecEnv(N, seed=23, autoreset=mode)
+        env.set_task(tasks)
+        env.engine.force_generic(generic)
+        env.reset()
+        tr = env.rollout(K, record=("obs", "reward", "done"))
+        outs.append((tr, env.engine.get_state(), env.episode_stats(), env.engine.debug_counters()))
+    (a, sa, ea, ca), (b, sb, eb, cb) = outs
+    for key in ("obs", "reward", "done"):
+        assert torch.equal(a[key], b[key]), key
+    assert torch.equal(sa["state"], sb["state"]) and torch.equal(sa["ep_return"], sb["ep_return"]) and ea == eb
+    assert cb["exact_fallbacks"] == 0
+    assert 20 <= ca["exact_fallbacks"] <= N * K // 20, ca

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "amdp_poll_errors": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32), _P]),
     "amdp_debug_cdf_row": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P]),
     "amdp_debug_force_generic": (ctypes.c_int, [_P, ctypes.c_int]),
+    "amdp_debug_counters": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),
     "amdp_launch_count": (ctypes.c_int64, [_P]),
     "amdp_rollout_host": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P]),
 }

@@ -30,6 +30,7 @@
 struct Tables {
     const double*  cdf;       // [T][n_pad][na][n_pad] normalised CDF rows, pad = 1.0
     const float2*  payload;   // [T][n_pad][na][n_pad] (reward, reward_noise) fp32
+    const uint16_t* sketch;   // [T][n_pad][na][n_pad] min(65535, floor(cdf * 2^16)): 2-byte filter in front of cdf
     const int32_t* sinfo;     // [T][n_pad]  state_mapping | (is_terminal << 31)
     const double*  s0_cdf;    // [T][s0_pad] pad = 2.0
     const int32_t* s0_idx;    // [T][s0_pad]
@@ -55,6 +56,7 @@ struct EnvArrays {
     double* min_ret;
     double* max_ret;
     unsigned int* faults;  // single word, sticky
+    unsigned long long* counters;  // [0] exact-row fallbacks of the fast kernel
     long long n_envs;
     unsigned long long env_id_base;
     uint2 key;
@@ -393,6 +395,12 @@ __device__ __forceinline__ double2 ldg_stream_f64x2(const double* p) {
     return v;
 }
 
+__device__ __forceinline__ uint2 ldg_stream_u32x2(const uint16_t* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ float2 ldg_stream_f32x2(const float2* p) {
     float2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
@@ -418,11 +426,12 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
     const int n_pad = T.n_pad, na = T.na;
     const long long t = E.task[e];
     const long long tsz = (long long)n_pad * na * n_pad;
-    const double* __restrict__ cdf_lane = T.cdf + t * tsz + lane * 4;
+    const double* __restrict__ cdf_lane = T.cdf + t * tsz + lane * 4;        // float64 rows: exact fallback only
+    const uint16_t* __restrict__ sk_lane = T.sketch + t * tsz + lane * 4;    // 16-bit filter rows: the common case
     const float2* __restrict__ pay_t = T.payload + t * tsz;
     const int32_t* __restrict__ sinfo_t = T.sinfo + t * n_pad;
     // keep these in registers (ptxas otherwise re-derives them from t / %tid every tick)
-    asm volatile("" : "+l"(cdf_lane));
+    asm volatile("" : "+l"(sk_lane));
     asm volatile("" : "+l"(pay_t));
     asm volatile("" : "+l"(sinfo_t));
     asm volatile("" : "+r"(lane));
@@ -487,100 +496,126 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
         sh_stat[2][gi] = E.min_ret[e]; sh_stat[3][gi] = E.max_ret[e];
     }
 
-    // draws of the current batch of G ticks (lane L: tick batch start + L), one Philox pass per batch
-    double b_ut = 0.0, b_ur = 0.0;
+    // Draws.  The G lanes of an env generate the draws of G consecutive ticks in one Philox pass.  Lane L of batch kb
+    // holds the draws of tick kb + L + 1 (one tick AHEAD of the tick that fetches them), so that the inputs of the next
+    // tick are available before the current row has arrived and the next row load can be issued speculatively.
+    // The transition uniform is kept as the top 21 bits of its 53-bit integer k (u = k * 2^-53): the filter needs only
+    // floor(u * 2^16) = k >> 37; the exact fallback recomputes u.
+    unsigned b_uhi = 0;
+    double b_ur = 0.0;        // reset draw of tick kb + L + 1
     float b_z = 0.f;
     int b_act = 0;
+    double ur_carry;          // reset draw of the first tick of the current batch (made by the previous batch)
+    unsigned n_fallback = 0;
     auto refill = [&](int kb) {
-        const unsigned long long tk = tick0 + (unsigned long long)(kb + lane);
+        const int kt = kb + lane + 1;
+        const unsigned long long tk = tick0 + (unsigned long long)kt;
         const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
-        b_ut = u53(w0.x, w0.y);
+        b_uhi = w0.x >> 11;                                       // == (k53 >> 32): k53 = (w0.x >> 5) << 26 | (w0.y >> 6)
         b_ur = u53(w0.z, w0.w);
         const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
         b_z = box_muller(w2.x, w2.y);
-        if (GIVEN) b_act = (kb + lane < K) ? actions[(long long)(kb + lane) * N + e] : 0;
+        if (GIVEN) b_act = (kt < K) ? actions[(long long)kt * N + e] : 0;
         else b_act = (int)__umulhi(w2.z, (uint32_t)na);
     };
 
-    // inputs of the tick whose row load is in flight
-    double u = 0.0;
-    float z = 0.f;
-    int a = 0;
-    bool valid = true;
-    unsigned rowi = 0;
-    double2 r[2 * CR];
-    // fetch the draws of the tick in batch slot j and issue its CDF row load (anymdp_env.py:99)
-    auto prepare = [&](int j) {
-        u = __shfl_sync(gmask, b_ut, j, G);
-        z = __shfl_sync(gmask, b_z, j, G);
-        a = __shfl_sync(gmask, b_act, j, G);
-        if (MAYSKIP) {
-            valid = !(NEXT && (flags & FLAG_PENDING));
-            if (GIVEN && valid && (unsigned)a >= (unsigned)na) { fault |= AMDP_FAULT_BAD_ACTION; valid = false; }   // :97
-        }
-        rowi = (unsigned)(s * na + ((!MAYSKIP || valid) ? a : 0)) * (unsigned)n_pad;
+    // inputs of the current tick (its row load is in flight)
+    unsigned v;               // floor(u * 2^16) of the transition uniform
+    float z;
+    int a;
+    uint2 q[CR];              // this lane's 4 * C filter entries (16 bit each) of row (s, a)
+    {
+        const uint4 w0 = philox_block(env_id, 0u, tick0, E.key);
+        v = w0.x >> 16;
+        ur_carry = u53(w0.z, w0.w);
+        const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0, E.key);
+        z = box_muller(w2.x, w2.y);
+        a = GIVEN ? actions[e] : (int)__umulhi(w2.z, (uint32_t)na);
+    }
+    refill(0);
+    bool pend = NEXT && (flags & FLAG_PENDING);
+    bool valid = !pend && (!GIVEN || (unsigned)a < (unsigned)na);
+    if (GIVEN && !pend && !valid) fault |= AMDP_FAULT_BAD_ACTION;                              // :97
+    unsigned rowi = (unsigned)(s * na + (valid ? a : 0)) * (unsigned)n_pad;
+    auto issue_row = [&](uint2* dst, unsigned ri, bool on) {      // anymdp_env.py:99 (the row of the transition table)
         if (C > 0) {
 #pragma unroll
             for (int c = 0; c < CR; ++c) {
-                const double* q = cdf_lane + rowi + c * (G * 4);
-                if (!MAYSKIP || valid) {
-                    r[2 * c] = ldg_stream_f64x2(q);
-                    r[2 * c + 1] = ldg_stream_f64x2(q + 2);
-                } else {
-                    r[2 * c] = make_double2(2.0, 2.0);
-                    r[2 * c + 1] = make_double2(2.0, 2.0);
-                }
+                if (on) dst[c] = ldg_stream_u32x2(sk_lane + ri + c * (G * 4));
+                else dst[c] = make_uint2(0xffffffffu, 0xffffffffu);
             }
         }
     };
+    issue_row(q, rowi, valid);
 
     // deferred reward of the previous tick: payload (0, 0) when that tick did not step
     float2 pay_p = make_float2(0.f, 0.f);
     float z_p = 0.f;
     bool close_p = false;     // the previous tick closed an episode ...
     int steps_p = 0;          // ... of this length
+    auto settle = [&](int k_prev) {
+        // reward = gt + noise * z (anymdp_env.py:103-105), episode return, closed-episode statistics
+        const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
+        ep_ret += rew;
+        if (lane == (k_prev & (G - 1))) { st_rew = (float)rew; st_rgt = pay_p.x; }
+        if (close_p) {
+            if (lane == 0) {
+                sh_cnt[0][gi] += 1; sh_cnt[1][gi] += (unsigned long long)steps_p;
+                sh_stat[0][gi] += ep_ret; sh_stat[1][gi] += ep_ret * ep_ret;
+                sh_stat[2][gi] = fmin(sh_stat[2][gi], ep_ret); sh_stat[3][gi] = fmax(sh_stat[3][gi], ep_ret);
+            }
+            ep_ret = 0.0;
+            close_p = false;
+        }
+    };
 
-    refill(0);
-    prepare(0);
     for (int k = 0; k < K; ++k) {
         const int j = k & (G - 1);
-        // (B) settle the previous tick: reward = gt + noise * z (anymdp_env.py:103-105), return, statistics.
-        //     Its payload load was issued AFTER this tick's row load, so both HBM round trips overlap.
-        {
-            const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
-            ep_ret += rew;
-            if (lane == ((k - 1) & (G - 1))) { st_rew = (float)rew; st_rgt = pay_p.x; }
-            if (close_p) {
-                if (lane == 0) {
-                    sh_cnt[0][gi] += 1; sh_cnt[1][gi] += (unsigned long long)steps_p;
-                    sh_stat[0][gi] += ep_ret; sh_stat[1][gi] += ep_ret * ep_ret;
-                    sh_stat[2][gi] = fmin(sh_stat[2][gi], ep_ret); sh_stat[3][gi] = fmax(sh_stat[3][gi], ep_ret);
-                }
-                ep_ret = 0.0;
-                close_p = false;
-            }
-        }
+        // inputs of the NEXT tick: independent of the row in flight
+        const unsigned nv = __shfl_sync(gmask, b_uhi, j, G) >> 5;
+        const float nz = __shfl_sync(gmask, b_z, j, G);
+        const int na_ = __shfl_sync(gmask, b_act, j, G);
+        const bool na_ok = !GIVEN || (unsigned)na_ < (unsigned)na;
+        const unsigned na_row = (unsigned)(na_ok ? na_ : 0) * (unsigned)n_pad;
 
-        // (C) next state = #{cdf <= u}  (numpy choice: searchsorted(cdf, u, 'right'))
-        int nxt;
-        if (C > 0) {
-            // every lane holds 4 * C entries; a ballot per entry position and a population count of each ballot
+        int nxt = s;
+        bool do_reset = NEXT && pend;                              // next_step mode: this tick only performs the reset
+        if (valid) {
+            // (C) next state = #{cdf <= u}  (numpy choice: searchsorted(cdf, u, 'right')), decided on the 16-bit filter:
+            //     q < v  =>  cdf < u;  q > v  =>  cdf > u;  only q == v is undecided.
             nxt = 0;
-#pragma unroll
-            for (int c = 0; c < CR; ++c) {
-                const unsigned b0 = __ballot_sync(gmask, r[2 * c].x <= u);
-                const unsigned b1 = __ballot_sync(gmask, r[2 * c].y <= u);
-                const unsigned b2 = __ballot_sync(gmask, r[2 * c + 1].x <= u);
-                const unsigned b3 = __ballot_sync(gmask, r[2 * c + 1].y <= u);
+            unsigned amb = 0;
+            const unsigned vhi = v << 16, v2 = vhi | v;
+            auto chunk = [&](const uint2 w) {
+                // entries: lo16(w.x), hi16(w.x), lo16(w.y), hi16(w.y); (w << 16) < (v << 16) <=> lo16 < v, w < (v << 16) <=> hi16 < v
+                const unsigned b0 = __ballot_sync(gmask, (w.x << 16) < vhi);
+                const unsigned b1 = __ballot_sync(gmask, w.x < vhi);
+                const unsigned b2 = __ballot_sync(gmask, (w.y << 16) < vhi);
+                const unsigned b3 = __ballot_sync(gmask, w.y < vhi);
                 if (G == 32) nxt += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
                 else {
                     const unsigned m = (1u << G) - 1u;
                     nxt += __popc((b0 >> gshift) & m) + __popc((b1 >> gshift) & m) + __popc((b2 >> gshift) & m) + __popc((b3 >> gshift) & m);
                 }
+                // any 16-bit field equal to v?  (x has a zero halfword  <=>  (x - 0x00010001) & ~x & 0x80008000 != 0)
+                const unsigned x0 = w.x ^ v2, x1 = w.y ^ v2;
+                amb |= ((x0 - 0x00010001u) & ~x0 & 0x80008000u) | ((x1 - 0x00010001u) & ~x1 & 0x80008000u);
+            };
+            if (C > 0) {
+#pragma unroll
+                for (int c = 0; c < CR; ++c) chunk(q[c]);
+            } else {
+                for (int i = 0; i < n_pad; i += G * 4) {
+                    // lanes past the end of the row contribute "not less"
+                    const bool in = (i + lane * 4 < n_pad);
+                    chunk(in ? ldg_stream_u32x2(sk_lane + rowi + i) : make_uint2(0xffffffffu, 0xffffffffu));
+                }
             }
-        } else {
-            int cnt = 0;
-            if (!MAYSKIP || valid) {
+            if (__any_sync(gmask, amb != 0)) {
+                // undecided (u and some cdf entry share a 2^-16 cell, ~n/65536 of the ticks): exact float64 row
+                const uint4 w0 = philox_block(env_id, 0u, tick0 + (unsigned long long)k, E.key);
+                const double u = u53(w0.x, w0.y);
+                int cnt = 0;
                 for (int i = 0; i < n_pad; i += G * 4) {
                     if (i + lane * 4 < n_pad) {
                         const double2 x = ldg_stream_f64x2(cdf_lane + rowi + i);
@@ -588,20 +623,27 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
                         cnt += (x.x <= u) + (x.y <= u) + (y.x <= u) + (y.y <= u);
                     }
                 }
-            }
 #pragma unroll
-            for (int o = G >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
-            nxt = cnt;
+                for (int o = G >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
+                nxt = cnt;
+                n_fallback += 1;
+            }
         }
+        // (A) SPECULATIVE row load of the next tick, assuming this tick neither terminates nor truncates: the dependent
+        //     chain per tick is  row (HBM) -> compare/ballot -> next row address.  Everything below runs in its shadow.
+        unsigned nrowi = (unsigned)(nxt * na) * (unsigned)n_pad + na_row;
+        uint2 nq[CR];
+        if (!do_reset) issue_row(nq, nrowi, na_ok);
 
-        // (E) state update, termination, truncation (anymdp_env.py:107-108,113-114), reset (:81-90)
+        // (B) settle the previous tick (its payload load was issued one tick ago, after this tick's row load)
+        settle(k - 1);
+        // (D) payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104): consumed by settle() of the next tick
+        if (valid) pay_p = ldg_stream_f32x2(pay_t + (rowi + (unsigned)nxt)); else pay_p = make_float2(0.f, 0.f);
+        z_p = z;
+
+        // (E) state update, termination, truncation (anymdp_env.py:107-108,113-114)
         int obs_out = 0, done_bits = 0;
-        bool do_reset = NEXT && !valid && (flags & FLAG_PENDING);
-        const bool stepped = !MAYSKIP || valid;
-        const unsigned pay_i = rowi + (unsigned)nxt;
-        const float z_k = z;
-        const int a_k = a;
-        if (stepped) {
+        if (valid) {
             const int si = __ldg(sinfo_t + nxt);
             s = nxt;
             steps += 1;
@@ -615,58 +657,52 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
                 if (NEXT) flags |= FLAG_PENDING; else do_reset = true;
             }
         }
-        if (do_reset) {
-            const double ur = __shfl_sync(gmask, b_ur, j, G);
+        if (do_reset) {                                            // anymdp_env.py:81-90
+            const double ur = (j == 0) ? ur_carry : __shfl_sync(gmask, b_ur, (j - 1) & (G - 1), G);
             int c = 0;
             for (int i = 0; i < T.s0_pad; ++i) c += (T.s0_cdf[t * T.s0_pad + i] <= ur);
             s = T.s0_idx[t * T.s0_pad + min(c, T.s0_pad - 1)];
             steps = 0;
             flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
             obs_out = __ldg(sinfo_t + s) & 0x7fffffff;
+            // the speculation was wrong (or not made): the next tick starts from the reset state
+            nrowi = (unsigned)(s * na) * (unsigned)n_pad + na_row;
+            issue_row(nq, nrowi, na_ok);
         }
         if (lane == j) {
             st_obs = obs_out;
-            st_ad = (a_k & 0x0fffffff) | (done_bits << 28);
+            st_ad = (a & 0x0fffffff) | (done_bits << 28);
         }
         // once per G ticks: write the batch's records (lane-parallel) and draw the next batch
         if (j == G - 1) {
             const int kb = k - (G - 1);
             flush_rec(kb, G);
             flush_rew(kb, G - 1);
+            ur_carry = __shfl_sync(gmask, b_ur, G - 1, G);
             refill(k + 1);
         }
-        // (A) the NEXT tick's row load goes out before this tick's payload load: the dependent chain per tick is one
-        //     HBM round trip: row -> compare/ballot -> per-task state table (L1) -> next row address.  (After the
-        //     last tick this prefetches one row that is never used.)
-        prepare((k + 1) & (G - 1));
-        // (D) payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104): consumed at the top of the next tick
-        if (stepped) pay_p = ldg_stream_f32x2(pay_t + pay_i); else pay_p = make_float2(0.f, 0.f);
-        z_p = z_k;
+        // rotate to the next tick
+        v = nv; z = nz; a = na_; rowi = nrowi;
+#pragma unroll
+        for (int c = 0; c < CR; ++c) q[c] = nq[c];
+        pend = NEXT && (flags & FLAG_PENDING);
+        valid = !pend && na_ok;
+        if (GIVEN && !pend && !na_ok && k + 1 < K) fault |= AMDP_FAULT_BAD_ACTION;           // :97
     }
     // settle the last tick and write what is still staged
     {
-        const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
-        ep_ret += rew;
-        if (lane == ((K - 1) & (G - 1))) { st_rew = (float)rew; st_rgt = pay_p.x; }
-        if (close_p) {
-            if (lane == 0) {
-                sh_cnt[0][gi] += 1; sh_cnt[1][gi] += (unsigned long long)steps_p;
-                sh_stat[0][gi] += ep_ret; sh_stat[1][gi] += ep_ret * ep_ret;
-                sh_stat[2][gi] = fmin(sh_stat[2][gi], ep_ret); sh_stat[3][gi] = fmax(sh_stat[3][gi], ep_ret);
-            }
-            ep_ret = 0.0;
-        }
+        settle(K - 1);
         const int kb = (K / G) * G;
         flush_rec(kb, K - kb);
         flush_rew(kb, K - kb);
     }
-    // a pending-reset flag raised by prepare() of the never-executed tick K must not leak: flags only change in (E)
     if (lane == 0) {
         E.state[e] = s; E.steps[e] = steps; E.flags[e] = (uint8_t)flags; E.ep_return[e] = ep_ret;
         E.ep_count[e] = sh_cnt[0][gi]; E.sum_len[e] = sh_cnt[1][gi];
         E.sum_ret[e] = sh_stat[0][gi]; E.sum_ret_sq[e] = sh_stat[1][gi];
         E.min_ret[e] = sh_stat[2][gi]; E.max_ret[e] = sh_stat[3][gi];
         if (fault) atomicOr(E.faults, fault);
+        if (n_fallback) atomicAdd(E.counters, (unsigned long long)n_fallback);
     }
 }
 
@@ -700,7 +736,8 @@ __global__ void k_reset(Tables T, EnvArrays E, unsigned long long tick, int n_sl
 __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __restrict__ transition,
                              const double* __restrict__ reward, const double* __restrict__ noise,
                              const int32_t* __restrict__ n_real, const uint8_t* __restrict__ is_terminal,
-                             double* __restrict__ cdf, float2* __restrict__ payload, int32_t* __restrict__ status) {
+                             double* __restrict__ cdf, float2* __restrict__ payload, uint16_t* __restrict__ sketch,
+                             int32_t* __restrict__ status) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long rows = cnt * n_pad * na;
     if (r >= rows) return;
@@ -711,7 +748,7 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
     double* c = cdf + r * n_pad;
     float2* pl = payload + r * n_pad;
     for (int i = 0; i < n_pad; ++i) pl[i] = make_float2((float)reward[r * n_pad + i], (float)noise[r * n_pad + i]);
-    if (s >= n) { for (int i = 0; i < n_pad; ++i) c[i] = 1.0; return; }
+    if (s >= n) { for (int i = 0; i < n_pad; ++i) { c[i] = 1.0; sketch[r * n_pad + i] = 65535; } return; }
     double acc = 0.0, ksum = 0.0, kc = 0.0;
     bool neg = false;
     for (int i = 0; i < n; ++i) {
@@ -744,6 +781,10 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
         for (int i = 0; i < n; ++i) c[i] = 1.0;
     }
     for (int i = n; i < n_pad; ++i) c[i] = 1.0;
+    // 16-bit filter: q = min(65535, floor(cdf * 2^16)).  With v = floor(u * 2^16): q < v => cdf < u, q > v => cdf > u,
+    // q == v => undecided (the fast kernel then falls back to the float64 row) — so the filter never changes a result.
+    uint16_t* sk = sketch + r * n_pad;
+    for (int i = 0; i < n_pad; ++i) sk[i] = (uint16_t)fmin(65535.0, floor(c[i] * 65536.0));
 }
 
 // per-task small tables; one thread per task
@@ -899,11 +940,12 @@ struct amdp {
     Tables T;
     EnvArrays E;
     // owned device memory
-    double* cdf; float2* payload; int32_t* sinfo; double* s0_cdf; int32_t* s0_idx; double* obs_cdf;
+    double* cdf; float2* payload; uint16_t* sketch; int32_t* sinfo; double* s0_cdf; int32_t* s0_idx; double* obs_cdf;
     int32_t* max_ceil; uint8_t* tflags; double* raw_t; int32_t* n_real;
     int32_t* env_task;
     Stat6* stat_part;
     unsigned int* faults;
+    unsigned long long* counters;
     unsigned long long tick;
     double total_steps;
     int64_t bytes;
@@ -977,8 +1019,8 @@ static int pick_group(int n_pad) {
 extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->cdf, h->payload, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
-                    h->n_real, h->env_task, h->stat_part, h->faults, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
+    void* ptrs[] = {h->cdf, h->payload, h->sketch, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
+                    h->n_real, h->env_task, h->stat_part, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
                     h->st_done[0], h->st_done[1]};
@@ -1016,6 +1058,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     int rc;
     if ((rc = dalloc(h, &h->cdf, rows * c.n_pad))) return rc;
     if ((rc = dalloc(h, &h->payload, rows * c.n_pad))) return rc;
+    if ((rc = dalloc(h, &h->sketch, rows * c.n_pad))) return rc;
     if (c.reserved0 & 1) { if ((rc = dalloc(h, &h->raw_t, rows * c.n_pad))) return rc; }
     if ((rc = dalloc(h, &h->sinfo, (size_t)c.n_tasks * c.n_pad))) return rc;
     if ((rc = dalloc(h, &h->s0_cdf, (size_t)c.n_tasks * c.s0_pad))) return rc;
@@ -1027,6 +1070,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     if ((rc = dalloc(h, &h->env_task, (size_t)c.n_envs))) return rc;
     if ((rc = dalloc(h, &h->stat_part, (size_t)STAT_BLOCKS))) return rc;
     if ((rc = dalloc(h, &h->faults, 1))) return rc;
+    if ((rc = dalloc(h, &h->counters, 4))) return rc;
     EnvArrays& E = h->E;
     if ((rc = dalloc(h, &E.state, (size_t)c.n_envs))) return rc;
     if ((rc = dalloc(h, &E.steps, (size_t)c.n_envs))) return rc;
@@ -1039,10 +1083,11 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     if ((rc = dalloc(h, &E.min_ret, (size_t)c.n_envs))) return rc;
     if ((rc = dalloc(h, &E.max_ret, (size_t)c.n_envs))) return rc;
     CK(cudaMemset(h->faults, 0, sizeof(unsigned int)));
-    E.task = h->env_task; E.faults = h->faults; E.n_envs = c.n_envs; E.env_id_base = c.env_id_base;
+    CK(cudaMemset(h->counters, 0, 4 * sizeof(unsigned long long)));
+    E.task = h->env_task; E.faults = h->faults; E.counters = h->counters; E.n_envs = c.n_envs; E.env_id_base = c.env_id_base;
     E.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
     Tables& T = h->T;
-    T.cdf = h->cdf; T.payload = h->payload; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
+    T.cdf = h->cdf; T.payload = h->payload; T.sketch = h->sketch; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
     T.obs_cdf = h->obs_cdf; T.max_ceil = h->max_ceil; T.tflags = h->tflags; T.raw_t = h->raw_t; T.n_real = h->n_real;
     T.n_pad = c.n_pad; T.na = c.na; T.no_pad = c.no_pad; T.d_o = c.n_obs_tok; T.d_a = c.n_act_tok; T.s0_pad = c.s0_pad;
     T.task_type = c.task_type; T.autoreset = c.autoreset;
@@ -1067,7 +1112,8 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
     const size_t per_task = (size_t)c.n_pad * c.na * c.n_pad;
     const long long rows = (long long)cnt * c.n_pad * c.na;
     k_build_rows<<<nblk(rows, 128), 128, 0, st>>>(cnt, c.n_pad, c.na, transition, reward, reward_noise, n_real, is_terminal,
-                                                  h->cdf + t0 * per_task, h->payload + t0 * per_task, status_out);
+                                                  h->cdf + t0 * per_task, h->payload + t0 * per_task,
+                                                  h->sketch + t0 * per_task, status_out);
     k_build_small<<<nblk(cnt, 128), 128, 0, st>>>(cnt, c.n_pad, c.s0_pad, state_mapping, n_real, is_terminal, s0_idx, s0_prob,
                                                   n_s0, max_steps, ns, h->sinfo + t0 * c.n_pad, h->s0_cdf + t0 * c.s0_pad,
                                                   h->s0_idx + t0 * c.s0_pad, h->max_ceil + t0, h->tflags + t0,
@@ -1258,6 +1304,13 @@ extern "C" int amdp_set_seed(amdp_t* h, uint64_t seed) {
     if (!h) return AMDP_EINVAL;
     h->cfg.seed = seed;
     h->E.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    return AMDP_OK;
+}
+
+extern "C" int amdp_debug_counters(amdp_t* h, uint64_t* out4) {
+    if (!h || !out4) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpy(out4, h->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return AMDP_OK;
 }
 

@@ -187,6 +187,11 @@ class Engine:
         """Debug: run rollouts through the generic per-tick kernel (used to cross-check the fast kernel)."""
         self._ck(lib.amdp_debug_force_generic(self._h, 1 if on else 0))
 
+    def debug_counters(self):
+        out = (ctypes.c_uint64 * 4)()
+        self._ck(lib.amdp_debug_counters(self._h, out))
+        return {"exact_fallbacks": int(out[0])}
+
     def set_seed(self, seed):
         self._ck(lib.amdp_set_seed(self._h, int(seed) & (2 ** 64 - 1)))
 
