@@ -99,50 +99,64 @@ def cpu_baseline_subprocess(args):
 # clocks (B200_PROFILING.md recipe), sampled DURING the timed region
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled in a background thread while the timed region runs (NVML, ~1 kHz; the
+    timed region of a short run lasts only milliseconds, too short for `nvidia-smi -lms`)."""
 
     def __init__(self, index):
-        self.index = index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.index, self.samples, self.reasons = index, [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:
+            self.err = str(e)
+
+    def _run(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.0005)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-i", str(self.index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+        if self.ok:
+            self._thread.start()
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.f.read().splitlines():
-            c = [x.strip() for x in ln.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.f.name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {getattr(self, 'err', '')}"]}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -189,17 +203,27 @@ def run_b200(args, name, envs, tasks, ns, na, no):
             "action": torch.empty((ticks, N, 1), dtype=torch.int32, device=dev),
             "reward": torch.empty((ticks, N), dtype=torch.float32, device=dev),
             "done": torch.empty((ticks, N), dtype=torch.uint8, device=dev)}
-    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    # per-iteration episode statistics: reduced on the main stream (one tiny kernel), all-reduced over ranks on a side
+    # stream so that the 64-byte NCCL call never sits between two rollout launches
+    stats = torch.zeros((K + W + 1, 8), dtype=torch.float64, device=dev)
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    it = [0]
 
     def one_step(ev=None):
+        buf = stats[it[0]]
+        it[0] += 1
         if ev:
             ev[0].record()
         env.rollout(ticks, out=traj)
         if ev:
             ev[1].record()
-        env.engine.stats_tensor(stats)               # per-iteration episode statistics
+        env.engine.stats_tensor(buf)
         if world > 1:
-            dist.all_reduce(stats[:4], op=dist.ReduceOp.SUM)
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                dist.all_reduce(buf[:4], op=dist.ReduceOp.SUM)
 
     for _ in range(W):
         one_step()
@@ -216,6 +240,8 @@ def run_b200(args, name, envs, tasks, ns, na, no):
     t0.record()
     for i in range(K):
         one_step(evs[i])
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)      # the timed region ends when the last all-reduce has landed
     t1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -296,7 +322,7 @@ def run_b200(args, name, envs, tasks, ns, na, no):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))

@@ -867,23 +867,33 @@ __device__ __forceinline__ Stat6 stat_block_reduce(Stat6 v) {
     return sh[0];
 }
 
-__global__ void __launch_bounds__(STAT_THREADS) k_stats_partial(EnvArrays E, Stat6* __restrict__ part) {
+// One launch: every block reduces a strided slice of the envs into part[blockIdx]; the block that finishes last
+// (device-wide ticket) combines the 148 partials in index order, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(STAT_THREADS) k_stats(EnvArrays E, Stat6* __restrict__ part, unsigned int* __restrict__ ticket,
+                                                        double total_steps, double* __restrict__ out8) {
     Stat6 v = {0, 0, 0, 0, INFINITY, -INFINITY};
     for (long long e = (long long)blockIdx.x * STAT_THREADS + threadIdx.x; e < E.n_envs; e += (long long)STAT_BLOCKS * STAT_THREADS) {
         Stat6 w = {(double)E.ep_count[e], E.sum_ret[e], E.sum_ret_sq[e], (double)E.sum_len[e], E.min_ret[e], E.max_ret[e]};
         v = stat_merge(v, w);
     }
     v = stat_block_reduce(v);
-    if (threadIdx.x == 0) part[blockIdx.x] = v;
-}
-
-__global__ void __launch_bounds__(STAT_THREADS) k_stats_final(const Stat6* __restrict__ part, double total_steps, double* __restrict__ out8) {
-    Stat6 v = {0, 0, 0, 0, INFINITY, -INFINITY};
-    if (threadIdx.x < STAT_BLOCKS) v = part[threadIdx.x];
-    v = stat_block_reduce(v);
+    __shared__ bool last;
     if (threadIdx.x == 0) {
-        out8[0] = v.n; out8[1] = v.sr; out8[2] = v.sq; out8[3] = v.sl; out8[4] = v.mn; out8[5] = v.mx;
+        part[blockIdx.x] = v;
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == STAT_BLOCKS - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    Stat6 f = {0, 0, 0, 0, INFINITY, -INFINITY};
+    if (threadIdx.x < STAT_BLOCKS) f = part[threadIdx.x];
+    __syncthreads();
+    f = stat_block_reduce(f);
+    if (threadIdx.x == 0) {
+        out8[0] = f.n; out8[1] = f.sr; out8[2] = f.sq; out8[3] = f.sl; out8[4] = f.mn; out8[5] = f.mx;
         out8[6] = total_steps; out8[7] = 0.0;
+        *ticket = 0;
     }
 }
 
@@ -944,6 +954,7 @@ struct amdp {
     int32_t* max_ceil; uint8_t* tflags; double* raw_t; int32_t* n_real;
     int32_t* env_task;
     Stat6* stat_part;
+    unsigned int* stat_ticket;
     unsigned int* faults;
     unsigned long long* counters;
     unsigned long long tick;
@@ -1020,7 +1031,7 @@ extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
     void* ptrs[] = {h->cdf, h->payload, h->sketch, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
-                    h->n_real, h->env_task, h->stat_part, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
+                    h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
                     h->st_done[0], h->st_done[1]};
@@ -1069,6 +1080,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     if ((rc = dalloc(h, &h->n_real, (size_t)c.n_tasks))) return rc;
     if ((rc = dalloc(h, &h->env_task, (size_t)c.n_envs))) return rc;
     if ((rc = dalloc(h, &h->stat_part, (size_t)STAT_BLOCKS))) return rc;
+    if ((rc = dalloc(h, &h->stat_ticket, 1))) return rc;
     if ((rc = dalloc(h, &h->faults, 1))) return rc;
     if ((rc = dalloc(h, &h->counters, 4))) return rc;
     EnvArrays& E = h->E;
@@ -1083,6 +1095,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     if ((rc = dalloc(h, &E.min_ret, (size_t)c.n_envs))) return rc;
     if ((rc = dalloc(h, &E.max_ret, (size_t)c.n_envs))) return rc;
     CK(cudaMemset(h->faults, 0, sizeof(unsigned int)));
+    CK(cudaMemset(h->stat_ticket, 0, sizeof(unsigned int)));
     CK(cudaMemset(h->counters, 0, 4 * sizeof(unsigned long long)));
     E.task = h->env_task; E.faults = h->faults; E.counters = h->counters; E.n_envs = c.n_envs; E.env_id_base = c.env_id_base;
     E.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
@@ -1250,9 +1263,8 @@ extern "C" int amdp_stats(amdp_t* h, double* out8, void* stream) {
     if (!h->assigned) return fail(h, AMDP_ESTATE, "stats before assign");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    k_stats_partial<<<STAT_BLOCKS, STAT_THREADS, 0, st>>>(h->E, h->stat_part);
-    k_stats_final<<<1, STAT_THREADS, 0, st>>>(h->stat_part, h->total_steps, out8);
-    h->launches += 2;
+    k_stats<<<STAT_BLOCKS, STAT_THREADS, 0, st>>>(h->E, h->stat_part, h->stat_ticket, h->total_steps, out8);
+    h->launches += 1;
     CK(cudaGetLastError());
     return AMDP_OK;
 }
