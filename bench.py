@@ -294,10 +294,13 @@ def run_b200(args, name, envs, tasks, ns, na, no):
             peak, which = 6650.0, "fallback (B200_PROFILING.md)"
         balg = b_alg(ns, no)
         achieved = balg * N * ticks / (kern_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tpath):
-            traffic = json.load(open(tpath)).get(name)
+            t = json.load(open(tpath)).get(name)
+            if t and t["envs"] == N and t["ticks"] == ticks:
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+                traffic_note = t["source"]
         value = world * N * ticks * K / (ms * 1e-3)
         line = {
             "metric": "AnyMDP env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
@@ -309,7 +312,9 @@ def run_b200(args, name, envs, tasks, ns, na, no):
                              else "tables may be L2 resident", "parallelism": f"env-sharded dp{world}",
                        "upload_s": round(t_up, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": which, "kernel": "k_rollout",
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_source": traffic_note, "algorithmic_bytes_per_launch": balg * N * ticks,
+                         "peak_source": which, "kernel": "k_rollout_mdp",
                          "algorithmic_bytes_per_env_step": balg, "kernel_ms_per_launch": kern_ms},
             "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
             "episodes": ep["episodes"], "mean_return": ep["mean_return"], "mean_length": ep["mean_length"],

@@ -10,6 +10,7 @@ import torch
 
 from . import _lib
 from .engine import Engine, task_geometry
+from .distributed import allreduce_stats, stats_dict
 
 _FAULT_MSG = (
     (_lib.FAULT_NEED_RESET, Exception, "Must \"set_task\" and \"reset\" before doing any actions"),   # anymdp_env.py:94
@@ -154,20 +155,8 @@ class AnyMDPVecEnv:
         initialised and group=True) they are all-reduced over the ranks (one tiny NCCL call)."""
         s = self.episode_stats_tensor().clone()
         if group is not None:
-            import torch.distributed as dist
-            g = None if group is True else group
-            sums, mn, mx = s[[0, 1, 2, 3, 6]].clone(), s[4:5].clone(), s[5:6].clone()
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=g)
-            dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=g)
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=g)
-            s[[0, 1, 2, 3, 6]] = sums
-            s[4], s[5] = mn[0], mx[0]
-        v = s.cpu().numpy()
-        n = int(v[0])
-        return {"episodes": n, "sum_return": float(v[1]), "sum_return_sq": float(v[2]), "sum_length": int(v[3]),
-                "min_return": float(v[4]), "max_return": float(v[5]), "total_steps": int(v[6]),
-                "mean_return": float(v[1] / n) if n else float("nan"),
-                "mean_length": float(v[3] / n) if n else float("nan")}
+            allreduce_stats(s, None if group is True else group)
+        return stats_dict(s.cpu().numpy())
 
     def clear_episode_stats(self):
         self.engine.clear_stats()
