@@ -9,6 +9,8 @@ from .gym_compat import register, make, spaces, HAVE_GYMNASIUM  # noqa: F401
 from .engine import Engine, AMDPError, task_geometry, pack_tasks  # noqa: F401
 from .anymdp_env import AnyMDPEnv  # noqa: F401
 from .vec_env import AnyMDPVecEnv  # noqa: F401
+from .task_sampler import (AnyMDPTaskSampler, AnyPOMDPTaskSampler, MultiTokensAnyPOMDPTaskSampler,  # noqa: F401
+                           GarnetTaskSampler)
 from .synth import synth_task, synth_packed, synth_geometry, packed_to_task  # noqa: F401
 
 __version__ = "0.1.0"
