@@ -261,28 +261,29 @@ def run_b200(args, name, envs, tasks, ns, na, no):
     # ---- end to end through the C ABI with HOST buffers (amdp_rollout_host) -----------------------
     e2e = None
     if not args.no_e2e:
+        # compact wire format of amdp_rollout_host_packed: uint8 actions in, one 8-byte record (obs, action, done,
+        # reward) per env-step out; pinned host buffers; copies inside the timed region
         eK = args.e2e_ticks
         g = torch.Generator().manual_seed(rank)
-        acts_h = torch.randint(0, na, (eK, N, 1), dtype=torch.int32, generator=g).pin_memory()
-        obs_h = torch.empty((eK, N, 1), dtype=torch.int32).pin_memory()
-        rew_h = torch.empty((eK, N), dtype=torch.float32).pin_memory()
-        done_h = torch.empty((eK, N), dtype=torch.uint8).pin_memory()
-        reps = max(3, min(K, 10))
-        for _ in range(2):
-            env.engine.rollout_host(eK, args.e2e_chunk, acts_h, obs_h, rew_h, done_h)
+        acts_h = torch.randint(0, na, (eK, N), dtype=torch.uint8, generator=g).pin_memory()
+        rec_h = torch.empty((eK, N), dtype=torch.int64).pin_memory()
+        reps = max(3, min(K, 20))
+        for _ in range(3):
+            env.engine.rollout_host_packed(eK, args.e2e_chunk, acts_h, rec_h)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         w0 = time.perf_counter()
         for _ in range(reps):
-            env.engine.rollout_host(eK, args.e2e_chunk, acts_h, obs_h, rew_h, done_h)   # synchronous
+            env.engine.rollout_host_packed(eK, args.e2e_chunk, acts_h, rec_h)   # synchronous
         w = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(w, op=dist.ReduceOp.MAX)
         e2e = {"value": world * N * eK * reps / float(w), "unit": "env-steps/s",
-               "h2d_bytes_per_step": int(acts_h.numel() * 4), "d2h_bytes_per_step": int(obs_h.numel() * 4 + rew_h.numel() * 4 + done_h.numel()),
-               "step": f"one amdp_rollout_host call = {eK} ticks x {N} envs, pinned host actions in, host obs/reward/done out, "
-                       f"chunks of {args.e2e_chunk} ticks double-buffered; wall clock around {reps} synchronous calls",
+               "h2d_bytes_per_step": int(acts_h.numel()), "d2h_bytes_per_step": int(rec_h.numel() * 8),
+               "step": f"one amdp_rollout_host_packed call = {eK} ticks x {N} envs: pinned uint8 host actions in, 8-byte host "
+                       f"records (obs, action, done, fp32 reward) out, chunks of {args.e2e_chunk} ticks double-buffered on 3 "
+                       f"streams; wall clock around {reps} synchronous calls (max over ranks)",
                "ms_per_step": 1e3 * float(w) / reps}
         env.check()
 
@@ -335,7 +336,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--tasks", type=int, default=0, help="override tasks per GPU")
     ap.add_argument("--e2e-ticks", type=int, default=512)
-    ap.add_argument("--e2e-chunk", type=int, default=64)
+    ap.add_argument("--e2e-chunk", type=int, default=128)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-steps-per-worker", type=int, default=20000)

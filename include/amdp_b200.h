@@ -190,6 +190,11 @@ typedef struct amdp_traj {
     uint8_t* done;          /* width 1: bit0 terminated, bit1 truncated */
     int64_t  step_stride;   /* in units of one record of width 1 (multiplied by the width internally) */
     int64_t  env_stride;
+    uint64_t* packed;       /* or NULL.  When set, the five arrays above are ignored and ONE 8-byte record per
+                               (tick, env) is written: bits 0-19 obs, 20-29 action, 30 terminated, 31 truncated,
+                               32-63 the fp32 reward.  Needs do == da == 1, ns <= 2^20, na <= 1024. */
+    int32_t  actions_u8;    /* non-zero: `actions` points to uint8 [K][n_envs][da] instead of int32 */
+    int32_t  reserved;
 } amdp_traj;
 
 int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const amdp_traj* traj,
@@ -256,6 +261,10 @@ int64_t amdp_launch_count(const amdp_t* h);
  */
 int amdp_rollout_host(amdp_t* h, int32_t K, int32_t chunk, const int32_t* actions_host,
                       int32_t* obs_host, float* reward_host, uint8_t* done_host);
+
+/* Same, in the compact wire format: uint8 actions in (1 byte per env-step over PCIe), packed 8-byte records out
+ * (see amdp_traj.packed).  actions_host uint8 [K][n_envs] or NULL; records_host uint64 [K][n_envs]. */
+int amdp_rollout_host_packed(amdp_t* h, int32_t K, int32_t chunk, const uint8_t* actions_host, uint64_t* records_host);
 
 #ifdef __cplusplus
 }

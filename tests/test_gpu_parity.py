@@ -361,3 +361,51 @@ def test_filter_fallback_is_exercised_and_exact(ns, na, mode):
     assert torch.equal(sa["state"], sb["state"]) and torch.equal(sa["ep_return"], sb["ep_return"]) and ea == eb
     assert cb["exact_fallbacks"] == 0
     assert 20 <= ca["exact_fallbacks"] <= N * K // 20, ca
+
+
+def test_packed_records_and_host_rollouts_match_device_rollout():
+    """amdp_rollout_host / amdp_rollout_host_packed (pinned host buffers, chunked, 3 streams) == one device rollout."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv, unpack_records
+    tasks = [synth_task(32, 5, 700 + t) for t in range(10)]
+    N, K = 300, 150
+    acts = torch.randint(0, 5, (K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(5))
+
+    def fresh():
+        env = AnyMDPVecEnv(N, seed=31)
+        env.set_task(tasks)
+        env.reset()
+        return env
+    ref = fresh().rollout(K, actions=acts.cuda())
+    # packed device records
+    rec = unpack_records(fresh().rollout(K, actions=acts.cuda(), record=("packed",))["packed"])
+    assert numpy.array_equal(rec["obs"], ref["obs"][..., 0].cpu().numpy())
+    assert numpy.array_equal(rec["action"], acts.numpy())
+    d = ref["done"].cpu().numpy()
+    assert numpy.array_equal(rec["terminated"], (d & 1).astype(bool)) and numpy.array_equal(rec["truncated"], (d >> 1).astype(bool))
+    assert numpy.array_equal(rec["reward"], ref["reward"].cpu().numpy())
+    # host path, separate arrays, chunk not dividing K
+    env = fresh()
+    obs_h = torch.empty((K, N, 1), dtype=torch.int32).pin_memory()
+    rew_h = torch.empty((K, N), dtype=torch.float32).pin_memory()
+    done_h = torch.empty((K, N), dtype=torch.uint8).pin_memory()
+    env.engine.rollout_host(K, 64, acts.reshape(K, N, 1).contiguous().pin_memory(), obs_h, rew_h, done_h)
+    assert torch.equal(obs_h, ref["obs"].cpu()) and torch.equal(rew_h, ref["reward"].cpu()) and torch.equal(done_h, ref["done"].cpu())
+    # host path, compact wire format
+    env = fresh()
+    rec_h = torch.empty((K, N), dtype=torch.int64).pin_memory()
+    env.engine.rollout_host_packed(K, 40, acts.to(torch.uint8).pin_memory(), rec_h)
+    rec2 = unpack_records(rec_h)
+    for key in rec:
+        assert numpy.array_equal(rec[key], rec2[key]), key
+    env.check()
+    # packed records from the generic kernel (POMDP)
+    ptasks = [synth_task(16, 4, 800 + t, no=12) for t in range(4)]
+    out = []
+    for packed in (False, True):
+        env = AnyMDPVecEnv(64, seed=3)
+        env.set_task(ptasks)
+        env.reset()
+        out.append(env.rollout(40, record=("packed",) if packed else ("obs", "action", "reward", "done")))
+    rec = unpack_records(out[1]["packed"])
+    assert numpy.array_equal(rec["obs"], out[0]["obs"][..., 0].cpu().numpy())
+    assert numpy.array_equal(rec["reward"], out[0]["reward"].cpu().numpy())

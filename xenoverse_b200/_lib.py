@@ -32,7 +32,8 @@ class Config(ctypes.Structure):
 class Traj(ctypes.Structure):
     _fields_ = [("obs", ctypes.c_void_p), ("actions_out", ctypes.c_void_p), ("reward", ctypes.c_void_p),
                 ("reward_gt", ctypes.c_void_p), ("done", ctypes.c_void_p),
-                ("step_stride", ctypes.c_int64), ("env_stride", ctypes.c_int64)]
+                ("step_stride", ctypes.c_int64), ("env_stride", ctypes.c_int64), ("packed", ctypes.c_void_p),
+                ("actions_u8", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 _P = ctypes.c_void_p
@@ -65,6 +66,7 @@ _SIGNATURES = {
     "amdp_debug_counters": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),
     "amdp_launch_count": (ctypes.c_int64, [_P]),
     "amdp_rollout_host": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P]),
+    "amdp_rollout_host_packed": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

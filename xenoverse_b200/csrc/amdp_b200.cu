@@ -281,6 +281,10 @@ __device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, lo
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int load_action(const int32_t* actions, long long i, int as_u8) {
+    return as_u8 ? (int)reinterpret_cast<const uint8_t*>(actions)[i] : actions[i];
+}
+
 __device__ __forceinline__ void load_regs(const EnvArrays& E, long long e, EnvRegs& R, bool with_stats) {
     R.state = E.state[e]; R.steps = E.steps[e]; R.flags = E.flags[e]; R.ep_return = E.ep_return[e];
     if (with_stats) {
@@ -362,10 +366,19 @@ __global__ void __launch_bounds__(256) k_rollout(Tables T, EnvArrays E, unsigned
         D.tick = tick0 + (unsigned long long)k;
         D.row = u_inject ? u_inject + ((long long)k * E.n_envs + ec) * n_slots : nullptr;
         TickOut O;
-        env_tick<G>(T, E, t, active, lane, D, actions ? actions + ((long long)k * E.n_envs + ec) * T.d_a : nullptr,
-                    R, O, obs, fobs, act);
+        int a8[MAX_TOK];
+        const int32_t* act_ptr = actions ? actions + ((long long)k * E.n_envs + ec) * T.d_a : nullptr;
+        if (actions && J.actions_u8) {
+            for (int j = 0; j < T.d_a; ++j) a8[j] = load_action(actions, ((long long)k * E.n_envs + ec) * T.d_a + j, 1);
+            act_ptr = a8;
+        }
+        env_tick<G>(T, E, t, active, lane, D, act_ptr, R, O, obs, fobs, act);
         if (active && lane == 0) {
             const long long o = (long long)k * J.step_stride + e * J.env_stride;
+            if (J.packed) {
+                const unsigned lo = ((unsigned)obs[0] & 0xfffffu) | (((unsigned)act[0] & 0x3ffu) << 20) | ((unsigned)(O.term | (O.trunc << 1)) << 30);
+                J.packed[o] = ((unsigned long long)__float_as_uint(O.reward) << 32) | lo;
+            }
             if (J.obs) for (int j = 0; j < T.d_o; ++j) J.obs[o * T.d_o + j] = obs[j];
             if (J.actions_out) for (int j = 0; j < T.d_a; ++j) J.actions_out[o * T.d_a + j] = act[j];
             if (J.reward) J.reward[o] = O.reward;
@@ -443,26 +456,24 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
     int s = E.state[e], steps = E.steps[e], flags = E.flags[e];
     double ep_ret = E.ep_return[e];
 
-    // staged trajectory records.  Lane L holds obs/action/done of tick (batch start + L) and the reward of the most
-    // recently SETTLED tick whose index is L mod G (rewards settle one tick late, see below).
+    // staged trajectory records: lane L holds the record of tick (batch start + L); a batch is written once all of its
+    // rewards have settled (rewards settle one tick late, see below)
     int st_obs = 0, st_ad = 0;                                    // st_ad = action | done_bits << 28
     float st_rew = 0.f, st_rgt = 0.f;
-    auto flush_rec = [&](int kb, int cnt) {                       // obs / action / done of ticks [kb, kb + cnt)
+    auto flush = [&](int kb, int cnt) {                           // records of ticks [kb, kb + cnt), one lane per tick
         if (lane < cnt) {
             const long long o = (long long)(kb + lane) * J.step_stride + e * J.env_stride;
-            if (J.obs) J.obs[o] = st_obs;
-            if (J.actions_out) J.actions_out[o] = st_ad & 0x0fffffff;
-            if (J.done) J.done[o] = (uint8_t)((unsigned)st_ad >> 28);
-        }
-    };
-    auto flush_rew = [&](int kb, int cnt) {                       // rewards of ticks [kb, kb + cnt) and of tick kb - 1 (lane G - 1)
-        int k = -1;
-        if (lane < cnt) k = kb + lane;
-        else if (lane == G - 1 && kb > 0) k = kb - 1;
-        if (k >= 0) {
-            const long long o = (long long)k * J.step_stride + e * J.env_stride;
-            if (J.reward) J.reward[o] = st_rew;
-            if (J.reward_gt) J.reward_gt[o] = st_rgt;
+            if (J.packed) {
+                // one 8-byte record per (tick, env): obs | action << 20 | done << 30, reward bits
+                const unsigned lo = ((unsigned)st_obs & 0xfffffu) | (((unsigned)st_ad & 0x3ffu) << 20) | (((unsigned)st_ad >> 28) << 30);
+                J.packed[o] = ((unsigned long long)__float_as_uint(st_rew) << 32) | lo;
+            } else {
+                if (J.obs) J.obs[o] = st_obs;
+                if (J.actions_out) J.actions_out[o] = st_ad & 0x0fffffff;
+                if (J.done) J.done[o] = (uint8_t)((unsigned)st_ad >> 28);
+                if (J.reward) J.reward[o] = st_rew;
+                if (J.reward_gt) J.reward_gt[o] = st_rgt;
+            }
         }
     };
 
@@ -475,17 +486,11 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
             const int k = kb + lane;
             int a = 0;
             if (k < K) {
-                if (GIVEN) a = actions[(long long)k * N + e];
+                if (GIVEN) a = load_action(actions, (long long)k * N + e, J.actions_u8);
                 else a = (int)__umulhi(philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key).z, (uint32_t)na);
             }
             st_ad = a & 0x0fffffff;
-            const int cnt = min(G, K - kb);
-            flush_rec(kb, cnt);
-            if (lane < cnt) {
-                const long long o = (long long)k * J.step_stride + e * J.env_stride;
-                if (J.reward) J.reward[o] = 0.f;
-                if (J.reward_gt) J.reward_gt[o] = 0.f;
-            }
+            flush(kb, min(G, K - kb));
         }
         if (lane == 0) atomicOr(E.faults, fault);
         return;
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
         b_ur = u53(w0.z, w0.w);
         const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
         b_z = box_muller(w2.x, w2.y);
-        if (GIVEN) b_act = (kt < K) ? actions[(long long)kt * N + e] : 0;
+        if (GIVEN) b_act = (kt < K) ? load_action(actions, (long long)kt * N + e, J.actions_u8) : 0;
         else b_act = (int)__umulhi(w2.z, (uint32_t)na);
     };
 
@@ -530,7 +535,7 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
         ur_carry = u53(w0.z, w0.w);
         const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0, E.key);
         z = box_muller(w2.x, w2.y);
-        a = GIVEN ? actions[e] : (int)__umulhi(w2.z, (uint32_t)na);
+        a = GIVEN ? load_action(actions, e, J.actions_u8) : (int)__umulhi(w2.z, (uint32_t)na);
     }
     refill(0);
     bool pend = NEXT && (flags & FLAG_PENDING);
@@ -635,8 +640,10 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
         uint2 nq[CR];
         if (!do_reset) issue_row(nq, nrowi, na_ok);
 
-        // (B) settle the previous tick (its payload load was issued one tick ago, after this tick's row load)
+        // (B) settle the previous tick (its payload load was issued one tick ago, after this tick's row load); once per
+        //     G ticks write the finished batch of records, lane-parallel
         settle(k - 1);
+        if (j == 0 && k > 0) flush(k - G, G);
         // (D) payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104): consumed by settle() of the next tick
         if (valid) pay_p = ldg_stream_f32x2(pay_t + (rowi + (unsigned)nxt)); else pay_p = make_float2(0.f, 0.f);
         z_p = z;
@@ -673,11 +680,8 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
             st_obs = obs_out;
             st_ad = (a & 0x0fffffff) | (done_bits << 28);
         }
-        // once per G ticks: write the batch's records (lane-parallel) and draw the next batch
+        // once per G ticks: draw the next batch
         if (j == G - 1) {
-            const int kb = k - (G - 1);
-            flush_rec(kb, G);
-            flush_rew(kb, G - 1);
             ur_carry = __shfl_sync(gmask, b_ur, G - 1, G);
             refill(k + 1);
         }
@@ -692,9 +696,8 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
     // settle the last tick and write what is still staged
     {
         settle(K - 1);
-        const int kb = (K / G) * G;
-        flush_rec(kb, K - kb);
-        flush_rew(kb, K - kb);
+        const int kb = ((K - 1) / G) * G;
+        flush(kb, K - kb);
     }
     if (lane == 0) {
         E.state[e] = s; E.steps[e] = steps; E.flags[e] = (uint8_t)flags; E.ep_return[e] = ep_ret;
@@ -965,7 +968,7 @@ struct amdp {
     bool force_generic;    // debug: route rollouts through the generic kernel
     char err[512];
     // rollout_host staging
-    int32_t* st_act[2]; int32_t* st_obs[2]; float* st_rew[2]; uint8_t* st_done[2];
+    int32_t* st_act[2]; int32_t* st_obs[2]; float* st_rew[2]; uint8_t* st_done[2]; unsigned long long* st_rec[2];
     int st_chunk;
     cudaStream_t st_stream[3];
     cudaEvent_t st_ev_in[2], st_ev_k[2], st_ev_out[2];
@@ -1034,7 +1037,7 @@ extern "C" int amdp_destroy(amdp_t* h) {
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
-                    h->st_done[0], h->st_done[1]};
+                    h->st_done[0], h->st_done[1], h->st_rec[0], h->st_rec[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->st_ready) {
         for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->st_stream[i]);
@@ -1239,6 +1242,9 @@ extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const 
     amdp_traj J;
     memset(&J, 0, sizeof(J));
     if (traj) J = *traj;
+    if (J.packed && (h->cfg.n_obs_tok != 1 || h->cfg.n_act_tok != 1 || h->cfg.n_pad > (1 << 20) || h->cfg.na > 1024 ||
+                     (h->cfg.task_type != AMDP_MDP && h->cfg.no_pad > (1 << 20))))
+        return fail(h, AMDP_EINVAL, "packed records need do == da == 1, at most 2^20 observations and 1024 actions");
     cudaStream_t st = (cudaStream_t)stream;
     const bool fast = h->cfg.task_type == AMDP_MDP && !u_inject && !h->force_generic;
     if (fast) {
@@ -1396,8 +1402,8 @@ static int staging_init(amdp* h, int chunk) {
     if (h->st_ready && h->st_chunk >= chunk) return AMDP_OK;
     if (h->st_ready) {
         for (int i = 0; i < 2; ++i) {
-            cudaFree(h->st_act[i]); cudaFree(h->st_obs[i]); cudaFree(h->st_rew[i]); cudaFree(h->st_done[i]);
-            h->st_act[i] = nullptr; h->st_obs[i] = nullptr; h->st_rew[i] = nullptr; h->st_done[i] = nullptr;
+            cudaFree(h->st_act[i]); cudaFree(h->st_obs[i]); cudaFree(h->st_rew[i]); cudaFree(h->st_done[i]); cudaFree(h->st_rec[i]);
+            h->st_act[i] = nullptr; h->st_obs[i] = nullptr; h->st_rew[i] = nullptr; h->st_done[i] = nullptr; h->st_rec[i] = nullptr;
         }
     } else {
         for (int i = 0; i < 3; ++i) CK(cudaStreamCreateWithFlags(&h->st_stream[i], cudaStreamNonBlocking));
@@ -1415,13 +1421,16 @@ static int staging_init(amdp* h, int chunk) {
         if ((rc = dalloc(h, &h->st_obs[i], per * c.n_obs_tok))) return rc;
         if ((rc = dalloc(h, &h->st_rew[i], per))) return rc;
         if ((rc = dalloc(h, &h->st_done[i], per))) return rc;
+        if ((rc = dalloc(h, &h->st_rec[i], per))) return rc;
     }
     h->st_chunk = chunk;
     return AMDP_OK;
 }
 
-extern "C" int amdp_rollout_host(amdp_t* h, int32_t K, int32_t chunk, const int32_t* actions_host, int32_t* obs_host,
-                                 float* reward_host, uint8_t* done_host) {
+// actions in / trajectory out through pinned host memory, `chunk` ticks at a time on three streams (copy-in, kernel,
+// copy-out) with two staging buffers, so that PCIe traffic in both directions overlaps the rollout kernel.
+static int rollout_host_impl(amdp* h, int K, int chunk, const void* actions_host, bool packed, int32_t* obs_host,
+                             float* reward_host, uint8_t* done_host, unsigned long long* rec_host) {
     if (!h || K < 1) return AMDP_EINVAL;
     if (!h->assigned) return fail(h, AMDP_ESTATE, "Must \"set_task\" and \"reset\" before doing any actions");
     const amdp_config& c = h->cfg;
@@ -1431,6 +1440,7 @@ extern "C" int amdp_rollout_host(amdp_t* h, int32_t K, int32_t chunk, const int3
     if (rc) return rc;
     cudaStream_t s_in = h->st_stream[0], s_k = h->st_stream[1], s_out = h->st_stream[2];
     const size_t N = (size_t)c.n_envs;
+    const size_t act_bytes = packed ? 1 : sizeof(int32_t);
     int i = 0;
     for (int k0 = 0; k0 < K; k0 += chunk, ++i) {
         const int b = i & 1;
@@ -1438,27 +1448,46 @@ extern "C" int amdp_rollout_host(amdp_t* h, int32_t K, int32_t chunk, const int3
         // buffer b is free once the copy-out of chunk i-2 has finished
         if (i >= 2) { CK(cudaStreamWaitEvent(s_in, h->st_ev_out[b], 0)); CK(cudaStreamWaitEvent(s_k, h->st_ev_out[b], 0)); }
         if (actions_host) {
-            CK(cudaMemcpyAsync(h->st_act[b], actions_host + (size_t)k0 * N * c.n_act_tok, sizeof(int32_t) * kc * N * c.n_act_tok,
-                               cudaMemcpyHostToDevice, s_in));
+            CK(cudaMemcpyAsync(h->st_act[b], (const char*)actions_host + (size_t)k0 * N * c.n_act_tok * act_bytes,
+                               act_bytes * kc * N * c.n_act_tok, cudaMemcpyHostToDevice, s_in));
             CK(cudaEventRecord(h->st_ev_in[b], s_in));
             CK(cudaStreamWaitEvent(s_k, h->st_ev_in[b], 0));
         }
         amdp_traj J;
         memset(&J, 0, sizeof(J));
-        J.obs = obs_host ? h->st_obs[b] : nullptr;
-        J.reward = reward_host ? h->st_rew[b] : nullptr;
-        J.done = done_host ? h->st_done[b] : nullptr;
+        if (packed) {
+            J.packed = (uint64_t*)h->st_rec[b];
+            J.actions_u8 = 1;
+        } else {
+            J.obs = obs_host ? h->st_obs[b] : nullptr;
+            J.reward = reward_host ? h->st_rew[b] : nullptr;
+            J.done = done_host ? h->st_done[b] : nullptr;
+        }
         J.step_stride = (int64_t)N; J.env_stride = 1;
         rc = amdp_rollout(h, kc, actions_host ? h->st_act[b] : nullptr, &J, nullptr, s_k);
         if (rc) return rc;
         CK(cudaEventRecord(h->st_ev_k[b], s_k));
         CK(cudaStreamWaitEvent(s_out, h->st_ev_k[b], 0));
-        if (obs_host) CK(cudaMemcpyAsync(obs_host + (size_t)k0 * N * c.n_obs_tok, h->st_obs[b], sizeof(int32_t) * kc * N * c.n_obs_tok, cudaMemcpyDeviceToHost, s_out));
-        if (reward_host) CK(cudaMemcpyAsync(reward_host + (size_t)k0 * N, h->st_rew[b], sizeof(float) * kc * N, cudaMemcpyDeviceToHost, s_out));
-        if (done_host) CK(cudaMemcpyAsync(done_host + (size_t)k0 * N, h->st_done[b], (size_t)kc * N, cudaMemcpyDeviceToHost, s_out));
+        if (packed) {
+            if (rec_host) CK(cudaMemcpyAsync(rec_host + (size_t)k0 * N, h->st_rec[b], sizeof(unsigned long long) * kc * N, cudaMemcpyDeviceToHost, s_out));
+        } else {
+            if (obs_host) CK(cudaMemcpyAsync(obs_host + (size_t)k0 * N * c.n_obs_tok, h->st_obs[b], sizeof(int32_t) * kc * N * c.n_obs_tok, cudaMemcpyDeviceToHost, s_out));
+            if (reward_host) CK(cudaMemcpyAsync(reward_host + (size_t)k0 * N, h->st_rew[b], sizeof(float) * kc * N, cudaMemcpyDeviceToHost, s_out));
+            if (done_host) CK(cudaMemcpyAsync(done_host + (size_t)k0 * N, h->st_done[b], (size_t)kc * N, cudaMemcpyDeviceToHost, s_out));
+        }
         CK(cudaEventRecord(h->st_ev_out[b], s_out));
     }
     CK(cudaStreamSynchronize(s_out));
     CK(cudaStreamSynchronize(s_k));
     return AMDP_OK;
+}
+
+extern "C" int amdp_rollout_host(amdp_t* h, int32_t K, int32_t chunk, const int32_t* actions_host, int32_t* obs_host,
+                                 float* reward_host, uint8_t* done_host) {
+    return rollout_host_impl(h, K, chunk, actions_host, false, obs_host, reward_host, done_host, nullptr);
+}
+
+extern "C" int amdp_rollout_host_packed(amdp_t* h, int32_t K, int32_t chunk, const uint8_t* actions_host, uint64_t* records_host) {
+    if (h && (h->cfg.na > 256)) return fail(h, AMDP_EINVAL, "uint8 actions need na <= 256");
+    return rollout_host_impl(h, K, chunk, actions_host, true, nullptr, nullptr, nullptr, (unsigned long long*)records_host);
 }

@@ -273,6 +273,8 @@ class Engine:
         traj = traj or {}
         J.obs, J.actions_out = _ptr(traj.get("obs")), _ptr(traj.get("action"))
         J.reward, J.reward_gt, J.done = _ptr(traj.get("reward")), _ptr(traj.get("reward_gt")), _ptr(traj.get("done"))
+        J.packed = _ptr(traj.get("packed"))
+        J.actions_u8 = 1 if (actions is not None and actions.dtype == torch.uint8) else 0
         if env_major:
             J.step_stride, J.env_stride = 1, int(K)
         else:
@@ -283,6 +285,10 @@ class Engine:
     def rollout_host(self, K, chunk, actions=None, obs=None, reward=None, done=None):
         """Host (pinned) buffers in / out; synchronous.  Tensors are CPU torch tensors."""
         self._ck(lib.amdp_rollout_host(self._h, int(K), int(chunk), _ptr(actions), _ptr(obs), _ptr(reward), _ptr(done)))
+
+    def rollout_host_packed(self, K, chunk, actions_u8=None, records=None):
+        """Compact wire format: uint8 actions [K, N] in, uint64 records [K, N] out (CPU, pinned); synchronous."""
+        self._ck(lib.amdp_rollout_host_packed(self._h, int(K), int(chunk), _ptr(actions_u8), _ptr(records)))
 
     # ---- statistics / introspection -----------------------------------------------------------
     def stats_tensor(self, out=None):
@@ -342,6 +348,16 @@ class Engine:
         with torch.cuda.device(self.device):
             self._ck(lib.amdp_debug_cdf_row(self._h, int(task), int(s), int(a), _ptr(out), _stream()))
         return out
+
+
+def unpack_records(rec):
+    """uint64 records (torch or numpy) -> dict(obs, action, terminated, truncated, reward); see amdp_traj.packed."""
+    r = rec.cpu().numpy() if isinstance(rec, torch.Tensor) else numpy.asarray(rec)
+    r = r.view(numpy.uint64)
+    lo = (r & numpy.uint64(0xffffffff)).astype(numpy.uint32)
+    return {"obs": (lo & 0xfffff).astype(numpy.int32), "action": ((lo >> 20) & 0x3ff).astype(numpy.int32),
+            "terminated": ((lo >> 30) & 1).astype(bool), "truncated": ((lo >> 31) & 1).astype(bool),
+            "reward": (r >> numpy.uint64(32)).astype(numpy.uint32).view(numpy.float32)}
 
 
 def ceil_max_steps(x):

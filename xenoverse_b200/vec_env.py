@@ -128,7 +128,10 @@ class AnyMDPVecEnv:
         self._require_task()
         if actions is None and policy != "uniform":
             raise ValueError("policy must be 'uniform' when no actions are given")
-        a = None if actions is None else self.engine._dev(actions, torch.int32).reshape(K, self.num_envs, self.da)
+        if actions is not None and isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8:
+            a = actions.to(self.device).reshape(K, self.num_envs, self.da).contiguous()
+        else:
+            a = None if actions is None else self.engine._dev(actions, torch.int32).reshape(K, self.num_envs, self.da)
         N, d = self.num_envs, self.device
         traj = out if out is not None else {}
         if out is None:
@@ -142,6 +145,8 @@ class AnyMDPVecEnv:
                 traj["reward_gt"] = torch.empty((K, N), dtype=torch.float32, device=d)
             if "done" in record:
                 traj["done"] = torch.empty((K, N), dtype=torch.uint8, device=d)
+            if "packed" in record:
+                traj = {"packed": torch.empty((K, N), dtype=torch.int64, device=d)}
         self.engine.rollout(K, actions=a, traj=traj, u_inject=u_inject)
         return traj
 
