@@ -101,7 +101,8 @@ typedef struct amdp_config {
     int32_t  n_obs_tok;     /* `do` (1 unless MTPOMDP) */
     int32_t  n_act_tok;     /* `da` (1 unless MTPOMDP) */
     int32_t  s0_pad;        /* max len(s_0) over tasks */
-    int32_t  reserved0;
+    int32_t  reserved0;     /* flags: 1 keep a copy of `transition` (amdp_gather_transition_gt); 2 / 4 force the one- / two-level
+                               row search of the fast rollout kernel (default: chosen from n_pad and n_envs) */
     int64_t  n_envs;        /* envs owned by this handle (this GPU's shard) */
     int64_t  n_tasks;       /* tasks resident on this handle */
     uint64_t seed;          /* Philox key */

@@ -409,3 +409,32 @@ def test_packed_records_and_host_rollouts_match_device_rollout():
     rec = unpack_records(out[1]["packed"])
     assert numpy.array_equal(rec["obs"], out[0]["obs"][..., 0].cpu().numpy())
     assert numpy.array_equal(rec["reward"], out[0]["reward"].cpu().numpy())
+
+
+@pytest.mark.parametrize("ns,na,N,mode,given,search", [
+    (256, 3, 40, "same_step", False, "two_level"), (256, 3, 40, "next_step", True, "one_level"),
+    (1000, 2, 12, "same_step", True, "auto"), (1024, 2, 10, "next_step", False, "auto"), (520, 2, 9, "same_step", False, "two_level")])
+def test_two_level_search_equals_generic_kernel(ns, na, N, mode, given, search):
+    """Large rows: pivots + one 32-entry block (incl. rows whose last block is partial) vs the generic kernel."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    tasks = [synth_task(ns, na, 900 + t) for t in range(3)]
+    for t in tasks:
+        t["max_steps"] = 45
+    K = 400
+    acts = torch.randint(0, na, (K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(ns)).cuda() if given else None
+    outs = []
+    for generic in (False, True):
+        env = AnyMDPVecEnv(N, seed=41, autoreset=mode, search=search)
+        env.set_task(tasks)
+        env.engine.force_generic(generic)
+        env.reset()
+        tr = env.rollout(K, actions=acts, record=("obs", "action", "reward", "done"))
+        env.check()
+        outs.append((tr, env.engine.get_state(), env.episode_stats(), env.engine.debug_counters()))
+    (a, sa, ea, ca), (b, sb, eb, cb) = outs
+    for key in ("obs", "action", "done", "reward"):
+        assert torch.equal(a[key], b[key]), key
+    for key in ("state", "steps", "flags", "ep_return"):
+        assert torch.equal(sa[key], sb[key]), key
+    assert ea == eb and ea["episodes"] > 0
+    assert ca["exact_fallbacks"] > 0            # n/65536 of the ticks are undecided on the filter

@@ -31,6 +31,7 @@ struct Tables {
     const double*  cdf;       // [T][n_pad][na][n_pad] normalised CDF rows, pad = 1.0
     const float2*  payload;   // [T][n_pad][na][n_pad] (reward, reward_noise) fp32
     const uint16_t* sketch;   // [T][n_pad][na][n_pad] min(65535, floor(cdf * 2^16)): 2-byte filter in front of cdf
+    const uint16_t* pivot;    // [T][n_pad][na][32] sketch value of the last entry of every 32-entry block (pad 65535); n_pad in [256, 1024]
     const int32_t* sinfo;     // [T][n_pad]  state_mapping | (is_terminal << 31)
     const double*  s0_cdf;    // [T][s0_pad] pad = 2.0
     const int32_t* s0_idx;    // [T][s0_pad]
@@ -420,9 +421,13 @@ __device__ __forceinline__ float2 ldg_stream_f32x2(const float2* p) {
     return v;
 }
 
-template <int G, int C, bool GIVEN, bool NEXT>
+// P2 (two-level search, large rows): level 1 = one 64-byte row of 32 pivots (the filter value of the last entry of every
+// 32-entry block), level 2 = the 64-byte filter block the pivots select; G is 8 (8 lanes x 8 bytes per level).  Two
+// small dependent reads per transition instead of streaming a 2-8 KB row.
+template <int G, int C, bool GIVEN, bool NEXT, bool P2>
 __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
                                                         const int32_t* __restrict__ actions, const amdp_traj J) {
+    static_assert(!P2 || (G == 8 && C == 1), "two-level search uses 8 lanes and one pivot chunk");
     constexpr int CR = C > 0 ? C : 1;
     constexpr int EPB = 128 / G;                                  // envs per block
     constexpr bool MAYSKIP = GIVEN || NEXT;                       // a tick may not step (bad action / pending reset)
@@ -441,10 +446,12 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
     const long long tsz = (long long)n_pad * na * n_pad;
     const double* __restrict__ cdf_lane = T.cdf + t * tsz + lane * 4;        // float64 rows: exact fallback only
     const uint16_t* __restrict__ sk_lane = T.sketch + t * tsz + lane * 4;    // 16-bit filter rows: the common case
+    const uint16_t* __restrict__ pv_lane = P2 ? T.pivot + t * ((long long)n_pad * na * 32) + lane * 4 : nullptr;
     const float2* __restrict__ pay_t = T.payload + t * tsz;
     const int32_t* __restrict__ sinfo_t = T.sinfo + t * n_pad;
     // keep these in registers (ptxas otherwise re-derives them from t / %tid every tick)
     asm volatile("" : "+l"(sk_lane));
+    if (P2) asm volatile("" : "+l"(pv_lane));
     asm volatile("" : "+l"(pay_t));
     asm volatile("" : "+l"(sinfo_t));
     asm volatile("" : "+r"(lane));
@@ -541,17 +548,19 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
     bool pend = NEXT && (flags & FLAG_PENDING);
     bool valid = !pend && (!GIVEN || (unsigned)a < (unsigned)na);
     if (GIVEN && !pend && !valid) fault |= AMDP_FAULT_BAD_ACTION;                              // :97
-    unsigned rowi = (unsigned)(s * na + (valid ? a : 0)) * (unsigned)n_pad;
-    auto issue_row = [&](uint2* dst, unsigned ri, bool on) {      // anymdp_env.py:99 (the row of the transition table)
-        if (C > 0) {
+    unsigned sa = (unsigned)(s * na + (valid ? a : 0));           // row index (s, a) inside the task
+    auto issue_row = [&](uint2* dst, unsigned sa_, bool on) {     // anymdp_env.py:99 (the row of the transition table)
+        if (P2) {
+            dst[0] = on ? ldg_stream_u32x2(pv_lane + sa_ * 32u) : make_uint2(0xffffffffu, 0xffffffffu);
+        } else if (C > 0) {
 #pragma unroll
             for (int c = 0; c < CR; ++c) {
-                if (on) dst[c] = ldg_stream_u32x2(sk_lane + ri + c * (G * 4));
+                if (on) dst[c] = ldg_stream_u32x2(sk_lane + sa_ * (unsigned)n_pad + c * (G * 4));
                 else dst[c] = make_uint2(0xffffffffu, 0xffffffffu);
             }
         }
     };
-    issue_row(q, rowi, valid);
+    issue_row(q, sa, valid);
 
     // deferred reward of the previous tick: payload (0, 0) when that tick did not step
     float2 pay_p = make_float2(0.f, 0.f);
@@ -581,64 +590,90 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
         const float nz = __shfl_sync(gmask, b_z, j, G);
         const int na_ = __shfl_sync(gmask, b_act, j, G);
         const bool na_ok = !GIVEN || (unsigned)na_ < (unsigned)na;
-        const unsigned na_row = (unsigned)(na_ok ? na_ : 0) * (unsigned)n_pad;
+        const unsigned na_col = (unsigned)(na_ok ? na_ : 0);
 
         int nxt = s;
         bool do_reset = NEXT && pend;                              // next_step mode: this tick only performs the reset
+        const unsigned rowi = sa * (unsigned)n_pad;
         if (valid) {
             // (C) next state = #{cdf <= u}  (numpy choice: searchsorted(cdf, u, 'right')), decided on the 16-bit filter:
             //     q < v  =>  cdf < u;  q > v  =>  cdf > u;  only q == v is undecided.
-            nxt = 0;
-            unsigned amb = 0;
             const unsigned vhi = v << 16, v2 = vhi | v;
-            auto chunk = [&](const uint2 w) {
+            auto chunk = [&](const uint2 w, int& cnt, unsigned& amb) {
                 // entries: lo16(w.x), hi16(w.x), lo16(w.y), hi16(w.y); (w << 16) < (v << 16) <=> lo16 < v, w < (v << 16) <=> hi16 < v
                 const unsigned b0 = __ballot_sync(gmask, (w.x << 16) < vhi);
                 const unsigned b1 = __ballot_sync(gmask, w.x < vhi);
                 const unsigned b2 = __ballot_sync(gmask, (w.y << 16) < vhi);
                 const unsigned b3 = __ballot_sync(gmask, w.y < vhi);
-                if (G == 32) nxt += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+                if (G == 32) cnt += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
                 else {
                     const unsigned m = (1u << G) - 1u;
-                    nxt += __popc((b0 >> gshift) & m) + __popc((b1 >> gshift) & m) + __popc((b2 >> gshift) & m) + __popc((b3 >> gshift) & m);
+                    cnt += __popc((b0 >> gshift) & m) + __popc((b1 >> gshift) & m) + __popc((b2 >> gshift) & m) + __popc((b3 >> gshift) & m);
                 }
                 // any 16-bit field equal to v?  (x has a zero halfword  <=>  (x - 0x00010001) & ~x & 0x80008000 != 0)
                 const unsigned x0 = w.x ^ v2, x1 = w.y ^ v2;
                 amb |= ((x0 - 0x00010001u) & ~x0 & 0x80008000u) | ((x1 - 0x00010001u) & ~x1 & 0x80008000u);
             };
-            if (C > 0) {
+            nxt = 0;
+            unsigned amb = 0;
+            int blk = 0;                                           // P2: the 32-entry block that holds the boundary
+            if (P2) {
+                unsigned amb1 = 0;
+                chunk(q[0], blk, amb1);                            // blocks whose last entry is < v lie entirely below u
+                const unsigned lo = (unsigned)blk * 32u;
+                const bool in = lo + lane * 4 < (unsigned)n_pad;   // the last block of a row may be partial
+                chunk(in ? ldg_stream_u32x2(sk_lane + rowi + lo) : make_uint2(0xffffffffu, 0xffffffffu), nxt, amb);
+                nxt += (int)lo;
+            } else if (C > 0) {
 #pragma unroll
-                for (int c = 0; c < CR; ++c) chunk(q[c]);
+                for (int c = 0; c < CR; ++c) chunk(q[c], nxt, amb);
             } else {
                 for (int i = 0; i < n_pad; i += G * 4) {
                     // lanes past the end of the row contribute "not less"
                     const bool in = (i + lane * 4 < n_pad);
-                    chunk(in ? ldg_stream_u32x2(sk_lane + rowi + i) : make_uint2(0xffffffffu, 0xffffffffu));
+                    chunk(in ? ldg_stream_u32x2(sk_lane + rowi + i) : make_uint2(0xffffffffu, 0xffffffffu), nxt, amb);
                 }
             }
             if (__any_sync(gmask, amb != 0)) {
-                // undecided (u and some cdf entry share a 2^-16 cell, ~n/65536 of the ticks): exact float64 row
+                // undecided (u and some cdf entry share a 2^-16 cell, ~n/65536 of the ticks): exact float64 entries
                 const uint4 w0 = philox_block(env_id, 0u, tick0 + (unsigned long long)k, E.key);
                 const double u = u53(w0.x, w0.y);
-                int cnt = 0;
-                for (int i = 0; i < n_pad; i += G * 4) {
-                    if (i + lane * 4 < n_pad) {
-                        const double2 x = ldg_stream_f64x2(cdf_lane + rowi + i);
-                        const double2 y = ldg_stream_f64x2(cdf_lane + rowi + i + 2);
-                        cnt += (x.x <= u) + (x.y <= u) + (y.x <= u) + (y.y <= u);
-                    }
-                }
+                if (P2) {
+                    // entries before block `blk` are below u; count block by block while a block is entirely <= u
+                    nxt = blk * 32;
+                    for (int base = blk * 32; base < n_pad; base += 32) {
+                        int cnt = 0;
+                        if (base + lane * 4 < n_pad) {
+                            const double2 x = ldg_stream_f64x2(cdf_lane + rowi + base);
+                            const double2 y = ldg_stream_f64x2(cdf_lane + rowi + base + 2);
+                            cnt = (x.x <= u) + (x.y <= u) + (y.x <= u) + (y.y <= u);
+                        }
 #pragma unroll
-                for (int o = G >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
-                nxt = cnt;
+                        for (int o = G >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
+                        nxt += cnt;
+                        if (cnt < 32) break;
+                    }
+                } else {
+                    int cnt = 0;
+                    for (int i = 0; i < n_pad; i += G * 4) {
+                        if (i + lane * 4 < n_pad) {
+                            const double2 x = ldg_stream_f64x2(cdf_lane + rowi + i);
+                            const double2 y = ldg_stream_f64x2(cdf_lane + rowi + i + 2);
+                            cnt += (x.x <= u) + (x.y <= u) + (y.x <= u) + (y.y <= u);
+                        }
+                    }
+#pragma unroll
+                    for (int o = G >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
+                    nxt = cnt;
+                }
                 n_fallback += 1;
             }
         }
         // (A) SPECULATIVE row load of the next tick, assuming this tick neither terminates nor truncates: the dependent
         //     chain per tick is  row (HBM) -> compare/ballot -> next row address.  Everything below runs in its shadow.
-        unsigned nrowi = (unsigned)(nxt * na) * (unsigned)n_pad + na_row;
+        unsigned nsa = (unsigned)(nxt * na) + na_col;
         uint2 nq[CR];
-        if (!do_reset) issue_row(nq, nrowi, na_ok);
+        if (!do_reset) issue_row(nq, nsa, na_ok);
 
         // (B) settle the previous tick (its payload load was issued one tick ago, after this tick's row load); once per
         //     G ticks write the finished batch of records, lane-parallel
@@ -673,8 +708,8 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
             flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
             obs_out = __ldg(sinfo_t + s) & 0x7fffffff;
             // the speculation was wrong (or not made): the next tick starts from the reset state
-            nrowi = (unsigned)(s * na) * (unsigned)n_pad + na_row;
-            issue_row(nq, nrowi, na_ok);
+            nsa = (unsigned)(s * na) + na_col;
+            issue_row(nq, nsa, na_ok);
         }
         if (lane == j) {
             st_obs = obs_out;
@@ -686,7 +721,7 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
             refill(k + 1);
         }
         // rotate to the next tick
-        v = nv; z = nz; a = na_; rowi = nrowi;
+        v = nv; z = nz; a = na_; sa = nsa;
 #pragma unroll
         for (int c = 0; c < CR; ++c) q[c] = nq[c];
         pend = NEXT && (flags & FLAG_PENDING);
@@ -740,7 +775,7 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
                              const double* __restrict__ reward, const double* __restrict__ noise,
                              const int32_t* __restrict__ n_real, const uint8_t* __restrict__ is_terminal,
                              double* __restrict__ cdf, float2* __restrict__ payload, uint16_t* __restrict__ sketch,
-                             int32_t* __restrict__ status) {
+                             uint16_t* __restrict__ pivot, int32_t* __restrict__ status) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long rows = cnt * n_pad * na;
     if (r >= rows) return;
@@ -751,7 +786,11 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
     double* c = cdf + r * n_pad;
     float2* pl = payload + r * n_pad;
     for (int i = 0; i < n_pad; ++i) pl[i] = make_float2((float)reward[r * n_pad + i], (float)noise[r * n_pad + i]);
-    if (s >= n) { for (int i = 0; i < n_pad; ++i) { c[i] = 1.0; sketch[r * n_pad + i] = 65535; } return; }
+    if (s >= n) {
+        for (int i = 0; i < n_pad; ++i) { c[i] = 1.0; sketch[r * n_pad + i] = 65535; }
+        if (pivot) for (int b = 0; b < 32; ++b) pivot[r * 32 + b] = 65535;
+        return;
+    }
     double acc = 0.0, ksum = 0.0, kc = 0.0;
     bool neg = false;
     for (int i = 0; i < n; ++i) {
@@ -788,6 +827,12 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
     // q == v => undecided (the fast kernel then falls back to the float64 row) — so the filter never changes a result.
     uint16_t* sk = sketch + r * n_pad;
     for (int i = 0; i < n_pad; ++i) sk[i] = (uint16_t)fmin(65535.0, floor(c[i] * 65536.0));
+    if (pivot) {
+        for (int b = 0; b < 32; ++b) {
+            const int last = min(32 * b + 31, n_pad - 1);
+            pivot[r * 32 + b] = (32 * b < n_pad) ? sk[last] : (uint16_t)65535;
+        }
+    }
 }
 
 // per-task small tables; one thread per task
@@ -953,7 +998,7 @@ struct amdp {
     Tables T;
     EnvArrays E;
     // owned device memory
-    double* cdf; float2* payload; uint16_t* sketch; int32_t* sinfo; double* s0_cdf; int32_t* s0_idx; double* obs_cdf;
+    double* cdf; float2* payload; uint16_t* sketch; uint16_t* pivot; int32_t* sinfo; double* s0_cdf; int32_t* s0_idx; double* obs_cdf;
     int32_t* max_ceil; uint8_t* tflags; double* raw_t; int32_t* n_real;
     int32_t* env_task;
     Stat6* stat_part;
@@ -966,6 +1011,7 @@ struct amdp {
     int64_t launches;
     bool uploaded, assigned;
     bool force_generic;    // debug: route rollouts through the generic kernel
+    bool two_level;        // the fast kernel searches pivots + one 32-entry block instead of streaming the whole row
     char err[512];
     // rollout_host staging
     int32_t* st_act[2]; int32_t* st_obs[2]; float* st_rew[2]; uint8_t* st_done[2]; unsigned long long* st_rec[2];
@@ -1033,7 +1079,7 @@ static int pick_group(int n_pad) {
 extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->cdf, h->payload, h->sketch, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
+    void* ptrs[] = {h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
@@ -1072,7 +1118,9 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     int rc;
     if ((rc = dalloc(h, &h->cdf, rows * c.n_pad))) return rc;
     if ((rc = dalloc(h, &h->payload, rows * c.n_pad))) return rc;
-    if ((rc = dalloc(h, &h->sketch, rows * c.n_pad))) return rc;
+    if ((rc = dalloc(h, &h->sketch, rows * c.n_pad + 64))) return rc;
+    h->two_level = (c.n_pad >= 256 && c.n_pad <= 1024) && !(c.reserved0 & 2) && ((c.reserved0 & 4) || c.n_pad >= 512 || c.n_envs >= 16384);
+    if (h->two_level) { if ((rc = dalloc(h, &h->pivot, rows * 32))) return rc; }
     if (c.reserved0 & 1) { if ((rc = dalloc(h, &h->raw_t, rows * c.n_pad))) return rc; }
     if ((rc = dalloc(h, &h->sinfo, (size_t)c.n_tasks * c.n_pad))) return rc;
     if ((rc = dalloc(h, &h->s0_cdf, (size_t)c.n_tasks * c.s0_pad))) return rc;
@@ -1103,7 +1151,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     E.task = h->env_task; E.faults = h->faults; E.counters = h->counters; E.n_envs = c.n_envs; E.env_id_base = c.env_id_base;
     E.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
     Tables& T = h->T;
-    T.cdf = h->cdf; T.payload = h->payload; T.sketch = h->sketch; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
+    T.cdf = h->cdf; T.payload = h->payload; T.sketch = h->sketch; T.pivot = h->pivot; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
     T.obs_cdf = h->obs_cdf; T.max_ceil = h->max_ceil; T.tflags = h->tflags; T.raw_t = h->raw_t; T.n_real = h->n_real;
     T.n_pad = c.n_pad; T.na = c.na; T.no_pad = c.no_pad; T.d_o = c.n_obs_tok; T.d_a = c.n_act_tok; T.s0_pad = c.s0_pad;
     T.task_type = c.task_type; T.autoreset = c.autoreset;
@@ -1129,7 +1177,8 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
     const long long rows = (long long)cnt * c.n_pad * c.na;
     k_build_rows<<<nblk(rows, 128), 128, 0, st>>>(cnt, c.n_pad, c.na, transition, reward, reward_noise, n_real, is_terminal,
                                                   h->cdf + t0 * per_task, h->payload + t0 * per_task,
-                                                  h->sketch + t0 * per_task, status_out);
+                                                  h->sketch + t0 * per_task,
+                                                  h->pivot ? h->pivot + (size_t)t0 * c.n_pad * c.na * 32 : nullptr, status_out);
     k_build_small<<<nblk(cnt, 128), 128, 0, st>>>(cnt, c.n_pad, c.s0_pad, state_mapping, n_real, is_terminal, s0_idx, s0_prob,
                                                   n_s0, max_steps, ns, h->sinfo + t0 * c.n_pad, h->s0_cdf + t0 * c.s0_pad,
                                                   h->s0_idx + t0 * c.s0_pad, h->max_ceil + t0, h->tflags + t0,
@@ -1205,31 +1254,30 @@ static void launch_rollout(amdp* h, int K, const int32_t* actions, const amdp_tr
     k_rollout<G><<<nblk(threads, 256), 256, 0, st>>>(h->T, h->E, h->tick, K, h->n_slots, actions, J, u);
 }
 
-template <int G, int C>
+template <int G, int C, bool P2>
 static void launch_fast_gc(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
     const unsigned int blocks = nblk(h->cfg.n_envs * G, 128);
     const bool next = h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP;
     if (actions) {
-        if (next) k_rollout_mdp<G, C, true, true><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
-        else k_rollout_mdp<G, C, true, false><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
+        if (next) k_rollout_mdp<G, C, true, true, P2><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
+        else k_rollout_mdp<G, C, true, false, P2><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
     } else {
-        if (next) k_rollout_mdp<G, C, false, true><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
-        else k_rollout_mdp<G, C, false, false><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
+        if (next) k_rollout_mdp<G, C, false, true, P2><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
+        else k_rollout_mdp<G, C, false, false, P2><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
     }
 }
 
 // lanes per env and register-resident chunks per lane for the fast kernel: n_pad == 4 * G * C
 static void launch_rollout_fast(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
     const int n_pad = h->cfg.n_pad;
+    if (h->two_level) { launch_fast_gc<8, 1, true>(h, K, actions, J, st); return; }
     const int G = h->G;
     const int C = (n_pad == 4 * G) ? 1 : (n_pad == 8 * G ? 2 : 0);
     switch (G) {
-        case 1: if (C == 1) launch_fast_gc<1, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<1, 2>(h, K, actions, J, st); else launch_fast_gc<1, 0>(h, K, actions, J, st); break;
-        case 2: if (C == 1) launch_fast_gc<2, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<2, 2>(h, K, actions, J, st); else launch_fast_gc<2, 0>(h, K, actions, J, st); break;
-        case 4: if (C == 1) launch_fast_gc<4, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<4, 2>(h, K, actions, J, st); else launch_fast_gc<4, 0>(h, K, actions, J, st); break;
-        case 8: if (C == 1) launch_fast_gc<8, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<8, 2>(h, K, actions, J, st); else launch_fast_gc<8, 0>(h, K, actions, J, st); break;
-        case 16: if (C == 1) launch_fast_gc<16, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<16, 2>(h, K, actions, J, st); else launch_fast_gc<16, 0>(h, K, actions, J, st); break;
-        default: if (C == 1) launch_fast_gc<32, 1>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<32, 2>(h, K, actions, J, st); else launch_fast_gc<32, 0>(h, K, actions, J, st); break;
+#define FAST(g) case g: if (C == 1) launch_fast_gc<g, 1, false>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<g, 2, false>(h, K, actions, J, st); else launch_fast_gc<g, 0, false>(h, K, actions, J, st); break;
+        FAST(1) FAST(2) FAST(4) FAST(8) FAST(16)
+        default: if (C == 1) launch_fast_gc<32, 1, false>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<32, 2, false>(h, K, actions, J, st); else launch_fast_gc<32, 0, false>(h, K, actions, J, st); break;
+#undef FAST
     }
 }
 

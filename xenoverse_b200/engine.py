@@ -117,7 +117,9 @@ _STATUS_MSG = {
 
 class Engine:
     def __init__(self, num_envs, num_tasks, geo, device=0, seed=0, autoreset="same_step", env_id_base=0,
-                 keep_transition=False):
+                 keep_transition=False, search="auto"):
+        """search: "auto" | "one_level" | "two_level" — how the fast rollout kernel searches a CDF row (two_level =
+        pivots + one 32-entry block, for 256 <= n_pad <= 1024; auto picks it for n_pad >= 512 or >= 16384 envs)."""
         if not torch.cuda.is_available():
             raise AMDPError("xenoverse_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
@@ -128,7 +130,8 @@ class Engine:
         cfg = _lib.Config(device=self.device.index, task_type=_lib.TASK_TYPES[geo["task_type"]],
                           autoreset=_lib.AUTORESET[autoreset], na=geo["na"], n_pad=geo["n_pad"], no_pad=geo["no_pad"],
                           n_obs_tok=geo["do"], n_act_tok=geo["da"], s0_pad=geo["s0_pad"],
-                          reserved0=1 if keep_transition else 0, n_envs=self.N, n_tasks=self.T,
+                          reserved0=(1 if keep_transition else 0) | {"auto": 0, "one_level": 2, "two_level": 4}[search],
+                          n_envs=self.N, n_tasks=self.T,
                           seed=int(seed) & (2 ** 64 - 1), env_id_base=int(env_id_base))
         h = ctypes.c_void_p()
         rc = lib.amdp_create(ctypes.byref(h), ctypes.byref(cfg))

@@ -37,12 +37,13 @@ class AnyMDPVecEnv:
     env_id_base global id of local env 0 when envs are sharded over several GPUs
     """
 
-    def __init__(self, num_envs, device=0, seed=0, autoreset="same_step", env_id_base=0, keep_transition=False):
+    def __init__(self, num_envs, device=0, seed=0, autoreset="same_step", env_id_base=0, keep_transition=False,
+                 search="auto"):
         if autoreset not in _lib.AUTORESET:
             raise ValueError(f"autoreset must be one of {sorted(_lib.AUTORESET)}")
         self.num_envs = int(num_envs)
         self.device_arg, self.seed, self.autoreset = device, int(seed), autoreset
-        self.env_id_base, self.keep_transition = int(env_id_base), keep_transition
+        self.env_id_base, self.keep_transition, self.search = int(env_id_base), keep_transition, search
         self.engine = None
         self.task_set = False
 
@@ -63,7 +64,7 @@ class AnyMDPVecEnv:
             self.engine.close()
         self.engine = Engine(self.num_envs, n_tasks, geo, device=self.device_arg, seed=self.seed,
                              autoreset=self.autoreset, env_id_base=self.env_id_base,
-                             keep_transition=self.keep_transition)
+                             keep_transition=self.keep_transition, search=self.search)
         if packed is not None:
             for t0, batch in batches:
                 st = self.engine.upload_packed(t0, batch)
