@@ -185,7 +185,7 @@ def run_b200(args, name, envs, tasks, ns, na, no):
     if name == "cfg4" and world > 1:
         tasks = max(1, tasks // world)                # cfg4 shards its 256 tasks over the ranks
     geo = synth_geometry(ns, na, no)
-    env = AnyMDPVecEnv(envs, device=local, seed=0, env_id_base=rank * envs)
+    env = AnyMDPVecEnv(envs, device=local, seed=0, env_id_base=rank * envs, search=args.search)
     per_task = 3 * 8 * geo["n_pad"] * na * geo["n_pad"]
     chunk = max(1, min(tasks, (768 << 20) // per_task))
 
@@ -340,6 +340,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-steps-per-worker", type=int, default=20000)
+    ap.add_argument("--search", default="auto", choices=["auto", "one_level", "two_level", "thread", "warp"],
+                    help="row-search / kernel selection of the engine (see Engine)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     envs, tasks, ns, na, no = WORKLOADS[args.workload]

@@ -101,7 +101,8 @@ typedef struct amdp_config {
     int32_t  n_obs_tok;     /* `do` (1 unless MTPOMDP) */
     int32_t  n_act_tok;     /* `da` (1 unless MTPOMDP) */
     int32_t  s0_pad;        /* max len(s_0) over tasks */
-    int32_t  reserved0;     /* flags: 1 keep a copy of `transition` (amdp_gather_transition_gt); 2 / 4 force the one- / two-level
+    int32_t  reserved0;     /* flags: 1 keep a copy of `transition` (amdp_gather_transition_gt); 8 / 16 force / forbid the thread-per-env rollout
+                               kernel (default: used from 16384 envs); 2 / 4 force the one- / two-level
                                row search of the fast rollout kernel (default: chosen from n_pad and n_envs) */
     int64_t  n_envs;        /* envs owned by this handle (this GPU's shard) */
     int64_t  n_tasks;       /* tasks resident on this handle */
@@ -245,6 +246,11 @@ int amdp_debug_cdf_row(amdp_t* h, int64_t task, int32_t s, int32_t a, double* ou
 /* Debug/verification (synchronises): out4 HOST uint64[4]; [0] = ticks on which the fast kernel's 16-bit CDF filter was
  * undecided and the exact float64 row was read instead. */
 int amdp_debug_counters(amdp_t* h, uint64_t* out4);
+
+/* Debug/verification: make the thread-per-env rollout kernel ignore the low `bits` (0..30) bits of its 31-bit CDF codes,
+ * so that its float64 fallback (code31(cdf[j]) == code31(u), ~n * 2^-31 of the ticks in production) runs often enough
+ * to be tested.  Results never depend on this setting. */
+int amdp_debug_tp_coarse_bits(amdp_t* h, int bits);
 
 /* Debug/verification: route amdp_rollout through the generic per-tick kernel instead of the fast MDP kernel. */
 int amdp_debug_force_generic(amdp_t* h, int on);

@@ -438,3 +438,91 @@ def test_two_level_search_equals_generic_kernel(ns, na, N, mode, given, search):
         assert torch.equal(sa[key], sb[key]), key
     assert ea == eb and ea["episodes"] > 0
     assert ca["exact_fallbacks"] > 0            # n/65536 of the ticks are undecided on the filter
+
+
+@pytest.mark.parametrize("ns,na,N,mode,given,coarse", [
+    (8, 3, 70, "same_step", False, 0), (16, 5, 300, "next_step", True, 0), (30, 5, 200, "same_step", True, 0),
+    (64, 8, 130, "same_step", False, 0), (128, 5, 257, "same_step", False, 0), (128, 5, 100, "next_step", True, 18),
+    (200, 3, 60, "same_step", True, 0), (256, 3, 40, "next_step", False, 16), (520, 2, 33, "same_step", False, 0),
+    (1000, 2, 12, "same_step", True, 14), (1024, 2, 40, "next_step", False, 0), (32, 5, 500, "same_step", False, 20)])
+def test_thread_per_env_kernel_equals_generic_kernel(ns, na, N, mode, given, coarse):
+    """k_rollout_tp (one thread per env; pivots + one block of 31-bit codes, is_terminal in bit 0) vs the generic per-tick
+    kernel: identical records, env state and statistics.  `coarse` > 0 drops low code bits so that the float64
+    fallback (code31(cdf) == code31(u)) runs often; with 0 the production path is compared."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    tasks = [synth_task(ns, na, 1200 + t) for t in range(5)]
+    if ns >= 200:
+        for t in tasks:
+            t["max_steps"] = 45
+    K = 300
+    acts = None
+    if given:
+        acts = torch.randint(0, na, (K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(ns + 1)).cuda()
+    outs = []
+    for generic in (False, True):
+        env = AnyMDPVecEnv(N, seed=43, autoreset=mode, search="thread")
+        env.set_task(tasks)
+        env.engine.force_generic(generic)
+        env.engine.tp_coarse_bits(coarse)
+        env.reset()
+        tr = env.rollout(K, actions=acts, record=("obs", "action", "reward", "reward_gt", "done"))
+        tr2 = env.rollout(7, actions=None if acts is None else acts[:7], record=("packed",))     # state carried across launches
+        env.check()
+        outs.append((tr, tr2, env.engine.get_state(), env.episode_stats(), env.engine.debug_counters()))
+    (a, a2, sa, ea, ca), (b, b2, sb, eb, cb) = outs
+    for key in ("obs", "action", "done", "reward", "reward_gt"):
+        assert torch.equal(a[key], b[key]), key
+    assert torch.equal(a2["packed"], b2["packed"])
+    for key in ("state", "steps", "flags", "ep_return"):
+        assert torch.equal(sa[key], sb[key]), key
+    assert ea == eb and ea["episodes"] > 0
+    if coarse:
+        assert ca["exact_fallbacks"] > 20, ca
+    assert cb["exact_fallbacks"] == 0
+
+
+def test_thread_per_env_kernel_faults_and_bad_actions():
+    """Same fault behaviour as the warp-per-env kernel: virgin envs and out-of-range actions are reported, not stepped."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    outs = []
+    for search in ("thread", "warp"):
+        env = AnyMDPVecEnv(64, seed=5, search=search)
+        env.set_task([synth_task(16, 5, 1), synth_task(16, 5, 2)])
+        tr0 = env.rollout(4)
+        with pytest.raises(Exception, match="reset"):
+            env.check()
+        env.reset()
+        bad = torch.randint(0, 5, (6, 64), dtype=torch.int32, generator=torch.Generator().manual_seed(3))
+        bad[2, 3] = 9
+        bad[4, 60] = -1
+        tr = env.rollout(6, actions=bad.cuda())
+        with pytest.raises(AssertionError):
+            env.check()
+        outs.append((tr0, tr, env.engine.get_state()))
+    for x, y in zip(outs[0][:2], outs[1][:2]):
+        for key in ("obs", "action", "done", "reward"):
+            assert torch.equal(x[key], y[key]), key
+    for key in ("state", "steps", "flags", "ep_return"):
+        assert torch.equal(outs[0][2][key], outs[1][2][key]), key
+
+
+def test_thread_per_env_kernel_matches_oracle_replay():
+    """Self-RNG trajectories of the thread-per-env kernel replayed through the CPU oracle with the dumped draws."""
+    from oracle import anymdp_oracle as ao
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    tasks = [synth_task(24, 4, 1300 + t) for t in range(6)]
+    N, K = 96, 80
+    env = AnyMDPVecEnv(N, seed=77, search="thread")
+    env.set_task(tasks)
+    obs0, _ = env.reset()
+    tr = env.rollout(K, record=("obs", "action", "reward", "done"))
+    draws = env.engine.dump_draws(0, K + 1).cpu().numpy()
+    orc = ao.OracleVecEnv(tasks, env_task=numpy.arange(N) % len(tasks))
+    assert numpy.array_equal(obs0.cpu().numpy(), orc.reset(draws[0])[:, 0])
+    for k in range(K):
+        o = orc.step(None, draws[k + 1])
+        assert numpy.array_equal(tr["obs"][k].cpu().numpy(), o["obs"]), k
+        d = tr["done"][k].cpu().numpy()
+        assert numpy.array_equal((d & 1).astype(bool), o["terminated"]) and numpy.array_equal((d >> 1).astype(bool), o["truncated"])
+        assert numpy.allclose(tr["reward"][k].cpu().numpy(), o["reward"], rtol=1e-6, atol=1e-6)
+    assert env.episode_stats()["episodes"] == orc.stats()["episodes"]

@@ -4,7 +4,12 @@ usage: tools_ncu_summary.py <report.ncu-rep> [ticks_per_launch*warps]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
 per = float(sys.argv[2]) if len(sys.argv) > 2 else None
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def page(name):
+    # either a .ncu-rep (needs ncu) or the prefix of <prefix>_raw.csv / <prefix>_source.csv exported on the GPU box
+    if rep.endswith(".ncu-rep"):
+        return subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    return open(f"{rep}_{name}.csv").read()
+raw = page("raw")
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 keys = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
@@ -18,7 +23,7 @@ for i, h in enumerate(hdr):
 for i, h in enumerate(hdr):
     if h.startswith('smsp__average_warps_issue_stalled') and h.endswith('per_issue_active.ratio') and float(vals[i] or 0) > 0.15:
         print(f"{h:90s} {vals[i]}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = page("source")
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
 tot = sum(int(r[ix['Instructions Executed']]) for r in rows[2:])

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libamdp_b200.so")
+# AMDP_B200_LIB selects another build of the SAME library (kernel A/B experiments); there is still no non-CUDA path
+LIB_PATH = os.environ.get("AMDP_B200_LIB") or os.path.join(_HERE, "libamdp_b200.so")
 
 OK, EINVAL, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4
 MDP, POMDP, MTPOMDP = 0, 1, 2
@@ -63,6 +64,7 @@ _SIGNATURES = {
     "amdp_poll_errors": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32), _P]),
     "amdp_debug_cdf_row": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P]),
     "amdp_debug_force_generic": (ctypes.c_int, [_P, ctypes.c_int]),
+    "amdp_debug_tp_coarse_bits": (ctypes.c_int, [_P, ctypes.c_int]),
     "amdp_debug_counters": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),
     "amdp_launch_count": (ctypes.c_int64, [_P]),
     "amdp_rollout_host": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P]),

@@ -13,8 +13,10 @@
 // transition instead of log2(n) dependent ones.  Everything else a step needs is either in the
 // per-task small tables (L1/L2 resident) or in the fp32 payload entry addressed by (s, a, s').
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <new>
@@ -40,6 +42,10 @@ struct Tables {
     const uint8_t* tflags;    // [T] bit0: ns < 2 (always terminated, anymdp_env.py:108)
     const double*  raw_t;     // [T][n_pad][na][n_pad] raw transition (only if keep_transition) or null
     const int32_t* n_real;    // [T]
+    // thread-per-env search tables (k_rollout_tp): two levels, both exact up to an equality that falls back to `cdf`
+    const uint32_t* c32;      // [T][n_pad][na][c32_stride] (floor(cdf * 2^31) << 1) | is_terminal[j]; pad = 0xfffffffe
+    const uint16_t* pv15;     // [T][n_pad][na][pv_stride] code15 of the LAST entry of every tp_B-entry block; pad = 0x7bff
+    int c32_stride, pv_stride, tp_B;
     int n_pad, na, no_pad, d_o, d_a, s0_pad, task_type, autoreset;
 };
 
@@ -93,6 +99,22 @@ __device__ __forceinline__ float box_muller(uint32_t w0, uint32_t w1) {
     const float u1 = (__uint2float_rn(w0 >> 8) + 0.5f) * 5.9604644775390625e-08f;
     const float u2 = (__uint2float_rn(w1 >> 8) + 0.5f) * 5.9604644775390625e-08f;
     return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// Monotone integer codes of a probability x in [0, 1] (used by the thread-per-env search tables).  With the SAME function
+// applied to a CDF entry c and to the uniform u:  code(c) < code(u) => c < u,  code(c) > code(u) => c > u; equality is
+// undecided and is resolved on the float64 row.
+//   code31(x) = floor(x * 2^31), 1.0 -> 2^31 - 1.            For u = k * 2^-53 this is k >> 22.
+//   code15(x) = 0x0400 + ((floor(x * 2^21) * 30719) >> 21), 1.0 -> 0x7bff: the bit pattern of a positive NORMAL fp16
+//               number, so that packed fp16 compares (HSET2) order the codes.  For u this uses k >> 32.
+__host__ __device__ __forceinline__ uint32_t code31(double x) {
+    return x >= 1.0 ? 0x7fffffffu : (uint32_t)floor(x * 2147483648.0);
+}
+__device__ __forceinline__ uint32_t code15_from_m21(uint32_t m21) {      // m21 = floor(x * 2^21) < 2^21
+    return 0x0400u + __umulhi(m21 << 11, 30719u);
+}
+__device__ __forceinline__ uint32_t code15(double x) {
+    return x >= 1.0 ? 0x7bffu : code15_from_m21((uint32_t)floor(x * 2097152.0));
 }
 
 // Source of the draws of one (env, tick): injected matrix row or Philox.
@@ -744,6 +766,296 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Throughput path: ONE THREAD PER ENV (MDP, one action token, engine Philox draws, auto-reset on), for engines with
+// enough envs to fill the machine (>= 16k per GPU).  The warp-per-env kernel above keeps at most ~4k envs in flight
+// per GPU (one row per warp); here every resident thread is an env, so 60k-110k dependent chains are in flight and
+// the path is bound by DRAM sectors instead of by latency x residency.
+//   * search = two dependent, sector-sized reads per transition: the row's pivots (15-bit fp16-ordered codes of the
+//     last entry of every B-entry block; packed HSET2 compares) pick the block, the block's B 31-bit codes pick the
+//     entry.  Both levels are exact; the only undecided case is code31(cdf[j]) == code31(u) (~n * 2^-31 of the ticks),
+//     which reads the float64 row.  No 16-bit ambiguity: with 32 envs per warp a per-env fallback rate of n/65536
+//     would stall most warps at n = 1024.
+//   * is_terminal[s'] rides in bit 0 of the block entries, so the chain per tick is  pivots -> block -> next pivots;
+//     the (reward, noise) payload and the observation lookup of tick k are consumed in the shadow of tick k+1's loads.
+//   * PVW = 16-byte words of pivots per row (0: single level), BW = 16-byte words per block (B = 4 * BW entries).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream_u128(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void ldg_stream_u256(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
+// W x 16 bytes as 256-bit loads (one request per 32-byte sector; measured 10-50 % faster than pairs of 128-bit loads:
+// what bounds this kernel is the number of sector requests, and every L2 miss fetches its whole 128-byte line from DRAM
+// whatever the request size — profiles/r1_gather_microbench.txt).  AMDP_TP_LDG128 keeps the narrow form for comparison.
+template <int W>
+__device__ __forceinline__ void ldg_words(const void* p, uint4 (&dst)[W]) {
+#ifndef AMDP_TP_LDG128
+    if (W == 1) dst[0] = ldg_stream_u128(p);
+    else {
+#pragma unroll
+        for (int i = 0; i + 1 < W; i += 2) ldg_stream_u256((const char*)p + 16 * i, dst[i], dst[i + 1]);
+    }
+#else
+#pragma unroll
+    for (int i = 0; i < W; ++i) dst[i] = ldg_stream_u128((const char*)p + 16 * i);
+#endif
+}
+
+// Pivot rows are small and re-read (every visit of (s, a)); blocks and payload entries are touched once.  Loads of
+// the pivots carry an L2 evict_last policy so that the streaming block / payload / record traffic does not push them out.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+template <int W>
+__device__ __forceinline__ void ldg_words_keep(const void* p, uint4 (&dst)[W], uint64_t pol) {
+#ifdef AMDP_TP_NO_L2_HINT
+    ldg_words<W>(p, dst);
+#else
+    if (W == 1) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=r"(dst[0].x), "=r"(dst[0].y), "=r"(dst[0].z), "=r"(dst[0].w) : "l"(p), "l"(pol));
+    } else {
+#pragma unroll
+        for (int i = 0; i + 1 < W; i += 2) {
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                         : "=r"(dst[i].x), "=r"(dst[i].y), "=r"(dst[i].z), "=r"(dst[i].w), "=r"(dst[i + 1].x), "=r"(dst[i + 1].y),
+                           "=r"(dst[i + 1].z), "=r"(dst[i + 1].w) : "l"((const char*)p + 16 * i), "l"(pol));
+        }
+    }
+#endif
+}
+
+__device__ __forceinline__ int h2_count_lt(unsigned w, unsigned v2, int acc) {     // acc - #{halfwords of w (as fp16) < v}
+    const __half2 a = *reinterpret_cast<const __half2*>(&w), b = *reinterpret_cast<const __half2*>(&v2);
+    return __dp2a_lo((int)__hlt2_mask(a, b), 0x0101, acc);
+}
+
+#define TP_S0 4
+template <int PVW, int BW>
+__global__ void __launch_bounds__(128, 5) k_rollout_tp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
+                                                       const int32_t* __restrict__ actions, const amdp_traj J, int given, int next, unsigned cmask) {
+    constexpr int B = BW * 4;
+    constexpr int PW = PVW > 0 ? PVW : 1;
+    __shared__ double sh_stat[4][128];                            // closed-episode statistics: sum_ret, sum_ret_sq, min, max
+    __shared__ unsigned long long sh_cnt[2][128];                 // ep_count, sum_len
+    __shared__ double sh_s0c[TP_S0][128];                         // the env's start-state CDF and states (s0_pad <= TP_S0):
+    __shared__ int sh_s0i[TP_S0][128];                            // a reset costs no global-memory round trip
+    const int tx = threadIdx.x;
+    const long long e = (long long)blockIdx.x * 128 + tx;
+    if (e >= E.n_envs) return;
+    const int n_pad = T.n_pad, na = T.na;
+    const long long N = E.n_envs;
+    const long long t = E.task[e];
+    const unsigned long long rbase = (unsigned long long)t * n_pad * na;      // first (s, a) row of the task
+    const int32_t* __restrict__ sinfo_t = T.sinfo + t * n_pad;
+    const int max_ceil = T.max_ceil[t];
+    const bool always_term = (T.tflags[t] & 1) != 0;
+    const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
+    const int n_blocks = T.c32_stride / B;
+    const uint64_t pol_keep = l2_policy_evict_last();
+
+    int s = E.state[e], steps = E.steps[e], flags = E.flags[e];
+    double ep_ret = E.ep_return[e];
+
+    auto write_rec = [&](int k, int obs, int a, int done, float rew, float rgt) {
+        const long long o = (long long)k * J.step_stride + e * J.env_stride;
+        if (J.packed) {
+            const unsigned lo = ((unsigned)obs & 0xfffffu) | (((unsigned)a & 0x3ffu) << 20) | ((unsigned)done << 30);
+            J.packed[o] = ((unsigned long long)__float_as_uint(rew) << 32) | lo;
+        } else {
+            if (J.obs) J.obs[o] = obs;
+            if (J.actions_out) J.actions_out[o] = a & 0x0fffffff;
+            if (J.done) J.done[o] = (uint8_t)done;
+            if (J.reward) J.reward[o] = rew;
+            if (J.reward_gt) J.reward_gt[o] = rgt;
+        }
+    };
+
+    unsigned fault = 0;
+    if (flags & FLAG_VIRGIN) fault = AMDP_FAULT_NEED_RESET;                                   // anymdp_env.py:93-94
+    else if (!(next && (flags & FLAG_PENDING)) && sinfo_t[s] < 0 && !always_term) fault = AMDP_FAULT_TERMINAL_STATE;
+    if (fault) {
+        // faulted envs are left untouched (as in env_tick); their records are zero except the action
+        for (int k = 0; k < K; ++k) {
+            int a;
+            if (given) a = load_action(actions, (long long)k * N + e, J.actions_u8);
+            else a = (int)__umulhi(philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key).z, (uint32_t)na);
+            write_rec(k, 0, a, 0, 0.f, 0.f);
+        }
+        atomicOr(E.faults, fault);
+        return;
+    }
+    sh_cnt[0][tx] = E.ep_count[e]; sh_cnt[1][tx] = E.sum_len[e];
+    sh_stat[0][tx] = E.sum_ret[e]; sh_stat[1][tx] = E.sum_ret_sq[e];
+    sh_stat[2][tx] = E.min_ret[e]; sh_stat[3][tx] = E.max_ret[e];
+    const int s0_pad = T.s0_pad;
+    const bool s0_local = s0_pad <= TP_S0;
+    if (s0_local) {
+#pragma unroll
+        for (int i = 0; i < TP_S0; ++i) {
+            sh_s0c[i][tx] = (i < s0_pad) ? T.s0_cdf[t * s0_pad + i] : 2.0;
+            sh_s0i[i][tx] = T.s0_idx[t * s0_pad + min(i, s0_pad - 1)];
+        }
+    }
+
+    // draws of one tick: words 0..3 of Philox block 0 (transition uniform = w.x, w.y; reset uniform = w.z, w.w), the reward
+    // normal and the action (given or uniform random policy)
+    struct Draw { uint32_t wx, wy, wz, ww; float z; int a; };
+    auto draw = [&](int k) {
+        Draw d;
+        const unsigned long long tk = tick0 + (unsigned long long)k;
+        const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
+        d.wx = w0.x; d.wy = w0.y; d.wz = w0.z; d.ww = w0.w;
+        const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
+        d.z = box_muller(w2.x, w2.y);
+        if (given) d.a = (k < K) ? load_action(actions, (long long)k * N + e, J.actions_u8) : 0;
+        else d.a = (int)__umulhi(w2.z, (uint32_t)na);
+        return d;
+    };
+    Draw cur = draw(0);
+
+    // the previous tick, settled one tick late (its payload / observation loads were issued at the end of that tick)
+    float2 pay_p = make_float2(0.f, 0.f);
+    float z_p = 0.f;
+    int si_p = 0, a_p = 0, done_p = 0, steps_p = 0;
+    bool close_p = false;
+    auto settle = [&](int kp) {
+        // reward = gt + noise * z (anymdp_env.py:103-105), episode return, closed-episode statistics, the record
+        const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
+        ep_ret += rew;
+        write_rec(kp, si_p & 0x7fffffff, a_p, done_p, (float)rew, pay_p.x);
+        if (close_p) {
+            sh_cnt[0][tx] += 1; sh_cnt[1][tx] += (unsigned long long)steps_p;
+            sh_stat[0][tx] += ep_ret; sh_stat[1][tx] += ep_ret * ep_ret;
+            sh_stat[2][tx] = fmin(sh_stat[2][tx], ep_ret); sh_stat[3][tx] = fmax(sh_stat[3][tx], ep_ret);
+            ep_ret = 0.0;
+            close_p = false;
+        }
+    };
+    unsigned n_fallback = 0;
+
+    for (int k = 0; k < K; ++k) {
+        const bool pend = next && (flags & FLAG_PENDING);          // next_step mode: this tick only performs the reset
+        const bool a_ok = !given || (unsigned)cur.a < (unsigned)na;
+        const bool valid = !pend && a_ok;
+        if (given && !pend && !a_ok) fault |= AMDP_FAULT_BAD_ACTION;                          // :97
+        const unsigned long long row = rbase + (unsigned long long)(s * na + (valid ? cur.a : 0));
+        // (1) level 1: the pivots of row (s, a)                                                 anymdp_env.py:99
+        uint4 pv[PW];
+        if (PVW > 0 && valid) ldg_words_keep<PW>(T.pv15 + row * (unsigned)T.pv_stride, pv, pol_keep);
+        // (2) in the shadow of that load: the previous tick's reward / record
+        if (k > 0) settle(k - 1);
+        Draw nx;
+        int done_bits = 0;
+        bool do_reset = pend;
+        bool touched = pend;                                       // the tick stepped or reset: it has an observation
+        if (valid) {
+            // (3) next state = #{cdf <= u}  (numpy choice: searchsorted(cdf, u, 'right'))         anymdp_env.py:100
+            int blk = 0;
+            if (PVW > 0) {
+                const uint32_t v15 = code15_from_m21(cur.wx >> 11);
+                const unsigned v2 = v15 | (v15 << 16);
+                int acc = 0;
+#pragma unroll
+                for (int i = 0; i < PW; ++i) {
+                    acc = h2_count_lt(pv[i].x, v2, acc); acc = h2_count_lt(pv[i].y, v2, acc);
+                    acc = h2_count_lt(pv[i].z, v2, acc); acc = h2_count_lt(pv[i].w, v2, acc);
+                }
+                blk = min(-acc, n_blocks - 1);                      // blocks whose last entry is < u lie entirely below u
+            }
+            // code31(u) << 1; cmask = 0xfffffffe drops the is_terminal bit of the entries (tests coarsen it further to
+            // exercise the float64 fallback)
+            const unsigned ve = ((((cur.wx >> 5) << 4) | (cur.wy >> 28)) << 1) & cmask;
+            const uint32_t* crow = T.c32 + row * (unsigned)T.c32_stride;
+            int lt, le;
+            unsigned mn;
+            for (bool first = true;; first = false) {
+                uint4 bw[BW];
+                ldg_words<BW>(crow + blk * B, bw);
+                if (first) nx = draw(k + 1);                       // in the shadow of the block load: the next tick's draws
+                lt = 0; le = 0; mn = 0xffffffffu;
+#pragma unroll
+                for (int i = 0; i < BW; ++i) {
+                    const unsigned x[4] = {bw[i].x, bw[i].y, bw[i].z, bw[i].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned xm = x[j] & cmask;
+                        lt += (xm < ve);
+                        le += (xm <= ve);
+                        mn = min(mn, xm >= ve ? x[j] : 0xffffffffu);
+                    }
+                }
+                if (lt < B || blk >= n_blocks - 1) break;
+                ++blk;                                             // the whole block is below u (its pivot shared u's 15-bit cell)
+            }
+            int nxt = blk * B + lt;
+            bool term = (mn & 1u) != 0;                            // is_terminal[nxt] (bit 0 of the first entry not below u)
+            if (le != lt) {
+                // code31(cdf[j]) == code31(u) for some j: decide those entries on the float64 row
+                const double u = u53(cur.wx, cur.wy);
+                const double* cr = T.cdf + row * (unsigned)n_pad;
+                while (nxt < n_pad - 1 && __ldg(cr + nxt) <= u) ++nxt;
+                term = sinfo_t[nxt] < 0;
+                n_fallback += 1;
+            }
+            // (4) payload (reward, noise) of (s, a, s')  (anymdp_env.py:103-104): consumed by settle() of the next tick
+            pay_p = ldg_stream_f32x2(T.payload + (row * (unsigned)n_pad + (unsigned)nxt));
+            // (5) state update, termination, truncation (anymdp_env.py:107-108,113-114)
+            s = nxt;
+            steps += 1;
+            done_bits = ((term || always_term) ? 1 : 0) | ((steps >= max_ceil) ? 2 : 0);
+            touched = true;
+            if (done_bits) {
+                close_p = true;
+                steps_p = steps;
+                if (next) flags |= FLAG_PENDING; else do_reset = true;
+            }
+        } else {
+            pay_p = make_float2(0.f, 0.f);
+            nx = draw(k + 1);
+        }
+        z_p = cur.z;
+        if (do_reset) {                                            // anymdp_env.py:81-90
+            const double ur = u53(cur.wz, cur.ww);
+            int c = 0;
+            if (s0_local) {
+#pragma unroll
+                for (int i = 0; i < TP_S0; ++i) c += (sh_s0c[i][tx] <= ur);          // pad 2.0 is never <= ur
+                c = min(c, s0_pad - 1);
+                s = sh_s0i[0][tx];
+#pragma unroll
+                for (int i = 1; i < TP_S0; ++i) if (c == i) s = sh_s0i[i][tx];
+            } else {
+                for (int i = 0; i < s0_pad; ++i) c += (T.s0_cdf[t * s0_pad + i] <= ur);
+                s = T.s0_idx[t * s0_pad + min(c, s0_pad - 1)];
+            }
+            steps = 0;
+            flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
+        }
+        si_p = touched ? __ldg(sinfo_t + s) : 0;                   // observation = state_mapping[s]  (anymdp_env.py:145-148)
+        a_p = cur.a;
+        done_p = done_bits;
+        cur = nx;
+    }
+    settle(K - 1);
+    E.state[e] = s; E.steps[e] = steps; E.flags[e] = (uint8_t)flags; E.ep_return[e] = ep_ret;
+    E.ep_count[e] = sh_cnt[0][tx]; E.sum_len[e] = sh_cnt[1][tx];
+    E.sum_ret[e] = sh_stat[0][tx]; E.sum_ret_sq[e] = sh_stat[1][tx];
+    E.min_ret[e] = sh_stat[2][tx]; E.max_ret[e] = sh_stat[3][tx];
+    if (fault) atomicOr(E.faults, fault);
+    if (n_fallback) atomicAdd(E.counters, (unsigned long long)n_fallback);
+}
+
 __global__ void k_reset(Tables T, EnvArrays E, unsigned long long tick, int n_slots, const uint8_t* __restrict__ mask,
                         int32_t* __restrict__ obs_out, const double* __restrict__ u_inject) {
     // one thread per env (G = 1): reset is rare and touches only the small per-task tables
@@ -775,7 +1087,8 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
                              const double* __restrict__ reward, const double* __restrict__ noise,
                              const int32_t* __restrict__ n_real, const uint8_t* __restrict__ is_terminal,
                              double* __restrict__ cdf, float2* __restrict__ payload, uint16_t* __restrict__ sketch,
-                             uint16_t* __restrict__ pivot, int32_t* __restrict__ status) {
+                             uint16_t* __restrict__ pivot, uint32_t* __restrict__ c32, uint16_t* __restrict__ pv15,
+                             int c32_stride, int pv_stride, int tp_B, int32_t* __restrict__ status) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long rows = cnt * n_pad * na;
     if (r >= rows) return;
@@ -789,6 +1102,10 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
     if (s >= n) {
         for (int i = 0; i < n_pad; ++i) { c[i] = 1.0; sketch[r * n_pad + i] = 65535; }
         if (pivot) for (int b = 0; b < 32; ++b) pivot[r * 32 + b] = 65535;
+        if (c32) {
+            for (int i = 0; i < c32_stride; ++i) c32[r * c32_stride + i] = 0xfffffffeu;
+            for (int b = 0; b < pv_stride; ++b) pv15[r * pv_stride + b] = 0x7bff;
+        }
         return;
     }
     double acc = 0.0, ksum = 0.0, kc = 0.0;
@@ -831,6 +1148,26 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
         for (int b = 0; b < 32; ++b) {
             const int last = min(32 * b + 31, n_pad - 1);
             pivot[r * 32 + b] = (32 * b < n_pad) ? sk[last] : (uint16_t)65535;
+        }
+    }
+    // thread-per-env tables: 31-bit fixed-point entries carrying is_terminal[j] in bit 0, and the 15-bit (fp16-ordered)
+    // code of the last entry of every tp_B-entry block.  Both codes are monotone in cdf, see code15()/code31().
+    if (c32) {
+        // Entries with equal codes (zero-probability next states repeat the previous CDF value) all carry the flag of the
+        // FIRST entry of their run: the search returns the first entry not below u, which is always the first of a run,
+        // and the kernel reads its flag as the minimum over the entries not below u.
+        uint32_t* cr = c32 + r * c32_stride;
+        uint32_t prev_code = 0xffffffffu, prev_f = 0;
+        for (int i = 0; i < c32_stride; ++i) {
+            const uint32_t code = code31((i < n_pad) ? c[i] : 1.0);
+            uint32_t f = (i < n && is_terminal[t * n_pad + i]) ? 1u : 0u;
+            if (code == prev_code) f = prev_f;
+            cr[i] = (code << 1) | f;
+            prev_code = code; prev_f = f;
+        }
+        for (int b = 0; b < pv_stride; ++b) {
+            const int last = min(tp_B * b + tp_B - 1, c32_stride - 1);
+            pv15[r * pv_stride + b] = (tp_B * b < c32_stride) ? (uint16_t)code15((last < n_pad) ? c[last] : 1.0) : (uint16_t)0x7bff;
         }
     }
 }
@@ -1012,6 +1349,10 @@ struct amdp {
     bool uploaded, assigned;
     bool force_generic;    // debug: route rollouts through the generic kernel
     bool two_level;        // the fast kernel searches pivots + one 32-entry block instead of streaming the whole row
+    bool tp;               // rollouts run on the thread-per-env kernel (k_rollout_tp)
+    int tp_coarse_bits;    // debug: low bits of the 31-bit codes ignored by k_rollout_tp (0 in production)
+    int tp_pvw, tp_bw;     // its template geometry: 16-byte words of pivots per row (0 = single level) / per block
+    uint32_t* c32; uint16_t* pv15;
     char err[512];
     // rollout_host staging
     int32_t* st_act[2]; int32_t* st_obs[2]; float* st_rew[2]; uint8_t* st_done[2]; unsigned long long* st_rec[2];
@@ -1079,7 +1420,7 @@ static int pick_group(int n_pad) {
 extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
+    void* ptrs[] = {h->c32, h->pv15, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
@@ -1121,6 +1462,23 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     if ((rc = dalloc(h, &h->sketch, rows * c.n_pad + 64))) return rc;
     h->two_level = (c.n_pad >= 256 && c.n_pad <= 1024) && !(c.reserved0 & 2) && ((c.reserved0 & 4) || c.n_pad >= 512 || c.n_envs >= 16384);
     if (h->two_level) { if ((rc = dalloc(h, &h->pivot, rows * 32))) return rc; }
+    // thread-per-env tables: chosen for engines with enough envs to fill the GPU (or forced by flag 8; never with 16)
+    h->tp = mdp && c.n_pad <= 1024 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= 16384));
+    if (h->tp) {
+        const int n = c.n_pad;
+        if (n <= 16) { h->tp_pvw = 0; h->tp_bw = 4; }
+        else if (n <= 64) { h->tp_pvw = 1; h->tp_bw = 2; }
+        else if (n <= 128) { h->tp_pvw = 2; h->tp_bw = 2; }
+        else if (n <= 256) { h->tp_pvw = 4; h->tp_bw = 2; }
+        else if (n <= 512) { h->tp_pvw = 4; h->tp_bw = 4; }
+        else { h->tp_pvw = 8; h->tp_bw = 4; }
+        const int B = 4 * h->tp_bw;
+        h->T.tp_B = B;
+        h->T.c32_stride = (n + B - 1) / B * B;
+        h->T.pv_stride = h->tp_pvw > 0 ? 8 * h->tp_pvw : 8;
+        if ((rc = dalloc(h, &h->c32, rows * h->T.c32_stride))) return rc;
+        if ((rc = dalloc(h, &h->pv15, rows * h->T.pv_stride))) return rc;
+    }
     if (c.reserved0 & 1) { if ((rc = dalloc(h, &h->raw_t, rows * c.n_pad))) return rc; }
     if ((rc = dalloc(h, &h->sinfo, (size_t)c.n_tasks * c.n_pad))) return rc;
     if ((rc = dalloc(h, &h->s0_cdf, (size_t)c.n_tasks * c.s0_pad))) return rc;
@@ -1151,6 +1509,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     E.task = h->env_task; E.faults = h->faults; E.counters = h->counters; E.n_envs = c.n_envs; E.env_id_base = c.env_id_base;
     E.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
     Tables& T = h->T;
+    T.c32 = h->c32; T.pv15 = h->pv15;
     T.cdf = h->cdf; T.payload = h->payload; T.sketch = h->sketch; T.pivot = h->pivot; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
     T.obs_cdf = h->obs_cdf; T.max_ceil = h->max_ceil; T.tflags = h->tflags; T.raw_t = h->raw_t; T.n_real = h->n_real;
     T.n_pad = c.n_pad; T.na = c.na; T.no_pad = c.no_pad; T.d_o = c.n_obs_tok; T.d_a = c.n_act_tok; T.s0_pad = c.s0_pad;
@@ -1178,7 +1537,10 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
     k_build_rows<<<nblk(rows, 128), 128, 0, st>>>(cnt, c.n_pad, c.na, transition, reward, reward_noise, n_real, is_terminal,
                                                   h->cdf + t0 * per_task, h->payload + t0 * per_task,
                                                   h->sketch + t0 * per_task,
-                                                  h->pivot ? h->pivot + (size_t)t0 * c.n_pad * c.na * 32 : nullptr, status_out);
+                                                  h->pivot ? h->pivot + (size_t)t0 * c.n_pad * c.na * 32 : nullptr,
+                                                  h->c32 ? h->c32 + (size_t)t0 * c.n_pad * c.na * h->T.c32_stride : nullptr,
+                                                  h->pv15 ? h->pv15 + (size_t)t0 * c.n_pad * c.na * h->T.pv_stride : nullptr,
+                                                  h->T.c32_stride, h->T.pv_stride, h->T.tp_B, status_out);
     k_build_small<<<nblk(cnt, 128), 128, 0, st>>>(cnt, c.n_pad, c.s0_pad, state_mapping, n_real, is_terminal, s0_idx, s0_prob,
                                                   n_s0, max_steps, ns, h->sinfo + t0 * c.n_pad, h->s0_cdf + t0 * c.s0_pad,
                                                   h->s0_idx + t0 * c.s0_pad, h->max_ceil + t0, h->tflags + t0,
@@ -1267,9 +1629,28 @@ static void launch_fast_gc(amdp* h, int K, const int32_t* actions, const amdp_tr
     }
 }
 
+template <int PVW, int BW>
+static void launch_tp(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
+    k_rollout_tp<PVW, BW><<<nblk(h->cfg.n_envs, 128), 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J, actions ? 1 : 0,
+                                                                    h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP ? 1 : 0,
+                                                                    0xfffffffeu << h->tp_coarse_bits);
+}
+
 // lanes per env and register-resident chunks per lane for the fast kernel: n_pad == 4 * G * C
 static void launch_rollout_fast(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
     const int n_pad = h->cfg.n_pad;
+    if (h->tp) {
+        const int key = h->tp_pvw * 16 + h->tp_bw;
+        switch (key) {
+            case 0 * 16 + 4: launch_tp<0, 4>(h, K, actions, J, st); break;
+            case 1 * 16 + 2: launch_tp<1, 2>(h, K, actions, J, st); break;
+            case 2 * 16 + 2: launch_tp<2, 2>(h, K, actions, J, st); break;
+            case 4 * 16 + 2: launch_tp<4, 2>(h, K, actions, J, st); break;
+            case 4 * 16 + 4: launch_tp<4, 4>(h, K, actions, J, st); break;
+            default: launch_tp<8, 4>(h, K, actions, J, st); break;
+        }
+        return;
+    }
     if (h->two_level) { launch_fast_gc<8, 1, true>(h, K, actions, J, st); return; }
     const int G = h->G;
     const int C = (n_pad == 4 * G) ? 1 : (n_pad == 8 * G ? 2 : 0);
@@ -1377,6 +1758,12 @@ extern "C" int amdp_debug_counters(amdp_t* h, uint64_t* out4) {
     if (!h || !out4) return AMDP_EINVAL;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemcpy(out4, h->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return AMDP_OK;
+}
+
+extern "C" int amdp_debug_tp_coarse_bits(amdp_t* h, int bits) {
+    if (!h || bits < 0 || bits > 30) return AMDP_EINVAL;
+    h->tp_coarse_bits = bits;
     return AMDP_OK;
 }
 

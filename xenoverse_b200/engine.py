@@ -118,8 +118,10 @@ _STATUS_MSG = {
 class Engine:
     def __init__(self, num_envs, num_tasks, geo, device=0, seed=0, autoreset="same_step", env_id_base=0,
                  keep_transition=False, search="auto"):
-        """search: "auto" | "one_level" | "two_level" — how the fast rollout kernel searches a CDF row (two_level =
-        pivots + one 32-entry block, for 256 <= n_pad <= 1024; auto picks it for n_pad >= 512 or >= 16384 envs)."""
+        """search: how MDP rollouts search a CDF row.  "thread": the thread-per-env throughput kernel (pivots + one
+        8/16-entry block of 31-bit codes; auto picks it for >= 16384 envs); "one_level" / "two_level": the warp-per-env
+        latency kernel streaming the 16-bit filter row / reading 32 pivots + one 32-entry block (auto: two_level for
+        n_pad >= 512); "warp": auto without the thread-per-env kernel."""
         if not torch.cuda.is_available():
             raise AMDPError("xenoverse_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
@@ -130,7 +132,7 @@ class Engine:
         cfg = _lib.Config(device=self.device.index, task_type=_lib.TASK_TYPES[geo["task_type"]],
                           autoreset=_lib.AUTORESET[autoreset], na=geo["na"], n_pad=geo["n_pad"], no_pad=geo["no_pad"],
                           n_obs_tok=geo["do"], n_act_tok=geo["da"], s0_pad=geo["s0_pad"],
-                          reserved0=(1 if keep_transition else 0) | {"auto": 0, "one_level": 2, "two_level": 4}[search],
+                          reserved0=(1 if keep_transition else 0) | {"auto": 0, "one_level": 2, "two_level": 4, "thread": 8, "warp": 16}[search],
                           n_envs=self.N, n_tasks=self.T,
                           seed=int(seed) & (2 ** 64 - 1), env_id_base=int(env_id_base))
         h = ctypes.c_void_p()
@@ -189,6 +191,11 @@ class Engine:
     def force_generic(self, on=True):
         """Debug: run rollouts through the generic per-tick kernel (used to cross-check the fast kernel)."""
         self._ck(lib.amdp_debug_force_generic(self._h, 1 if on else 0))
+
+    def tp_coarse_bits(self, bits):
+        """Debug: the thread-per-env kernel ignores the low `bits` bits of its 31-bit CDF codes (exercises its float64
+        fallback; results do not change)."""
+        self._ck(lib.amdp_debug_tp_coarse_bits(self._h, int(bits)))
 
     def debug_counters(self):
         out = (ctypes.c_uint64 * 4)()
