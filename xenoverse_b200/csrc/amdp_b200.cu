@@ -43,9 +43,12 @@ struct Tables {
     const double*  raw_t;     // [T][n_pad][na][n_pad] raw transition (only if keep_transition) or null
     const int32_t* n_real;    // [T]
     // thread-per-env search tables (k_rollout_tp): two levels, both exact up to an equality that falls back to `cdf`
-    const uint32_t* c32;      // [T][n_pad][na][c32_stride] (floor(cdf * 2^31) << 1) | is_terminal[j]; pad = 0xfffffffe
-    const uint16_t* pv15;     // [T][n_pad][na][pv_stride] code15 of the LAST entry of every tp_B-entry block; pad = 0x7bff
-    int c32_stride, pv_stride, tp_B;
+    const uint4*    fat;      // [T][n_pad][na][tp_blocks] 128-byte lines, one per 8-entry block of a row:
+                              //   bytes 0-31 8 x ((floor(cdf * 2^31) << 1) | is_terminal[j]), 32-95 8 x (reward, noise) fp32,
+                              //   96-127 8 x sinfo[j]  — everything a transition into the block needs, in ONE DRAM line
+    const uint16_t* pv;       // [T][n_pad][na][tp_groups][16] code15 of the LAST entry of each block of a group of 16; pad 0x7bff
+    const uint16_t* top;      // [T][n_pad][na][16] code15 of the last entry of each group (three-level rows only)
+    int tp_levels, tp_groups, tp_blocks;
     int n_pad, na, no_pad, d_o, d_a, s0_pad, task_type, autoreset;
 };
 
@@ -769,16 +772,21 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
 // ------------------------------------------------------------------------------------------------
 // Throughput path: ONE THREAD PER ENV (MDP, one action token, engine Philox draws, auto-reset on), for engines with
 // enough envs to fill the machine (>= 16k per GPU).  The warp-per-env kernel above keeps at most ~4k envs in flight
-// per GPU (one row per warp); here every resident thread is an env, so 60k-110k dependent chains are in flight and
-// the path is bound by DRAM sectors instead of by latency x residency.
-//   * search = two dependent, sector-sized reads per transition: the row's pivots (15-bit fp16-ordered codes of the
-//     last entry of every B-entry block; packed HSET2 compares) pick the block, the block's B 31-bit codes pick the
-//     entry.  Both levels are exact; the only undecided case is code31(cdf[j]) == code31(u) (~n * 2^-31 of the ticks),
-//     which reads the float64 row.  No 16-bit ambiguity: with 32 envs per warp a per-env fallback rate of n/65536
-//     would stall most warps at n = 1024.
-//   * is_terminal[s'] rides in bit 0 of the block entries, so the chain per tick is  pivots -> block -> next pivots;
-//     the (reward, noise) payload and the observation lookup of tick k are consumed in the shadow of tick k+1's loads.
-//   * PVW = 16-byte words of pivots per row (0: single level), BW = 16-byte words per block (B = 4 * BW entries).
+// per GPU (one row per warp); here every resident thread is an env, so 60k-95k dependent chains are in flight and
+// the path is bound by DRAM lines instead of by latency x residency.
+//   Measured on B200 (profiles/r1_gather_microbench.txt, r1_tp_*): every L2 miss fetches its whole 128-byte line from
+//   DRAM whatever the request size, and what the kernel pays for is (a) DRAM lines and (b) 32-byte sector requests.
+//   Hence the layout: a row is cut into 8-entry blocks, and ONE 128-byte line per block holds the 8 CDF codes, the 8
+//   (reward, noise) payloads and the 8 state words (mapping | terminal) — a transition touches exactly one DRAM line
+//   below the pivots, with 3 sector requests (codes; payload entry; state word — the last two hit L2).
+//   * search = a 1..3-level tree, one 32-byte request per level: [top: <= 16 groups] -> [pivots: <= 16 blocks of the
+//     group] -> [block: 8 codes].  Pivots are 15-bit fp16-ordered codes of the LAST entry of a block / group, counted
+//     with packed HSET2 compares; block entries are 31-bit codes.  All levels are exact; the only undecided case is
+//     code31(cdf[j]) == code31(u) (~n * 2^-31 of the ticks), which reads the float64 row.  (A 16-bit filter would
+//     send n/65536 of the ticks to the float64 row, which at 32 envs per warp stalls most warps when n = 1024.)
+//   * is_terminal[s'] rides in bit 0 of the block codes, so the dependent chain per tick is  [top ->] pivots -> codes
+//     -> next pivots; payload and state word of tick k are consumed in the shadow of tick k+1's loads.
+//   * LEVELS = 1 (n_pad <= 8), 2 (<= 128) or 3 (<= 2048).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ldg_stream_u128(const void* p) {
     uint4 v;
@@ -841,11 +849,9 @@ __device__ __forceinline__ int h2_count_lt(unsigned w, unsigned v2, int acc) {  
 }
 
 #define TP_S0 4
-template <int PVW, int BW>
+template <int LEVELS>
 __global__ void __launch_bounds__(128, 5) k_rollout_tp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
                                                        const int32_t* __restrict__ actions, const amdp_traj J, int given, int next, unsigned cmask) {
-    constexpr int B = BW * 4;
-    constexpr int PW = PVW > 0 ? PVW : 1;
     __shared__ double sh_stat[4][128];                            // closed-episode statistics: sum_ret, sum_ret_sq, min, max
     __shared__ unsigned long long sh_cnt[2][128];                 // ep_count, sum_len
     __shared__ double sh_s0c[TP_S0][128];                         // the env's start-state CDF and states (s0_pad <= TP_S0):
@@ -861,7 +867,7 @@ __global__ void __launch_bounds__(128, 5) k_rollout_tp(const Tables T, const Env
     const int max_ceil = T.max_ceil[t];
     const bool always_term = (T.tflags[t] & 1) != 0;
     const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
-    const int n_blocks = T.c32_stride / B;
+    const int n_blocks = T.tp_blocks, n_groups = T.tp_groups;
     const uint64_t pol_keep = l2_policy_evict_last();
 
     int s = E.state[e], steps = E.steps[e], flags = E.flags[e];
@@ -950,42 +956,50 @@ __global__ void __launch_bounds__(128, 5) k_rollout_tp(const Tables T, const Env
         const bool valid = !pend && a_ok;
         if (given && !pend && !a_ok) fault |= AMDP_FAULT_BAD_ACTION;                          // :97
         const unsigned long long row = rbase + (unsigned long long)(s * na + (valid ? cur.a : 0));
-        // (1) level 1: the pivots of row (s, a)                                                 anymdp_env.py:99
-        uint4 pv[PW];
-        if (PVW > 0 && valid) ldg_words_keep<PW>(T.pv15 + row * (unsigned)T.pv_stride, pv, pol_keep);
+        // (1) first level of the search tree of row (s, a)                                      anymdp_env.py:99
+        uint4 lv[2];                                               // 16 pivots (15-bit codes)
+        if (LEVELS == 3 && valid) ldg_words_keep<2>(T.top + row * 16u, lv, pol_keep);
+        if (LEVELS == 2 && valid) ldg_words_keep<2>(T.pv + row * 16u, lv, pol_keep);
         // (2) in the shadow of that load: the previous tick's reward / record
         if (k > 0) settle(k - 1);
         Draw nx;
         int done_bits = 0;
         bool do_reset = pend;
         bool touched = pend;                                       // the tick stepped or reset: it has an observation
+        bool si_from_line = false;
         if (valid) {
             // (3) next state = #{cdf <= u}  (numpy choice: searchsorted(cdf, u, 'right'))         anymdp_env.py:100
-            int blk = 0;
-            if (PVW > 0) {
-                const uint32_t v15 = code15_from_m21(cur.wx >> 11);
-                const unsigned v2 = v15 | (v15 << 16);
+            const uint32_t v15 = code15_from_m21(cur.wx >> 11);
+            const unsigned v2 = v15 | (v15 << 16);
+            auto count16 = [&]() {                                 // #{pivots < code15(u)}: blocks / groups entirely below u
                 int acc = 0;
 #pragma unroll
-                for (int i = 0; i < PW; ++i) {
-                    acc = h2_count_lt(pv[i].x, v2, acc); acc = h2_count_lt(pv[i].y, v2, acc);
-                    acc = h2_count_lt(pv[i].z, v2, acc); acc = h2_count_lt(pv[i].w, v2, acc);
+                for (int i = 0; i < 2; ++i) {
+                    acc = h2_count_lt(lv[i].x, v2, acc); acc = h2_count_lt(lv[i].y, v2, acc);
+                    acc = h2_count_lt(lv[i].z, v2, acc); acc = h2_count_lt(lv[i].w, v2, acc);
                 }
-                blk = min(-acc, n_blocks - 1);                      // blocks whose last entry is < u lie entirely below u
+                return -acc;
+            };
+            int blk = 0;
+            if (LEVELS == 3) {
+                const int g = min(count16(), n_groups - 1);
+                ldg_words_keep<2>(T.pv + (row * (unsigned)n_groups + (unsigned)g) * 16u, lv, pol_keep);
+                blk = g * 16;
             }
+            if (LEVELS >= 2) blk = min(blk + count16(), n_blocks - 1);
             // code31(u) << 1; cmask = 0xfffffffe drops the is_terminal bit of the entries (tests coarsen it further to
             // exercise the float64 fallback)
             const unsigned ve = ((((cur.wx >> 5) << 4) | (cur.wy >> 28)) << 1) & cmask;
-            const uint32_t* crow = T.c32 + row * (unsigned)T.c32_stride;
+            const uint4* frow = T.fat + row * (unsigned)n_blocks * 8u;                  // 8 x 16 bytes per block line
             int lt, le;
             unsigned mn;
             for (bool first = true;; first = false) {
-                uint4 bw[BW];
-                ldg_words<BW>(crow + blk * B, bw);
+                uint4 bw[2];
+                ldg_words<2>(frow + blk * 8, bw);
                 if (first) nx = draw(k + 1);                       // in the shadow of the block load: the next tick's draws
                 lt = 0; le = 0; mn = 0xffffffffu;
 #pragma unroll
-                for (int i = 0; i < BW; ++i) {
+                for (int i = 0; i < 2; ++i) {
                     const unsigned x[4] = {bw[i].x, bw[i].y, bw[i].z, bw[i].w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -995,10 +1009,10 @@ __global__ void __launch_bounds__(128, 5) k_rollout_tp(const Tables T, const Env
                         mn = min(mn, xm >= ve ? x[j] : 0xffffffffu);
                     }
                 }
-                if (lt < B || blk >= n_blocks - 1) break;
+                if (lt < 8 || blk >= n_blocks - 1) break;
                 ++blk;                                             // the whole block is below u (its pivot shared u's 15-bit cell)
             }
-            int nxt = blk * B + lt;
+            int nxt = blk * 8 + lt;
             bool term = (mn & 1u) != 0;                            // is_terminal[nxt] (bit 0 of the first entry not below u)
             if (le != lt) {
                 // code31(cdf[j]) == code31(u) for some j: decide those entries on the float64 row
@@ -1007,9 +1021,14 @@ __global__ void __launch_bounds__(128, 5) k_rollout_tp(const Tables T, const Env
                 while (nxt < n_pad - 1 && __ldg(cr + nxt) <= u) ++nxt;
                 term = sinfo_t[nxt] < 0;
                 n_fallback += 1;
+                // (4) payload (reward, noise) of (s, a, s')  (anymdp_env.py:103-104): consumed by settle() of the next tick
+                pay_p = ldg_stream_f32x2(T.payload + (row * (unsigned)n_pad + (unsigned)nxt));
+            } else {
+                const char* line = reinterpret_cast<const char*>(frow + blk * 8);
+                pay_p = ldg_stream_f32x2(reinterpret_cast<const float2*>(line + 32) + lt);
+                si_p = __ldg(reinterpret_cast<const int*>(line + 96) + lt);
+                si_from_line = true;
             }
-            // (4) payload (reward, noise) of (s, a, s')  (anymdp_env.py:103-104): consumed by settle() of the next tick
-            pay_p = ldg_stream_f32x2(T.payload + (row * (unsigned)n_pad + (unsigned)nxt));
             // (5) state update, termination, truncation (anymdp_env.py:107-108,113-114)
             s = nxt;
             steps += 1;
@@ -1042,7 +1061,8 @@ __global__ void __launch_bounds__(128, 5) k_rollout_tp(const Tables T, const Env
             steps = 0;
             flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
         }
-        si_p = touched ? __ldg(sinfo_t + s) : 0;                   // observation = state_mapping[s]  (anymdp_env.py:145-148)
+        // observation = state_mapping[s] (anymdp_env.py:145-148): from the block line unless the env was reset / fell back
+        if (!(si_from_line && !do_reset)) si_p = touched ? __ldg(sinfo_t + s) : 0;
         a_p = cur.a;
         done_p = done_bits;
         cur = nx;
@@ -1087,8 +1107,9 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
                              const double* __restrict__ reward, const double* __restrict__ noise,
                              const int32_t* __restrict__ n_real, const uint8_t* __restrict__ is_terminal,
                              double* __restrict__ cdf, float2* __restrict__ payload, uint16_t* __restrict__ sketch,
-                             uint16_t* __restrict__ pivot, uint32_t* __restrict__ c32, uint16_t* __restrict__ pv15,
-                             int c32_stride, int pv_stride, int tp_B, int32_t* __restrict__ status) {
+                             uint16_t* __restrict__ pivot, const int32_t* __restrict__ state_mapping, uint4* __restrict__ fat,
+                             uint16_t* __restrict__ pv, uint16_t* __restrict__ top, int tp_blocks, int tp_groups,
+                             int32_t* __restrict__ status) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long rows = cnt * n_pad * na;
     if (r >= rows) return;
@@ -1102,9 +1123,14 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
     if (s >= n) {
         for (int i = 0; i < n_pad; ++i) { c[i] = 1.0; sketch[r * n_pad + i] = 65535; }
         if (pivot) for (int b = 0; b < 32; ++b) pivot[r * 32 + b] = 65535;
-        if (c32) {
-            for (int i = 0; i < c32_stride; ++i) c32[r * c32_stride + i] = 0xfffffffeu;
-            for (int b = 0; b < pv_stride; ++b) pv15[r * pv_stride + b] = 0x7bff;
+        if (fat) {
+            for (int b = 0; b < tp_blocks; ++b) {
+                uint4* line = fat + (r * tp_blocks + b) * 8;
+                line[0] = line[1] = make_uint4(0xfffffffeu, 0xfffffffeu, 0xfffffffeu, 0xfffffffeu);
+                for (int i = 2; i < 8; ++i) line[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            if (pv) for (int b = 0; b < tp_groups * 16; ++b) pv[r * tp_groups * 16 + b] = 0x7bff;
+            if (top) for (int g = 0; g < 16; ++g) top[r * 16 + g] = 0x7bff;
         }
         return;
     }
@@ -1150,24 +1176,41 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
             pivot[r * 32 + b] = (32 * b < n_pad) ? sk[last] : (uint16_t)65535;
         }
     }
-    // thread-per-env tables: 31-bit fixed-point entries carrying is_terminal[j] in bit 0, and the 15-bit (fp16-ordered)
-    // code of the last entry of every tp_B-entry block.  Both codes are monotone in cdf, see code15()/code31().
-    if (c32) {
+    // thread-per-env tables (k_rollout_tp): per 8-entry block one 128-byte line with 31-bit codes carrying is_terminal[j] in
+    // bit 0, the fp32 payloads and the state words; above them the 15-bit (fp16-ordered) codes of the last entry of every
+    // block (pv) and of every group of 16 blocks (top).  All codes are monotone in cdf, see code15()/code31().
+    if (fat) {
         // Entries with equal codes (zero-probability next states repeat the previous CDF value) all carry the flag of the
         // FIRST entry of their run: the search returns the first entry not below u, which is always the first of a run,
         // and the kernel reads its flag as the minimum over the entries not below u.
-        uint32_t* cr = c32 + r * c32_stride;
         uint32_t prev_code = 0xffffffffu, prev_f = 0;
-        for (int i = 0; i < c32_stride; ++i) {
-            const uint32_t code = code31((i < n_pad) ? c[i] : 1.0);
-            uint32_t f = (i < n && is_terminal[t * n_pad + i]) ? 1u : 0u;
-            if (code == prev_code) f = prev_f;
-            cr[i] = (code << 1) | f;
-            prev_code = code; prev_f = f;
+        for (int b = 0; b < tp_blocks; ++b) {
+            uint32_t* line = reinterpret_cast<uint32_t*>(fat + (r * tp_blocks + b) * 8);
+            for (int i = 0; i < 8; ++i) {
+                const int j = 8 * b + i;
+                const uint32_t code = code31((j < n_pad) ? c[j] : 1.0);
+                const bool real = j < n;
+                const uint32_t is_t = (real && is_terminal[t * n_pad + j]) ? 1u : 0u;
+                uint32_t f = is_t;
+                if (code == prev_code) f = prev_f;
+                line[i] = (code << 1) | f;
+                prev_code = code; prev_f = f;
+                line[8 + 2 * i] = (j < n_pad) ? __float_as_uint(pl[j].x) : 0u;
+                line[8 + 2 * i + 1] = (j < n_pad) ? __float_as_uint(pl[j].y) : 0u;
+                line[24 + i] = (j < n_pad) ? ((uint32_t)(state_mapping[t * n_pad + j] & 0x7fffffff) | (is_t << 31)) : 0u;
+            }
         }
-        for (int b = 0; b < pv_stride; ++b) {
-            const int last = min(tp_B * b + tp_B - 1, c32_stride - 1);
-            pv15[r * pv_stride + b] = (tp_B * b < c32_stride) ? (uint16_t)code15((last < n_pad) ? c[last] : 1.0) : (uint16_t)0x7bff;
+        if (pv) {
+            for (int b = 0; b < tp_groups * 16; ++b) {
+                const int last = 8 * b + 7;
+                pv[r * tp_groups * 16 + b] = (b < tp_blocks) ? (uint16_t)code15((last < n_pad) ? c[last] : 1.0) : (uint16_t)0x7bff;
+            }
+        }
+        if (top) {
+            for (int g = 0; g < 16; ++g) {
+                const int last = 128 * g + 127;
+                top[r * 16 + g] = (g < tp_groups) ? (uint16_t)code15((last < n_pad) ? c[last] : 1.0) : (uint16_t)0x7bff;
+            }
         }
     }
 }
@@ -1351,8 +1394,7 @@ struct amdp {
     bool two_level;        // the fast kernel searches pivots + one 32-entry block instead of streaming the whole row
     bool tp;               // rollouts run on the thread-per-env kernel (k_rollout_tp)
     int tp_coarse_bits;    // debug: low bits of the 31-bit codes ignored by k_rollout_tp (0 in production)
-    int tp_pvw, tp_bw;     // its template geometry: 16-byte words of pivots per row (0 = single level) / per block
-    uint32_t* c32; uint16_t* pv15;
+    uint4* fat; uint16_t* pv; uint16_t* top;   // its tables (see Tables)
     char err[512];
     // rollout_host staging
     int32_t* st_act[2]; int32_t* st_obs[2]; float* st_rew[2]; uint8_t* st_done[2]; unsigned long long* st_rec[2];
@@ -1420,7 +1462,7 @@ static int pick_group(int n_pad) {
 extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->c32, h->pv15, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
+    void* ptrs[] = {h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
@@ -1463,21 +1505,15 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     h->two_level = (c.n_pad >= 256 && c.n_pad <= 1024) && !(c.reserved0 & 2) && ((c.reserved0 & 4) || c.n_pad >= 512 || c.n_envs >= 16384);
     if (h->two_level) { if ((rc = dalloc(h, &h->pivot, rows * 32))) return rc; }
     // thread-per-env tables: chosen for engines with enough envs to fill the GPU (or forced by flag 8; never with 16)
-    h->tp = mdp && c.n_pad <= 1024 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= 16384));
+    h->tp = mdp && c.n_pad <= 2048 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= 16384));
     if (h->tp) {
-        const int n = c.n_pad;
-        if (n <= 16) { h->tp_pvw = 0; h->tp_bw = 4; }
-        else if (n <= 64) { h->tp_pvw = 1; h->tp_bw = 2; }
-        else if (n <= 128) { h->tp_pvw = 2; h->tp_bw = 2; }
-        else if (n <= 256) { h->tp_pvw = 4; h->tp_bw = 2; }
-        else if (n <= 512) { h->tp_pvw = 4; h->tp_bw = 4; }
-        else { h->tp_pvw = 8; h->tp_bw = 4; }
-        const int B = 4 * h->tp_bw;
-        h->T.tp_B = B;
-        h->T.c32_stride = (n + B - 1) / B * B;
-        h->T.pv_stride = h->tp_pvw > 0 ? 8 * h->tp_pvw : 8;
-        if ((rc = dalloc(h, &h->c32, rows * h->T.c32_stride))) return rc;
-        if ((rc = dalloc(h, &h->pv15, rows * h->T.pv_stride))) return rc;
+        const int nb = (c.n_pad + 7) / 8;
+        h->T.tp_blocks = nb;
+        h->T.tp_levels = nb == 1 ? 1 : (nb <= 16 ? 2 : 3);
+        h->T.tp_groups = h->T.tp_levels == 3 ? (nb + 15) / 16 : 1;
+        if ((rc = dalloc(h, &h->fat, rows * nb * 8))) return rc;
+        if (h->T.tp_levels >= 2) { if ((rc = dalloc(h, &h->pv, rows * h->T.tp_groups * 16))) return rc; }
+        if (h->T.tp_levels == 3) { if ((rc = dalloc(h, &h->top, rows * 16))) return rc; }
     }
     if (c.reserved0 & 1) { if ((rc = dalloc(h, &h->raw_t, rows * c.n_pad))) return rc; }
     if ((rc = dalloc(h, &h->sinfo, (size_t)c.n_tasks * c.n_pad))) return rc;
@@ -1509,7 +1545,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     E.task = h->env_task; E.faults = h->faults; E.counters = h->counters; E.n_envs = c.n_envs; E.env_id_base = c.env_id_base;
     E.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
     Tables& T = h->T;
-    T.c32 = h->c32; T.pv15 = h->pv15;
+    T.fat = h->fat; T.pv = h->pv; T.top = h->top;
     T.cdf = h->cdf; T.payload = h->payload; T.sketch = h->sketch; T.pivot = h->pivot; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
     T.obs_cdf = h->obs_cdf; T.max_ceil = h->max_ceil; T.tflags = h->tflags; T.raw_t = h->raw_t; T.n_real = h->n_real;
     T.n_pad = c.n_pad; T.na = c.na; T.no_pad = c.no_pad; T.d_o = c.n_obs_tok; T.d_a = c.n_act_tok; T.s0_pad = c.s0_pad;
@@ -1538,9 +1574,11 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
                                                   h->cdf + t0 * per_task, h->payload + t0 * per_task,
                                                   h->sketch + t0 * per_task,
                                                   h->pivot ? h->pivot + (size_t)t0 * c.n_pad * c.na * 32 : nullptr,
-                                                  h->c32 ? h->c32 + (size_t)t0 * c.n_pad * c.na * h->T.c32_stride : nullptr,
-                                                  h->pv15 ? h->pv15 + (size_t)t0 * c.n_pad * c.na * h->T.pv_stride : nullptr,
-                                                  h->T.c32_stride, h->T.pv_stride, h->T.tp_B, status_out);
+                                                  state_mapping,
+                                                  h->fat ? h->fat + (size_t)t0 * c.n_pad * c.na * h->T.tp_blocks * 8 : nullptr,
+                                                  h->pv ? h->pv + (size_t)t0 * c.n_pad * c.na * h->T.tp_groups * 16 : nullptr,
+                                                  h->top ? h->top + (size_t)t0 * c.n_pad * c.na * 16 : nullptr,
+                                                  h->T.tp_blocks, h->T.tp_groups, status_out);
     k_build_small<<<nblk(cnt, 128), 128, 0, st>>>(cnt, c.n_pad, c.s0_pad, state_mapping, n_real, is_terminal, s0_idx, s0_prob,
                                                   n_s0, max_steps, ns, h->sinfo + t0 * c.n_pad, h->s0_cdf + t0 * c.s0_pad,
                                                   h->s0_idx + t0 * c.s0_pad, h->max_ceil + t0, h->tflags + t0,
@@ -1629,26 +1667,20 @@ static void launch_fast_gc(amdp* h, int K, const int32_t* actions, const amdp_tr
     }
 }
 
-template <int PVW, int BW>
+template <int LEVELS>
 static void launch_tp(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
-    k_rollout_tp<PVW, BW><<<nblk(h->cfg.n_envs, 128), 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J, actions ? 1 : 0,
-                                                                    h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP ? 1 : 0,
-                                                                    0xfffffffeu << h->tp_coarse_bits);
+    k_rollout_tp<LEVELS><<<nblk(h->cfg.n_envs, 128), 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J, actions ? 1 : 0,
+                                                                   h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP ? 1 : 0,
+                                                                   0xfffffffeu << h->tp_coarse_bits);
 }
 
 // lanes per env and register-resident chunks per lane for the fast kernel: n_pad == 4 * G * C
 static void launch_rollout_fast(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
     const int n_pad = h->cfg.n_pad;
     if (h->tp) {
-        const int key = h->tp_pvw * 16 + h->tp_bw;
-        switch (key) {
-            case 0 * 16 + 4: launch_tp<0, 4>(h, K, actions, J, st); break;
-            case 1 * 16 + 2: launch_tp<1, 2>(h, K, actions, J, st); break;
-            case 2 * 16 + 2: launch_tp<2, 2>(h, K, actions, J, st); break;
-            case 4 * 16 + 2: launch_tp<4, 2>(h, K, actions, J, st); break;
-            case 4 * 16 + 4: launch_tp<4, 4>(h, K, actions, J, st); break;
-            default: launch_tp<8, 4>(h, K, actions, J, st); break;
-        }
+        if (h->T.tp_levels == 1) launch_tp<1>(h, K, actions, J, st);
+        else if (h->T.tp_levels == 2) launch_tp<2>(h, K, actions, J, st);
+        else launch_tp<3>(h, K, actions, J, st);
         return;
     }
     if (h->two_level) { launch_fast_gc<8, 1, true>(h, K, actions, J, st); return; }
