@@ -6,7 +6,4 @@ prof() { tag=$1; shift
   ncu -i /tmp/prof_$tag.ncu-rep --page raw --csv > gpurun_out/prof_${tag}_raw.csv
   ncu -i /tmp/prof_$tag.ncu-rep --page source --csv > gpurun_out/prof_${tag}_source.csv
 }
-prof tp2_cfg2_64k_128 --workload cfg2 --envs 65536 --ticks 128 --search thread
-export AMDP_B200_LIB=build/libamdp_ldg256.so
-prof tp2_cfg2_64k_256 --workload cfg2 --envs 65536 --ticks 128 --search thread
-prof tp2_cfg4_256 --workload cfg4 --tasks 32 --ticks 64 --search thread
+prof tp3c_cfg2_64k --workload cfg2 --envs 65536 --ticks 128 --search thread

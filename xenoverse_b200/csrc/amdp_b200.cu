@@ -849,15 +849,27 @@ __device__ __forceinline__ int h2_count_lt(unsigned w, unsigned v2, int acc) {  
 }
 
 #define TP_S0 4
-template <int LEVELS>
-__global__ void __launch_bounds__(128, 5) k_rollout_tp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
-                                                       const int32_t* __restrict__ actions, const amdp_traj J, int given, int next, unsigned cmask) {
-    __shared__ double sh_stat[4][128];                            // closed-episode statistics: sum_ret, sum_ret_sq, min, max
-    __shared__ unsigned long long sh_cnt[2][128];                 // ep_count, sum_len
-    __shared__ double sh_s0c[TP_S0][128];                         // the env's start-state CDF and states (s0_pad <= TP_S0):
-    __shared__ int sh_s0i[TP_S0][128];                            // a reset costs no global-memory round trip
+#ifndef TP_TPB
+#define TP_TPB 64
+#endif
+#define TP_MINB_LO (640 / TP_TPB)
+#define TP_MINB_HI (896 / TP_TPB)
+// TP_TPB threads (= envs) per block: small blocks keep the last wave of a launch balanced over the 148 SMs
+// MINB = resident blocks per SM the register budget is sized for: 10 (96 registers, 640 envs per SM) or 14 (72 registers,
+// 896 envs per SM, chosen when that is what it takes to keep every env of the engine resident at once)
+template <int LEVELS, int MINB, bool GIVEN>
+__global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
+                                                       const int32_t* __restrict__ actions, const amdp_traj J, int next, unsigned cmask) {
+    // GIVEN is a template parameter on purpose: with a runtime flag the (predicated-off) action load still owns a
+    // scoreboard slot, which ptxas shares with the deferred payload / state-word loads, and the first use of the action at
+    // the top of a tick then waits for those loads BEFORE the tick's first search load is issued (ncu: +15 % time).
+    constexpr bool given = GIVEN;
+    __shared__ double sh_stat[4][TP_TPB];                         // closed-episode statistics: sum_ret, sum_ret_sq, min, max
+    __shared__ unsigned long long sh_cnt[2][TP_TPB];              // ep_count, sum_len
+    __shared__ double sh_s0c[TP_S0][TP_TPB];                         // the env's start-state CDF and states (s0_pad <= TP_S0):
+    __shared__ int sh_s0i[TP_S0][TP_TPB];                            // a reset costs no global-memory round trip
     const int tx = threadIdx.x;
-    const long long e = (long long)blockIdx.x * 128 + tx;
+    const long long e = (long long)blockIdx.x * TP_TPB + tx;
     if (e >= E.n_envs) return;
     const int n_pad = T.n_pad, na = T.na;
     const long long N = E.n_envs;
@@ -904,14 +916,14 @@ __global__ void __launch_bounds__(128, 5) k_rollout_tp(const Tables T, const Env
     sh_cnt[0][tx] = E.ep_count[e]; sh_cnt[1][tx] = E.sum_len[e];
     sh_stat[0][tx] = E.sum_ret[e]; sh_stat[1][tx] = E.sum_ret_sq[e];
     sh_stat[2][tx] = E.min_ret[e]; sh_stat[3][tx] = E.max_ret[e];
+    // s0_pad <= TP_S0 (the host never selects this kernel otherwise).  Keeping the start-state table on chip also keeps
+    // global loads out of the registers that carry the state from tick to tick: a load there, even on a path that is
+    // never taken, makes the top of every tick wait for the scoreboard slot it shares with the deferred loads.
     const int s0_pad = T.s0_pad;
-    const bool s0_local = s0_pad <= TP_S0;
-    if (s0_local) {
 #pragma unroll
-        for (int i = 0; i < TP_S0; ++i) {
-            sh_s0c[i][tx] = (i < s0_pad) ? T.s0_cdf[t * s0_pad + i] : 2.0;
-            sh_s0i[i][tx] = T.s0_idx[t * s0_pad + min(i, s0_pad - 1)];
-        }
+    for (int i = 0; i < TP_S0; ++i) {
+        sh_s0c[i][tx] = (i < s0_pad) ? T.s0_cdf[t * s0_pad + i] : 2.0;
+        sh_s0i[i][tx] = T.s0_idx[t * s0_pad + min(i, s0_pad - 1)];
     }
 
     // draws of one tick: words 0..3 of Philox block 0 (transition uniform = w.x, w.y; reset uniform = w.z, w.w), the reward
@@ -966,7 +978,7 @@ __global__ void __launch_bounds__(128, 5) k_rollout_tp(const Tables T, const Env
         int done_bits = 0;
         bool do_reset = pend;
         bool touched = pend;                                       // the tick stepped or reset: it has an observation
-        bool si_from_line = false;
+        bool si_from_line = false;                                 // the state word of s' came with the block line
         if (valid) {
             // (3) next state = #{cdf <= u}  (numpy choice: searchsorted(cdf, u, 'right'))         anymdp_env.py:100
             const uint32_t v15 = code15_from_m21(cur.wx >> 11);
@@ -1047,22 +1059,19 @@ __global__ void __launch_bounds__(128, 5) k_rollout_tp(const Tables T, const Env
         if (do_reset) {                                            // anymdp_env.py:81-90
             const double ur = u53(cur.wz, cur.ww);
             int c = 0;
-            if (s0_local) {
 #pragma unroll
-                for (int i = 0; i < TP_S0; ++i) c += (sh_s0c[i][tx] <= ur);          // pad 2.0 is never <= ur
-                c = min(c, s0_pad - 1);
-                s = sh_s0i[0][tx];
+            for (int i = 0; i < TP_S0; ++i) c += (sh_s0c[i][tx] <= ur);              // pad 2.0 is never <= ur
+            c = min(c, s0_pad - 1);
+            s = sh_s0i[0][tx];
 #pragma unroll
-                for (int i = 1; i < TP_S0; ++i) if (c == i) s = sh_s0i[i][tx];
-            } else {
-                for (int i = 0; i < s0_pad; ++i) c += (T.s0_cdf[t * s0_pad + i] <= ur);
-                s = T.s0_idx[t * s0_pad + min(c, s0_pad - 1)];
-            }
+            for (int i = 1; i < TP_S0; ++i) if (c == i) s = sh_s0i[i][tx];
             steps = 0;
             flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
         }
         // observation = state_mapping[s] (anymdp_env.py:145-148): from the block line unless the env was reset / fell back
-        if (!(si_from_line && !do_reset)) si_p = touched ? __ldg(sinfo_t + s) : 0;
+        // (measured: issuing the state-word load right behind the payload load and selecting here is ~8 % faster than one
+        // deferred load from a selected address, which ptxas schedules after the reset logic)
+        if (do_reset || !si_from_line) si_p = touched ? __ldg(sinfo_t + s) : 0;
         a_p = cur.a;
         done_p = done_bits;
         cur = nx;
@@ -1393,6 +1402,7 @@ struct amdp {
     bool force_generic;    // debug: route rollouts through the generic kernel
     bool two_level;        // the fast kernel searches pivots + one 32-entry block instead of streaming the whole row
     bool tp;               // rollouts run on the thread-per-env kernel (k_rollout_tp)
+    int n_sm;              // multiprocessors of the device
     int tp_coarse_bits;    // debug: low bits of the 31-bit codes ignored by k_rollout_tp (0 in production)
     uint4* fat; uint16_t* pv; uint16_t* top;   // its tables (see Tables)
     char err[512];
@@ -1494,6 +1504,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     }
     *out = h;   // from here on errors are reported through the handle; the caller destroys it
     CK(cudaSetDevice(c.device));
+    CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, c.device));
     const int toks = c.n_obs_tok > c.n_act_tok ? c.n_obs_tok : c.n_act_tok;
     h->n_slots = AMDP_SLOTS_PER_TOKEN * toks;
     h->G = pick_group(c.n_pad);
@@ -1505,7 +1516,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     h->two_level = (c.n_pad >= 256 && c.n_pad <= 1024) && !(c.reserved0 & 2) && ((c.reserved0 & 4) || c.n_pad >= 512 || c.n_envs >= 16384);
     if (h->two_level) { if ((rc = dalloc(h, &h->pivot, rows * 32))) return rc; }
     // thread-per-env tables: chosen for engines with enough envs to fill the GPU (or forced by flag 8; never with 16)
-    h->tp = mdp && c.n_pad <= 2048 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= 16384));
+    h->tp = mdp && c.n_pad <= 2048 && c.s0_pad <= TP_S0 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= 16384));
     if (h->tp) {
         const int nb = (c.n_pad + 7) / 8;
         h->T.tp_blocks = nb;
@@ -1669,9 +1680,16 @@ static void launch_fast_gc(amdp* h, int K, const int32_t* actions, const amdp_tr
 
 template <int LEVELS>
 static void launch_tp(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
-    k_rollout_tp<LEVELS><<<nblk(h->cfg.n_envs, 128), 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J, actions ? 1 : 0,
-                                                                   h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP ? 1 : 0,
-                                                                   0xfffffffeu << h->tp_coarse_bits);
+    const unsigned int blocks = nblk(h->cfg.n_envs, TP_TPB);
+    const int next = h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP ? 1 : 0;
+    const unsigned cmask = 0xfffffffeu << h->tp_coarse_bits;
+    // every env resident at once when the smaller register budget makes that possible (one wave instead of 1.x)
+    const long long cap10 = (long long)h->n_sm * 640, cap14 = (long long)h->n_sm * 896;
+    const bool hi = h->cfg.n_envs > cap10 && h->cfg.n_envs <= cap14;
+#define TP_LAUNCH(MINB, GIVEN) k_rollout_tp<LEVELS, MINB, GIVEN><<<blocks, TP_TPB, 0, st>>>(h->T, h->E, h->tick, K, actions, J, next, cmask)
+    if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, true); else TP_LAUNCH(TP_MINB_LO, true); }
+    else { if (hi) TP_LAUNCH(TP_MINB_HI, false); else TP_LAUNCH(TP_MINB_LO, false); }
+#undef TP_LAUNCH
 }
 
 // lanes per env and register-resident chunks per lane for the fast kernel: n_pad == 4 * G * C
