@@ -159,6 +159,42 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def quick_measure(name, envs, tasks, ns, na, no, ticks, steps, dev, local, search="auto"):
+    """Device-timed rollouts of another workload on this GPU (same method as the headline: CUDA events around `steps`
+    launches after 3 warm-ups, tables >> L2) — reported under "other_workloads", never as the headline value."""
+    import torch
+    from xenoverse_b200 import AnyMDPVecEnv, synth_packed, synth_geometry
+    geo = synth_geometry(ns, na, no)
+    env = AnyMDPVecEnv(envs, device=local, seed=0, search=search)
+    per_task = 3 * 8 * geo["n_pad"] * na * geo["n_pad"]
+    chunk = max(1, min(tasks, (768 << 20) // per_task))
+    env.set_task(None, packed=(geo, tasks, ((t0, synth_packed(ns, na, min(chunk, tasks - t0), seed=1000 + t0, device=dev, no=no))
+                                            for t0 in range(0, tasks, chunk))))
+    env.reset()
+    traj = {"obs": torch.empty((ticks, envs, 1), dtype=torch.int32, device=dev),
+            "action": torch.empty((ticks, envs, 1), dtype=torch.int32, device=dev),
+            "reward": torch.empty((ticks, envs), dtype=torch.float32, device=dev),
+            "done": torch.empty((ticks, envs), dtype=torch.uint8, device=dev)}
+    for _ in range(3):
+        env.rollout(ticks, out=traj)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        env.rollout(ticks, out=traj)
+    t1.record()
+    torch.cuda.synchronize()
+    env.check()
+    ms = t0.elapsed_time(t1) / steps
+    out = {"workload": describe(name, envs, tasks, ns, na, no, ticks), "value": envs * ticks / (ms * 1e-3), "unit": "env-steps/s",
+           "ms_per_launch": ms, "kernel": env.engine.rollout_kernel, "table_bytes": env.engine.device_bytes,
+           "algorithmic_bytes_per_env_step": b_alg(ns, no)}
+    env.close()
+    del env, traj
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # the B200 arm
 # --------------------------------------------------------------------------------------------------
@@ -249,6 +285,7 @@ def run_b200(args, name, envs, tasks, ns, na, no):
     torch.cuda.synchronize()
     clk = clocks.stop() if rank == 0 else None
     launches = env.engine.launch_count - launches0
+    kernel_name = env.engine.rollout_kernel
     ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     kern_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / K], dtype=torch.float64, device=dev)
     if world > 1:
@@ -287,6 +324,23 @@ def run_b200(args, name, envs, tasks, ns, na, no):
                "ms_per_step": 1e3 * float(w) / reps}
         env.check()
 
+    others = None
+    if world == 1 and not args.no_other:
+        # the other BASELINE.json configs at their per-GPU sizes (cfg4 with the 32 tasks one of 8 GPUs owns), plus the
+        # cfg2 tables with enough envs to fill the GPU: the regimes where the path is bound by DRAM, not by latency
+        device_bytes = env.engine.device_bytes
+        env.close()
+        torch.cuda.empty_cache()
+        others = {}
+        for key, (wl, n_envs, n_tasks, tk) in {"cfg2_x65536_envs": ("cfg2", 65536, 4096, 128), "cfg3": ("cfg3", 65536, 4096, 64),
+                                               "cfg4_32_tasks": ("cfg4", 65536, 32, 64), "cfg5": ("cfg5", 131072, 131072, 128)}.items():
+            _, _, o_ns, o_na, o_no = WORKLOADS[wl]
+            try:
+                others[key] = quick_measure(wl, n_envs, n_tasks, o_ns, o_na, o_no, tk, 10, dev, local)
+            except Exception as ex:           # never lose the headline line to an extra
+                others[key] = {"error": str(ex)[:200]}
+    else:
+        device_bytes = env.engine.device_bytes
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.isfile(peaks_path):
@@ -308,18 +362,23 @@ def run_b200(args, name, envs, tasks, ns, na, no):
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": describe(name, envs, tasks, ns, na, no, ticks), "envs_per_gpu": N, "tasks_per_gpu": tasks,
-                       "ticks_per_step": ticks, "table_bytes_per_gpu": env.engine.device_bytes,
-                       "l2": "inputs larger than L2 (tables >> 126 MB; no flush needed)" if env.engine.device_bytes > (1 << 30)
+                       "ticks_per_step": ticks, "table_bytes_per_gpu": device_bytes,
+                       "l2": "inputs larger than L2 (tables >> 126 MB; no flush needed)" if device_bytes > (1 << 30)
                              else "tables may be L2 resident", "parallelism": f"env-sharded dp{world}",
                        "upload_s": round(t_up, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                          "traffic_source": traffic_note, "algorithmic_bytes_per_launch": balg * N * ticks,
-                         "peak_source": which, "kernel": "k_rollout_mdp",
+                         "peak_source": which, "kernel": kernel_name,
                          "algorithmic_bytes_per_env_step": balg, "kernel_ms_per_launch": kern_ms},
             "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
             "episodes": ep["episodes"], "mean_return": ep["mean_return"], "mean_length": ep["mean_length"],
         }
+        if others:
+            for o in others.values():
+                if "value" in o:
+                    o["roofline_frac"] = o["algorithmic_bytes_per_env_step"] * o["value"] / 1e9 / peak
+            line["other_workloads"] = others
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -339,6 +398,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=128)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other workloads (N = 1 only)")
     ap.add_argument("--ref-steps-per-worker", type=int, default=20000)
     ap.add_argument("--search", default="auto", choices=["auto", "one_level", "two_level", "thread", "warp"],
                     help="row-search / kernel selection of the engine (see Engine)")

@@ -255,6 +255,11 @@ int amdp_debug_tp_coarse_bits(amdp_t* h, int bits);
 /* Debug/verification: route amdp_rollout through the generic per-tick kernel instead of the fast MDP kernel. */
 int amdp_debug_force_generic(amdp_t* h, int on);
 
+/* Name of the kernel amdp_rollout() runs for engine-generated draws on this handle (bench.py's roofline.kernel):
+ * "k_rollout_tp<...>" (one thread per env), "k_rollout_mdp<...>" (one warp / lane group per env) or "k_rollout<...>"
+ * (generic per-tick kernel).  HOST string owned by the handle. */
+const char* amdp_rollout_kernel(amdp_t* h);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t amdp_launch_count(const amdp_t* h);
 

@@ -526,3 +526,41 @@ def test_thread_per_env_kernel_matches_oracle_replay():
         assert numpy.array_equal((d & 1).astype(bool), o["terminated"]) and numpy.array_equal((d >> 1).astype(bool), o["truncated"])
         assert numpy.allclose(tr["reward"][k].cpu().numpy(), o["reward"], rtol=1e-6, atol=1e-6)
     assert env.episode_stats()["episodes"] == orc.stats()["episodes"]
+
+
+@pytest.mark.parametrize("ns,na,no,N,mode,given,coarse", [
+    (16, 4, 12, 200, "same_step", False, 0), (64, 8, 64, 130, "same_step", False, 0), (64, 8, 64, 90, "next_step", True, 16),
+    (30, 3, 100, 64, "same_step", True, 0), (8, 2, 8, 40, "next_step", False, 0), (200, 2, 33, 30, "same_step", False, 18)])
+def test_thread_per_env_pomdp_equals_generic_kernel(ns, na, no, N, mode, given, coarse):
+    """POMDP on k_rollout_tp: the observation draw (anymdp_env.py:153) is a second pivots + codes search, pipelined one
+    tick behind the transition; records, state and statistics must equal the generic kernel bit for bit."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    tasks = [synth_task(ns, na, 1500 + t, no=no) for t in range(4)]
+    if ns >= 200:
+        for t in tasks:
+            t["max_steps"] = 45
+    K = 250
+    acts = None
+    if given:
+        acts = torch.randint(0, na, (K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(no)).cuda()
+    outs = []
+    for generic in (False, True):
+        env = AnyMDPVecEnv(N, seed=47, autoreset=mode, search="thread")
+        env.set_task(tasks)
+        assert env.engine.rollout_kernel.startswith("k_rollout_tp") and "POMDP" in env.engine.rollout_kernel
+        env.engine.force_generic(generic)
+        env.engine.tp_coarse_bits(coarse)
+        env.reset()
+        tr = env.rollout(K, actions=acts, record=("obs", "action", "reward", "reward_gt", "done"))
+        tr2 = env.rollout(3, actions=None if acts is None else acts[:3], record=("packed",))
+        env.check()
+        outs.append((tr, tr2, env.engine.get_state(), env.episode_stats(), env.engine.debug_counters()))
+    (a, a2, sa, ea, ca), (b, b2, sb, eb, cb) = outs
+    for key in ("obs", "action", "done", "reward", "reward_gt"):
+        assert torch.equal(a[key], b[key]), key
+    assert torch.equal(a2["packed"], b2["packed"])
+    for key in ("state", "steps", "flags", "ep_return"):
+        assert torch.equal(sa[key], sb[key]), key
+    assert ea == eb and ea["episodes"] > 0
+    if coarse:
+        assert ca["exact_fallbacks"] > 20, ca

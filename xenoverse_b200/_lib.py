@@ -67,6 +67,7 @@ _SIGNATURES = {
     "amdp_debug_tp_coarse_bits": (ctypes.c_int, [_P, ctypes.c_int]),
     "amdp_debug_counters": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),
     "amdp_launch_count": (ctypes.c_int64, [_P]),
+    "amdp_rollout_kernel": (ctypes.c_char_p, [_P]),
     "amdp_rollout_host": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P]),
     "amdp_rollout_host_packed": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P, _P]),
 }

@@ -49,6 +49,9 @@ struct Tables {
     const uint16_t* pv;       // [T][n_pad][na][tp_groups][16] code15 of the LAST entry of each block of a group of 16; pad 0x7bff
     const uint16_t* top;      // [T][n_pad][na][16] code15 of the last entry of each group (three-level rows only)
     int tp_levels, tp_groups, tp_blocks;
+    const uint32_t* ofat;     // POMDP (do = 1): [T][n_pad][8 + 8 * o_blocks] words per observation row: 16 pivots (code15 of the last
+                              // entry of each 8-entry block; pad 0x7bff), then o_blocks x 8 codes (floor(cdf * 2^31) << 1)
+    int o_blocks;
     int n_pad, na, no_pad, d_o, d_a, s0_pad, task_type, autoreset;
 };
 
@@ -857,7 +860,7 @@ __device__ __forceinline__ int h2_count_lt(unsigned w, unsigned v2, int acc) {  
 // TP_TPB threads (= envs) per block: small blocks keep the last wave of a launch balanced over the 148 SMs
 // MINB = resident blocks per SM the register budget is sized for: 10 (96 registers, 640 envs per SM) or 14 (72 registers,
 // 896 envs per SM, chosen when that is what it takes to keep every env of the engine resident at once)
-template <int LEVELS, int MINB, bool GIVEN>
+template <int LEVELS, int MINB, bool GIVEN, bool POMDP>
 __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
                                                        const int32_t* __restrict__ actions, const amdp_traj J, int next, unsigned cmask) {
     // GIVEN is a template parameter on purpose: with a runtime flag the (predicated-off) action load still owns a
@@ -928,7 +931,8 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
 
     // draws of one tick: words 0..3 of Philox block 0 (transition uniform = w.x, w.y; reset uniform = w.z, w.w), the reward
     // normal and the action (given or uniform random policy)
-    struct Draw { uint32_t wx, wy, wz, ww; float z; int a; };
+    // POMDP: also block 1 = (observation uniform, reset-observation uniform)           anymdp_env.py:153 under step / reset
+    struct Draw { uint32_t wx, wy, wz, ww; float z; int a; uint32_t ox, oy, rx, ry; };
     auto draw = [&](int k) {
         Draw d;
         const unsigned long long tk = tick0 + (unsigned long long)k;
@@ -936,6 +940,10 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
         d.wx = w0.x; d.wy = w0.y; d.wz = w0.z; d.ww = w0.w;
         const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
         d.z = box_muller(w2.x, w2.y);
+        if (POMDP) {
+            const uint4 w1 = philox_block(env_id, (uint32_t)(AMDP_SLOT_OBS >> 1), tk, E.key);
+            d.ox = w1.x; d.oy = w1.y; d.rx = w1.z; d.ry = w1.w;
+        } else { d.ox = d.oy = d.rx = d.ry = 0; }
         if (given) d.a = (k < K) ? load_action(actions, (long long)k * N + e, J.actions_u8) : 0;
         else d.a = (int)__umulhi(w2.z, (uint32_t)na);
         return d;
@@ -947,11 +955,64 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
     float z_p = 0.f;
     int si_p = 0, a_p = 0, done_p = 0, steps_p = 0;
     bool close_p = false;
+    unsigned n_fallback = 0;
+    // POMDP: the observation of tick k is a second two-level search (anymdp_env.py:153), taken off the chain: its pivots are
+    // requested at the end of tick k, its code block early in tick k+1, and the record of tick k is written at the end of
+    // tick k+1.
+    float rew_q = 0.f, rgt_q = 0.f;
+    int a_q = 0, done_q = 0;
+    uint4 opv[2], ocd[2];                      // observation pivots / codes in flight
+    uint32_t oux = 0, ouy = 0;                 // the uniform of the observation draw (two Philox words)
+    const uint32_t* orow = nullptr;            // its row in T.ofat (null: the tick has no observation)
+    int oblk = 0, so_p = 0;
+    const int o_blocks = T.o_blocks;
+    auto obs_stage1 = [&]() {                  // pivots -> block; request the block's codes
+        if (orow) {
+            const uint32_t v15 = code15_from_m21(oux >> 11);
+            const unsigned v2 = v15 | (v15 << 16);
+            int acc = 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                acc = h2_count_lt(opv[i].x, v2, acc); acc = h2_count_lt(opv[i].y, v2, acc);
+                acc = h2_count_lt(opv[i].z, v2, acc); acc = h2_count_lt(opv[i].w, v2, acc);
+            }
+            oblk = min(-acc, o_blocks - 1);
+            ldg_words<2>(orow + 8 + 8 * oblk, ocd);
+        }
+    };
+    auto obs_stage2 = [&](int kp) {            // codes -> observation; write the record of tick kp
+        int obs = 0;
+        if (orow) {
+            const unsigned ve = ((((oux >> 5) << 4) | (ouy >> 28)) << 1) & cmask;
+            int lt, le;
+            for (;;) {
+                lt = 0; le = 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const unsigned x[4] = {ocd[i].x, ocd[i].y, ocd[i].z, ocd[i].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const unsigned xm = x[j] & cmask; lt += (xm < ve); le += (xm <= ve); }
+                }
+                if (lt < 8 || oblk >= o_blocks - 1) break;
+                ++oblk;
+                ldg_words<2>(orow + 8 + 8 * oblk, ocd);
+            }
+            obs = oblk * 8 + lt;
+            if (le != lt) {
+                const double u = u53(oux, ouy);
+                const double* cr = T.obs_cdf + (t * n_pad + so_p) * (long long)T.no_pad;
+                while (obs < T.no_pad - 1 && __ldg(cr + obs) <= u) ++obs;
+                n_fallback += 1;
+            }
+        }
+        write_rec(kp, obs, a_q, done_q, rew_q, rgt_q);
+    };
     auto settle = [&](int kp) {
         // reward = gt + noise * z (anymdp_env.py:103-105), episode return, closed-episode statistics, the record
         const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
         ep_ret += rew;
-        write_rec(kp, si_p & 0x7fffffff, a_p, done_p, (float)rew, pay_p.x);
+        if (POMDP) { rew_q = (float)rew; rgt_q = pay_p.x; a_q = a_p; done_q = done_p; }
+        else write_rec(kp, si_p & 0x7fffffff, a_p, done_p, (float)rew, pay_p.x);
         if (close_p) {
             sh_cnt[0][tx] += 1; sh_cnt[1][tx] += (unsigned long long)steps_p;
             sh_stat[0][tx] += ep_ret; sh_stat[1][tx] += ep_ret * ep_ret;
@@ -960,8 +1021,6 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
             close_p = false;
         }
     };
-    unsigned n_fallback = 0;
-
     for (int k = 0; k < K; ++k) {
         const bool pend = next && (flags & FLAG_PENDING);          // next_step mode: this tick only performs the reset
         const bool a_ok = !given || (unsigned)cur.a < (unsigned)na;
@@ -973,8 +1032,12 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
         if (LEVELS == 3 && valid) ldg_words_keep<2>(T.top + row * 16u, lv, pol_keep);
         if (LEVELS == 2 && valid) ldg_words_keep<2>(T.pv + row * 16u, lv, pol_keep);
         // (2) in the shadow of that load: the previous tick's reward / record
-        if (k > 0) settle(k - 1);
+        if (k > 0) { settle(k - 1); if (POMDP) obs_stage1(); }
+        // the next tick's draws: in the shadow of the block load, or (small register budget) here, before the search data
+        // occupies registers
+        constexpr bool DRAW_EARLY = (MINB == TP_MINB_HI);
         Draw nx;
+        if (DRAW_EARLY) nx = draw(k + 1);
         int done_bits = 0;
         bool do_reset = pend;
         bool touched = pend;                                       // the tick stepped or reset: it has an observation
@@ -1008,7 +1071,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
             for (bool first = true;; first = false) {
                 uint4 bw[2];
                 ldg_words<2>(frow + blk * 8, bw);
-                if (first) nx = draw(k + 1);                       // in the shadow of the block load: the next tick's draws
+                if (first && !DRAW_EARLY) nx = draw(k + 1);        // in the shadow of the block load: the next tick's draws
                 lt = 0; le = 0; mn = 0xffffffffu;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
@@ -1038,8 +1101,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
             } else {
                 const char* line = reinterpret_cast<const char*>(frow + blk * 8);
                 pay_p = ldg_stream_f32x2(reinterpret_cast<const float2*>(line + 32) + lt);
-                si_p = __ldg(reinterpret_cast<const int*>(line + 96) + lt);
-                si_from_line = true;
+                if (!POMDP) { si_p = __ldg(reinterpret_cast<const int*>(line + 96) + lt); si_from_line = true; }
             }
             // (5) state update, termination, truncation (anymdp_env.py:107-108,113-114)
             s = nxt;
@@ -1053,7 +1115,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
             }
         } else {
             pay_p = make_float2(0.f, 0.f);
-            nx = draw(k + 1);
+            if (!DRAW_EARLY) nx = draw(k + 1);
         }
         z_p = cur.z;
         if (do_reset) {                                            // anymdp_env.py:81-90
@@ -1071,12 +1133,21 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
         // observation = state_mapping[s] (anymdp_env.py:145-148): from the block line unless the env was reset / fell back
         // (measured: issuing the state-word load right behind the payload load and selecting here is ~8 % faster than one
         // deferred load from a selected address, which ptxas schedules after the reset logic)
-        if (do_reset || !si_from_line) si_p = touched ? __ldg(sinfo_t + s) : 0;
+        if (!POMDP) { if (do_reset || !si_from_line) si_p = touched ? __ldg(sinfo_t + s) : 0; }
+        if (POMDP) {
+            if (k > 0) obs_stage2(k - 1);                          // the previous tick's record (its codes arrived long ago)
+            // this tick's observation: drawn from the state after the step, or after the reset    anymdp_env.py:90,132
+            orow = touched ? T.ofat + (unsigned long long)(t * n_pad + s) * (unsigned)(8 + 8 * o_blocks) : nullptr;
+            oux = do_reset ? cur.rx : cur.ox; ouy = do_reset ? cur.ry : cur.oy;
+            so_p = s;
+            if (orow) ldg_words<2>(orow, opv);
+        }
         a_p = cur.a;
         done_p = done_bits;
         cur = nx;
     }
     settle(K - 1);
+    if (POMDP) { obs_stage1(); obs_stage2(K - 1); }
     E.state[e] = s; E.steps[e] = steps; E.flags[e] = (uint8_t)flags; E.ep_return[e] = ep_ret;
     E.ep_count[e] = sh_cnt[0][tx]; E.sum_len[e] = sh_cnt[1][tx];
     E.sum_ret[e] = sh_stat[0][tx]; E.sum_ret_sq[e] = sh_stat[1][tx];
@@ -1255,7 +1326,8 @@ __global__ void k_build_small(int64_t cnt, int n_pad, int s0_pad, const int32_t*
 }
 
 // observation CDF rows: one thread per (task, token, state)
-__global__ void k_build_obs(int64_t rows, int n_pad, int no_pad, const double* __restrict__ obs_t, double* __restrict__ obs_cdf) {
+__global__ void k_build_obs(int64_t rows, int n_pad, int no_pad, const double* __restrict__ obs_t, double* __restrict__ obs_cdf,
+                            uint32_t* __restrict__ ofat, int o_blocks) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const double* p = obs_t + r * no_pad;
@@ -1265,6 +1337,16 @@ __global__ void k_build_obs(int64_t rows, int n_pad, int no_pad, const double* _
     // zero padding leaves the tail at the final partial sum, i.e. 1.0 after the divide
     if (acc > 0.0) for (int i = 0; i < no_pad; ++i) { double v = __ddiv_rn(c[i], acc); c[i] = (v == 0.0) ? 0.0 : v; }
     else for (int i = 0; i < no_pad; ++i) c[i] = 1.0;
+    if (ofat) {
+        // thread-per-env observation row (do = 1): 16 pivots, then the 31-bit codes block by block
+        uint32_t* o = ofat + r * (8 + 8 * o_blocks);
+        uint16_t* pvt = reinterpret_cast<uint16_t*>(o);
+        for (int b = 0; b < 16; ++b) {
+            const int last = 8 * b + 7;
+            pvt[b] = (b < o_blocks) ? (uint16_t)code15((last < no_pad) ? c[last] : 1.0) : (uint16_t)0x7bff;
+        }
+        for (int i = 0; i < 8 * o_blocks; ++i) o[8 + i] = code31((i < no_pad) ? c[i] : 1.0) << 1;
+    }
 }
 
 __global__ void k_assign(EnvArrays E, int32_t* task_dst, const int32_t* __restrict__ env_task) {
@@ -1404,8 +1486,9 @@ struct amdp {
     bool tp;               // rollouts run on the thread-per-env kernel (k_rollout_tp)
     int n_sm;              // multiprocessors of the device
     int tp_coarse_bits;    // debug: low bits of the 31-bit codes ignored by k_rollout_tp (0 in production)
-    uint4* fat; uint16_t* pv; uint16_t* top;   // its tables (see Tables)
+    uint4* fat; uint16_t* pv; uint16_t* top; uint32_t* ofat;   // its tables (see Tables)
     char err[512];
+    char kname[64];
     // rollout_host staging
     int32_t* st_act[2]; int32_t* st_obs[2]; float* st_rew[2]; uint8_t* st_done[2]; unsigned long long* st_rec[2];
     int st_chunk;
@@ -1472,7 +1555,7 @@ static int pick_group(int n_pad) {
 extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
+    void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
@@ -1516,7 +1599,8 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     h->two_level = (c.n_pad >= 256 && c.n_pad <= 1024) && !(c.reserved0 & 2) && ((c.reserved0 & 4) || c.n_pad >= 512 || c.n_envs >= 16384);
     if (h->two_level) { if ((rc = dalloc(h, &h->pivot, rows * 32))) return rc; }
     // thread-per-env tables: chosen for engines with enough envs to fill the GPU (or forced by flag 8; never with 16)
-    h->tp = mdp && c.n_pad <= 2048 && c.s0_pad <= TP_S0 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= 16384));
+    const bool tp_kind = mdp || (c.task_type == AMDP_POMDP && c.no_pad <= 128);      // POMDP: one observation token, <= 16 blocks
+    h->tp = tp_kind && c.n_pad <= 2048 && c.s0_pad <= TP_S0 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= 16384));
     if (h->tp) {
         const int nb = (c.n_pad + 7) / 8;
         h->T.tp_blocks = nb;
@@ -1525,6 +1609,10 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
         if ((rc = dalloc(h, &h->fat, rows * nb * 8))) return rc;
         if (h->T.tp_levels >= 2) { if ((rc = dalloc(h, &h->pv, rows * h->T.tp_groups * 16))) return rc; }
         if (h->T.tp_levels == 3) { if ((rc = dalloc(h, &h->top, rows * 16))) return rc; }
+        if (!mdp) {
+            h->T.o_blocks = (c.no_pad + 7) / 8;
+            if ((rc = dalloc(h, &h->ofat, (size_t)c.n_tasks * c.n_pad * (8 + 8 * h->T.o_blocks)))) return rc;
+        }
     }
     if (c.reserved0 & 1) { if ((rc = dalloc(h, &h->raw_t, rows * c.n_pad))) return rc; }
     if ((rc = dalloc(h, &h->sinfo, (size_t)c.n_tasks * c.n_pad))) return rc;
@@ -1556,7 +1644,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     E.task = h->env_task; E.faults = h->faults; E.counters = h->counters; E.n_envs = c.n_envs; E.env_id_base = c.env_id_base;
     E.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
     Tables& T = h->T;
-    T.fat = h->fat; T.pv = h->pv; T.top = h->top;
+    T.fat = h->fat; T.pv = h->pv; T.top = h->top; T.ofat = h->ofat;
     T.cdf = h->cdf; T.payload = h->payload; T.sketch = h->sketch; T.pivot = h->pivot; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
     T.obs_cdf = h->obs_cdf; T.max_ceil = h->max_ceil; T.tflags = h->tflags; T.raw_t = h->raw_t; T.n_real = h->n_real;
     T.n_pad = c.n_pad; T.na = c.na; T.no_pad = c.no_pad; T.d_o = c.n_obs_tok; T.d_a = c.n_act_tok; T.s0_pad = c.s0_pad;
@@ -1598,7 +1686,9 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
     if (c.task_type != AMDP_MDP) {
         const long long orows = (long long)cnt * c.n_obs_tok * c.n_pad;
         k_build_obs<<<nblk(orows, 128), 128, 0, st>>>(orows, c.n_pad, c.no_pad, obs_transition,
-                                                      h->obs_cdf + (size_t)t0 * c.n_obs_tok * c.n_pad * c.no_pad);
+                                                      h->obs_cdf + (size_t)t0 * c.n_obs_tok * c.n_pad * c.no_pad,
+                                                      h->ofat ? h->ofat + (size_t)t0 * c.n_pad * (8 + 8 * h->T.o_blocks) : nullptr,
+                                                      h->T.o_blocks);
         h->launches += 1;
     }
     if (h->raw_t) CK(cudaMemcpyAsync(h->raw_t + t0 * per_task, transition, per_task * cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1683,12 +1773,18 @@ static void launch_tp(amdp* h, int K, const int32_t* actions, const amdp_traj& J
     const unsigned int blocks = nblk(h->cfg.n_envs, TP_TPB);
     const int next = h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP ? 1 : 0;
     const unsigned cmask = 0xfffffffeu << h->tp_coarse_bits;
-    // every env resident at once when the smaller register budget makes that possible (one wave instead of 1.x)
-    const long long cap10 = (long long)h->n_sm * 640, cap14 = (long long)h->n_sm * 896;
-    const bool hi = h->cfg.n_envs > cap10 && h->cfg.n_envs <= cap14;
-#define TP_LAUNCH(MINB, GIVEN) k_rollout_tp<LEVELS, MINB, GIVEN><<<blocks, TP_TPB, 0, st>>>(h->T, h->E, h->tick, K, actions, J, next, cmask)
-    if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, true); else TP_LAUNCH(TP_MINB_LO, true); }
-    else { if (hi) TP_LAUNCH(TP_MINB_HI, false); else TP_LAUNCH(TP_MINB_LO, false); }
+    // Two register budgets: 72 registers (896 envs resident per SM, the next tick's draws generated before the search
+    // loads are issued) and 96 (640 per SM, draws generated in the shadow of the block load).  Measured on cfg2 / cfg4 /
+    // cfg5 at 65536-131072 envs the small budget wins everywhere (+3 .. +50 %, most where it turns 1.4 waves into one);
+    // AMDP_TP_MINB=lo selects the large one for experiments.  The POMDP variant carries the observation search as well.
+    bool hi = h->cfg.task_type != AMDP_POMDP;         // (the POMDP variant spills at 72 registers)
+    if (const char* o = getenv("AMDP_TP_MINB")) hi = (o[0] == 'h');
+#define TP_LAUNCH(MINB, GIVEN, POMDP) k_rollout_tp<LEVELS, MINB, GIVEN, POMDP><<<blocks, TP_TPB, 0, st>>>(h->T, h->E, h->tick, K, actions, J, next, cmask)
+    if (h->cfg.task_type == AMDP_POMDP) {
+        if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, true, true); else TP_LAUNCH(TP_MINB_LO, true, true); }
+        else { if (hi) TP_LAUNCH(TP_MINB_HI, false, true); else TP_LAUNCH(TP_MINB_LO, false, true); }
+    } else if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, true, false); else TP_LAUNCH(TP_MINB_LO, true, false); }
+    else { if (hi) TP_LAUNCH(TP_MINB_HI, false, false); else TP_LAUNCH(TP_MINB_LO, false, false); }
 #undef TP_LAUNCH
 }
 
@@ -1725,7 +1821,7 @@ extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const 
                      (h->cfg.task_type != AMDP_MDP && h->cfg.no_pad > (1 << 20))))
         return fail(h, AMDP_EINVAL, "packed records need do == da == 1, at most 2^20 observations and 1024 actions");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fast = h->cfg.task_type == AMDP_MDP && !u_inject && !h->force_generic;
+    const bool fast = (h->cfg.task_type == AMDP_MDP || (h->tp && h->cfg.task_type == AMDP_POMDP)) && !u_inject && !h->force_generic;
     if (fast) {
         launch_rollout_fast(h, K, actions, J, st);
     } else {
@@ -1809,6 +1905,17 @@ extern "C" int amdp_debug_counters(amdp_t* h, uint64_t* out4) {
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemcpy(out4, h->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return AMDP_OK;
+}
+
+extern "C" const char* amdp_rollout_kernel(amdp_t* h) {
+    if (!h) return "";
+    const amdp_config& c = h->cfg;
+    const bool fast = (c.task_type == AMDP_MDP || (h->tp && c.task_type == AMDP_POMDP)) && !h->force_generic;
+    if (!fast) snprintf(h->kname, sizeof(h->kname), "k_rollout<G=%d>", h->G);
+    else if (h->tp) snprintf(h->kname, sizeof(h->kname), "k_rollout_tp<levels=%d,%s>", h->T.tp_levels, c.task_type == AMDP_POMDP ? "POMDP" : "MDP");
+    else if (h->two_level) snprintf(h->kname, sizeof(h->kname), "k_rollout_mdp<G=8,two-level>");
+    else snprintf(h->kname, sizeof(h->kname), "k_rollout_mdp<G=%d>", h->G);
+    return h->kname;
 }
 
 extern "C" int amdp_debug_tp_coarse_bits(amdp_t* h, int bits) {

@@ -175,6 +175,11 @@ class Engine:
         return int(lib.amdp_device_bytes(self._h))
 
     @property
+    def rollout_kernel(self):
+        """Name of the kernel `rollout()` runs on this engine (with engine-generated draws)."""
+        return lib.amdp_rollout_kernel(self._h).decode()
+
+    @property
     def launch_count(self):
         return int(lib.amdp_launch_count(self._h))
 
