@@ -400,7 +400,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other workloads (N = 1 only)")
     ap.add_argument("--ref-steps-per-worker", type=int, default=20000)
-    ap.add_argument("--search", default="auto", choices=["auto", "one_level", "two_level", "thread", "warp"],
+    ap.add_argument("--search", default="auto", choices=["auto", "one_level", "two_level", "thread", "warp", "warp_v1"],
                     help="row-search / kernel selection of the engine (see Engine)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

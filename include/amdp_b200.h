@@ -103,7 +103,8 @@ typedef struct amdp_config {
     int32_t  s0_pad;        /* max len(s_0) over tasks */
     int32_t  reserved0;     /* flags: 1 keep a copy of `transition` (amdp_gather_transition_gt); 8 / 16 force / forbid the thread-per-env rollout
                                kernel (default: used from 16384 envs); 2 / 4 force the one- / two-level
-                               row search of the fast rollout kernel (default: chosen from n_pad and n_envs) */
+                               row search of the fast rollout kernel (default: chosen from n_pad and n_envs); 32 keeps MDP engines
+                               off k_rollout_w (the REDUX.MIN warp-per-env kernel for rows of 64 / 128 / 256 states) */
     int64_t  n_envs;        /* envs owned by this handle (this GPU's shard) */
     int64_t  n_tasks;       /* tasks resident on this handle */
     uint64_t seed;          /* Philox key */

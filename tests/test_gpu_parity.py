@@ -564,3 +564,88 @@ def test_thread_per_env_pomdp_equals_generic_kernel(ns, na, no, N, mode, given, 
     assert ea == eb and ea["episodes"] > 0
     if coarse:
         assert ca["exact_fallbacks"] > 20, ca
+
+
+@pytest.mark.parametrize("ns,na,N,given,K", [
+    (64, 8, 130, False, 300), (128, 5, 257, False, 300), (128, 5, 100, True, 45), (256, 3, 40, False, 200),
+    (256, 3, 37, True, 333), (64, 2, 3000, True, 64), (128, 5, 2000, False, 97)])
+def test_warp_per_env_redux_kernel_equals_generic_kernel(ns, na, N, given, K):
+    """k_rollout_w (one warp per env, fp16-ordered 15-bit filter codes counted with HSET2, one REDUX.MIN per transition,
+    reset state and termination known without a memory access) vs the generic per-tick kernel and vs the older
+    k_rollout_mdp: identical records, env state and statistics; the float64 fallback must have run."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    tasks = [synth_task(ns, na, 1700 + t) for t in range(6)]
+    if ns >= 200:
+        for t in tasks:
+            t["max_steps"] = 45
+    acts = None
+    if given:
+        acts = torch.randint(0, na, (K, N), dtype=torch.int32, generator=torch.Generator().manual_seed(ns + 7)).cuda()
+    outs = []
+    for search, generic in (("auto", False), ("auto", True), ("warp_v1", False)):
+        env = AnyMDPVecEnv(N, seed=53, search=search)
+        env.set_task(tasks)
+        assert env.engine.rollout_kernel.startswith("k_rollout_w<") == (search == "auto"), env.engine.rollout_kernel
+        env.engine.force_generic(generic)
+        env.reset()
+        tr = env.rollout(K, actions=acts, record=("obs", "action", "reward", "reward_gt", "done"))
+        tr2 = env.rollout(7, actions=None if acts is None else acts[:7], record=("packed",))     # state carried across launches
+        env.check()
+        outs.append((tr, tr2, env.engine.get_state(), env.episode_stats(), env.engine.debug_counters()))
+    a, a2, sa, ea, ca = outs[0]
+    for b, b2, sb, eb, cb in outs[1:]:
+        for key in ("obs", "action", "done", "reward", "reward_gt"):
+            assert torch.equal(a[key], b[key]), key
+        assert torch.equal(a2["packed"], b2["packed"])
+        for key in ("state", "steps", "flags", "ep_return"):
+            assert torch.equal(sa[key], sb[key]), key
+        assert ea == eb and ea["episodes"] > 0
+    if N * K > 100000:
+        assert ca["exact_fallbacks"] > 20, ca
+    assert outs[1][4]["exact_fallbacks"] == 0
+
+
+def test_warp_per_env_redux_kernel_faults_and_oracle_replay():
+    """k_rollout_w: virgin envs and out-of-range actions are reported and not stepped (as k_rollout_mdp); its self-RNG
+    trajectories replay bit-exactly through the CPU oracle with the dumped draws."""
+    from oracle import anymdp_oracle as ao
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    tasks = [synth_task(64, 5, 1800 + t) for t in range(3)]
+    outs = []
+    for search in ("auto", "warp_v1"):
+        env = AnyMDPVecEnv(50, seed=5, search=search)
+        env.set_task(tasks)
+        tr0 = env.rollout(4)
+        with pytest.raises(Exception, match="reset"):
+            env.check()
+        env.reset()
+        bad = torch.randint(0, 5, (40, 50), dtype=torch.int32, generator=torch.Generator().manual_seed(3))
+        bad[0, 7] = 5
+        bad[2, 3] = 9
+        bad[33, 49] = -1
+        bad[39, 0] = 1000
+        tr = env.rollout(40, actions=bad.cuda())
+        with pytest.raises(AssertionError):
+            env.check()
+        outs.append((tr0, tr, env.engine.get_state()))
+    for x, y in zip(outs[0][:2], outs[1][:2]):
+        for key in ("obs", "action", "done", "reward"):
+            assert torch.equal(x[key], y[key]), key
+    for key in ("state", "steps", "flags", "ep_return"):
+        assert torch.equal(outs[0][2][key], outs[1][2][key]), key
+    N, K = 96, 80
+    env = AnyMDPVecEnv(N, seed=78)
+    env.set_task(tasks)
+    assert env.engine.rollout_kernel.startswith("k_rollout_w<")
+    obs0, _ = env.reset()
+    tr = env.rollout(K, record=("obs", "action", "reward", "done"))
+    draws = env.engine.dump_draws(0, K + 1).cpu().numpy()
+    orc = ao.OracleVecEnv(tasks, env_task=numpy.arange(N) % len(tasks))
+    assert numpy.array_equal(obs0.cpu().numpy(), orc.reset(draws[0])[:, 0])
+    for k in range(K):
+        o = orc.step(None, draws[k + 1])
+        assert numpy.array_equal(tr["obs"][k].cpu().numpy(), o["obs"]), k
+        d = tr["done"][k].cpu().numpy()
+        assert numpy.array_equal((d & 1).astype(bool), o["terminated"]) and numpy.array_equal((d >> 1).astype(bool), o["truncated"])
+        assert numpy.allclose(tr["reward"][k].cpu().numpy(), o["reward"], rtol=1e-6, atol=1e-6)
+    assert env.episode_stats()["episodes"] == orc.stats()["episodes"]

@@ -32,8 +32,8 @@
 struct Tables {
     const double*  cdf;       // [T][n_pad][na][n_pad] normalised CDF rows, pad = 1.0
     const float2*  payload;   // [T][n_pad][na][n_pad] (reward, reward_noise) fp32
-    const uint16_t* sketch;   // [T][n_pad][na][n_pad] min(65535, floor(cdf * 2^16)): 2-byte filter in front of cdf
-    const uint16_t* pivot;    // [T][n_pad][na][32] sketch value of the last entry of every 32-entry block (pad 65535); n_pad in [256, 1024]
+    const uint16_t* sketch;   // [T][n_pad][na][n_pad] code15(cdf): 2-byte filter in front of cdf (fp16-ordered AND unsigned-ordered)
+    const uint16_t* pivot;    // [T][n_pad][na][32] sketch value of the last entry of every 32-entry block (pad 0x7bff); n_pad in [256, 1024]
     const int32_t* sinfo;     // [T][n_pad]  state_mapping | (is_terminal << 31)
     const double*  s0_cdf;    // [T][s0_pad] pad = 2.0
     const int32_t* s0_idx;    // [T][s0_pad]
@@ -42,6 +42,8 @@ struct Tables {
     const uint8_t* tflags;    // [T] bit0: ns < 2 (always terminated, anymdp_env.py:108)
     const double*  raw_t;     // [T][n_pad][na][n_pad] raw transition (only if keep_transition) or null
     const int32_t* n_real;    // [T]
+    const uint32_t* tbits;    // [T][tb_words] is_terminal bitmap (bit j of word j / 32), tb_words = ceil(n_pad / 32)
+    int tb_words;
     // thread-per-env search tables (k_rollout_tp): two levels, both exact up to an equality that falls back to `cdf`
     const uint4*    fat;      // [T][n_pad][na][tp_blocks] 128-byte lines, one per 8-entry block of a row:
                               //   bytes 0-31 8 x ((floor(cdf * 2^31) << 1) | is_terminal[j]), 32-95 8 x (reward, noise) fp32,
@@ -539,8 +541,8 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
     // Draws.  The G lanes of an env generate the draws of G consecutive ticks in one Philox pass.  Lane L of batch kb
     // holds the draws of tick kb + L + 1 (one tick AHEAD of the tick that fetches them), so that the inputs of the next
     // tick are available before the current row has arrived and the next row load can be issued speculatively.
-    // The transition uniform is kept as the top 21 bits of its 53-bit integer k (u = k * 2^-53): the filter needs only
-    // floor(u * 2^16) = k >> 37; the exact fallback recomputes u.
+    // The transition uniform is kept as its filter code code15(u) (a function of the top 21 bits of its 53-bit integer);
+    // the exact fallback recomputes u.
     unsigned b_uhi = 0;
     double b_ur = 0.0;        // reset draw of tick kb + L + 1
     float b_z = 0.f;
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
         const int kt = kb + lane + 1;
         const unsigned long long tk = tick0 + (unsigned long long)kt;
         const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
-        b_uhi = w0.x >> 11;                                       // == (k53 >> 32): k53 = (w0.x >> 5) << 26 | (w0.y >> 6)
+        b_uhi = code15_from_m21(w0.x >> 11);                      // code15(u): w0.x >> 11 == floor(u * 2^21)
         b_ur = u53(w0.z, w0.w);
         const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
         b_z = box_muller(w2.x, w2.y);
@@ -560,13 +562,13 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
     };
 
     // inputs of the current tick (its row load is in flight)
-    unsigned v;               // floor(u * 2^16) of the transition uniform
+    unsigned v;               // code15(u) of the transition uniform
     float z;
     int a;
     uint2 q[CR];              // this lane's 4 * C filter entries (16 bit each) of row (s, a)
     {
         const uint4 w0 = philox_block(env_id, 0u, tick0, E.key);
-        v = w0.x >> 16;
+        v = code15_from_m21(w0.x >> 11);
         ur_carry = u53(w0.z, w0.w);
         const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0, E.key);
         z = box_muller(w2.x, w2.y);
@@ -614,7 +616,7 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
     for (int k = 0; k < K; ++k) {
         const int j = k & (G - 1);
         // inputs of the NEXT tick: independent of the row in flight
-        const unsigned nv = __shfl_sync(gmask, b_uhi, j, G) >> 5;
+        const unsigned nv = __shfl_sync(gmask, b_uhi, j, G);
         const float nz = __shfl_sync(gmask, b_z, j, G);
         const int na_ = __shfl_sync(gmask, b_act, j, G);
         const bool na_ok = !GIVEN || (unsigned)na_ < (unsigned)na;
@@ -663,7 +665,7 @@ __global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const En
                 }
             }
             if (__any_sync(gmask, amb != 0)) {
-                // undecided (u and some cdf entry share a 2^-16 cell, ~n/65536 of the ticks): exact float64 entries
+                // undecided (u and some cdf entry share a code15 cell, ~n/30720 of the ticks): exact float64 entries
                 const uint4 w0 = philox_block(env_id, 0u, tick0 + (unsigned long long)k, E.key);
                 const double u = u53(w0.x, w0.y);
                 if (P2) {
@@ -1156,6 +1158,274 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
     if (n_fallback) atomicAdd(E.counters, (unsigned long long)n_fallback);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Latency path: ONE WARP PER ENV with the shortest dependent chain (k_rollout_w): MDP, one action token, engine Philox
+// draws or given actions, same-step auto-reset, rows of exactly 32 * EPL states (64 / 128 / 256), engines too small for
+// the thread-per-env kernel (cfg2: 4096 envs).  Such an engine is a set of Markov chains, each with ONE row in flight:
+// env-steps/s = envs / (DRAM latency + what sits between "row arrived" and "next row requested").  Measured on B200
+// (tools/warplat.cu, profiles/r1_warplat.txt): REDUX.MIN 22 cycles, VOTE + POPC 45, SHFL 33, LDS 34, LDG (L1 hit) 56,
+// REDUX.SUM 47, REDUX over a partial mask 427.  Hence:
+//   * the row is 32 lanes x EPL fp16-ordered 15-bit codes (the filter in front of the float64 row); a lane counts its
+//     own entries below code15(u) with HSET2 + IDP.2A and the warp takes ONE REDUX.MIN over
+//         (index of the lane's first entry not below u) << 2 | is_terminal[that entry] << 1 | undecided
+//     (rows are sorted, so the minimum is the next state; is_terminal bits of a lane's own entries sit in a register);
+//   * termination and truncation are then known without a memory access and the state a reset would lead to was
+//     computed when the draws were made (lane-parallel, start-state table in shared memory): the next row address is
+//     one select and one IMAD.WIDE away, and there is exactly ONE row-load site in the loop (no speculation, nothing
+//     to re-issue);
+//   * nothing else on the chain: the payload (reward, noise) and the state word of tick k are requested after the next
+//     row and consumed one tick later; no global load on a rare path feeds a register that is read after the paths
+//     merge (ptxas gives such loads the barrier of the row load and the merge point then waits for the row:
+//     tools/sass_ctrl.py shows the assignment);
+//   * draws of 32 consecutive ticks are generated in one lane-parallel Philox pass; records are staged one per lane
+//     and written once per 32 ticks.
+// Undecided (code15(cdf[j]) == code15(u), ~n/30720 of the ticks): the float64 row decides, as everywhere else.
+// ------------------------------------------------------------------------------------------------
+template <int NW> struct RowW { unsigned w[NW]; };
+
+template <int NW>
+__device__ __forceinline__ RowW<NW> ldg_row(const char* p) {
+    RowW<NW> r;
+    if constexpr (NW == 1) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r.w[0]) : "l"(p));
+    else if constexpr (NW == 2) asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[1]) : "l"(p));
+    else asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(p));
+    return r;
+}
+
+template <int EPL, bool GIVEN>
+__global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
+                                                      const int32_t* __restrict__ actions, const amdp_traj J) {
+    constexpr int NW = EPL / 2;                                   // 32-bit words of filter codes per lane
+    constexpr int N_PAD = 32 * EPL;
+    constexpr unsigned ROW_BYTES = 2u * N_PAD;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ double sh_stat[4][4];                              // closed-episode statistics: sum_ret, sum_ret_sq, min, max
+    __shared__ unsigned long long sh_cnt[2][4];                   // ep_count, sum_len
+    __shared__ double sh_s0c[TP_S0][4];                           // start-state CDF / states of the warp's env
+    __shared__ int sh_s0i[TP_S0][4];
+    const int lane = threadIdx.x & 31, gi = threadIdx.x >> 5;
+    const long long e = (long long)blockIdx.x * 4 + gi;
+    if (e >= E.n_envs) return;                                    // whole warps leave: one env per warp
+    const int na = T.na;
+    const long long N = E.n_envs;
+    const long long t = E.task[e];
+    const long long tsz = (long long)N_PAD * na * N_PAD;
+    const char* __restrict__ sk_lane = reinterpret_cast<const char*>(T.sketch + t * tsz) + lane * (EPL * 2);
+    const double* __restrict__ cdf_lane = T.cdf + t * tsz + lane * EPL;
+    const float2* __restrict__ pay_t = T.payload + t * tsz;
+    const int32_t* __restrict__ sinfo_t = T.sinfo + t * N_PAD;
+    const unsigned srow = (unsigned)na * ROW_BYTES;               // bytes between the filter rows of states s and s + 1
+    const int max_ceil = T.max_ceil[t];
+    const bool always_term = (T.tflags[t] & 1) != 0;
+    const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
+    // is_terminal of this lane's own EPL entries (ns < 2: every state terminates, anymdp_env.py:108)
+    unsigned myterm = (T.tbits[t * T.tb_words + ((lane * EPL) >> 5)] >> ((lane * EPL) & 31)) & ((1u << EPL) - 1u);
+    if (always_term) myterm = (1u << EPL) - 1u;
+
+    int s = E.state[e], steps = E.steps[e];
+    const int flags = E.flags[e];
+    double ep_ret = E.ep_return[e];
+
+    // staged records: lane L holds the record of tick (batch start + L)
+    int st_obs = 0, st_ad = 0;                                    // st_ad = action | done_bits << 28
+    float st_rew = 0.f, st_rgt = 0.f;
+    const long long rec0 = e * J.env_stride;
+    auto flush = [&](int kb, int cnt) {                           // records of ticks [kb, kb + cnt), one lane per tick
+        if (lane < cnt) {
+            const long long o = (long long)(kb + lane) * J.step_stride + rec0;
+            if (J.packed) {
+                const unsigned lo = ((unsigned)st_obs & 0xfffffu) | (((unsigned)st_ad & 0x3ffu) << 20) | (((unsigned)st_ad >> 28) << 30);
+                J.packed[o] = ((unsigned long long)__float_as_uint(st_rew) << 32) | lo;
+            } else {
+                if (J.obs) J.obs[o] = st_obs;
+                if (J.actions_out) J.actions_out[o] = st_ad & 0x0fffffff;
+                if (J.done) J.done[o] = (uint8_t)((unsigned)st_ad >> 28);
+                if (J.reward) J.reward[o] = st_rew;
+                if (J.reward_gt) J.reward_gt[o] = st_rgt;
+            }
+        }
+    };
+
+    unsigned fault = 0;
+    if (flags & FLAG_VIRGIN) fault = AMDP_FAULT_NEED_RESET;                                   // anymdp_env.py:93-94
+    else if (sinfo_t[s] < 0 && !always_term) fault = AMDP_FAULT_TERMINAL_STATE;               // :95-96
+    if (fault) {
+        // faulted envs are left untouched (as in env_tick); their records are zero except the action
+        for (int kb = 0; kb < K; kb += 32) {
+            const int k = kb + lane;
+            int a = 0;
+            if (k < K) {
+                if (GIVEN) a = load_action(actions, (long long)k * N + e, J.actions_u8);
+                else a = (int)__umulhi(philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key).z, (uint32_t)na);
+            }
+            st_ad = a & 0x0fffffff;
+            flush(kb, min(32, K - kb));
+        }
+        if (lane == 0) atomicOr(E.faults, fault);
+        return;
+    }
+    const int s0_pad = T.s0_pad;                                  // <= TP_S0 (the host never selects this kernel otherwise)
+    if (lane == 0) {
+        sh_cnt[0][gi] = E.ep_count[e]; sh_cnt[1][gi] = E.sum_len[e];
+        sh_stat[0][gi] = E.sum_ret[e]; sh_stat[1][gi] = E.sum_ret_sq[e];
+        sh_stat[2][gi] = E.min_ret[e]; sh_stat[3][gi] = E.max_ret[e];
+    }
+    if (lane < TP_S0) {
+        sh_s0c[lane][gi] = (lane < s0_pad) ? T.s0_cdf[t * s0_pad + lane] : 2.0;
+        sh_s0i[lane][gi] = T.s0_idx[t * s0_pad + min(lane, s0_pad - 1)];
+    }
+    __syncwarp();
+    auto reset_state = [&](double ur) {                           // anymdp_env.py:89 (pad 2.0 is never <= ur)
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < TP_S0; ++i) c += (sh_s0c[i][gi] <= ur);
+        c = min(c, s0_pad - 1);
+        int r = sh_s0i[0][gi];
+#pragma unroll
+        for (int i = 1; i < TP_S0; ++i) if (c == i) r = sh_s0i[i][gi];
+        return r;
+    };
+
+    // Draws of one tick, packed: bits 0-14 code15(u_transition), 15-22 action (engine policy), 23-30 the state a reset in
+    // this tick leads to, 31 given action out of range.  Lane L of a batch holds tick kb + L + 1.
+    unsigned b_pk = 0;
+    float b_z = 0.f;
+    int b_act = 0;
+    unsigned n_fallback = 0;
+    auto make = [&](int kt, unsigned& pk, float& z, int& act) {
+        const unsigned long long tk = tick0 + (unsigned long long)kt;
+        const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
+        const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
+        z = box_muller(w2.x, w2.y);
+        pk = code15_from_m21(w0.x >> 11) | ((unsigned)reset_state(u53(w0.z, w0.w)) << 23);
+        if (GIVEN) {
+            act = (kt < K) ? load_action(actions, (long long)kt * N + e, J.actions_u8) : 0;
+            if ((unsigned)act >= (unsigned)na) pk |= 0x80000000u;
+        } else {
+            act = 0;
+            pk |= __umulhi(w2.z, (uint32_t)na) << 15;
+        }
+    };
+    unsigned pk;
+    float z;
+    int a_raw;
+    make(0, pk, z, a_raw);
+    make(lane + 1, b_pk, b_z, b_act);
+    if (GIVEN && (pk >> 31)) fault |= AMDP_FAULT_BAD_ACTION;                                  // :97
+    int a = GIVEN ? ((pk >> 31) ? 0 : a_raw) : (int)((pk >> 15) & 0xffu);
+    unsigned sa = (unsigned)(s * na + a);                         // row (s, a) inside the task
+    unsigned v2 = (pk & 0x7fffu) * 0x00010001u;
+    RowW<NW> q = ldg_row<NW>(sk_lane + (unsigned long long)sa * ROW_BYTES);
+
+    // the previous tick, settled one tick late (its payload / state-word loads were issued behind the next row load)
+    float2 pay_p = make_float2(0.f, 0.f);
+    float z_p = 0.f;
+    int si_p = 0, ad_p = 0, steps_p = 0;
+    bool close_p = false;
+    auto settle = [&](int kp) {
+        // reward = gt + noise * z (anymdp_env.py:103-105), episode return, closed-episode statistics, the record
+        const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
+        ep_ret += rew;
+        if (lane == (kp & 31)) { st_obs = si_p; st_ad = ad_p; st_rew = (float)rew; st_rgt = pay_p.x; }
+        if (close_p) {
+            if (lane == 0) {
+                sh_cnt[0][gi] += 1; sh_cnt[1][gi] += (unsigned long long)steps_p;
+                sh_stat[0][gi] += ep_ret; sh_stat[1][gi] += ep_ret * ep_ret;
+                sh_stat[2][gi] = fmin(sh_stat[2][gi], ep_ret); sh_stat[3][gi] = fmax(sh_stat[3][gi], ep_ret);
+            }
+            ep_ret = 0.0;
+            close_p = false;
+        }
+    };
+
+    for (int k = 0; k < K; ++k) {
+        const int j = k & 31;
+        // (A) inputs of the NEXT tick: independent of the row in flight
+        const unsigned npk = __shfl_sync(FULL, b_pk, j);
+        const float nz = __shfl_sync(FULL, b_z, j);
+        int na_raw = 0;
+        if (GIVEN) na_raw = __shfl_sync(FULL, b_act, j);
+        const int n_a = GIVEN ? ((npk >> 31) ? 0 : na_raw) : (int)((npk >> 15) & 0xffu);
+        const char* nbase = sk_lane + (unsigned)n_a * ROW_BYTES;
+        const unsigned nv2 = (npk & 0x7fffu) * 0x00010001u;
+        const bool valid = !GIVEN || !(pk >> 31);                 // a tick with a bad action does not step
+        const int sreset = (int)((pk >> 23) & 0xffu);
+        const bool trunc = steps + 1 >= max_ceil;                 // anymdp_env.py:113-114
+
+        // (B) the chain: row -> count below code15(u) -> REDUX.MIN -> next state -> next row address
+        const unsigned v2le = v2 + 0x00010001u;                   // entries <= code15(u): below the next code
+        int alt = 0, ale = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) { alt = h2_count_lt(q.w[i], v2, alt); ale = h2_count_lt(q.w[i], v2le, ale); }
+        const int ltl = -alt;                                     // this lane's entries below u
+        unsigned val = ((unsigned)(lane * EPL + ltl) << 2) | (((myterm >> ltl) & 1u) << 1) | (alt != ale ? 1u : 0u);
+        if (ltl == EPL) val = FULL;                               // all below: the boundary is in a later lane
+        unsigned r = __reduce_min_sync(FULL, val);
+        if (r & 1u) {
+            // undecided: exact float64 entries (numpy choice: searchsorted(cdf, u, 'right'))   anymdp_env.py:100
+            const uint4 w0 = philox_block(env_id, 0u, tick0 + (unsigned long long)k, E.key);
+            const double u = u53(w0.x, w0.y);
+            const double* cr = cdf_lane + (unsigned long long)sa * N_PAD;
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < EPL; i += 2) {
+                const double2 x = ldg_stream_f64x2(cr + i);
+                cnt += (x.x <= u) + (x.y <= u);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+            cnt = min(cnt, N_PAD - 1);
+            r = ((unsigned)cnt << 2) | ((sinfo_t[cnt] < 0 || always_term) ? 2u : 0u);
+            n_fallback += 1;
+        }
+        const int nxt = (int)(r >> 2);
+        const bool term = (r & 2u) != 0;                          // anymdp_env.py:108
+        const bool done = term || trunc;
+        int s_next = done ? sreset : nxt;                         // same-step auto-reset (anymdp_env.py:81-90)
+        if (GIVEN && !valid) s_next = s;
+        const RowW<NW> nq = ldg_row<NW>(nbase + (unsigned long long)((unsigned)s_next * (unsigned long long)srow));
+
+        // (D) settle the previous tick; once per 32 ticks write the finished batch of records, lane-parallel
+        settle(k - 1);
+        if (j == 0 && k > 0) flush(k - 32, 32);
+        // (C) payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104) and the state word of the observation
+        //     (anymdp_env.py:145-148; after a reset: of the start state): consumed by settle() of the next tick
+        pay_p = ldg_stream_f32x2(pay_t + ((unsigned long long)sa * N_PAD + (unsigned)nxt));
+        si_p = __ldg(sinfo_t + s_next) & 0x7fffffff;
+        z_p = z;
+        ad_p = GIVEN ? (a_raw & 0x0fffffff) : a;
+        if (valid) {
+            ad_p |= ((term ? 1 : 0) | (trunc ? 2 : 0)) << 28;
+            steps += 1;
+            if (done) { close_p = true; steps_p = steps; steps = 0; }
+            s = s_next;
+        } else {
+            pay_p = make_float2(0.f, 0.f);
+            si_p = 0;
+        }
+        // once per 32 ticks: draw the next batch
+        if (j == 31) make(k + 2 + lane, b_pk, b_z, b_act);
+        // rotate to the next tick
+        if (GIVEN && (npk >> 31) && k + 1 < K) fault |= AMDP_FAULT_BAD_ACTION;               // :97
+        pk = npk; z = nz; a = n_a; a_raw = na_raw; v2 = nv2;
+        sa = (unsigned)(s * na + n_a);
+        q = nq;
+    }
+    settle(K - 1);
+    {
+        const int kb = ((K - 1) / 32) * 32;
+        flush(kb, K - kb);
+    }
+    if (lane == 0) {
+        E.state[e] = s; E.steps[e] = steps; E.ep_return[e] = ep_ret;
+        E.ep_count[e] = sh_cnt[0][gi]; E.sum_len[e] = sh_cnt[1][gi];
+        E.sum_ret[e] = sh_stat[0][gi]; E.sum_ret_sq[e] = sh_stat[1][gi];
+        E.min_ret[e] = sh_stat[2][gi]; E.max_ret[e] = sh_stat[3][gi];
+        if (fault) atomicOr(E.faults, fault);
+        if (n_fallback) atomicAdd(E.counters, (unsigned long long)n_fallback);
+    }
+}
+
 __global__ void k_reset(Tables T, EnvArrays E, unsigned long long tick, int n_slots, const uint8_t* __restrict__ mask,
                         int32_t* __restrict__ obs_out, const double* __restrict__ u_inject) {
     // one thread per env (G = 1): reset is rare and touches only the small per-task tables
@@ -1201,8 +1471,8 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
     float2* pl = payload + r * n_pad;
     for (int i = 0; i < n_pad; ++i) pl[i] = make_float2((float)reward[r * n_pad + i], (float)noise[r * n_pad + i]);
     if (s >= n) {
-        for (int i = 0; i < n_pad; ++i) { c[i] = 1.0; sketch[r * n_pad + i] = 65535; }
-        if (pivot) for (int b = 0; b < 32; ++b) pivot[r * 32 + b] = 65535;
+        for (int i = 0; i < n_pad; ++i) { c[i] = 1.0; sketch[r * n_pad + i] = 0x7bff; }
+        if (pivot) for (int b = 0; b < 32; ++b) pivot[r * 32 + b] = 0x7bff;
         if (fat) {
             for (int b = 0; b < tp_blocks; ++b) {
                 uint4* line = fat + (r * tp_blocks + b) * 8;
@@ -1246,14 +1516,14 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
         for (int i = 0; i < n; ++i) c[i] = 1.0;
     }
     for (int i = n; i < n_pad; ++i) c[i] = 1.0;
-    // 16-bit filter: q = min(65535, floor(cdf * 2^16)).  With v = floor(u * 2^16): q < v => cdf < u, q > v => cdf > u,
+    // 16-bit filter: q = code15(cdf) (monotone; ordered both as fp16 and as unsigned).  With v = code15(u): q < v => cdf < u, q > v => cdf > u,
     // q == v => undecided (the fast kernel then falls back to the float64 row) — so the filter never changes a result.
     uint16_t* sk = sketch + r * n_pad;
-    for (int i = 0; i < n_pad; ++i) sk[i] = (uint16_t)fmin(65535.0, floor(c[i] * 65536.0));
+    for (int i = 0; i < n_pad; ++i) sk[i] = (uint16_t)code15(c[i]);
     if (pivot) {
         for (int b = 0; b < 32; ++b) {
             const int last = min(32 * b + 31, n_pad - 1);
-            pivot[r * 32 + b] = (32 * b < n_pad) ? sk[last] : (uint16_t)65535;
+            pivot[r * 32 + b] = (32 * b < n_pad) ? sk[last] : (uint16_t)0x7bff;
         }
     }
     // thread-per-env tables (k_rollout_tp): per 8-entry block one 128-byte line with 31-bit codes carrying is_terminal[j] in
@@ -1303,12 +1573,17 @@ __global__ void k_build_small(int64_t cnt, int n_pad, int s0_pad, const int32_t*
                               const int32_t* __restrict__ ns, int32_t* __restrict__ sinfo, double* __restrict__ s0_cdf,
                               int32_t* __restrict__ s0_idx_out, int32_t* __restrict__ max_ceil,
                               uint8_t* __restrict__ tflags, int32_t* __restrict__ n_real_out,
-                              int32_t* __restrict__ status) {
+                              uint32_t* __restrict__ tbits, int tb_words, int32_t* __restrict__ status) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt) return;
     for (int i = 0; i < n_pad; ++i) {
         const int m = state_mapping[t * n_pad + i] & 0x7fffffff;
         sinfo[t * n_pad + i] = m | (is_terminal[t * n_pad + i] ? (int)0x80000000 : 0);
+    }
+    for (int w = 0; w < tb_words; ++w) {
+        uint32_t m = 0;
+        for (int b = 0; b < 32; ++b) if (32 * w + b < n_pad && is_terminal[t * n_pad + 32 * w + b]) m |= 1u << b;
+        tbits[t * tb_words + w] = m;
     }
     const int k = n_s0[t];
     double acc = 0.0;
@@ -1470,7 +1745,7 @@ struct amdp {
     EnvArrays E;
     // owned device memory
     double* cdf; float2* payload; uint16_t* sketch; uint16_t* pivot; int32_t* sinfo; double* s0_cdf; int32_t* s0_idx; double* obs_cdf;
-    int32_t* max_ceil; uint8_t* tflags; double* raw_t; int32_t* n_real;
+    int32_t* max_ceil; uint8_t* tflags; double* raw_t; int32_t* n_real; uint32_t* tbits;
     int32_t* env_task;
     Stat6* stat_part;
     unsigned int* stat_ticket;
@@ -1484,6 +1759,7 @@ struct amdp {
     bool force_generic;    // debug: route rollouts through the generic kernel
     bool two_level;        // the fast kernel searches pivots + one 32-entry block instead of streaming the whole row
     bool tp;               // rollouts run on the thread-per-env kernel (k_rollout_tp)
+    bool wv2;              // MDP rollouts with same-step auto-reset run on k_rollout_w (one warp per env, REDUX.MIN search)
     int n_sm;              // multiprocessors of the device
     int tp_coarse_bits;    // debug: low bits of the 31-bit codes ignored by k_rollout_tp (0 in production)
     uint4* fat; uint16_t* pv; uint16_t* top; uint32_t* ofat;   // its tables (see Tables)
@@ -1555,7 +1831,7 @@ static int pick_group(int n_pad) {
 extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t,
+    void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
@@ -1614,6 +1890,9 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
             if ((rc = dalloc(h, &h->ofat, (size_t)c.n_tasks * c.n_pad * (8 + 8 * h->T.o_blocks)))) return rc;
         }
     }
+    // one warp per env, shortest dependent chain: rows of exactly 64 / 128 / 256 states (flag 32 keeps the older k_rollout_mdp)
+    h->wv2 = mdp && !h->tp && !h->two_level && !(c.reserved0 & 32) && c.autoreset == AMDP_AUTORESET_SAME_STEP &&
+             (c.n_pad == 64 || c.n_pad == 128 || c.n_pad == 256) && c.na <= 256 && c.s0_pad <= TP_S0;
     if (c.reserved0 & 1) { if ((rc = dalloc(h, &h->raw_t, rows * c.n_pad))) return rc; }
     if ((rc = dalloc(h, &h->sinfo, (size_t)c.n_tasks * c.n_pad))) return rc;
     if ((rc = dalloc(h, &h->s0_cdf, (size_t)c.n_tasks * c.s0_pad))) return rc;
@@ -1622,6 +1901,8 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     if ((rc = dalloc(h, &h->max_ceil, (size_t)c.n_tasks))) return rc;
     if ((rc = dalloc(h, &h->tflags, (size_t)c.n_tasks))) return rc;
     if ((rc = dalloc(h, &h->n_real, (size_t)c.n_tasks))) return rc;
+    h->T.tb_words = (c.n_pad + 31) / 32;
+    if ((rc = dalloc(h, &h->tbits, (size_t)c.n_tasks * h->T.tb_words))) return rc;
     if ((rc = dalloc(h, &h->env_task, (size_t)c.n_envs))) return rc;
     if ((rc = dalloc(h, &h->stat_part, (size_t)STAT_BLOCKS))) return rc;
     if ((rc = dalloc(h, &h->stat_ticket, 1))) return rc;
@@ -1646,7 +1927,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     Tables& T = h->T;
     T.fat = h->fat; T.pv = h->pv; T.top = h->top; T.ofat = h->ofat;
     T.cdf = h->cdf; T.payload = h->payload; T.sketch = h->sketch; T.pivot = h->pivot; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
-    T.obs_cdf = h->obs_cdf; T.max_ceil = h->max_ceil; T.tflags = h->tflags; T.raw_t = h->raw_t; T.n_real = h->n_real;
+    T.obs_cdf = h->obs_cdf; T.max_ceil = h->max_ceil; T.tflags = h->tflags; T.raw_t = h->raw_t; T.n_real = h->n_real; T.tbits = h->tbits;
     T.n_pad = c.n_pad; T.na = c.na; T.no_pad = c.no_pad; T.d_o = c.n_obs_tok; T.d_a = c.n_act_tok; T.s0_pad = c.s0_pad;
     T.task_type = c.task_type; T.autoreset = c.autoreset;
     return AMDP_OK;
@@ -1681,7 +1962,7 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
     k_build_small<<<nblk(cnt, 128), 128, 0, st>>>(cnt, c.n_pad, c.s0_pad, state_mapping, n_real, is_terminal, s0_idx, s0_prob,
                                                   n_s0, max_steps, ns, h->sinfo + t0 * c.n_pad, h->s0_cdf + t0 * c.s0_pad,
                                                   h->s0_idx + t0 * c.s0_pad, h->max_ceil + t0, h->tflags + t0,
-                                                  h->n_real + t0, status_out);
+                                                  h->n_real + t0, h->tbits + t0 * h->T.tb_words, h->T.tb_words, status_out);
     h->launches += 2;
     if (c.task_type != AMDP_MDP) {
         const long long orows = (long long)cnt * c.n_obs_tok * c.n_pad;
@@ -1798,6 +2079,14 @@ static void launch_rollout_fast(amdp* h, int K, const int32_t* actions, const am
         return;
     }
     if (h->two_level) { launch_fast_gc<8, 1, true>(h, K, actions, J, st); return; }
+    if (h->wv2) {
+        const unsigned int blocks = nblk(h->cfg.n_envs, 4);
+#define WV2(epl) { if (actions) k_rollout_w<epl, true><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J); \
+                   else k_rollout_w<epl, false><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J); }
+        if (n_pad == 64) WV2(2) else if (n_pad == 128) WV2(4) else WV2(8)
+#undef WV2
+        return;
+    }
     const int G = h->G;
     const int C = (n_pad == 4 * G) ? 1 : (n_pad == 8 * G ? 2 : 0);
     switch (G) {
@@ -1914,6 +2203,7 @@ extern "C" const char* amdp_rollout_kernel(amdp_t* h) {
     if (!fast) snprintf(h->kname, sizeof(h->kname), "k_rollout<G=%d>", h->G);
     else if (h->tp) snprintf(h->kname, sizeof(h->kname), "k_rollout_tp<levels=%d,%s>", h->T.tp_levels, c.task_type == AMDP_POMDP ? "POMDP" : "MDP");
     else if (h->two_level) snprintf(h->kname, sizeof(h->kname), "k_rollout_mdp<G=8,two-level>");
+    else if (h->wv2) snprintf(h->kname, sizeof(h->kname), "k_rollout_w<EPL=%d>", c.n_pad / 32);
     else snprintf(h->kname, sizeof(h->kname), "k_rollout_mdp<G=%d>", h->G);
     return h->kname;
 }

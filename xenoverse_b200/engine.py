@@ -121,7 +121,8 @@ class Engine:
         """search: how MDP rollouts search a CDF row.  "thread": the thread-per-env throughput kernel (pivots + one
         8/16-entry block of 31-bit codes; auto picks it for >= 16384 envs); "one_level" / "two_level": the warp-per-env
         latency kernel streaming the 16-bit filter row / reading 32 pivots + one 32-entry block (auto: two_level for
-        n_pad >= 512); "warp": auto without the thread-per-env kernel."""
+        n_pad >= 512); "warp": auto without the thread-per-env kernel; "warp_v1": additionally without k_rollout_w (the
+        REDUX.MIN warp-per-env kernel auto picks for same-step MDP engines with rows of 64 / 128 / 256 states)."""
         if not torch.cuda.is_available():
             raise AMDPError("xenoverse_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
@@ -132,7 +133,7 @@ class Engine:
         cfg = _lib.Config(device=self.device.index, task_type=_lib.TASK_TYPES[geo["task_type"]],
                           autoreset=_lib.AUTORESET[autoreset], na=geo["na"], n_pad=geo["n_pad"], no_pad=geo["no_pad"],
                           n_obs_tok=geo["do"], n_act_tok=geo["da"], s0_pad=geo["s0_pad"],
-                          reserved0=(1 if keep_transition else 0) | {"auto": 0, "one_level": 2, "two_level": 4, "thread": 8, "warp": 16}[search],
+                          reserved0=(1 if keep_transition else 0) | {"auto": 0, "one_level": 2, "two_level": 4, "thread": 8, "warp": 16, "warp_v1": 48}[search],
                           n_envs=self.N, n_tasks=self.T,
                           seed=int(seed) & (2 ** 64 - 1), env_id_base=int(env_id_base))
         h = ctypes.c_void_p()
