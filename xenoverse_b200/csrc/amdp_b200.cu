@@ -853,6 +853,11 @@ __device__ __forceinline__ int h2_count_lt(unsigned w, unsigned v2, int acc) {  
     return __dp2a_lo((int)__hlt2_mask(a, b), 0x0101, acc);
 }
 
+__device__ __forceinline__ int h2_count_lt_pos(unsigned w, unsigned v2, int acc) {  // acc + #{halfwords of w (as fp16) < v}
+    const __half2 a = *reinterpret_cast<const __half2*>(&w), b = *reinterpret_cast<const __half2*>(&v2);
+    return __dp2a_lo((int)__hlt2_mask(a, b), 0xffff, acc);      // (-1) x (-1) per halfword that compares true
+}
+
 #define TP_S0 4
 #ifndef TP_TPB
 #define TP_TPB 64
@@ -1317,16 +1322,18 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
     unsigned v2 = (pk & 0x7fffu) * 0x00010001u;
     RowW<NW> q = ldg_row<NW>(sk_lane + (unsigned long long)sa * ROW_BYTES);
 
-    // the previous tick, settled one tick late (its payload / state-word loads were issued behind the next row load)
+    // the previous tick, settled one tick late (its payload / state-word loads travel with the next row load)
     float2 pay_p = make_float2(0.f, 0.f);
     float z_p = 0.f;
     int si_p = 0, ad_p = 0, steps_p = 0;
-    bool close_p = false;
+    bool close_p = false, valid_p = false;
     auto settle = [&](int kp) {
         // reward = gt + noise * z (anymdp_env.py:103-105), episode return, closed-episode statistics, the record
-        const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
+        const double rew = valid_p ? (double)pay_p.x + (double)pay_p.y * (double)z_p : 0.0;
         ep_ret += rew;
-        if (lane == (kp & 31)) { st_obs = si_p; st_ad = ad_p; st_rew = (float)rew; st_rgt = pay_p.x; }
+        if (lane == (kp & 31)) {
+            st_obs = valid_p ? (si_p & 0x7fffffff) : 0; st_ad = ad_p; st_rew = (float)rew; st_rgt = valid_p ? pay_p.x : 0.f;
+        }
         if (close_p) {
             if (lane == 0) {
                 sh_cnt[0][gi] += 1; sh_cnt[1][gi] += (unsigned long long)steps_p;
@@ -1337,6 +1344,11 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
             close_p = false;
         }
     };
+    // loop-invariant pieces of the REDUX operand, kept in registers (ptxas would re-derive them from %tid every tick)
+    unsigned lane_base32 = (unsigned)(lane * EPL) << 5;
+    unsigned myterm16 = myterm << 4;
+    asm volatile("" : "+r"(lane_base32), "+r"(myterm16));
+    const float2* pay_row = pay_t + (unsigned long long)sa * N_PAD;   // payload row of (s, a)
 
     for (int k = 0; k < K; ++k) {
         const int j = k & 31;
@@ -1347,21 +1359,40 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
         if (GIVEN) na_raw = __shfl_sync(FULL, b_act, j);
         const int n_a = GIVEN ? ((npk >> 31) ? 0 : na_raw) : (int)((npk >> 15) & 0xffu);
         const char* nbase = sk_lane + (unsigned)n_a * ROW_BYTES;
+        asm volatile("" : "+l"(nbase));                           // one IMAD.WIDE from the next row address
         const unsigned nv2 = (npk & 0x7fffu) * 0x00010001u;
         const bool valid = !GIVEN || !(pk >> 31);                 // a tick with a bad action does not step
-        const int sreset = (int)((pk >> 23) & 0xffu);
+        const unsigned sreset = (pk >> 23) & 0xffu;
         const bool trunc = steps + 1 >= max_ceil;                 // anymdp_env.py:113-114
+        const unsigned trunc16 = trunc ? 16u : 0u;
 
         // (B) the chain: row -> count below code15(u) -> REDUX.MIN -> next state -> next row address
         const unsigned v2le = v2 + 0x00010001u;                   // entries <= code15(u): below the next code
-        int alt = 0, ale = 0;
+        int lt = 0, le = 0;                                       // this lane's entries below u / not above u
 #pragma unroll
-        for (int i = 0; i < NW; ++i) { alt = h2_count_lt(q.w[i], v2, alt); ale = h2_count_lt(q.w[i], v2le, ale); }
-        const int ltl = -alt;                                     // this lane's entries below u
-        unsigned val = ((unsigned)(lane * EPL + ltl) << 2) | (((myterm >> ltl) & 1u) << 1) | (alt != ale ? 1u : 0u);
-        if (ltl == EPL) val = FULL;                               // all below: the boundary is in a later lane
+        for (int i = 0; i < NW; ++i) { lt = h2_count_lt_pos(q.w[i], v2, lt); le = h2_count_lt_pos(q.w[i], v2le, le); }
+        // (index of the first entry not below u) << 5 | is_terminal[it] << 4 | entries sharing u's code (undecided)
+        unsigned val = lane_base32 + ((unsigned)lt << 5) + (unsigned)(le - lt) + ((myterm16 >> lt) & 16u);
+        if (lt == EPL) val = FULL;                                // all below: the boundary is in a later lane
         unsigned r = __reduce_min_sync(FULL, val);
-        if (r & 1u) {
+        unsigned nxt, s_next;
+        float2 npay;
+        int nsi;
+        RowW<NW> nq;
+        auto advance = [&]() {
+            nxt = r >> 5;
+            const bool done = ((r | trunc16) & 16u) != 0;         // anymdp_env.py:108,114
+            s_next = done ? sreset : nxt;                         // same-step auto-reset (anymdp_env.py:81-90)
+            if (GIVEN && !valid) s_next = (unsigned)s;
+            // payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104), the next row, the state word of the observation
+            // (anymdp_env.py:145-148; after a reset: of the start state).  Issued together: ptxas puts loads of one kind on
+            // one barrier, and a payload load issued later than the row would make the chain wait for it.
+            npay = ldg_stream_f32x2(pay_row + nxt);
+            nq = ldg_row<NW>(nbase + (unsigned long long)(s_next * (unsigned long long)srow));
+            nsi = __ldg(sinfo_t + s_next);
+        };
+        advance();
+        if (r & 15u) {
             // undecided: exact float64 entries (numpy choice: searchsorted(cdf, u, 'right'))   anymdp_env.py:100
             const uint4 w0 = philox_block(env_id, 0u, tick0 + (unsigned long long)k, E.key);
             const double u = u53(w0.x, w0.y);
@@ -1375,33 +1406,22 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
             cnt = min(cnt, N_PAD - 1);
-            r = ((unsigned)cnt << 2) | ((sinfo_t[cnt] < 0 || always_term) ? 2u : 0u);
+            r = ((unsigned)cnt << 5) | ((sinfo_t[cnt] < 0 || always_term) ? 16u : 0u);
             n_fallback += 1;
+            advance();
         }
-        const int nxt = (int)(r >> 2);
-        const bool term = (r & 2u) != 0;                          // anymdp_env.py:108
-        const bool done = term || trunc;
-        int s_next = done ? sreset : nxt;                         // same-step auto-reset (anymdp_env.py:81-90)
-        if (GIVEN && !valid) s_next = s;
-        const RowW<NW> nq = ldg_row<NW>(nbase + (unsigned long long)((unsigned)s_next * (unsigned long long)srow));
 
-        // (D) settle the previous tick; once per 32 ticks write the finished batch of records, lane-parallel
+        // (C) settle the previous tick; once per 32 ticks write the finished batch of records, lane-parallel
         settle(k - 1);
         if (j == 0 && k > 0) flush(k - 32, 32);
-        // (C) payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104) and the state word of the observation
-        //     (anymdp_env.py:145-148; after a reset: of the start state): consumed by settle() of the next tick
-        pay_p = ldg_stream_f32x2(pay_t + ((unsigned long long)sa * N_PAD + (unsigned)nxt));
-        si_p = __ldg(sinfo_t + s_next) & 0x7fffffff;
-        z_p = z;
+        // (D) this tick becomes the previous one
+        pay_p = npay; si_p = nsi; z_p = z; valid_p = valid;
         ad_p = GIVEN ? (a_raw & 0x0fffffff) : a;
         if (valid) {
-            ad_p |= ((term ? 1 : 0) | (trunc ? 2 : 0)) << 28;
+            ad_p |= (int)((((r >> 4) & 1u) | (trunc ? 2u : 0u)) << 28);
             steps += 1;
-            if (done) { close_p = true; steps_p = steps; steps = 0; }
-            s = s_next;
-        } else {
-            pay_p = make_float2(0.f, 0.f);
-            si_p = 0;
+            if ((r | trunc16) & 16u) { close_p = true; steps_p = steps; steps = 0; }
+            s = (int)s_next;
         }
         // once per 32 ticks: draw the next batch
         if (j == 31) make(k + 2 + lane, b_pk, b_z, b_act);
@@ -1409,6 +1429,7 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
         if (GIVEN && (npk >> 31) && k + 1 < K) fault |= AMDP_FAULT_BAD_ACTION;               // :97
         pk = npk; z = nz; a = n_a; a_raw = na_raw; v2 = nv2;
         sa = (unsigned)(s * na + n_a);
+        pay_row = pay_t + (unsigned long long)sa * N_PAD;
         q = nq;
     }
     settle(K - 1);
