@@ -1320,14 +1320,18 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
     int a = GIVEN ? ((pk >> 31) ? 0 : a_raw) : (int)((pk >> 15) & 0xffu);
     unsigned sa = (unsigned)(s * na + a);                         // row (s, a) inside the task
     unsigned v2 = (pk & 0x7fffu) * 0x00010001u;
-    RowW<NW> q = ldg_row<NW>(sk_lane + (unsigned long long)sa * ROW_BYTES);
+    // What is in flight between two ticks: the filter row of tick k, and the payload / state word of tick k - 1 (settled
+    // one tick late; their loads travel with the row load).  Two sets, used alternately (the loop is unrolled by two):
+    // with one set the loaded registers would have to be MOVed at the end of a tick, and a MOV waits for the load.
+    struct Flight { RowW<NW> q; float2 pay; int si; };
+    Flight fa, fb;
+    fa.q = ldg_row<NW>(sk_lane + (unsigned long long)sa * ROW_BYTES);
+    fa.pay = make_float2(0.f, 0.f); fa.si = 0;
 
-    // the previous tick, settled one tick late (its payload / state-word loads travel with the next row load)
-    float2 pay_p = make_float2(0.f, 0.f);
     float z_p = 0.f;
-    int si_p = 0, ad_p = 0, steps_p = 0;
+    int ad_p = 0, steps_p = 0;
     bool close_p = false, valid_p = false;
-    auto settle = [&](int kp) {
+    auto settle = [&](int kp, const float2 pay_p, const int si_p) {
         // reward = gt + noise * z (anymdp_env.py:103-105), episode return, closed-episode statistics, the record
         const double rew = valid_p ? (double)pay_p.x + (double)pay_p.y * (double)z_p : 0.0;
         ep_ret += rew;
@@ -1350,7 +1354,7 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
     asm volatile("" : "+r"(lane_base32), "+r"(myterm16));
     const float2* pay_row = pay_t + (unsigned long long)sa * N_PAD;   // payload row of (s, a)
 
-    for (int k = 0; k < K; ++k) {
+    auto tick = [&](const int k, const Flight& cur, Flight& nxf) {
         const int j = k & 31;
         // (A) inputs of the NEXT tick: independent of the row in flight
         const unsigned npk = __shfl_sync(FULL, b_pk, j);
@@ -1370,15 +1374,12 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
         const unsigned v2le = v2 + 0x00010001u;                   // entries <= code15(u): below the next code
         int lt = 0, le = 0;                                       // this lane's entries below u / not above u
 #pragma unroll
-        for (int i = 0; i < NW; ++i) { lt = h2_count_lt_pos(q.w[i], v2, lt); le = h2_count_lt_pos(q.w[i], v2le, le); }
+        for (int i = 0; i < NW; ++i) { lt = h2_count_lt_pos(cur.q.w[i], v2, lt); le = h2_count_lt_pos(cur.q.w[i], v2le, le); }
         // (index of the first entry not below u) << 5 | is_terminal[it] << 4 | entries sharing u's code (undecided)
         unsigned val = lane_base32 + ((unsigned)lt << 5) + (unsigned)(le - lt) + ((myterm16 >> lt) & 16u);
         if (lt == EPL) val = FULL;                                // all below: the boundary is in a later lane
         unsigned r = __reduce_min_sync(FULL, val);
         unsigned nxt, s_next;
-        float2 npay;
-        int nsi;
-        RowW<NW> nq;
         auto advance = [&]() {
             nxt = r >> 5;
             const bool done = ((r | trunc16) & 16u) != 0;         // anymdp_env.py:108,114
@@ -1387,9 +1388,9 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
             // payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104), the next row, the state word of the observation
             // (anymdp_env.py:145-148; after a reset: of the start state).  Issued together: ptxas puts loads of one kind on
             // one barrier, and a payload load issued later than the row would make the chain wait for it.
-            npay = ldg_stream_f32x2(pay_row + nxt);
-            nq = ldg_row<NW>(nbase + (unsigned long long)(s_next * (unsigned long long)srow));
-            nsi = __ldg(sinfo_t + s_next);
+            nxf.pay = ldg_stream_f32x2(pay_row + nxt);
+            nxf.q = ldg_row<NW>(nbase + (unsigned long long)(s_next * (unsigned long long)srow));
+            nxf.si = __ldg(sinfo_t + s_next);
         };
         advance();
         if (r & 15u) {
@@ -1412,10 +1413,10 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
         }
 
         // (C) settle the previous tick; once per 32 ticks write the finished batch of records, lane-parallel
-        settle(k - 1);
+        settle(k - 1, cur.pay, cur.si);
         if (j == 0 && k > 0) flush(k - 32, 32);
         // (D) this tick becomes the previous one
-        pay_p = npay; si_p = nsi; z_p = z; valid_p = valid;
+        z_p = z; valid_p = valid;
         ad_p = GIVEN ? (a_raw & 0x0fffffff) : a;
         if (valid) {
             ad_p |= (int)((((r >> 4) & 1u) | (trunc ? 2u : 0u)) << 28);
@@ -1430,9 +1431,11 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
         pk = npk; z = nz; a = n_a; a_raw = na_raw; v2 = nv2;
         sa = (unsigned)(s * na + n_a);
         pay_row = pay_t + (unsigned long long)sa * N_PAD;
-        q = nq;
-    }
-    settle(K - 1);
+    };
+    int k = 0;
+    for (; k + 1 < K; k += 2) { tick(k, fa, fb); tick(k + 1, fb, fa); }
+    if (k < K) { tick(k, fa, fb); settle(K - 1, fb.pay, fb.si); }
+    else settle(K - 1, fa.pay, fa.si);
     {
         const int kb = ((K - 1) / 32) * 32;
         flush(kb, K - kb);
