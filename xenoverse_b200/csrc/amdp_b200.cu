@@ -12,138 +12,9 @@
 // draw index #{i : cdf[i] <= u} is a compare + group reduction — one memory round trip per
 // transition instead of log2(n) dependent ones.  Everything else a step needs is either in the
 // per-task small tables (L1/L2 resident) or in the fp32 payload entry addressed by (s, a, s').
-#include <cuda_runtime.h>
-#include <cuda_fp16.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-#include <math.h>
 #include <new>
 
-#include "amdp_b200.h"
-
-#define FLAG_PENDING 1   // next_step mode: the next step() performs the reset
-#define FLAG_VIRGIN  2   // never reset since assign (anymdp_env.py:79 need_reset = True)
-
-// ------------------------------------------------------------------------------------------------
-// device tables / state (passed to kernels by value)
-// ------------------------------------------------------------------------------------------------
-struct Tables {
-    const double*  cdf;       // [T][n_pad][na][n_pad] normalised CDF rows, pad = 1.0
-    const float2*  payload;   // [T][n_pad][na][n_pad] (reward, reward_noise) fp32
-    const uint16_t* sketch;   // [T][n_pad][na][n_pad] code15(cdf): 2-byte filter in front of cdf (fp16-ordered AND unsigned-ordered)
-    const uint16_t* pivot;    // [T][n_pad][na][32] sketch value of the last entry of every 32-entry block (pad 0x7bff); n_pad in [256, 1024]
-    const int32_t* sinfo;     // [T][n_pad]  state_mapping | (is_terminal << 31)
-    const double*  s0_cdf;    // [T][s0_pad] pad = 2.0
-    const int32_t* s0_idx;    // [T][s0_pad]
-    const double*  obs_cdf;   // [T][do][n_pad][no_pad] pad = 1.0 (POMDP / MTPOMDP)
-    const int32_t* max_ceil;  // [T] ceil(max_steps)
-    const uint8_t* tflags;    // [T] bit0: ns < 2 (always terminated, anymdp_env.py:108)
-    const double*  raw_t;     // [T][n_pad][na][n_pad] raw transition (only if keep_transition) or null
-    const int32_t* n_real;    // [T]
-    const uint32_t* tbits;    // [T][tb_words] is_terminal bitmap (bit j of word j / 32), tb_words = ceil(n_pad / 32)
-    int tb_words;
-    // thread-per-env search tables (k_rollout_tp): two levels, both exact up to an equality that falls back to `cdf`
-    const uint4*    fat;      // [T][n_pad][na][tp_blocks] 128-byte lines, one per 8-entry block of a row:
-                              //   bytes 0-31 8 x ((floor(cdf * 2^31) << 1) | is_terminal[j]), 32-95 8 x (reward, noise) fp32,
-                              //   96-127 8 x sinfo[j]  — everything a transition into the block needs, in ONE DRAM line
-    const uint16_t* pv;       // [T][n_pad][na][tp_groups][16] code15 of the LAST entry of each block of a group of 16; pad 0x7bff
-    const uint16_t* top;      // [T][n_pad][na][16] code15 of the last entry of each group (three-level rows only)
-    int tp_levels, tp_groups, tp_blocks;
-    const uint32_t* ofat;     // POMDP (do = 1): [T][n_pad][8 + 8 * o_blocks] words per observation row: 16 pivots (code15 of the last
-                              // entry of each 8-entry block; pad 0x7bff), then o_blocks x 8 codes (floor(cdf * 2^31) << 1)
-    int o_blocks;
-    int n_pad, na, no_pad, d_o, d_a, s0_pad, task_type, autoreset;
-};
-
-struct EnvArrays {
-    int32_t* state;      // inner state index
-    int32_t* steps;      // steps in the current episode
-    uint8_t* flags;      // FLAG_*
-    double*  ep_return;  // running return of the current episode (fp64: SURVEY §7.2)
-    const int32_t* task; // task of each env
-    // per-env episode statistics (closed episodes only)
-    unsigned long long* ep_count;
-    double* sum_ret;
-    double* sum_ret_sq;
-    unsigned long long* sum_len;
-    double* min_ret;
-    double* max_ret;
-    unsigned int* faults;  // single word, sticky
-    unsigned long long* counters;  // [0] exact-row fallbacks of the fast kernel
-    long long n_envs;
-    unsigned long long env_id_base;
-    uint2 key;
-};
-
-// ------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Random123; constants as curand_philox4x32_x.h:88-91) and the draw constructions
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-
-// numpy MT19937 double: ((a >> 5) * 2^26 + (b >> 6)) / 2^53 — exact in fp64
-__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
-    const unsigned long long v = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
-    return (double)(long long)v * 1.1102230246251565e-16;
-}
-
-__device__ __forceinline__ uint4 philox_block(unsigned long long env, uint32_t block, unsigned long long tick, uint2 key) {
-    const uint4 ctr = make_uint4((uint32_t)env, block + ((uint32_t)(env >> 32) << 16), (uint32_t)tick, (uint32_t)(tick >> 32));
-    return philox4x32_10(ctr, key);
-}
-
-__device__ __forceinline__ float box_muller(uint32_t w0, uint32_t w1) {
-    const float u1 = (__uint2float_rn(w0 >> 8) + 0.5f) * 5.9604644775390625e-08f;
-    const float u2 = (__uint2float_rn(w1 >> 8) + 0.5f) * 5.9604644775390625e-08f;
-    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-}
-
-// Monotone integer codes of a probability x in [0, 1] (used by the thread-per-env search tables).  With the SAME function
-// applied to a CDF entry c and to the uniform u:  code(c) < code(u) => c < u,  code(c) > code(u) => c > u; equality is
-// undecided and is resolved on the float64 row.
-//   code31(x) = floor(x * 2^31), 1.0 -> 2^31 - 1.            For u = k * 2^-53 this is k >> 22.
-//   code15(x) = 0x0400 + ((floor(x * 2^21) * 30719) >> 21), 1.0 -> 0x7bff: the bit pattern of a positive NORMAL fp16
-//               number, so that packed fp16 compares (HSET2) order the codes.  For u this uses k >> 32.
-__host__ __device__ __forceinline__ uint32_t code31(double x) {
-    return x >= 1.0 ? 0x7fffffffu : (uint32_t)floor(x * 2147483648.0);
-}
-__device__ __forceinline__ uint32_t code15_from_m21(uint32_t m21) {      // m21 = floor(x * 2^21) < 2^21
-    return 0x0400u + __umulhi(m21 << 11, 30719u);
-}
-__device__ __forceinline__ uint32_t code15(double x) {
-    return x >= 1.0 ? 0x7bffu : code15_from_m21((uint32_t)floor(x * 2097152.0));
-}
-
-// Source of the draws of one (env, tick): injected matrix row or Philox.
-struct Draws {
-    const double* row;          // injected row (n_slots doubles) or null
-    unsigned long long env, tick;
-    uint2 key;
-    __device__ __forceinline__ void pair(int block, double& a, double& b) const {   // slots 2b, 2b+1 as uniforms
-        if (row) { a = row[2 * block]; b = row[2 * block + 1]; return; }
-        const uint4 w = philox_block(env, (uint32_t)block, tick, key);
-        a = u53(w.x, w.y);
-        b = u53(w.z, w.w);
-    }
-    __device__ __forceinline__ void z_action(int tok, int na, double& z, int& act) const {  // slots 4,5 of token
-        const int s = AMDP_SLOT_Z + AMDP_SLOTS_PER_TOKEN * tok;
-        if (row) { z = row[s]; act = (int)row[s + 1]; return; }
-        const uint4 w = philox_block(env, (uint32_t)(s >> 1), tick, key);
-        z = (double)box_muller(w.x, w.y);
-        act = (int)__umulhi(w.z, (uint32_t)na);
-    }
-};
+#include "amdp_dev.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // group primitives: G adjacent lanes own one env
@@ -312,10 +183,6 @@ __device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, lo
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int load_action(const int32_t* actions, long long i, int as_u8) {
-    return as_u8 ? (int)reinterpret_cast<const uint8_t*>(actions)[i] : actions[i];
-}
-
 __device__ __forceinline__ void load_regs(const EnvArrays& E, long long e, EnvRegs& R, bool with_stats) {
     R.state = E.state[e]; R.steps = E.steps[e]; R.flags = E.flags[e]; R.ep_return = E.ep_return[e];
     if (with_stats) {
@@ -420,1035 +287,6 @@ __global__ void __launch_bounds__(256) k_rollout(Tables T, EnvArrays E, unsigned
     if (active && lane == 0) { store_regs(E, e, R); store_stats(E, e, R); }
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// Fast path: MDP, one action token, engine Philox draws, auto-reset on (the benchmark / data-
-// collection configuration).  Same arithmetic as env_tick, restructured for issue slots and latency:
-//   * the G lanes of an env generate the draws of G consecutive ticks in ONE Philox pass (lane j
-//     computes tick k0 + j) and broadcast them tick by tick, so the RNG costs ~1/G of a
-//     per-lane evaluation per tick;
-//   * the (reward, noise) payload load is taken off the dependent chain: it is issued when s' is
-//     known and consumed one tick later, after the NEXT row load is already in flight.  The chain
-//     per tick is: CDF row (HBM) -> compare/ballot -> per-task state table (L1) -> next row address;
-//   * rows and payload are streamed past L1 (no reuse), keeping L1 for the per-task tables.
-// C = 4-double chunks per lane held in registers (n_pad == 4*G*C); C == 0: any n_pad, looped.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double2 ldg_stream_f64x2(const double* p) {
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-
-__device__ __forceinline__ uint2 ldg_stream_u32x2(const uint16_t* p) {
-    uint2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
-}
-
-__device__ __forceinline__ float2 ldg_stream_f32x2(const float2* p) {
-    float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    return v;
-}
-
-// P2 (two-level search, large rows): level 1 = one 64-byte row of 32 pivots (the filter value of the last entry of every
-// 32-entry block), level 2 = the 64-byte filter block the pivots select; G is 8 (8 lanes x 8 bytes per level).  Two
-// small dependent reads per transition instead of streaming a 2-8 KB row.
-template <int G, int C, bool GIVEN, bool NEXT, bool P2>
-__global__ void __launch_bounds__(128, 7) k_rollout_mdp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
-                                                        const int32_t* __restrict__ actions, const amdp_traj J) {
-    static_assert(!P2 || (G == 8 && C == 1), "two-level search uses 8 lanes and one pivot chunk");
-    constexpr int CR = C > 0 ? C : 1;
-    constexpr int EPB = 128 / G;                                  // envs per block
-    constexpr bool MAYSKIP = GIVEN || NEXT;                       // a tick may not step (bad action / pending reset)
-    // closed-episode statistics live in shared memory (touched by lane 0 of the group only, ~10 % of ticks)
-    __shared__ double sh_stat[4][EPB];                            // sum_ret, sum_ret_sq, min_ret, max_ret
-    __shared__ unsigned long long sh_cnt[2][EPB];                 // ep_count, sum_len
-    const int wl = threadIdx.x & 31;
-    int lane = threadIdx.x & (G - 1);
-    const int gi = threadIdx.x / G;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(G - 1)));
-    const int gshift = wl & ~(G - 1);
-    const long long e = (long long)blockIdx.x * EPB + gi;
-    if (e >= E.n_envs) return;                                    // groups are independent (group-local sync masks)
-    const int n_pad = T.n_pad, na = T.na;
-    const long long t = E.task[e];
-    const long long tsz = (long long)n_pad * na * n_pad;
-    const double* __restrict__ cdf_lane = T.cdf + t * tsz + lane * 4;        // float64 rows: exact fallback only
-    const uint16_t* __restrict__ sk_lane = T.sketch + t * tsz + lane * 4;    // 16-bit filter rows: the common case
-    const uint16_t* __restrict__ pv_lane = P2 ? T.pivot + t * ((long long)n_pad * na * 32) + lane * 4 : nullptr;
-    const float2* __restrict__ pay_t = T.payload + t * tsz;
-    const int32_t* __restrict__ sinfo_t = T.sinfo + t * n_pad;
-    // keep these in registers (ptxas otherwise re-derives them from t / %tid every tick)
-    asm volatile("" : "+l"(sk_lane));
-    if (P2) asm volatile("" : "+l"(pv_lane));
-    asm volatile("" : "+l"(pay_t));
-    asm volatile("" : "+l"(sinfo_t));
-    asm volatile("" : "+r"(lane));
-    const int max_ceil = T.max_ceil[t];
-    const bool always_term = (T.tflags[t] & 1) != 0;
-    const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
-    const long long N = E.n_envs;
-
-    int s = E.state[e], steps = E.steps[e], flags = E.flags[e];
-    double ep_ret = E.ep_return[e];
-
-    // staged trajectory records: lane L holds the record of tick (batch start + L); a batch is written once all of its
-    // rewards have settled (rewards settle one tick late, see below)
-    int st_obs = 0, st_ad = 0;                                    // st_ad = action | done_bits << 28
-    float st_rew = 0.f, st_rgt = 0.f;
-    auto flush = [&](int kb, int cnt) {                           // records of ticks [kb, kb + cnt), one lane per tick
-        if (lane < cnt) {
-            const long long o = (long long)(kb + lane) * J.step_stride + e * J.env_stride;
-            if (J.packed) {
-                // one 8-byte record per (tick, env): obs | action << 20 | done << 30, reward bits
-                const unsigned lo = ((unsigned)st_obs & 0xfffffu) | (((unsigned)st_ad & 0x3ffu) << 20) | (((unsigned)st_ad >> 28) << 30);
-                J.packed[o] = ((unsigned long long)__float_as_uint(st_rew) << 32) | lo;
-            } else {
-                if (J.obs) J.obs[o] = st_obs;
-                if (J.actions_out) J.actions_out[o] = st_ad & 0x0fffffff;
-                if (J.done) J.done[o] = (uint8_t)((unsigned)st_ad >> 28);
-                if (J.reward) J.reward[o] = st_rew;
-                if (J.reward_gt) J.reward_gt[o] = st_rgt;
-            }
-        }
-    };
-
-    unsigned fault = 0;
-    if (flags & FLAG_VIRGIN) fault = AMDP_FAULT_NEED_RESET;                                   // anymdp_env.py:93-94
-    else if (!(NEXT && (flags & FLAG_PENDING)) && sinfo_t[s] < 0 && !always_term) fault = AMDP_FAULT_TERMINAL_STATE;
-    if (fault) {
-        // faulted envs are left untouched (as in env_tick); their records are zero except the action
-        for (int kb = 0; kb < K; kb += G) {
-            const int k = kb + lane;
-            int a = 0;
-            if (k < K) {
-                if (GIVEN) a = load_action(actions, (long long)k * N + e, J.actions_u8);
-                else a = (int)__umulhi(philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key).z, (uint32_t)na);
-            }
-            st_ad = a & 0x0fffffff;
-            flush(kb, min(G, K - kb));
-        }
-        if (lane == 0) atomicOr(E.faults, fault);
-        return;
-    }
-    if (lane == 0) {
-        sh_cnt[0][gi] = E.ep_count[e]; sh_cnt[1][gi] = E.sum_len[e];
-        sh_stat[0][gi] = E.sum_ret[e]; sh_stat[1][gi] = E.sum_ret_sq[e];
-        sh_stat[2][gi] = E.min_ret[e]; sh_stat[3][gi] = E.max_ret[e];
-    }
-
-    // Draws.  The G lanes of an env generate the draws of G consecutive ticks in one Philox pass.  Lane L of batch kb
-    // holds the draws of tick kb + L + 1 (one tick AHEAD of the tick that fetches them), so that the inputs of the next
-    // tick are available before the current row has arrived and the next row load can be issued speculatively.
-    // The transition uniform is kept as its filter code code15(u) (a function of the top 21 bits of its 53-bit integer);
-    // the exact fallback recomputes u.
-    unsigned b_uhi = 0;
-    double b_ur = 0.0;        // reset draw of tick kb + L + 1
-    float b_z = 0.f;
-    int b_act = 0;
-    double ur_carry;          // reset draw of the first tick of the current batch (made by the previous batch)
-    unsigned n_fallback = 0;
-    auto refill = [&](int kb) {
-        const int kt = kb + lane + 1;
-        const unsigned long long tk = tick0 + (unsigned long long)kt;
-        const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
-        b_uhi = code15_from_m21(w0.x >> 11);                      // code15(u): w0.x >> 11 == floor(u * 2^21)
-        b_ur = u53(w0.z, w0.w);
-        const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
-        b_z = box_muller(w2.x, w2.y);
-        if (GIVEN) b_act = (kt < K) ? load_action(actions, (long long)kt * N + e, J.actions_u8) : 0;
-        else b_act = (int)__umulhi(w2.z, (uint32_t)na);
-    };
-
-    // inputs of the current tick (its row load is in flight)
-    unsigned v;               // code15(u) of the transition uniform
-    float z;
-    int a;
-    uint2 q[CR];              // this lane's 4 * C filter entries (16 bit each) of row (s, a)
-    {
-        const uint4 w0 = philox_block(env_id, 0u, tick0, E.key);
-        v = code15_from_m21(w0.x >> 11);
-        ur_carry = u53(w0.z, w0.w);
-        const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0, E.key);
-        z = box_muller(w2.x, w2.y);
-        a = GIVEN ? load_action(actions, e, J.actions_u8) : (int)__umulhi(w2.z, (uint32_t)na);
-    }
-    refill(0);
-    bool pend = NEXT && (flags & FLAG_PENDING);
-    bool valid = !pend && (!GIVEN || (unsigned)a < (unsigned)na);
-    if (GIVEN && !pend && !valid) fault |= AMDP_FAULT_BAD_ACTION;                              // :97
-    unsigned sa = (unsigned)(s * na + (valid ? a : 0));           // row index (s, a) inside the task
-    auto issue_row = [&](uint2* dst, unsigned sa_, bool on) {     // anymdp_env.py:99 (the row of the transition table)
-        if (P2) {
-            dst[0] = on ? ldg_stream_u32x2(pv_lane + sa_ * 32u) : make_uint2(0xffffffffu, 0xffffffffu);
-        } else if (C > 0) {
-#pragma unroll
-            for (int c = 0; c < CR; ++c) {
-                if (on) dst[c] = ldg_stream_u32x2(sk_lane + sa_ * (unsigned)n_pad + c * (G * 4));
-                else dst[c] = make_uint2(0xffffffffu, 0xffffffffu);
-            }
-        }
-    };
-    issue_row(q, sa, valid);
-
-    // deferred reward of the previous tick: payload (0, 0) when that tick did not step
-    float2 pay_p = make_float2(0.f, 0.f);
-    float z_p = 0.f;
-    bool close_p = false;     // the previous tick closed an episode ...
-    int steps_p = 0;          // ... of this length
-    auto settle = [&](int k_prev) {
-        // reward = gt + noise * z (anymdp_env.py:103-105), episode return, closed-episode statistics
-        const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
-        ep_ret += rew;
-        if (lane == (k_prev & (G - 1))) { st_rew = (float)rew; st_rgt = pay_p.x; }
-        if (close_p) {
-            if (lane == 0) {
-                sh_cnt[0][gi] += 1; sh_cnt[1][gi] += (unsigned long long)steps_p;
-                sh_stat[0][gi] += ep_ret; sh_stat[1][gi] += ep_ret * ep_ret;
-                sh_stat[2][gi] = fmin(sh_stat[2][gi], ep_ret); sh_stat[3][gi] = fmax(sh_stat[3][gi], ep_ret);
-            }
-            ep_ret = 0.0;
-            close_p = false;
-        }
-    };
-
-    for (int k = 0; k < K; ++k) {
-        const int j = k & (G - 1);
-        // inputs of the NEXT tick: independent of the row in flight
-        const unsigned nv = __shfl_sync(gmask, b_uhi, j, G);
-        const float nz = __shfl_sync(gmask, b_z, j, G);
-        const int na_ = __shfl_sync(gmask, b_act, j, G);
-        const bool na_ok = !GIVEN || (unsigned)na_ < (unsigned)na;
-        const unsigned na_col = (unsigned)(na_ok ? na_ : 0);
-
-        int nxt = s;
-        bool do_reset = NEXT && pend;                              // next_step mode: this tick only performs the reset
-        const unsigned rowi = sa * (unsigned)n_pad;
-        if (valid) {
-            // (C) next state = #{cdf <= u}  (numpy choice: searchsorted(cdf, u, 'right')), decided on the 16-bit filter:
-            //     q < v  =>  cdf < u;  q > v  =>  cdf > u;  only q == v is undecided.
-            const unsigned vhi = v << 16, v2 = vhi | v;
-            auto chunk = [&](const uint2 w, int& cnt, unsigned& amb) {
-                // entries: lo16(w.x), hi16(w.x), lo16(w.y), hi16(w.y); (w << 16) < (v << 16) <=> lo16 < v, w < (v << 16) <=> hi16 < v
-                const unsigned b0 = __ballot_sync(gmask, (w.x << 16) < vhi);
-                const unsigned b1 = __ballot_sync(gmask, w.x < vhi);
-                const unsigned b2 = __ballot_sync(gmask, (w.y << 16) < vhi);
-                const unsigned b3 = __ballot_sync(gmask, w.y < vhi);
-                if (G == 32) cnt += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
-                else {
-                    const unsigned m = (1u << G) - 1u;
-                    cnt += __popc((b0 >> gshift) & m) + __popc((b1 >> gshift) & m) + __popc((b2 >> gshift) & m) + __popc((b3 >> gshift) & m);
-                }
-                // any 16-bit field equal to v?  (x has a zero halfword  <=>  (x - 0x00010001) & ~x & 0x80008000 != 0)
-                const unsigned x0 = w.x ^ v2, x1 = w.y ^ v2;
-                amb |= ((x0 - 0x00010001u) & ~x0 & 0x80008000u) | ((x1 - 0x00010001u) & ~x1 & 0x80008000u);
-            };
-            nxt = 0;
-            unsigned amb = 0;
-            int blk = 0;                                           // P2: the 32-entry block that holds the boundary
-            if (P2) {
-                unsigned amb1 = 0;
-                chunk(q[0], blk, amb1);                            // blocks whose last entry is < v lie entirely below u
-                const unsigned lo = (unsigned)blk * 32u;
-                const bool in = lo + lane * 4 < (unsigned)n_pad;   // the last block of a row may be partial
-                chunk(in ? ldg_stream_u32x2(sk_lane + rowi + lo) : make_uint2(0xffffffffu, 0xffffffffu), nxt, amb);
-                nxt += (int)lo;
-            } else if (C > 0) {
-#pragma unroll
-                for (int c = 0; c < CR; ++c) chunk(q[c], nxt, amb);
-            } else {
-                for (int i = 0; i < n_pad; i += G * 4) {
-                    // lanes past the end of the row contribute "not less"
-                    const bool in = (i + lane * 4 < n_pad);
-                    chunk(in ? ldg_stream_u32x2(sk_lane + rowi + i) : make_uint2(0xffffffffu, 0xffffffffu), nxt, amb);
-                }
-            }
-            if (__any_sync(gmask, amb != 0)) {
-                // undecided (u and some cdf entry share a code15 cell, ~n/30720 of the ticks): exact float64 entries
-                const uint4 w0 = philox_block(env_id, 0u, tick0 + (unsigned long long)k, E.key);
-                const double u = u53(w0.x, w0.y);
-                if (P2) {
-                    // entries before block `blk` are below u; count block by block while a block is entirely <= u
-                    nxt = blk * 32;
-                    for (int base = blk * 32; base < n_pad; base += 32) {
-                        int cnt = 0;
-                        if (base + lane * 4 < n_pad) {
-                            const double2 x = ldg_stream_f64x2(cdf_lane + rowi + base);
-                            const double2 y = ldg_stream_f64x2(cdf_lane + rowi + base + 2);
-                            cnt = (x.x <= u) + (x.y <= u) + (y.x <= u) + (y.y <= u);
-                        }
-#pragma unroll
-                        for (int o = G >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
-                        nxt += cnt;
-                        if (cnt < 32) break;
-                    }
-                } else {
-                    int cnt = 0;
-                    for (int i = 0; i < n_pad; i += G * 4) {
-                        if (i + lane * 4 < n_pad) {
-                            const double2 x = ldg_stream_f64x2(cdf_lane + rowi + i);
-                            const double2 y = ldg_stream_f64x2(cdf_lane + rowi + i + 2);
-                            cnt += (x.x <= u) + (x.y <= u) + (y.x <= u) + (y.y <= u);
-                        }
-                    }
-#pragma unroll
-                    for (int o = G >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
-                    nxt = cnt;
-                }
-                n_fallback += 1;
-            }
-        }
-        // (A) SPECULATIVE row load of the next tick, assuming this tick neither terminates nor truncates: the dependent
-        //     chain per tick is  row (HBM) -> compare/ballot -> next row address.  Everything below runs in its shadow.
-        unsigned nsa = (unsigned)(nxt * na) + na_col;
-        uint2 nq[CR];
-        if (!do_reset) issue_row(nq, nsa, na_ok);
-
-        // (B) settle the previous tick (its payload load was issued one tick ago, after this tick's row load); once per
-        //     G ticks write the finished batch of records, lane-parallel
-        settle(k - 1);
-        if (j == 0 && k > 0) flush(k - G, G);
-        // (D) payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104): consumed by settle() of the next tick
-        if (valid) pay_p = ldg_stream_f32x2(pay_t + (rowi + (unsigned)nxt)); else pay_p = make_float2(0.f, 0.f);
-        z_p = z;
-
-        // (E) state update, termination, truncation (anymdp_env.py:107-108,113-114)
-        int obs_out = 0, done_bits = 0;
-        if (valid) {
-            const int si = __ldg(sinfo_t + nxt);
-            s = nxt;
-            steps += 1;
-            const bool term = (si < 0) || always_term;
-            const bool trunc = steps >= max_ceil;
-            obs_out = si & 0x7fffffff;
-            done_bits = (term ? 1 : 0) | (trunc ? 2 : 0);
-            if (done_bits) {
-                close_p = true;
-                steps_p = steps;
-                if (NEXT) flags |= FLAG_PENDING; else do_reset = true;
-            }
-        }
-        if (do_reset) {                                            // anymdp_env.py:81-90
-            const double ur = (j == 0) ? ur_carry : __shfl_sync(gmask, b_ur, (j - 1) & (G - 1), G);
-            int c = 0;
-            for (int i = 0; i < T.s0_pad; ++i) c += (T.s0_cdf[t * T.s0_pad + i] <= ur);
-            s = T.s0_idx[t * T.s0_pad + min(c, T.s0_pad - 1)];
-            steps = 0;
-            flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
-            obs_out = __ldg(sinfo_t + s) & 0x7fffffff;
-            // the speculation was wrong (or not made): the next tick starts from the reset state
-            nsa = (unsigned)(s * na) + na_col;
-            issue_row(nq, nsa, na_ok);
-        }
-        if (lane == j) {
-            st_obs = obs_out;
-            st_ad = (a & 0x0fffffff) | (done_bits << 28);
-        }
-        // once per G ticks: draw the next batch
-        if (j == G - 1) {
-            ur_carry = __shfl_sync(gmask, b_ur, G - 1, G);
-            refill(k + 1);
-        }
-        // rotate to the next tick
-        v = nv; z = nz; a = na_; sa = nsa;
-#pragma unroll
-        for (int c = 0; c < CR; ++c) q[c] = nq[c];
-        pend = NEXT && (flags & FLAG_PENDING);
-        valid = !pend && na_ok;
-        if (GIVEN && !pend && !na_ok && k + 1 < K) fault |= AMDP_FAULT_BAD_ACTION;           // :97
-    }
-    // settle the last tick and write what is still staged
-    {
-        settle(K - 1);
-        const int kb = ((K - 1) / G) * G;
-        flush(kb, K - kb);
-    }
-    if (lane == 0) {
-        E.state[e] = s; E.steps[e] = steps; E.flags[e] = (uint8_t)flags; E.ep_return[e] = ep_ret;
-        E.ep_count[e] = sh_cnt[0][gi]; E.sum_len[e] = sh_cnt[1][gi];
-        E.sum_ret[e] = sh_stat[0][gi]; E.sum_ret_sq[e] = sh_stat[1][gi];
-        E.min_ret[e] = sh_stat[2][gi]; E.max_ret[e] = sh_stat[3][gi];
-        if (fault) atomicOr(E.faults, fault);
-        if (n_fallback) atomicAdd(E.counters, (unsigned long long)n_fallback);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Throughput path: ONE THREAD PER ENV (MDP, one action token, engine Philox draws, auto-reset on), for engines with
-// enough envs to fill the machine (>= 16k per GPU).  The warp-per-env kernel above keeps at most ~4k envs in flight
-// per GPU (one row per warp); here every resident thread is an env, so 60k-95k dependent chains are in flight and
-// the path is bound by DRAM lines instead of by latency x residency.
-//   Measured on B200 (profiles/r1_gather_microbench.txt, r1_tp_*): every L2 miss fetches its whole 128-byte line from
-//   DRAM whatever the request size, and what the kernel pays for is (a) DRAM lines and (b) 32-byte sector requests.
-//   Hence the layout: a row is cut into 8-entry blocks, and ONE 128-byte line per block holds the 8 CDF codes, the 8
-//   (reward, noise) payloads and the 8 state words (mapping | terminal) — a transition touches exactly one DRAM line
-//   below the pivots, with 3 sector requests (codes; payload entry; state word — the last two hit L2).
-//   * search = a 1..3-level tree, one 32-byte request per level: [top: <= 16 groups] -> [pivots: <= 16 blocks of the
-//     group] -> [block: 8 codes].  Pivots are 15-bit fp16-ordered codes of the LAST entry of a block / group, counted
-//     with packed HSET2 compares; block entries are 31-bit codes.  All levels are exact; the only undecided case is
-//     code31(cdf[j]) == code31(u) (~n * 2^-31 of the ticks), which reads the float64 row.  (A 16-bit filter would
-//     send n/65536 of the ticks to the float64 row, which at 32 envs per warp stalls most warps when n = 1024.)
-//   * is_terminal[s'] rides in bit 0 of the block codes, so the dependent chain per tick is  [top ->] pivots -> codes
-//     -> next pivots; payload and state word of tick k are consumed in the shadow of tick k+1's loads.
-//   * LEVELS = 1 (n_pad <= 8), 2 (<= 128) or 3 (<= 2048).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 ldg_stream_u128(const void* p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-
-__device__ __forceinline__ void ldg_stream_u256(const void* p, uint4& a, uint4& b) {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
-}
-
-// W x 16 bytes as 256-bit loads (one request per 32-byte sector; measured 10-50 % faster than pairs of 128-bit loads:
-// what bounds this kernel is the number of sector requests, and every L2 miss fetches its whole 128-byte line from DRAM
-// whatever the request size — profiles/r1_gather_microbench.txt).  AMDP_TP_LDG128 keeps the narrow form for comparison.
-template <int W>
-__device__ __forceinline__ void ldg_words(const void* p, uint4 (&dst)[W]) {
-#ifndef AMDP_TP_LDG128
-    if (W == 1) dst[0] = ldg_stream_u128(p);
-    else {
-#pragma unroll
-        for (int i = 0; i + 1 < W; i += 2) ldg_stream_u256((const char*)p + 16 * i, dst[i], dst[i + 1]);
-    }
-#else
-#pragma unroll
-    for (int i = 0; i < W; ++i) dst[i] = ldg_stream_u128((const char*)p + 16 * i);
-#endif
-}
-
-// Pivot rows are small and re-read (every visit of (s, a)); blocks and payload entries are touched once.  Loads of
-// the pivots carry an L2 evict_last policy so that the streaming block / payload / record traffic does not push them out.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-
-template <int W>
-__device__ __forceinline__ void ldg_words_keep(const void* p, uint4 (&dst)[W], uint64_t pol) {
-#ifdef AMDP_TP_NO_L2_HINT
-    ldg_words<W>(p, dst);
-#else
-    if (W == 1) {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-                     : "=r"(dst[0].x), "=r"(dst[0].y), "=r"(dst[0].z), "=r"(dst[0].w) : "l"(p), "l"(pol));
-    } else {
-#pragma unroll
-        for (int i = 0; i + 1 < W; i += 2) {
-            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
-                         : "=r"(dst[i].x), "=r"(dst[i].y), "=r"(dst[i].z), "=r"(dst[i].w), "=r"(dst[i + 1].x), "=r"(dst[i + 1].y),
-                           "=r"(dst[i + 1].z), "=r"(dst[i + 1].w) : "l"((const char*)p + 16 * i), "l"(pol));
-        }
-    }
-#endif
-}
-
-__device__ __forceinline__ int h2_count_lt(unsigned w, unsigned v2, int acc) {     // acc - #{halfwords of w (as fp16) < v}
-    const __half2 a = *reinterpret_cast<const __half2*>(&w), b = *reinterpret_cast<const __half2*>(&v2);
-    return __dp2a_lo((int)__hlt2_mask(a, b), 0x0101, acc);
-}
-
-__device__ __forceinline__ int h2_count_lt_pos(unsigned w, unsigned v2, int acc) {  // acc + #{halfwords of w (as fp16) < v}
-    const __half2 a = *reinterpret_cast<const __half2*>(&w), b = *reinterpret_cast<const __half2*>(&v2);
-    return __dp2a_lo((int)__hlt2_mask(a, b), 0xffff, acc);      // (-1) x (-1) per halfword that compares true
-}
-
-#define TP_S0 4
-#ifndef TP_TPB
-#define TP_TPB 64
-#endif
-#define TP_MINB_LO (640 / TP_TPB)
-#define TP_MINB_HI (896 / TP_TPB)
-// TP_TPB threads (= envs) per block: small blocks keep the last wave of a launch balanced over the 148 SMs
-// MINB = resident blocks per SM the register budget is sized for: 10 (96 registers, 640 envs per SM) or 14 (72 registers,
-// 896 envs per SM, chosen when that is what it takes to keep every env of the engine resident at once)
-template <int LEVELS, int MINB, bool GIVEN, bool POMDP>
-__global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
-                                                       const int32_t* __restrict__ actions, const amdp_traj J, int next, unsigned cmask) {
-    // GIVEN is a template parameter on purpose: with a runtime flag the (predicated-off) action load still owns a
-    // scoreboard slot, which ptxas shares with the deferred payload / state-word loads, and the first use of the action at
-    // the top of a tick then waits for those loads BEFORE the tick's first search load is issued (ncu: +15 % time).
-    constexpr bool given = GIVEN;
-    __shared__ double sh_stat[4][TP_TPB];                         // closed-episode statistics: sum_ret, sum_ret_sq, min, max
-    __shared__ unsigned long long sh_cnt[2][TP_TPB];              // ep_count, sum_len
-    __shared__ double sh_s0c[TP_S0][TP_TPB];                         // the env's start-state CDF and states (s0_pad <= TP_S0):
-    __shared__ int sh_s0i[TP_S0][TP_TPB];                            // a reset costs no global-memory round trip
-    const int tx = threadIdx.x;
-    const long long e = (long long)blockIdx.x * TP_TPB + tx;
-    if (e >= E.n_envs) return;
-    const int n_pad = T.n_pad, na = T.na;
-    const long long N = E.n_envs;
-    const long long t = E.task[e];
-    const unsigned long long rbase = (unsigned long long)t * n_pad * na;      // first (s, a) row of the task
-    const int32_t* __restrict__ sinfo_t = T.sinfo + t * n_pad;
-    const int max_ceil = T.max_ceil[t];
-    const bool always_term = (T.tflags[t] & 1) != 0;
-    const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
-    const int n_blocks = T.tp_blocks, n_groups = T.tp_groups;
-    const uint64_t pol_keep = l2_policy_evict_last();
-
-    int s = E.state[e], steps = E.steps[e], flags = E.flags[e];
-    double ep_ret = E.ep_return[e];
-
-    auto write_rec = [&](int k, int obs, int a, int done, float rew, float rgt) {
-        const long long o = (long long)k * J.step_stride + e * J.env_stride;
-        if (J.packed) {
-            const unsigned lo = ((unsigned)obs & 0xfffffu) | (((unsigned)a & 0x3ffu) << 20) | ((unsigned)done << 30);
-            J.packed[o] = ((unsigned long long)__float_as_uint(rew) << 32) | lo;
-        } else {
-            if (J.obs) J.obs[o] = obs;
-            if (J.actions_out) J.actions_out[o] = a & 0x0fffffff;
-            if (J.done) J.done[o] = (uint8_t)done;
-            if (J.reward) J.reward[o] = rew;
-            if (J.reward_gt) J.reward_gt[o] = rgt;
-        }
-    };
-
-    unsigned fault = 0;
-    if (flags & FLAG_VIRGIN) fault = AMDP_FAULT_NEED_RESET;                                   // anymdp_env.py:93-94
-    else if (!(next && (flags & FLAG_PENDING)) && sinfo_t[s] < 0 && !always_term) fault = AMDP_FAULT_TERMINAL_STATE;
-    if (fault) {
-        // faulted envs are left untouched (as in env_tick); their records are zero except the action
-        for (int k = 0; k < K; ++k) {
-            int a;
-            if (given) a = load_action(actions, (long long)k * N + e, J.actions_u8);
-            else a = (int)__umulhi(philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key).z, (uint32_t)na);
-            write_rec(k, 0, a, 0, 0.f, 0.f);
-        }
-        atomicOr(E.faults, fault);
-        return;
-    }
-    sh_cnt[0][tx] = E.ep_count[e]; sh_cnt[1][tx] = E.sum_len[e];
-    sh_stat[0][tx] = E.sum_ret[e]; sh_stat[1][tx] = E.sum_ret_sq[e];
-    sh_stat[2][tx] = E.min_ret[e]; sh_stat[3][tx] = E.max_ret[e];
-    // s0_pad <= TP_S0 (the host never selects this kernel otherwise).  Keeping the start-state table on chip also keeps
-    // global loads out of the registers that carry the state from tick to tick: a load there, even on a path that is
-    // never taken, makes the top of every tick wait for the scoreboard slot it shares with the deferred loads.
-    const int s0_pad = T.s0_pad;
-#pragma unroll
-    for (int i = 0; i < TP_S0; ++i) {
-        sh_s0c[i][tx] = (i < s0_pad) ? T.s0_cdf[t * s0_pad + i] : 2.0;
-        sh_s0i[i][tx] = T.s0_idx[t * s0_pad + min(i, s0_pad - 1)];
-    }
-
-    // draws of one tick: words 0..3 of Philox block 0 (transition uniform = w.x, w.y; reset uniform = w.z, w.w), the reward
-    // normal and the action (given or uniform random policy)
-    // POMDP: also block 1 = (observation uniform, reset-observation uniform)           anymdp_env.py:153 under step / reset
-    struct Draw { uint32_t wx, wy, wz, ww; float z; int a; uint32_t ox, oy, rx, ry; };
-    auto draw = [&](int k) {
-        Draw d;
-        const unsigned long long tk = tick0 + (unsigned long long)k;
-        const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
-        d.wx = w0.x; d.wy = w0.y; d.wz = w0.z; d.ww = w0.w;
-        const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
-        d.z = box_muller(w2.x, w2.y);
-        if (POMDP) {
-            const uint4 w1 = philox_block(env_id, (uint32_t)(AMDP_SLOT_OBS >> 1), tk, E.key);
-            d.ox = w1.x; d.oy = w1.y; d.rx = w1.z; d.ry = w1.w;
-        } else { d.ox = d.oy = d.rx = d.ry = 0; }
-        if (given) d.a = (k < K) ? load_action(actions, (long long)k * N + e, J.actions_u8) : 0;
-        else d.a = (int)__umulhi(w2.z, (uint32_t)na);
-        return d;
-    };
-    Draw cur = draw(0);
-
-    // the previous tick, settled one tick late (its payload / observation loads were issued at the end of that tick)
-    float2 pay_p = make_float2(0.f, 0.f);
-    float z_p = 0.f;
-    int si_p = 0, a_p = 0, done_p = 0, steps_p = 0;
-    bool close_p = false;
-    unsigned n_fallback = 0;
-    // POMDP: the observation of tick k is a second two-level search (anymdp_env.py:153), taken off the chain: its pivots are
-    // requested at the end of tick k, its code block early in tick k+1, and the record of tick k is written at the end of
-    // tick k+1.
-    float rew_q = 0.f, rgt_q = 0.f;
-    int a_q = 0, done_q = 0;
-    uint4 opv[2], ocd[2];                      // observation pivots / codes in flight
-    uint32_t oux = 0, ouy = 0;                 // the uniform of the observation draw (two Philox words)
-    const uint32_t* orow = nullptr;            // its row in T.ofat (null: the tick has no observation)
-    int oblk = 0, so_p = 0;
-    const int o_blocks = T.o_blocks;
-    auto obs_stage1 = [&]() {                  // pivots -> block; request the block's codes
-        if (orow) {
-            const uint32_t v15 = code15_from_m21(oux >> 11);
-            const unsigned v2 = v15 | (v15 << 16);
-            int acc = 0;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                acc = h2_count_lt(opv[i].x, v2, acc); acc = h2_count_lt(opv[i].y, v2, acc);
-                acc = h2_count_lt(opv[i].z, v2, acc); acc = h2_count_lt(opv[i].w, v2, acc);
-            }
-            oblk = min(-acc, o_blocks - 1);
-            ldg_words<2>(orow + 8 + 8 * oblk, ocd);
-        }
-    };
-    auto obs_stage2 = [&](int kp) {            // codes -> observation; write the record of tick kp
-        int obs = 0;
-        if (orow) {
-            const unsigned ve = ((((oux >> 5) << 4) | (ouy >> 28)) << 1) & cmask;
-            int lt, le;
-            for (;;) {
-                lt = 0; le = 0;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const unsigned x[4] = {ocd[i].x, ocd[i].y, ocd[i].z, ocd[i].w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { const unsigned xm = x[j] & cmask; lt += (xm < ve); le += (xm <= ve); }
-                }
-                if (lt < 8 || oblk >= o_blocks - 1) break;
-                ++oblk;
-                ldg_words<2>(orow + 8 + 8 * oblk, ocd);
-            }
-            obs = oblk * 8 + lt;
-            if (le != lt) {
-                const double u = u53(oux, ouy);
-                const double* cr = T.obs_cdf + (t * n_pad + so_p) * (long long)T.no_pad;
-                while (obs < T.no_pad - 1 && __ldg(cr + obs) <= u) ++obs;
-                n_fallback += 1;
-            }
-        }
-        write_rec(kp, obs, a_q, done_q, rew_q, rgt_q);
-    };
-    auto settle = [&](int kp) {
-        // reward = gt + noise * z (anymdp_env.py:103-105), episode return, closed-episode statistics, the record
-        const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
-        ep_ret += rew;
-        if (POMDP) { rew_q = (float)rew; rgt_q = pay_p.x; a_q = a_p; done_q = done_p; }
-        else write_rec(kp, si_p & 0x7fffffff, a_p, done_p, (float)rew, pay_p.x);
-        if (close_p) {
-            sh_cnt[0][tx] += 1; sh_cnt[1][tx] += (unsigned long long)steps_p;
-            sh_stat[0][tx] += ep_ret; sh_stat[1][tx] += ep_ret * ep_ret;
-            sh_stat[2][tx] = fmin(sh_stat[2][tx], ep_ret); sh_stat[3][tx] = fmax(sh_stat[3][tx], ep_ret);
-            ep_ret = 0.0;
-            close_p = false;
-        }
-    };
-    for (int k = 0; k < K; ++k) {
-        const bool pend = next && (flags & FLAG_PENDING);          // next_step mode: this tick only performs the reset
-        const bool a_ok = !given || (unsigned)cur.a < (unsigned)na;
-        const bool valid = !pend && a_ok;
-        if (given && !pend && !a_ok) fault |= AMDP_FAULT_BAD_ACTION;                          // :97
-        const unsigned long long row = rbase + (unsigned long long)(s * na + (valid ? cur.a : 0));
-        // (1) first level of the search tree of row (s, a)                                      anymdp_env.py:99
-        uint4 lv[2];                                               // 16 pivots (15-bit codes)
-        if (LEVELS == 3 && valid) ldg_words_keep<2>(T.top + row * 16u, lv, pol_keep);
-        if (LEVELS == 2 && valid) ldg_words_keep<2>(T.pv + row * 16u, lv, pol_keep);
-        // (2) in the shadow of that load: the previous tick's reward / record
-        if (k > 0) { settle(k - 1); if (POMDP) obs_stage1(); }
-        // the next tick's draws: in the shadow of the block load, or (small register budget) here, before the search data
-        // occupies registers
-        constexpr bool DRAW_EARLY = (MINB == TP_MINB_HI);
-        Draw nx;
-        if (DRAW_EARLY) nx = draw(k + 1);
-        int done_bits = 0;
-        bool do_reset = pend;
-        bool touched = pend;                                       // the tick stepped or reset: it has an observation
-        bool si_from_line = false;                                 // the state word of s' came with the block line
-        if (valid) {
-            // (3) next state = #{cdf <= u}  (numpy choice: searchsorted(cdf, u, 'right'))         anymdp_env.py:100
-            const uint32_t v15 = code15_from_m21(cur.wx >> 11);
-            const unsigned v2 = v15 | (v15 << 16);
-            auto count16 = [&]() {                                 // #{pivots < code15(u)}: blocks / groups entirely below u
-                int acc = 0;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    acc = h2_count_lt(lv[i].x, v2, acc); acc = h2_count_lt(lv[i].y, v2, acc);
-                    acc = h2_count_lt(lv[i].z, v2, acc); acc = h2_count_lt(lv[i].w, v2, acc);
-                }
-                return -acc;
-            };
-            int blk = 0;
-            if (LEVELS == 3) {
-                const int g = min(count16(), n_groups - 1);
-                ldg_words_keep<2>(T.pv + (row * (unsigned)n_groups + (unsigned)g) * 16u, lv, pol_keep);
-                blk = g * 16;
-            }
-            if (LEVELS >= 2) blk = min(blk + count16(), n_blocks - 1);
-            // code31(u) << 1; cmask = 0xfffffffe drops the is_terminal bit of the entries (tests coarsen it further to
-            // exercise the float64 fallback)
-            const unsigned ve = ((((cur.wx >> 5) << 4) | (cur.wy >> 28)) << 1) & cmask;
-            const uint4* frow = T.fat + row * (unsigned)n_blocks * 8u;                  // 8 x 16 bytes per block line
-            int lt, le;
-            unsigned mn;
-            for (bool first = true;; first = false) {
-                uint4 bw[2];
-                ldg_words<2>(frow + blk * 8, bw);
-                if (first && !DRAW_EARLY) nx = draw(k + 1);        // in the shadow of the block load: the next tick's draws
-                lt = 0; le = 0; mn = 0xffffffffu;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const unsigned x[4] = {bw[i].x, bw[i].y, bw[i].z, bw[i].w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const unsigned xm = x[j] & cmask;
-                        lt += (xm < ve);
-                        le += (xm <= ve);
-                        mn = min(mn, xm >= ve ? x[j] : 0xffffffffu);
-                    }
-                }
-                if (lt < 8 || blk >= n_blocks - 1) break;
-                ++blk;                                             // the whole block is below u (its pivot shared u's 15-bit cell)
-            }
-            int nxt = blk * 8 + lt;
-            bool term = (mn & 1u) != 0;                            // is_terminal[nxt] (bit 0 of the first entry not below u)
-            if (le != lt) {
-                // code31(cdf[j]) == code31(u) for some j: decide those entries on the float64 row
-                const double u = u53(cur.wx, cur.wy);
-                const double* cr = T.cdf + row * (unsigned)n_pad;
-                while (nxt < n_pad - 1 && __ldg(cr + nxt) <= u) ++nxt;
-                term = sinfo_t[nxt] < 0;
-                n_fallback += 1;
-                // (4) payload (reward, noise) of (s, a, s')  (anymdp_env.py:103-104): consumed by settle() of the next tick
-                pay_p = ldg_stream_f32x2(T.payload + (row * (unsigned)n_pad + (unsigned)nxt));
-            } else {
-                const char* line = reinterpret_cast<const char*>(frow + blk * 8);
-                pay_p = ldg_stream_f32x2(reinterpret_cast<const float2*>(line + 32) + lt);
-                if (!POMDP) { si_p = __ldg(reinterpret_cast<const int*>(line + 96) + lt); si_from_line = true; }
-            }
-            // (5) state update, termination, truncation (anymdp_env.py:107-108,113-114)
-            s = nxt;
-            steps += 1;
-            done_bits = ((term || always_term) ? 1 : 0) | ((steps >= max_ceil) ? 2 : 0);
-            touched = true;
-            if (done_bits) {
-                close_p = true;
-                steps_p = steps;
-                if (next) flags |= FLAG_PENDING; else do_reset = true;
-            }
-        } else {
-            pay_p = make_float2(0.f, 0.f);
-            if (!DRAW_EARLY) nx = draw(k + 1);
-        }
-        z_p = cur.z;
-        if (do_reset) {                                            // anymdp_env.py:81-90
-            const double ur = u53(cur.wz, cur.ww);
-            int c = 0;
-#pragma unroll
-            for (int i = 0; i < TP_S0; ++i) c += (sh_s0c[i][tx] <= ur);              // pad 2.0 is never <= ur
-            c = min(c, s0_pad - 1);
-            s = sh_s0i[0][tx];
-#pragma unroll
-            for (int i = 1; i < TP_S0; ++i) if (c == i) s = sh_s0i[i][tx];
-            steps = 0;
-            flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
-        }
-        // observation = state_mapping[s] (anymdp_env.py:145-148): from the block line unless the env was reset / fell back
-        // (measured: issuing the state-word load right behind the payload load and selecting here is ~8 % faster than one
-        // deferred load from a selected address, which ptxas schedules after the reset logic)
-        if (!POMDP) { if (do_reset || !si_from_line) si_p = touched ? __ldg(sinfo_t + s) : 0; }
-        if (POMDP) {
-            if (k > 0) obs_stage2(k - 1);                          // the previous tick's record (its codes arrived long ago)
-            // this tick's observation: drawn from the state after the step, or after the reset    anymdp_env.py:90,132
-            orow = touched ? T.ofat + (unsigned long long)(t * n_pad + s) * (unsigned)(8 + 8 * o_blocks) : nullptr;
-            oux = do_reset ? cur.rx : cur.ox; ouy = do_reset ? cur.ry : cur.oy;
-            so_p = s;
-            if (orow) ldg_words<2>(orow, opv);
-        }
-        a_p = cur.a;
-        done_p = done_bits;
-        cur = nx;
-    }
-    settle(K - 1);
-    if (POMDP) { obs_stage1(); obs_stage2(K - 1); }
-    E.state[e] = s; E.steps[e] = steps; E.flags[e] = (uint8_t)flags; E.ep_return[e] = ep_ret;
-    E.ep_count[e] = sh_cnt[0][tx]; E.sum_len[e] = sh_cnt[1][tx];
-    E.sum_ret[e] = sh_stat[0][tx]; E.sum_ret_sq[e] = sh_stat[1][tx];
-    E.min_ret[e] = sh_stat[2][tx]; E.max_ret[e] = sh_stat[3][tx];
-    if (fault) atomicOr(E.faults, fault);
-    if (n_fallback) atomicAdd(E.counters, (unsigned long long)n_fallback);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Latency path: ONE WARP PER ENV with the shortest dependent chain (k_rollout_w): MDP, one action token, engine Philox
-// draws or given actions, same-step auto-reset, rows of exactly 32 * EPL states (64 / 128 / 256), engines too small for
-// the thread-per-env kernel (cfg2: 4096 envs).  Such an engine is a set of Markov chains, each with ONE row in flight:
-// env-steps/s = envs / (DRAM latency + what sits between "row arrived" and "next row requested").  Measured on B200
-// (tools/warplat.cu, profiles/r1_warplat.txt): REDUX.MIN 22 cycles, VOTE + POPC 45, SHFL 33, LDS 34, LDG (L1 hit) 56,
-// REDUX.SUM 47, REDUX over a partial mask 427.  Hence:
-//   * the row is 32 lanes x EPL fp16-ordered 15-bit codes (the filter in front of the float64 row); a lane counts its
-//     own entries below code15(u) with HSET2 + IDP.2A and the warp takes ONE REDUX.MIN over
-//         (index of the lane's first entry not below u) << 2 | is_terminal[that entry] << 1 | undecided
-//     (rows are sorted, so the minimum is the next state; is_terminal bits of a lane's own entries sit in a register);
-//   * termination and truncation are then known without a memory access and the state a reset would lead to was
-//     computed when the draws were made (lane-parallel, start-state table in shared memory): the next row address is
-//     one select and one IMAD.WIDE away, and there is exactly ONE row-load site in the loop (no speculation, nothing
-//     to re-issue);
-//   * nothing else on the chain: the payload (reward, noise) and the state word of tick k are requested after the next
-//     row and consumed one tick later; no global load on a rare path feeds a register that is read after the paths
-//     merge (ptxas gives such loads the barrier of the row load and the merge point then waits for the row:
-//     tools/sass_ctrl.py shows the assignment);
-//   * draws of 32 consecutive ticks are generated in one lane-parallel Philox pass; records are staged one per lane
-//     and written once per 32 ticks.
-// Undecided (code15(cdf[j]) == code15(u), ~n/30720 of the ticks): the float64 row decides, as everywhere else.
-// ------------------------------------------------------------------------------------------------
-template <int NW> struct RowW { unsigned w[NW]; };
-
-template <int NW>
-__device__ __forceinline__ RowW<NW> ldg_row(const char* p) {
-    RowW<NW> r;
-    if constexpr (NW == 1) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r.w[0]) : "l"(p));
-    else if constexpr (NW == 2) asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[1]) : "l"(p));
-    else asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(p));
-    return r;
-}
-
-template <int EPL, bool GIVEN>
-__global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
-                                                      const int32_t* __restrict__ actions, const amdp_traj J) {
-    constexpr int NW = EPL / 2;                                   // 32-bit words of filter codes per lane
-    constexpr int N_PAD = 32 * EPL;
-    constexpr unsigned ROW_BYTES = 2u * N_PAD;
-    constexpr unsigned FULL = 0xffffffffu;
-    __shared__ double sh_stat[4][4];                              // closed-episode statistics: sum_ret, sum_ret_sq, min, max
-    __shared__ unsigned long long sh_cnt[2][4];                   // ep_count, sum_len
-    __shared__ double sh_s0c[TP_S0][4];                           // start-state CDF / states of the warp's env
-    __shared__ int sh_s0i[TP_S0][4];
-    const int lane = threadIdx.x & 31, gi = threadIdx.x >> 5;
-    const long long e = (long long)blockIdx.x * 4 + gi;
-    if (e >= E.n_envs) return;                                    // whole warps leave: one env per warp
-    const int na = T.na;
-    const long long N = E.n_envs;
-    const long long t = E.task[e];
-    const long long tsz = (long long)N_PAD * na * N_PAD;
-    const char* __restrict__ sk_lane = reinterpret_cast<const char*>(T.sketch + t * tsz) + lane * (EPL * 2);
-    const double* __restrict__ cdf_lane = T.cdf + t * tsz + lane * EPL;
-    const float2* __restrict__ pay_t = T.payload + t * tsz;
-    const int32_t* __restrict__ sinfo_t = T.sinfo + t * N_PAD;
-    const unsigned srow = (unsigned)na * ROW_BYTES;               // bytes between the filter rows of states s and s + 1
-    const int max_ceil = T.max_ceil[t];
-    const bool always_term = (T.tflags[t] & 1) != 0;
-    const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
-    // is_terminal of this lane's own EPL entries (ns < 2: every state terminates, anymdp_env.py:108)
-    unsigned myterm = (T.tbits[t * T.tb_words + ((lane * EPL) >> 5)] >> ((lane * EPL) & 31)) & ((1u << EPL) - 1u);
-    if (always_term) myterm = (1u << EPL) - 1u;
-
-    int s = E.state[e], steps = E.steps[e];
-    const int flags = E.flags[e];
-    double ep_ret = E.ep_return[e];
-
-    // staged records: lane L holds the record of tick (batch start + L)
-    int st_obs = 0, st_ad = 0;                                    // st_ad = action | done_bits << 28
-    float st_rew = 0.f, st_rgt = 0.f;
-    const long long rec0 = e * J.env_stride;
-    auto flush = [&](int kb, int cnt) {                           // records of ticks [kb, kb + cnt), one lane per tick
-        if (lane < cnt) {
-            const long long o = (long long)(kb + lane) * J.step_stride + rec0;
-            if (J.packed) {
-                const unsigned lo = ((unsigned)st_obs & 0xfffffu) | (((unsigned)st_ad & 0x3ffu) << 20) | (((unsigned)st_ad >> 28) << 30);
-                J.packed[o] = ((unsigned long long)__float_as_uint(st_rew) << 32) | lo;
-            } else {
-                if (J.obs) J.obs[o] = st_obs;
-                if (J.actions_out) J.actions_out[o] = st_ad & 0x0fffffff;
-                if (J.done) J.done[o] = (uint8_t)((unsigned)st_ad >> 28);
-                if (J.reward) J.reward[o] = st_rew;
-                if (J.reward_gt) J.reward_gt[o] = st_rgt;
-            }
-        }
-    };
-
-    unsigned fault = 0;
-    if (flags & FLAG_VIRGIN) fault = AMDP_FAULT_NEED_RESET;                                   // anymdp_env.py:93-94
-    else if (sinfo_t[s] < 0 && !always_term) fault = AMDP_FAULT_TERMINAL_STATE;               // :95-96
-    if (fault) {
-        // faulted envs are left untouched (as in env_tick); their records are zero except the action
-        for (int kb = 0; kb < K; kb += 32) {
-            const int k = kb + lane;
-            int a = 0;
-            if (k < K) {
-                if (GIVEN) a = load_action(actions, (long long)k * N + e, J.actions_u8);
-                else a = (int)__umulhi(philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key).z, (uint32_t)na);
-            }
-            st_ad = a & 0x0fffffff;
-            flush(kb, min(32, K - kb));
-        }
-        if (lane == 0) atomicOr(E.faults, fault);
-        return;
-    }
-    const int s0_pad = T.s0_pad;                                  // <= TP_S0 (the host never selects this kernel otherwise)
-    if (lane == 0) {
-        sh_cnt[0][gi] = E.ep_count[e]; sh_cnt[1][gi] = E.sum_len[e];
-        sh_stat[0][gi] = E.sum_ret[e]; sh_stat[1][gi] = E.sum_ret_sq[e];
-        sh_stat[2][gi] = E.min_ret[e]; sh_stat[3][gi] = E.max_ret[e];
-    }
-    if (lane < TP_S0) {
-        sh_s0c[lane][gi] = (lane < s0_pad) ? T.s0_cdf[t * s0_pad + lane] : 2.0;
-        sh_s0i[lane][gi] = T.s0_idx[t * s0_pad + min(lane, s0_pad - 1)];
-    }
-    __syncwarp();
-    auto reset_state = [&](double ur) {                           // anymdp_env.py:89 (pad 2.0 is never <= ur)
-        int c = 0;
-#pragma unroll
-        for (int i = 0; i < TP_S0; ++i) c += (sh_s0c[i][gi] <= ur);
-        c = min(c, s0_pad - 1);
-        int r = sh_s0i[0][gi];
-#pragma unroll
-        for (int i = 1; i < TP_S0; ++i) if (c == i) r = sh_s0i[i][gi];
-        return r;
-    };
-
-    // Draws of one tick, packed: bits 0-14 code15(u_transition), 15-22 action (engine policy), 23-30 the state a reset in
-    // this tick leads to, 31 given action out of range.  Lane L of a batch holds tick kb + L + 1.
-    unsigned b_pk = 0;
-    float b_z = 0.f;
-    int b_act = 0;
-    unsigned n_fallback = 0;
-    auto make = [&](int kt, unsigned& pk, float& z, int& act) {
-        const unsigned long long tk = tick0 + (unsigned long long)kt;
-        const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
-        const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
-        z = box_muller(w2.x, w2.y);
-        pk = code15_from_m21(w0.x >> 11) | ((unsigned)reset_state(u53(w0.z, w0.w)) << 23);
-        if (GIVEN) {
-            act = (kt < K) ? load_action(actions, (long long)kt * N + e, J.actions_u8) : 0;
-            if ((unsigned)act >= (unsigned)na) pk |= 0x80000000u;
-        } else {
-            act = 0;
-            pk |= __umulhi(w2.z, (uint32_t)na) << 15;
-        }
-    };
-    unsigned pk;
-    float z;
-    int a_raw;
-    make(0, pk, z, a_raw);
-    make(lane + 1, b_pk, b_z, b_act);
-    if (GIVEN && (pk >> 31)) fault |= AMDP_FAULT_BAD_ACTION;                                  // :97
-    int a = GIVEN ? ((pk >> 31) ? 0 : a_raw) : (int)((pk >> 15) & 0xffu);
-    unsigned sa = (unsigned)(s * na + a);                         // row (s, a) inside the task
-    unsigned v2 = (pk & 0x7fffu) * 0x00010001u;
-    // What is in flight between two ticks: the filter row of tick k, and the payload / state word of tick k - 1 (settled
-    // one tick late; their loads travel with the row load).  Two sets, used alternately (the loop is unrolled by two):
-    // with one set the loaded registers would have to be MOVed at the end of a tick, and a MOV waits for the load.
-    struct Flight { RowW<NW> q; float2 pay; int si; };
-    Flight fa, fb;
-    fa.q = ldg_row<NW>(sk_lane + (unsigned long long)sa * ROW_BYTES);
-    fa.pay = make_float2(0.f, 0.f); fa.si = 0;
-
-    float z_p = 0.f;
-    int ad_p = 0, steps_p = 0;
-    bool close_p = false, valid_p = false;
-    auto settle = [&](int kp, const float2 pay_p, const int si_p) {
-        // reward = gt + noise * z (anymdp_env.py:103-105), episode return, closed-episode statistics, the record
-        const double rew = valid_p ? (double)pay_p.x + (double)pay_p.y * (double)z_p : 0.0;
-        ep_ret += rew;
-        if (lane == (kp & 31)) {
-            st_obs = valid_p ? (si_p & 0x7fffffff) : 0; st_ad = ad_p; st_rew = (float)rew; st_rgt = valid_p ? pay_p.x : 0.f;
-        }
-        if (close_p) {
-            if (lane == 0) {
-                sh_cnt[0][gi] += 1; sh_cnt[1][gi] += (unsigned long long)steps_p;
-                sh_stat[0][gi] += ep_ret; sh_stat[1][gi] += ep_ret * ep_ret;
-                sh_stat[2][gi] = fmin(sh_stat[2][gi], ep_ret); sh_stat[3][gi] = fmax(sh_stat[3][gi], ep_ret);
-            }
-            ep_ret = 0.0;
-            close_p = false;
-        }
-    };
-    // loop-invariant pieces of the REDUX operand, kept in registers (ptxas would re-derive them from %tid every tick)
-    unsigned lane_base32 = (unsigned)(lane * EPL) << 5;
-    unsigned myterm16 = myterm << 4;
-    asm volatile("" : "+r"(lane_base32), "+r"(myterm16));
-    const float2* pay_row = pay_t + (unsigned long long)sa * N_PAD;   // payload row of (s, a)
-
-    auto tick = [&](const int k, const Flight& cur, Flight& nxf) {
-        const int j = k & 31;
-        // (A) inputs of the NEXT tick: independent of the row in flight
-        const unsigned npk = __shfl_sync(FULL, b_pk, j);
-        const float nz = __shfl_sync(FULL, b_z, j);
-        int na_raw = 0;
-        if (GIVEN) na_raw = __shfl_sync(FULL, b_act, j);
-        const int n_a = GIVEN ? ((npk >> 31) ? 0 : na_raw) : (int)((npk >> 15) & 0xffu);
-        const char* nbase = sk_lane + (unsigned)n_a * ROW_BYTES;
-        asm volatile("" : "+l"(nbase));                           // one IMAD.WIDE from the next row address
-        const unsigned nv2 = (npk & 0x7fffu) * 0x00010001u;
-        const bool valid = !GIVEN || !(pk >> 31);                 // a tick with a bad action does not step
-        const unsigned sreset = (pk >> 23) & 0xffu;
-        const bool trunc = steps + 1 >= max_ceil;                 // anymdp_env.py:113-114
-        const unsigned trunc16 = trunc ? 16u : 0u;
-
-        // (B) the chain: row -> count below code15(u) -> REDUX.MIN -> next state -> next row address
-        const unsigned v2le = v2 + 0x00010001u;                   // entries <= code15(u): below the next code
-        int lt = 0, le = 0;                                       // this lane's entries below u / not above u
-#pragma unroll
-        for (int i = 0; i < NW; ++i) { lt = h2_count_lt_pos(cur.q.w[i], v2, lt); le = h2_count_lt_pos(cur.q.w[i], v2le, le); }
-        // (index of the first entry not below u) << 5 | is_terminal[it] << 4 | entries sharing u's code (undecided)
-        unsigned val = lane_base32 + ((unsigned)lt << 5) + (unsigned)(le - lt) + ((myterm16 >> lt) & 16u);
-        if (lt == EPL) val = FULL;                                // all below: the boundary is in a later lane
-        unsigned r = __reduce_min_sync(FULL, val);
-        unsigned nxt, s_next;
-        auto advance = [&]() {
-            nxt = r >> 5;
-            const bool done = ((r | trunc16) & 16u) != 0;         // anymdp_env.py:108,114
-            s_next = done ? sreset : nxt;                         // same-step auto-reset (anymdp_env.py:81-90)
-            if (GIVEN && !valid) s_next = (unsigned)s;
-            // payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104), the next row, the state word of the observation
-            // (anymdp_env.py:145-148; after a reset: of the start state).  Issued together: ptxas puts loads of one kind on
-            // one barrier, and a payload load issued later than the row would make the chain wait for it.
-            nxf.pay = ldg_stream_f32x2(pay_row + nxt);
-            nxf.q = ldg_row<NW>(nbase + (unsigned long long)(s_next * (unsigned long long)srow));
-            nxf.si = __ldg(sinfo_t + s_next);
-        };
-        advance();
-        if (r & 15u) {
-            // undecided: exact float64 entries (numpy choice: searchsorted(cdf, u, 'right'))   anymdp_env.py:100
-            const uint4 w0 = philox_block(env_id, 0u, tick0 + (unsigned long long)k, E.key);
-            const double u = u53(w0.x, w0.y);
-            const double* cr = cdf_lane + (unsigned long long)sa * N_PAD;
-            int cnt = 0;
-#pragma unroll
-            for (int i = 0; i < EPL; i += 2) {
-                const double2 x = ldg_stream_f64x2(cr + i);
-                cnt += (x.x <= u) + (x.y <= u);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
-            cnt = min(cnt, N_PAD - 1);
-            r = ((unsigned)cnt << 5) | ((sinfo_t[cnt] < 0 || always_term) ? 16u : 0u);
-            n_fallback += 1;
-            advance();
-        }
-
-        // (C) settle the previous tick; once per 32 ticks write the finished batch of records, lane-parallel
-        settle(k - 1, cur.pay, cur.si);
-        if (j == 0 && k > 0) flush(k - 32, 32);
-        // (D) this tick becomes the previous one
-        z_p = z; valid_p = valid;
-        ad_p = GIVEN ? (a_raw & 0x0fffffff) : a;
-        if (valid) {
-            ad_p |= (int)((((r >> 4) & 1u) | (trunc ? 2u : 0u)) << 28);
-            steps += 1;
-            if ((r | trunc16) & 16u) { close_p = true; steps_p = steps; steps = 0; }
-            s = (int)s_next;
-        }
-        // once per 32 ticks: draw the next batch
-        if (j == 31) make(k + 2 + lane, b_pk, b_z, b_act);
-        // rotate to the next tick
-        if (GIVEN && (npk >> 31) && k + 1 < K) fault |= AMDP_FAULT_BAD_ACTION;               // :97
-        pk = npk; z = nz; a = n_a; a_raw = na_raw; v2 = nv2;
-        sa = (unsigned)(s * na + n_a);
-        pay_row = pay_t + (unsigned long long)sa * N_PAD;
-    };
-    int k = 0;
-    for (; k + 1 < K; k += 2) { tick(k, fa, fb); tick(k + 1, fb, fa); }
-    if (k < K) { tick(k, fa, fb); settle(K - 1, fb.pay, fb.si); }
-    else settle(K - 1, fa.pay, fa.si);
-    {
-        const int kb = ((K - 1) / 32) * 32;
-        flush(kb, K - kb);
-    }
-    if (lane == 0) {
-        E.state[e] = s; E.steps[e] = steps; E.ep_return[e] = ep_ret;
-        E.ep_count[e] = sh_cnt[0][gi]; E.sum_len[e] = sh_cnt[1][gi];
-        E.sum_ret[e] = sh_stat[0][gi]; E.sum_ret_sq[e] = sh_stat[1][gi];
-        E.min_ret[e] = sh_stat[2][gi]; E.max_ret[e] = sh_stat[3][gi];
-        if (fault) atomicOr(E.faults, fault);
-        if (n_fallback) atomicAdd(E.counters, (unsigned long long)n_fallback);
-    }
-}
 
 __global__ void k_reset(Tables T, EnvArrays E, unsigned long long tick, int n_slots, const uint8_t* __restrict__ mask,
                         int32_t* __restrict__ obs_out, const double* __restrict__ u_inject) {
@@ -1826,7 +664,6 @@ static int dalloc(amdp* h, Tp** p, size_t count) {
     return AMDP_OK;
 }
 
-static inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
 
 extern "C" int amdp_abi_version(void) { return AMDP_ABI_VERSION; }
 
@@ -2060,65 +897,11 @@ static void launch_rollout(amdp* h, int K, const int32_t* actions, const amdp_tr
     k_rollout<G><<<nblk(threads, 256), 256, 0, st>>>(h->T, h->E, h->tick, K, h->n_slots, actions, J, u);
 }
 
-template <int G, int C, bool P2>
-static void launch_fast_gc(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
-    const unsigned int blocks = nblk(h->cfg.n_envs * G, 128);
-    const bool next = h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP;
-    if (actions) {
-        if (next) k_rollout_mdp<G, C, true, true, P2><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
-        else k_rollout_mdp<G, C, true, false, P2><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
-    } else {
-        if (next) k_rollout_mdp<G, C, false, true, P2><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
-        else k_rollout_mdp<G, C, false, false, P2><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J);
-    }
-}
-
-template <int LEVELS>
-static void launch_tp(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
-    const unsigned int blocks = nblk(h->cfg.n_envs, TP_TPB);
-    const int next = h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP ? 1 : 0;
-    const unsigned cmask = 0xfffffffeu << h->tp_coarse_bits;
-    // Two register budgets: 72 registers (896 envs resident per SM, the next tick's draws generated before the search
-    // loads are issued) and 96 (640 per SM, draws generated in the shadow of the block load).  Measured on cfg2 / cfg4 /
-    // cfg5 at 65536-131072 envs the small budget wins everywhere (+3 .. +50 %, most where it turns 1.4 waves into one);
-    // AMDP_TP_MINB=lo selects the large one for experiments.  The POMDP variant carries the observation search as well.
-    bool hi = h->cfg.task_type != AMDP_POMDP;         // (the POMDP variant spills at 72 registers)
-    if (const char* o = getenv("AMDP_TP_MINB")) hi = (o[0] == 'h');
-#define TP_LAUNCH(MINB, GIVEN, POMDP) k_rollout_tp<LEVELS, MINB, GIVEN, POMDP><<<blocks, TP_TPB, 0, st>>>(h->T, h->E, h->tick, K, actions, J, next, cmask)
-    if (h->cfg.task_type == AMDP_POMDP) {
-        if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, true, true); else TP_LAUNCH(TP_MINB_LO, true, true); }
-        else { if (hi) TP_LAUNCH(TP_MINB_HI, false, true); else TP_LAUNCH(TP_MINB_LO, false, true); }
-    } else if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, true, false); else TP_LAUNCH(TP_MINB_LO, true, false); }
-    else { if (hi) TP_LAUNCH(TP_MINB_HI, false, false); else TP_LAUNCH(TP_MINB_LO, false, false); }
-#undef TP_LAUNCH
-}
-
-// lanes per env and register-resident chunks per lane for the fast kernel: n_pad == 4 * G * C
 static void launch_rollout_fast(amdp* h, int K, const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
-    const int n_pad = h->cfg.n_pad;
-    if (h->tp) {
-        if (h->T.tp_levels == 1) launch_tp<1>(h, K, actions, J, st);
-        else if (h->T.tp_levels == 2) launch_tp<2>(h, K, actions, J, st);
-        else launch_tp<3>(h, K, actions, J, st);
-        return;
-    }
-    if (h->two_level) { launch_fast_gc<8, 1, true>(h, K, actions, J, st); return; }
-    if (h->wv2) {
-        const unsigned int blocks = nblk(h->cfg.n_envs, 4);
-#define WV2(epl) { if (actions) k_rollout_w<epl, true><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J); \
-                   else k_rollout_w<epl, false><<<blocks, 128, 0, st>>>(h->T, h->E, h->tick, K, actions, J); }
-        if (n_pad == 64) WV2(2) else if (n_pad == 128) WV2(4) else WV2(8)
-#undef WV2
-        return;
-    }
-    const int G = h->G;
-    const int C = (n_pad == 4 * G) ? 1 : (n_pad == 8 * G ? 2 : 0);
-    switch (G) {
-#define FAST(g) case g: if (C == 1) launch_fast_gc<g, 1, false>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<g, 2, false>(h, K, actions, J, st); else launch_fast_gc<g, 0, false>(h, K, actions, J, st); break;
-        FAST(1) FAST(2) FAST(4) FAST(8) FAST(16)
-        default: if (C == 1) launch_fast_gc<32, 1, false>(h, K, actions, J, st); else if (C == 2) launch_fast_gc<32, 2, false>(h, K, actions, J, st); else launch_fast_gc<32, 0, false>(h, K, actions, J, st); break;
-#undef FAST
-    }
+    const bool next = h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP;
+    if (h->tp) amdp_launch_tp(h->T, h->E, h->cfg.n_envs, h->cfg.task_type == AMDP_POMDP, next, h->tp_coarse_bits, h->tick, K, actions, J, st);
+    else if (h->wv2) amdp_launch_w(h->T, h->E, h->cfg.n_envs, h->tick, K, actions, J, st);
+    else amdp_launch_mdp(h->T, h->E, h->cfg.n_envs, h->G, h->two_level, next, h->tick, K, actions, J, st);
 }
 
 extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const amdp_traj* traj, const double* u_inject,

@@ -1,0 +1,345 @@
+// amdp_tp.cu — k_rollout_tp: thread-per-env rollout kernel (MDP and single-token POMDP); see amdp_dev.cuh / amdp_b200.cu.
+#include "amdp_dev.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Throughput path: ONE THREAD PER ENV (MDP, one action token, engine Philox draws, auto-reset on), for engines with
+// enough envs to fill the machine (>= 16k per GPU).  The warp-per-env kernel above keeps at most ~4k envs in flight
+// per GPU (one row per warp); here every resident thread is an env, so 60k-95k dependent chains are in flight and
+// the path is bound by DRAM lines instead of by latency x residency.
+//   Measured on B200 (profiles/r1_gather_microbench.txt, r1_tp_*): every L2 miss fetches its whole 128-byte line from
+//   DRAM whatever the request size, and what the kernel pays for is (a) DRAM lines and (b) 32-byte sector requests.
+//   Hence the layout: a row is cut into 8-entry blocks, and ONE 128-byte line per block holds the 8 CDF codes, the 8
+//   (reward, noise) payloads and the 8 state words (mapping | terminal) — a transition touches exactly one DRAM line
+//   below the pivots, with 3 sector requests (codes; payload entry; state word — the last two hit L2).
+//   * search = a 1..3-level tree, one 32-byte request per level: [top: <= 16 groups] -> [pivots: <= 16 blocks of the
+//     group] -> [block: 8 codes].  Pivots are 15-bit fp16-ordered codes of the LAST entry of a block / group, counted
+//     with packed HSET2 compares; block entries are 31-bit codes.  All levels are exact; the only undecided case is
+//     code31(cdf[j]) == code31(u) (~n * 2^-31 of the ticks), which reads the float64 row.  (A 16-bit filter would
+//     send n/65536 of the ticks to the float64 row, which at 32 envs per warp stalls most warps when n = 1024.)
+//   * is_terminal[s'] rides in bit 0 of the block codes, so the dependent chain per tick is  [top ->] pivots -> codes
+//     -> next pivots; payload and state word of tick k are consumed in the shadow of tick k+1's loads.
+//   * LEVELS = 1 (n_pad <= 8), 2 (<= 128) or 3 (<= 2048).
+// ------------------------------------------------------------------------------------------------
+template <int LEVELS, int MINB, bool GIVEN, bool POMDP>
+__global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
+                                                       const int32_t* __restrict__ actions, const amdp_traj J, int next, unsigned cmask) {
+    // GIVEN is a template parameter on purpose: with a runtime flag the (predicated-off) action load still owns a
+    // scoreboard slot, which ptxas shares with the deferred payload / state-word loads, and the first use of the action at
+    // the top of a tick then waits for those loads BEFORE the tick's first search load is issued (ncu: +15 % time).
+    constexpr bool given = GIVEN;
+    __shared__ double sh_stat[4][TP_TPB];                         // closed-episode statistics: sum_ret, sum_ret_sq, min, max
+    __shared__ unsigned long long sh_cnt[2][TP_TPB];              // ep_count, sum_len
+    __shared__ double sh_s0c[TP_S0][TP_TPB];                         // the env's start-state CDF and states (s0_pad <= TP_S0):
+    __shared__ int sh_s0i[TP_S0][TP_TPB];                            // a reset costs no global-memory round trip
+    const int tx = threadIdx.x;
+    const long long e = (long long)blockIdx.x * TP_TPB + tx;
+    if (e >= E.n_envs) return;
+    const int n_pad = T.n_pad, na = T.na;
+    const long long N = E.n_envs;
+    const long long t = E.task[e];
+    const unsigned long long rbase = (unsigned long long)t * n_pad * na;      // first (s, a) row of the task
+    const int32_t* __restrict__ sinfo_t = T.sinfo + t * n_pad;
+    const int max_ceil = T.max_ceil[t];
+    const bool always_term = (T.tflags[t] & 1) != 0;
+    const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
+    const int n_blocks = T.tp_blocks, n_groups = T.tp_groups;
+    const uint64_t pol_keep = l2_policy_evict_last();
+
+    int s = E.state[e], steps = E.steps[e], flags = E.flags[e];
+    double ep_ret = E.ep_return[e];
+
+    auto write_rec = [&](int k, int obs, int a, int done, float rew, float rgt) {
+        const long long o = (long long)k * J.step_stride + e * J.env_stride;
+        if (J.packed) {
+            const unsigned lo = ((unsigned)obs & 0xfffffu) | (((unsigned)a & 0x3ffu) << 20) | ((unsigned)done << 30);
+            J.packed[o] = ((unsigned long long)__float_as_uint(rew) << 32) | lo;
+        } else {
+            if (J.obs) J.obs[o] = obs;
+            if (J.actions_out) J.actions_out[o] = a & 0x0fffffff;
+            if (J.done) J.done[o] = (uint8_t)done;
+            if (J.reward) J.reward[o] = rew;
+            if (J.reward_gt) J.reward_gt[o] = rgt;
+        }
+    };
+
+    unsigned fault = 0;
+    if (flags & FLAG_VIRGIN) fault = AMDP_FAULT_NEED_RESET;                                   // anymdp_env.py:93-94
+    else if (!(next && (flags & FLAG_PENDING)) && sinfo_t[s] < 0 && !always_term) fault = AMDP_FAULT_TERMINAL_STATE;
+    if (fault) {
+        // faulted envs are left untouched (as in env_tick); their records are zero except the action
+        for (int k = 0; k < K; ++k) {
+            int a;
+            if (given) a = load_action(actions, (long long)k * N + e, J.actions_u8);
+            else a = (int)__umulhi(philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key).z, (uint32_t)na);
+            write_rec(k, 0, a, 0, 0.f, 0.f);
+        }
+        atomicOr(E.faults, fault);
+        return;
+    }
+    sh_cnt[0][tx] = E.ep_count[e]; sh_cnt[1][tx] = E.sum_len[e];
+    sh_stat[0][tx] = E.sum_ret[e]; sh_stat[1][tx] = E.sum_ret_sq[e];
+    sh_stat[2][tx] = E.min_ret[e]; sh_stat[3][tx] = E.max_ret[e];
+    // s0_pad <= TP_S0 (the host never selects this kernel otherwise).  Keeping the start-state table on chip also keeps
+    // global loads out of the registers that carry the state from tick to tick: a load there, even on a path that is
+    // never taken, makes the top of every tick wait for the scoreboard slot it shares with the deferred loads.
+    const int s0_pad = T.s0_pad;
+#pragma unroll
+    for (int i = 0; i < TP_S0; ++i) {
+        sh_s0c[i][tx] = (i < s0_pad) ? T.s0_cdf[t * s0_pad + i] : 2.0;
+        sh_s0i[i][tx] = T.s0_idx[t * s0_pad + min(i, s0_pad - 1)];
+    }
+
+    // draws of one tick: words 0..3 of Philox block 0 (transition uniform = w.x, w.y; reset uniform = w.z, w.w), the reward
+    // normal and the action (given or uniform random policy)
+    // POMDP: also block 1 = (observation uniform, reset-observation uniform)           anymdp_env.py:153 under step / reset
+    struct Draw { uint32_t wx, wy, wz, ww; float z; int a; uint32_t ox, oy, rx, ry; };
+    auto draw = [&](int k) {
+        Draw d;
+        const unsigned long long tk = tick0 + (unsigned long long)k;
+        const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
+        d.wx = w0.x; d.wy = w0.y; d.wz = w0.z; d.ww = w0.w;
+        const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
+        d.z = box_muller(w2.x, w2.y);
+        if (POMDP) {
+            const uint4 w1 = philox_block(env_id, (uint32_t)(AMDP_SLOT_OBS >> 1), tk, E.key);
+            d.ox = w1.x; d.oy = w1.y; d.rx = w1.z; d.ry = w1.w;
+        } else { d.ox = d.oy = d.rx = d.ry = 0; }
+        if (given) d.a = (k < K) ? load_action(actions, (long long)k * N + e, J.actions_u8) : 0;
+        else d.a = (int)__umulhi(w2.z, (uint32_t)na);
+        return d;
+    };
+    Draw cur = draw(0);
+
+    // the previous tick, settled one tick late (its payload / observation loads were issued at the end of that tick)
+    float2 pay_p = make_float2(0.f, 0.f);
+    float z_p = 0.f;
+    int si_p = 0, a_p = 0, done_p = 0, steps_p = 0;
+    bool close_p = false;
+    unsigned n_fallback = 0;
+    // POMDP: the observation of tick k is a second two-level search (anymdp_env.py:153), taken off the chain: its pivots are
+    // requested at the end of tick k, its code block early in tick k+1, and the record of tick k is written at the end of
+    // tick k+1.
+    float rew_q = 0.f, rgt_q = 0.f;
+    int a_q = 0, done_q = 0;
+    uint4 opv[2], ocd[2];                      // observation pivots / codes in flight
+    uint32_t oux = 0, ouy = 0;                 // the uniform of the observation draw (two Philox words)
+    const uint32_t* orow = nullptr;            // its row in T.ofat (null: the tick has no observation)
+    int oblk = 0, so_p = 0;
+    const int o_blocks = T.o_blocks;
+    auto obs_stage1 = [&]() {                  // pivots -> block; request the block's codes
+        if (orow) {
+            const uint32_t v15 = code15_from_m21(oux >> 11);
+            const unsigned v2 = v15 | (v15 << 16);
+            int acc = 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                acc = h2_count_lt(opv[i].x, v2, acc); acc = h2_count_lt(opv[i].y, v2, acc);
+                acc = h2_count_lt(opv[i].z, v2, acc); acc = h2_count_lt(opv[i].w, v2, acc);
+            }
+            oblk = min(-acc, o_blocks - 1);
+            ldg_words<2>(orow + 8 + 8 * oblk, ocd);
+        }
+    };
+    auto obs_stage2 = [&](int kp) {            // codes -> observation; write the record of tick kp
+        int obs = 0;
+        if (orow) {
+            const unsigned ve = ((((oux >> 5) << 4) | (ouy >> 28)) << 1) & cmask;
+            int lt, le;
+            for (;;) {
+                lt = 0; le = 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const unsigned x[4] = {ocd[i].x, ocd[i].y, ocd[i].z, ocd[i].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const unsigned xm = x[j] & cmask; lt += (xm < ve); le += (xm <= ve); }
+                }
+                if (lt < 8 || oblk >= o_blocks - 1) break;
+                ++oblk;
+                ldg_words<2>(orow + 8 + 8 * oblk, ocd);
+            }
+            obs = oblk * 8 + lt;
+            if (le != lt) {
+                const double u = u53(oux, ouy);
+                const double* cr = T.obs_cdf + (t * n_pad + so_p) * (long long)T.no_pad;
+                while (obs < T.no_pad - 1 && __ldg(cr + obs) <= u) ++obs;
+                n_fallback += 1;
+            }
+        }
+        write_rec(kp, obs, a_q, done_q, rew_q, rgt_q);
+    };
+    auto settle = [&](int kp) {
+        // reward = gt + noise * z (anymdp_env.py:103-105), episode return, closed-episode statistics, the record
+        const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
+        ep_ret += rew;
+        if (POMDP) { rew_q = (float)rew; rgt_q = pay_p.x; a_q = a_p; done_q = done_p; }
+        else write_rec(kp, si_p & 0x7fffffff, a_p, done_p, (float)rew, pay_p.x);
+        if (close_p) {
+            sh_cnt[0][tx] += 1; sh_cnt[1][tx] += (unsigned long long)steps_p;
+            sh_stat[0][tx] += ep_ret; sh_stat[1][tx] += ep_ret * ep_ret;
+            sh_stat[2][tx] = fmin(sh_stat[2][tx], ep_ret); sh_stat[3][tx] = fmax(sh_stat[3][tx], ep_ret);
+            ep_ret = 0.0;
+            close_p = false;
+        }
+    };
+    for (int k = 0; k < K; ++k) {
+        const bool pend = next && (flags & FLAG_PENDING);          // next_step mode: this tick only performs the reset
+        const bool a_ok = !given || (unsigned)cur.a < (unsigned)na;
+        const bool valid = !pend && a_ok;
+        if (given && !pend && !a_ok) fault |= AMDP_FAULT_BAD_ACTION;                          // :97
+        const unsigned long long row = rbase + (unsigned long long)(s * na + (valid ? cur.a : 0));
+        // (1) first level of the search tree of row (s, a)                                      anymdp_env.py:99
+        uint4 lv[2];                                               // 16 pivots (15-bit codes)
+        if (LEVELS == 3 && valid) ldg_words_keep<2>(T.top + row * 16u, lv, pol_keep);
+        if (LEVELS == 2 && valid) ldg_words_keep<2>(T.pv + row * 16u, lv, pol_keep);
+        // (2) in the shadow of that load: the previous tick's reward / record
+        if (k > 0) { settle(k - 1); if (POMDP) obs_stage1(); }
+        // the next tick's draws: in the shadow of the block load, or (small register budget) here, before the search data
+        // occupies registers
+        constexpr bool DRAW_EARLY = (MINB == TP_MINB_HI);
+        Draw nx;
+        if (DRAW_EARLY) nx = draw(k + 1);
+        int done_bits = 0;
+        bool do_reset = pend;
+        bool touched = pend;                                       // the tick stepped or reset: it has an observation
+        bool si_from_line = false;                                 // the state word of s' came with the block line
+        if (valid) {
+            // (3) next state = #{cdf <= u}  (numpy choice: searchsorted(cdf, u, 'right'))         anymdp_env.py:100
+            const uint32_t v15 = code15_from_m21(cur.wx >> 11);
+            const unsigned v2 = v15 | (v15 << 16);
+            auto count16 = [&]() {                                 // #{pivots < code15(u)}: blocks / groups entirely below u
+                int acc = 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    acc = h2_count_lt(lv[i].x, v2, acc); acc = h2_count_lt(lv[i].y, v2, acc);
+                    acc = h2_count_lt(lv[i].z, v2, acc); acc = h2_count_lt(lv[i].w, v2, acc);
+                }
+                return -acc;
+            };
+            int blk = 0;
+            if (LEVELS == 3) {
+                const int g = min(count16(), n_groups - 1);
+                ldg_words_keep<2>(T.pv + (row * (unsigned)n_groups + (unsigned)g) * 16u, lv, pol_keep);
+                blk = g * 16;
+            }
+            if (LEVELS >= 2) blk = min(blk + count16(), n_blocks - 1);
+            // code31(u) << 1; cmask = 0xfffffffe drops the is_terminal bit of the entries (tests coarsen it further to
+            // exercise the float64 fallback)
+            const unsigned ve = ((((cur.wx >> 5) << 4) | (cur.wy >> 28)) << 1) & cmask;
+            const uint4* frow = T.fat + row * (unsigned)n_blocks * 8u;                  // 8 x 16 bytes per block line
+            int lt, le;
+            unsigned mn;
+            for (bool first = true;; first = false) {
+                uint4 bw[2];
+                ldg_words<2>(frow + blk * 8, bw);
+                if (first && !DRAW_EARLY) nx = draw(k + 1);        // in the shadow of the block load: the next tick's draws
+                lt = 0; le = 0; mn = 0xffffffffu;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const unsigned x[4] = {bw[i].x, bw[i].y, bw[i].z, bw[i].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned xm = x[j] & cmask;
+                        lt += (xm < ve);
+                        le += (xm <= ve);
+                        mn = min(mn, xm >= ve ? x[j] : 0xffffffffu);
+                    }
+                }
+                if (lt < 8 || blk >= n_blocks - 1) break;
+                ++blk;                                             // the whole block is below u (its pivot shared u's 15-bit cell)
+            }
+            int nxt = blk * 8 + lt;
+            bool term = (mn & 1u) != 0;                            // is_terminal[nxt] (bit 0 of the first entry not below u)
+            if (le != lt) {
+                // code31(cdf[j]) == code31(u) for some j: decide those entries on the float64 row
+                const double u = u53(cur.wx, cur.wy);
+                const double* cr = T.cdf + row * (unsigned)n_pad;
+                while (nxt < n_pad - 1 && __ldg(cr + nxt) <= u) ++nxt;
+                term = sinfo_t[nxt] < 0;
+                n_fallback += 1;
+                // (4) payload (reward, noise) of (s, a, s')  (anymdp_env.py:103-104): consumed by settle() of the next tick
+                pay_p = ldg_stream_f32x2(T.payload + (row * (unsigned)n_pad + (unsigned)nxt));
+            } else {
+                const char* line = reinterpret_cast<const char*>(frow + blk * 8);
+                pay_p = ldg_stream_f32x2(reinterpret_cast<const float2*>(line + 32) + lt);
+                if (!POMDP) { si_p = __ldg(reinterpret_cast<const int*>(line + 96) + lt); si_from_line = true; }
+            }
+            // (5) state update, termination, truncation (anymdp_env.py:107-108,113-114)
+            s = nxt;
+            steps += 1;
+            done_bits = ((term || always_term) ? 1 : 0) | ((steps >= max_ceil) ? 2 : 0);
+            touched = true;
+            if (done_bits) {
+                close_p = true;
+                steps_p = steps;
+                if (next) flags |= FLAG_PENDING; else do_reset = true;
+            }
+        } else {
+            pay_p = make_float2(0.f, 0.f);
+            if (!DRAW_EARLY) nx = draw(k + 1);
+        }
+        z_p = cur.z;
+        if (do_reset) {                                            // anymdp_env.py:81-90
+            const double ur = u53(cur.wz, cur.ww);
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < TP_S0; ++i) c += (sh_s0c[i][tx] <= ur);              // pad 2.0 is never <= ur
+            c = min(c, s0_pad - 1);
+            s = sh_s0i[0][tx];
+#pragma unroll
+            for (int i = 1; i < TP_S0; ++i) if (c == i) s = sh_s0i[i][tx];
+            steps = 0;
+            flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
+        }
+        // observation = state_mapping[s] (anymdp_env.py:145-148): from the block line unless the env was reset / fell back
+        // (measured: issuing the state-word load right behind the payload load and selecting here is ~8 % faster than one
+        // deferred load from a selected address, which ptxas schedules after the reset logic)
+        if (!POMDP) { if (do_reset || !si_from_line) si_p = touched ? __ldg(sinfo_t + s) : 0; }
+        if (POMDP) {
+            if (k > 0) obs_stage2(k - 1);                          // the previous tick's record (its codes arrived long ago)
+            // this tick's observation: drawn from the state after the step, or after the reset    anymdp_env.py:90,132
+            orow = touched ? T.ofat + (unsigned long long)(t * n_pad + s) * (unsigned)(8 + 8 * o_blocks) : nullptr;
+            oux = do_reset ? cur.rx : cur.ox; ouy = do_reset ? cur.ry : cur.oy;
+            so_p = s;
+            if (orow) ldg_words<2>(orow, opv);
+        }
+        a_p = cur.a;
+        done_p = done_bits;
+        cur = nx;
+    }
+    settle(K - 1);
+    if (POMDP) { obs_stage1(); obs_stage2(K - 1); }
+    E.state[e] = s; E.steps[e] = steps; E.flags[e] = (uint8_t)flags; E.ep_return[e] = ep_ret;
+    E.ep_count[e] = sh_cnt[0][tx]; E.sum_len[e] = sh_cnt[1][tx];
+    E.sum_ret[e] = sh_stat[0][tx]; E.sum_ret_sq[e] = sh_stat[1][tx];
+    E.min_ret[e] = sh_stat[2][tx]; E.max_ret[e] = sh_stat[3][tx];
+    if (fault) atomicOr(E.faults, fault);
+    if (n_fallback) atomicAdd(E.counters, (unsigned long long)n_fallback);
+}
+
+
+template <int LEVELS>
+static void launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, bool pomdp, int next, unsigned cmask, unsigned long long tick, int K,
+                      const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
+    const unsigned int blocks = nblk(n_envs, TP_TPB);
+    // Two register budgets: 72 registers (896 envs resident per SM, the next tick's draws generated before the search
+    // loads are issued) and 96 (640 per SM, draws generated in the shadow of the block load).  Measured on cfg2 / cfg4 /
+    // cfg5 at 65536-131072 envs the small budget wins everywhere (+3 .. +50 %, most where it turns 1.4 waves into one);
+    // AMDP_TP_MINB=lo selects the large one for experiments.  The POMDP variant carries the observation search as well.
+    bool hi = !pomdp;                                 // (the POMDP variant spills at 72 registers)
+    if (const char* o = getenv("AMDP_TP_MINB")) hi = (o[0] == 'h');
+#define TP_LAUNCH(MINB, GIVEN, POMDP) k_rollout_tp<LEVELS, MINB, GIVEN, POMDP><<<blocks, TP_TPB, 0, st>>>(T, E, tick, K, actions, J, next, cmask)
+    if (pomdp) {
+        if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, true, true); else TP_LAUNCH(TP_MINB_LO, true, true); }
+        else { if (hi) TP_LAUNCH(TP_MINB_HI, false, true); else TP_LAUNCH(TP_MINB_LO, false, true); }
+    } else if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, true, false); else TP_LAUNCH(TP_MINB_LO, true, false); }
+    else { if (hi) TP_LAUNCH(TP_MINB_HI, false, false); else TP_LAUNCH(TP_MINB_LO, false, false); }
+#undef TP_LAUNCH
+}
+
+void amdp_launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, bool pomdp, bool next, int coarse_bits, unsigned long long tick, int K,
+                    const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
+    const unsigned cmask = 0xfffffffeu << coarse_bits;
+    if (T.tp_levels == 1) launch_tp<1>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
+    else if (T.tp_levels == 2) launch_tp<2>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
+    else launch_tp<3>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
+}

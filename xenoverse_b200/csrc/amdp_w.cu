@@ -1,0 +1,336 @@
+// amdp_w.cu — k_rollout_w: warp-per-env rollout kernel with the shortest dependent chain; see amdp_dev.cuh / amdp_b200.cu.
+#include "amdp_dev.cuh"
+
+#ifndef AMDP_W_HINT
+#define AMDP_W_HINT 0      // L2 eviction hints: 1 payload evict_first, 2 rows of reset states evict_last (measured: both lose)
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// Latency path: ONE WARP PER ENV with the shortest dependent chain (k_rollout_w): MDP, one action token, engine Philox
+// draws or given actions, same-step auto-reset, rows of exactly 32 * EPL states (64 / 128 / 256), engines too small for
+// the thread-per-env kernel (cfg2: 4096 envs).  Such an engine is a set of Markov chains, each with ONE row in flight:
+// env-steps/s = envs / (DRAM latency + what sits between "row arrived" and "next row requested").  Measured on B200
+// (tools/warplat.cu, profiles/r1_warplat.txt): REDUX.MIN 22 cycles, VOTE + POPC 45, SHFL 33, LDS 34, LDG (L1 hit) 56,
+// REDUX.SUM 47, REDUX over a partial mask 427.  Hence:
+//   * the row is 32 lanes x EPL fp16-ordered 15-bit codes (the filter in front of the float64 row); a lane counts its
+//     own entries below code15(u) with HSET2 + IDP.2A and the warp takes ONE REDUX.MIN over
+//         (index of the lane's first entry not below u) << 2 | is_terminal[that entry] << 1 | undecided
+//     (rows are sorted, so the minimum is the next state; is_terminal bits of a lane's own entries sit in a register);
+//   * termination and truncation are then known without a memory access and the state a reset would lead to was
+//     computed when the draws were made (lane-parallel, start-state table in shared memory): the next row address is
+//     one select and one IMAD.WIDE away, and there is exactly ONE row-load site in the loop (no speculation, nothing
+//     to re-issue);
+//   * nothing else on the chain: the payload (reward, noise) and the state word of tick k are requested after the next
+//     row and consumed one tick later; no global load on a rare path feeds a register that is read after the paths
+//     merge (ptxas gives such loads the barrier of the row load and the merge point then waits for the row:
+//     tools/sass_ctrl.py shows the assignment);
+//   * draws of 32 consecutive ticks are generated in one lane-parallel Philox pass; records are staged one per lane
+//     and written once per 32 ticks.
+// Undecided (code15(cdf[j]) == code15(u), ~n/30720 of the ticks): the float64 row decides, as everywhere else.
+// ------------------------------------------------------------------------------------------------
+template <int NW> struct RowW { unsigned w[NW]; };
+
+template <int NW>
+__device__ __forceinline__ RowW<NW> ldg_row(const char* p) {
+    RowW<NW> r;
+    if constexpr (NW == 1) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r.w[0]) : "l"(p));
+    else if constexpr (NW == 2) asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[1]) : "l"(p));
+    else asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(p));
+    return r;
+}
+
+// the same with an L2 eviction policy (createpolicy): rows of start states are re-read after every reset and are kept
+// (evict_last); payload lines are touched once and must not push filter rows out of L2 (evict_first)
+template <int NW>
+__device__ __forceinline__ RowW<NW> ldg_row_hint(const char* p, uint64_t pol) {
+    RowW<NW> r;
+    if constexpr (NW == 1) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r.w[0]) : "l"(p), "l"(pol));
+    else if constexpr (NW == 2) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(r.w[0]), "=r"(r.w[1]) : "l"(p), "l"(pol));
+    else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(p), "l"(pol));
+    return r;
+}
+
+__device__ __forceinline__ float2 ldg_f32x2_hint(const float2* p, uint64_t pol) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+
+template <int EPL, bool GIVEN>
+__global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
+                                                      const int32_t* __restrict__ actions, const amdp_traj J) {
+    constexpr int NW = EPL / 2;                                   // 32-bit words of filter codes per lane
+    constexpr int N_PAD = 32 * EPL;
+    constexpr unsigned ROW_BYTES = 2u * N_PAD;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ double sh_stat[4][4];                              // closed-episode statistics: sum_ret, sum_ret_sq, min, max
+    __shared__ unsigned long long sh_cnt[2][4];                   // ep_count, sum_len
+    __shared__ double sh_s0c[TP_S0][4];                           // start-state CDF / states of the warp's env
+    __shared__ int sh_s0i[TP_S0][4];
+    const int lane = threadIdx.x & 31, gi = threadIdx.x >> 5;
+    const long long e = (long long)blockIdx.x * 4 + gi;
+    if (e >= E.n_envs) return;                                    // whole warps leave: one env per warp
+    const int na = T.na;
+    const long long N = E.n_envs;
+    const long long t = E.task[e];
+    const long long tsz = (long long)N_PAD * na * N_PAD;
+    const char* __restrict__ sk_lane = reinterpret_cast<const char*>(T.sketch + t * tsz) + lane * (EPL * 2);
+    const double* __restrict__ cdf_lane = T.cdf + t * tsz + lane * EPL;
+    const float2* __restrict__ pay_t = T.payload + t * tsz;
+    const int32_t* __restrict__ sinfo_t = T.sinfo + t * N_PAD;
+    const unsigned srow = (unsigned)na * ROW_BYTES;               // bytes between the filter rows of states s and s + 1
+    const int max_ceil = T.max_ceil[t];
+    const bool always_term = (T.tflags[t] & 1) != 0;
+    const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
+    // is_terminal of this lane's own EPL entries (ns < 2: every state terminates, anymdp_env.py:108)
+    unsigned myterm = (T.tbits[t * T.tb_words + ((lane * EPL) >> 5)] >> ((lane * EPL) & 31)) & ((1u << EPL) - 1u);
+    if (always_term) myterm = (1u << EPL) - 1u;
+
+    int s = E.state[e], steps = E.steps[e];
+    const int flags = E.flags[e];
+    double ep_ret = E.ep_return[e];
+
+    // staged records: lane L holds the record of tick (batch start + L)
+    int st_obs = 0, st_ad = 0;                                    // st_ad = action | done_bits << 28
+    float st_rew = 0.f, st_rgt = 0.f;
+    const long long rec0 = e * J.env_stride;
+    auto flush = [&](int kb, int cnt) {                           // records of ticks [kb, kb + cnt), one lane per tick
+        if (lane < cnt) {
+            const long long o = (long long)(kb + lane) * J.step_stride + rec0;
+            if (J.packed) {
+                const unsigned lo = ((unsigned)st_obs & 0xfffffu) | (((unsigned)st_ad & 0x3ffu) << 20) | (((unsigned)st_ad >> 28) << 30);
+                J.packed[o] = ((unsigned long long)__float_as_uint(st_rew) << 32) | lo;
+            } else {
+                if (J.obs) J.obs[o] = st_obs;
+                if (J.actions_out) J.actions_out[o] = st_ad & 0x0fffffff;
+                if (J.done) J.done[o] = (uint8_t)((unsigned)st_ad >> 28);
+                if (J.reward) J.reward[o] = st_rew;
+                if (J.reward_gt) J.reward_gt[o] = st_rgt;
+            }
+        }
+    };
+
+    unsigned fault = 0;
+    if (flags & FLAG_VIRGIN) fault = AMDP_FAULT_NEED_RESET;                                   // anymdp_env.py:93-94
+    else if (sinfo_t[s] < 0 && !always_term) fault = AMDP_FAULT_TERMINAL_STATE;               // :95-96
+    if (fault) {
+        // faulted envs are left untouched (as in env_tick); their records are zero except the action
+        for (int kb = 0; kb < K; kb += 32) {
+            const int k = kb + lane;
+            int a = 0;
+            if (k < K) {
+                if (GIVEN) a = load_action(actions, (long long)k * N + e, J.actions_u8);
+                else a = (int)__umulhi(philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key).z, (uint32_t)na);
+            }
+            st_ad = a & 0x0fffffff;
+            flush(kb, min(32, K - kb));
+        }
+        if (lane == 0) atomicOr(E.faults, fault);
+        return;
+    }
+    const int s0_pad = T.s0_pad;                                  // <= TP_S0 (the host never selects this kernel otherwise)
+    if (lane == 0) {
+        sh_cnt[0][gi] = E.ep_count[e]; sh_cnt[1][gi] = E.sum_len[e];
+        sh_stat[0][gi] = E.sum_ret[e]; sh_stat[1][gi] = E.sum_ret_sq[e];
+        sh_stat[2][gi] = E.min_ret[e]; sh_stat[3][gi] = E.max_ret[e];
+    }
+    if (lane < TP_S0) {
+        sh_s0c[lane][gi] = (lane < s0_pad) ? T.s0_cdf[t * s0_pad + lane] : 2.0;
+        sh_s0i[lane][gi] = T.s0_idx[t * s0_pad + min(lane, s0_pad - 1)];
+    }
+    __syncwarp();
+    auto reset_state = [&](double ur) {                           // anymdp_env.py:89 (pad 2.0 is never <= ur)
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < TP_S0; ++i) c += (sh_s0c[i][gi] <= ur);
+        c = min(c, s0_pad - 1);
+        int r = sh_s0i[0][gi];
+#pragma unroll
+        for (int i = 1; i < TP_S0; ++i) if (c == i) r = sh_s0i[i][gi];
+        return r;
+    };
+
+    // Draws of one tick, packed: bits 0-14 code15(u_transition), 15-22 action (engine policy), 23-30 the state a reset in
+    // this tick leads to, 31 given action out of range.  Lane L of a batch holds tick kb + L + 1.
+    unsigned b_pk = 0;
+    float b_z = 0.f;
+    int b_act = 0;
+    unsigned n_fallback = 0;
+    auto make = [&](int kt, unsigned& pk, float& z, int& act) {
+        const unsigned long long tk = tick0 + (unsigned long long)kt;
+        const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
+        const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tk, E.key);
+        z = box_muller(w2.x, w2.y);
+        pk = code15_from_m21(w0.x >> 11) | ((unsigned)reset_state(u53(w0.z, w0.w)) << 23);
+        if (GIVEN) {
+            act = (kt < K) ? load_action(actions, (long long)kt * N + e, J.actions_u8) : 0;
+            if ((unsigned)act >= (unsigned)na) pk |= 0x80000000u;
+        } else {
+            act = 0;
+            pk |= __umulhi(w2.z, (uint32_t)na) << 15;
+        }
+    };
+    unsigned pk;
+    float z;
+    int a_raw;
+    make(0, pk, z, a_raw);
+    make(lane + 1, b_pk, b_z, b_act);
+    if (GIVEN && (pk >> 31)) fault |= AMDP_FAULT_BAD_ACTION;                                  // :97
+    int a = GIVEN ? ((pk >> 31) ? 0 : a_raw) : (int)((pk >> 15) & 0xffu);
+    unsigned sa = (unsigned)(s * na + a);                         // row (s, a) inside the task
+    unsigned v2 = (pk & 0x7fffu) * 0x00010001u;
+    // What is in flight between two ticks: the filter row of tick k, and the payload / state word of tick k - 1 (settled
+    // one tick late; their loads travel with the row load).  Two sets, used alternately (the loop is unrolled by two):
+    // with one set the loaded registers would have to be MOVed at the end of a tick, and a MOV waits for the load.
+    struct Flight { RowW<NW> q; float2 pay; int si; };
+    Flight fa, fb;
+    fa.q = ldg_row<NW>(sk_lane + (unsigned long long)sa * ROW_BYTES);
+    fa.pay = make_float2(0.f, 0.f); fa.si = 0;
+
+    float z_p = 0.f;
+    int ad_p = 0, steps_p = 0;
+    bool close_p = false, valid_p = false;
+    auto settle = [&](int kp, const float2 pay_p, const int si_p) {
+        // reward = gt + noise * z (anymdp_env.py:103-105), episode return, closed-episode statistics, the record
+        const double rew = valid_p ? (double)pay_p.x + (double)pay_p.y * (double)z_p : 0.0;
+        ep_ret += rew;
+        if (lane == (kp & 31)) {
+            st_obs = valid_p ? (si_p & 0x7fffffff) : 0; st_ad = ad_p; st_rew = (float)rew; st_rgt = valid_p ? pay_p.x : 0.f;
+        }
+        if (close_p) {
+            if (lane == 0) {
+                sh_cnt[0][gi] += 1; sh_cnt[1][gi] += (unsigned long long)steps_p;
+                sh_stat[0][gi] += ep_ret; sh_stat[1][gi] += ep_ret * ep_ret;
+                sh_stat[2][gi] = fmin(sh_stat[2][gi], ep_ret); sh_stat[3][gi] = fmax(sh_stat[3][gi], ep_ret);
+            }
+            ep_ret = 0.0;
+            close_p = false;
+        }
+    };
+#if AMDP_W_HINT & 1
+    uint64_t pol_first;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+#endif
+#if AMDP_W_HINT & 2
+    uint64_t pol_keep, pol_norm;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_norm));
+#endif
+    // loop-invariant pieces of the REDUX operand, kept in registers (ptxas would re-derive them from %tid every tick)
+    unsigned lane_base32 = (unsigned)(lane * EPL) << 5;
+    unsigned myterm16 = myterm << 4;
+    asm volatile("" : "+r"(lane_base32), "+r"(myterm16));
+    const float2* pay_row = pay_t + (unsigned long long)sa * N_PAD;   // payload row of (s, a)
+
+    auto tick = [&](const int k, const Flight& cur, Flight& nxf) {
+        const int j = k & 31;
+        // (A) inputs of the NEXT tick: independent of the row in flight
+        const unsigned npk = __shfl_sync(FULL, b_pk, j);
+        const float nz = __shfl_sync(FULL, b_z, j);
+        int na_raw = 0;
+        if (GIVEN) na_raw = __shfl_sync(FULL, b_act, j);
+        const int n_a = GIVEN ? ((npk >> 31) ? 0 : na_raw) : (int)((npk >> 15) & 0xffu);
+        const char* nbase = sk_lane + (unsigned)n_a * ROW_BYTES;
+        asm volatile("" : "+l"(nbase));                           // one IMAD.WIDE from the next row address
+        const unsigned nv2 = (npk & 0x7fffu) * 0x00010001u;
+        const bool valid = !GIVEN || !(pk >> 31);                 // a tick with a bad action does not step
+        const unsigned sreset = (pk >> 23) & 0xffu;
+        const bool trunc = steps + 1 >= max_ceil;                 // anymdp_env.py:113-114
+        const unsigned trunc16 = trunc ? 16u : 0u;
+
+        // (B) the chain: row -> count below code15(u) -> REDUX.MIN -> next state -> next row address
+        const unsigned v2le = v2 + 0x00010001u;                   // entries <= code15(u): below the next code
+        int lt = 0, le = 0;                                       // this lane's entries below u / not above u
+#pragma unroll
+        for (int i = 0; i < NW; ++i) { lt = h2_count_lt_pos(cur.q.w[i], v2, lt); le = h2_count_lt_pos(cur.q.w[i], v2le, le); }
+        // (index of the first entry not below u) << 5 | is_terminal[it] << 4 | entries sharing u's code (undecided)
+        unsigned val = lane_base32 + ((unsigned)lt << 5) + (unsigned)(le - lt) + ((myterm16 >> lt) & 16u);
+        if (lt == EPL) val = FULL;                                // all below: the boundary is in a later lane
+        unsigned r = __reduce_min_sync(FULL, val);
+        unsigned nxt, s_next;
+        auto advance = [&]() {
+            nxt = r >> 5;
+            const bool done = ((r | trunc16) & 16u) != 0;         // anymdp_env.py:108,114
+            s_next = done ? sreset : nxt;                         // same-step auto-reset (anymdp_env.py:81-90)
+            if (GIVEN && !valid) s_next = (unsigned)s;
+            // payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104), the next row, the state word of the observation
+            // (anymdp_env.py:145-148; after a reset: of the start state).  Issued together: ptxas puts loads of one kind on
+            // one barrier, and a payload load issued later than the row would make the chain wait for it.
+#if AMDP_W_HINT & 1
+            nxf.pay = ldg_f32x2_hint(pay_row + nxt, pol_first);
+#else
+            nxf.pay = ldg_stream_f32x2(pay_row + nxt);
+#endif
+#if AMDP_W_HINT & 2
+            nxf.q = ldg_row_hint<NW>(nbase + (unsigned long long)(s_next * (unsigned long long)srow), done ? pol_keep : pol_norm);
+#else
+            nxf.q = ldg_row<NW>(nbase + (unsigned long long)(s_next * (unsigned long long)srow));
+#endif
+            nxf.si = __ldg(sinfo_t + s_next);
+        };
+        advance();
+        if (r & 15u) {
+            // undecided: exact float64 entries (numpy choice: searchsorted(cdf, u, 'right'))   anymdp_env.py:100
+            const uint4 w0 = philox_block(env_id, 0u, tick0 + (unsigned long long)k, E.key);
+            const double u = u53(w0.x, w0.y);
+            const double* cr = cdf_lane + (unsigned long long)sa * N_PAD;
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < EPL; i += 2) {
+                const double2 x = ldg_stream_f64x2(cr + i);
+                cnt += (x.x <= u) + (x.y <= u);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+            cnt = min(cnt, N_PAD - 1);
+            r = ((unsigned)cnt << 5) | ((sinfo_t[cnt] < 0 || always_term) ? 16u : 0u);
+            n_fallback += 1;
+            advance();
+        }
+
+        // (C) settle the previous tick; once per 32 ticks write the finished batch of records, lane-parallel
+        settle(k - 1, cur.pay, cur.si);
+        if (j == 0 && k > 0) flush(k - 32, 32);
+        // (D) this tick becomes the previous one
+        z_p = z; valid_p = valid;
+        ad_p = GIVEN ? (a_raw & 0x0fffffff) : a;
+        if (valid) {
+            ad_p |= (int)((((r >> 4) & 1u) | (trunc ? 2u : 0u)) << 28);
+            steps += 1;
+            if ((r | trunc16) & 16u) { close_p = true; steps_p = steps; steps = 0; }
+            s = (int)s_next;
+        }
+        // once per 32 ticks: draw the next batch
+        if (j == 31) make(k + 2 + lane, b_pk, b_z, b_act);
+        // rotate to the next tick
+        if (GIVEN && (npk >> 31) && k + 1 < K) fault |= AMDP_FAULT_BAD_ACTION;               // :97
+        pk = npk; z = nz; a = n_a; a_raw = na_raw; v2 = nv2;
+        sa = (unsigned)(s * na + n_a);
+        pay_row = pay_t + (unsigned long long)sa * N_PAD;
+    };
+    int k = 0;
+    for (; k + 1 < K; k += 2) { tick(k, fa, fb); tick(k + 1, fb, fa); }
+    if (k < K) { tick(k, fa, fb); settle(K - 1, fb.pay, fb.si); }
+    else settle(K - 1, fa.pay, fa.si);
+    {
+        const int kb = ((K - 1) / 32) * 32;
+        flush(kb, K - kb);
+    }
+    if (lane == 0) {
+        E.state[e] = s; E.steps[e] = steps; E.ep_return[e] = ep_ret;
+        E.ep_count[e] = sh_cnt[0][gi]; E.sum_len[e] = sh_cnt[1][gi];
+        E.sum_ret[e] = sh_stat[0][gi]; E.sum_ret_sq[e] = sh_stat[1][gi];
+        E.min_ret[e] = sh_stat[2][gi]; E.max_ret[e] = sh_stat[3][gi];
+        if (fault) atomicOr(E.faults, fault);
+        if (n_fallback) atomicAdd(E.counters, (unsigned long long)n_fallback);
+    }
+}
+
+void amdp_launch_w(const Tables& T, const EnvArrays& E, long long n_envs, unsigned long long tick, int K, const int32_t* actions,
+                   const amdp_traj& J, cudaStream_t st) {
+    const unsigned int blocks = nblk(n_envs, 4);
+#define WV2(epl) { if (actions) k_rollout_w<epl, true><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); \
+                   else k_rollout_w<epl, false><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); }
+    if (T.n_pad == 64) WV2(2) else if (T.n_pad == 128) WV2(4) else WV2(8)
+#undef WV2
+}
