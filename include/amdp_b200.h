@@ -77,6 +77,7 @@ extern "C" {
 #define AMDP_TASK_NOT_NORMALISED 2  /* numpy choice(): 'probabilities do not sum to 1' (|kahan_sum(p)-1| > sqrt(eps)) */
 #define AMDP_TASK_NEGATIVE_P    3   /* numpy choice(): 'probabilities are not non-negative' */
 #define AMDP_TASK_S0_IN_SE      4   /* anymdp_env.py:74-76 a start state is also terminal */
+#define AMDP_TASK_OBS_RANGE     5   /* a state_mapping value does not fit the observation bits stated in amdp_config.reserved0 (bits 8-12) */
 
 #define AMDP_SLOTS_PER_TOKEN 8
 #define AMDP_SLOT_TRANS      0
@@ -104,7 +105,9 @@ typedef struct amdp_config {
     int32_t  reserved0;     /* flags: 1 keep a copy of `transition` (amdp_gather_transition_gt); 8 / 16 force / forbid the thread-per-env rollout
                                kernel (default: used from 16384 envs); 2 / 4 force the one- / two-level
                                row search of the fast rollout kernel (default: chosen from n_pad and n_envs); 32 keeps MDP engines
-                               off k_rollout_w (the REDUX.MIN warp-per-env kernel for rows of 64 / 128 / 256 states) */
+                               off k_rollout_w (the REDUX.MIN warp-per-env kernel for rows of 64 / 128 / 256 states);
+                               bits 8-12: bit_length(max ns - 1) over all tasks (0 = not stated, 15 assumed): the thread-per-env tables
+                               carry state_mapping in that many low bits of their CDF code words; more than 15 disables that kernel */
     int64_t  n_envs;        /* envs owned by this handle (this GPU's shard) */
     int64_t  n_tasks;       /* tasks resident on this handle */
     uint64_t seed;          /* Philox key */

@@ -320,7 +320,8 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
                              const int32_t* __restrict__ n_real, const uint8_t* __restrict__ is_terminal,
                              double* __restrict__ cdf, float2* __restrict__ payload, uint16_t* __restrict__ sketch,
                              uint16_t* __restrict__ pivot, const int32_t* __restrict__ state_mapping, uint4* __restrict__ fat,
-                             uint16_t* __restrict__ pv, uint16_t* __restrict__ top, int tp_blocks, int tp_groups,
+                             uint16_t* __restrict__ pv, uint16_t* __restrict__ top, uint8_t* __restrict__ pv8, int tp_blocks, int tp_groups,
+                             int tp_obs_bits,
                              int32_t* __restrict__ status) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long rows = cnt * n_pad * na;
@@ -342,6 +343,7 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
                 for (int i = 2; i < 8; ++i) line[i] = make_uint4(0u, 0u, 0u, 0u);
             }
             if (pv) for (int b = 0; b < tp_groups * 16; ++b) pv[r * tp_groups * 16 + b] = 0x7bff;
+            if (pv8) for (int b = 0; b < tp_groups * 16; ++b) pv8[r * tp_groups * 16 + b] = 255;
             if (top) for (int g = 0; g < 16; ++g) top[r * 16 + g] = 0x7bff;
         }
         return;
@@ -395,21 +397,25 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
         // Entries with equal codes (zero-probability next states repeat the previous CDF value) all carry the flag of the
         // FIRST entry of their run: the search returns the first entry not below u, which is always the first of a run,
         // and the kernel reads its flag as the minimum over the entries not below u.
-        uint32_t prev_code = 0xffffffffu, prev_f = 0;
+        // The low 1 + tp_obs_bits bits of a code word carry is_terminal[j] and state_mapping[j] (the observation of a
+        // transition into j), so that the search needs no state-word request; the search compares the remaining high bits.
+        const uint32_t hmask = 0xffffffffu << (1 + tp_obs_bits);
+        uint32_t prev_code = 1u, prev_f = 0;                       // (1: not a masked code)
         for (int b = 0; b < tp_blocks; ++b) {
             uint32_t* line = reinterpret_cast<uint32_t*>(fat + (r * tp_blocks + b) * 8);
             for (int i = 0; i < 8; ++i) {
                 const int j = 8 * b + i;
-                const uint32_t code = code31((j < n_pad) ? c[j] : 1.0);
+                const uint32_t code = (code31((j < n_pad) ? c[j] : 1.0) << 1) & hmask;
                 const bool real = j < n;
                 const uint32_t is_t = (real && is_terminal[t * n_pad + j]) ? 1u : 0u;
-                uint32_t f = is_t;
+                uint32_t f = is_t | (real ? ((uint32_t)state_mapping[t * n_pad + j] << 1) & ~hmask : 0u);
+                if (real && ((uint32_t)state_mapping[t * n_pad + j] >> tp_obs_bits) && status) atomicMax(status + t, AMDP_TASK_OBS_RANGE);
                 if (code == prev_code) f = prev_f;
-                line[i] = (code << 1) | f;
+                line[i] = code | f;
                 prev_code = code; prev_f = f;
                 line[8 + 2 * i] = (j < n_pad) ? __float_as_uint(pl[j].x) : 0u;
                 line[8 + 2 * i + 1] = (j < n_pad) ? __float_as_uint(pl[j].y) : 0u;
-                line[24 + i] = (j < n_pad) ? ((uint32_t)(state_mapping[t * n_pad + j] & 0x7fffffff) | (is_t << 31)) : 0u;
+                line[24 + i] = 0u;
             }
         }
         if (pv) {
@@ -422,6 +428,20 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
             for (int g = 0; g < 16; ++g) {
                 const int last = 128 * g + 127;
                 top[r * 16 + g] = (g < tp_groups) ? (uint16_t)code15((last < n_pad) ? c[last] : 1.0) : (uint16_t)0x7bff;
+            }
+        }
+        if (pv8) {
+            // block pivots of a three-level row: 8 bits, relative to the code range of their group (lo15, hi15] — the two
+            // neighbouring entries of `top`, which the search has in registers when it needs them
+            uint32_t lo15 = 0x3ffu;
+            for (int g = 0; g < tp_groups; ++g) {
+                const int glast = 128 * g + 127;
+                const uint32_t hi15 = code15((glast < n_pad) ? c[glast] : 1.0);
+                for (int b = 16 * g; b < 16 * g + 16; ++b) {
+                    const int last = 8 * b + 7;
+                    pv8[r * tp_groups * 16 + b] = (b < tp_blocks) ? (uint8_t)code8_rel(code15((last < n_pad) ? c[last] : 1.0), lo15, hi15) : (uint8_t)255;
+                }
+                lo15 = hi15;
             }
         }
     }
@@ -624,7 +644,7 @@ struct amdp {
     bool wv2;              // MDP rollouts with same-step auto-reset run on k_rollout_w (one warp per env, REDUX.MIN search)
     int n_sm;              // multiprocessors of the device
     int tp_coarse_bits;    // debug: low bits of the 31-bit codes ignored by k_rollout_tp (0 in production)
-    uint4* fat; uint16_t* pv; uint16_t* top; uint32_t* ofat;   // its tables (see Tables)
+    uint4* fat; uint16_t* pv; uint16_t* top; uint8_t* pv8; uint32_t* ofat;   // its tables (see Tables)
     char err[512];
     char kname[64];
     // rollout_host staging
@@ -692,7 +712,7 @@ static int pick_group(int n_pad) {
 extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits,
+    void* ptrs[] = {h->ofat, h->fat, h->pv, h->pv8, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
@@ -737,7 +757,11 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     if (h->two_level) { if ((rc = dalloc(h, &h->pivot, rows * 32))) return rc; }
     // thread-per-env tables: chosen for engines with enough envs to fill the GPU (or forced by flag 8; never with 16)
     const bool tp_kind = mdp || (c.task_type == AMDP_POMDP && c.no_pad <= 128);      // POMDP: one observation token, <= 16 blocks
-    h->tp = tp_kind && c.n_pad <= 2048 && c.s0_pad <= TP_S0 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= 16384));
+    // flags bits 8-12: bit_length(max ns - 1), the bits of state_mapping the thread-per-env tables carry in their code words
+    // (0 = not stated: 15 is assumed and larger mappings are rejected at upload)
+    const int obs_bits = ((c.reserved0 >> 8) & 31) ? ((c.reserved0 >> 8) & 31) : 15;
+    h->T.tp_obs_bits = obs_bits;
+    h->tp = tp_kind && obs_bits <= 15 && c.n_pad <= 2048 && c.s0_pad <= TP_S0 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= 16384));
     if (h->tp) {
         const int nb = (c.n_pad + 7) / 8;
         h->T.tp_blocks = nb;
@@ -745,6 +769,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
         h->T.tp_groups = h->T.tp_levels == 3 ? (nb + 15) / 16 : 1;
         if ((rc = dalloc(h, &h->fat, rows * nb * 8))) return rc;
         if (h->T.tp_levels >= 2) { if ((rc = dalloc(h, &h->pv, rows * h->T.tp_groups * 16))) return rc; }
+        if (h->T.tp_levels == 3 && getenv("AMDP_TP_PV8")) { if ((rc = dalloc(h, &h->pv8, rows * h->T.tp_groups * 16))) return rc; }
         if (h->T.tp_levels == 3) { if ((rc = dalloc(h, &h->top, rows * 16))) return rc; }
         if (!mdp) {
             h->T.o_blocks = (c.no_pad + 7) / 8;
@@ -786,7 +811,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     E.task = h->env_task; E.faults = h->faults; E.counters = h->counters; E.n_envs = c.n_envs; E.env_id_base = c.env_id_base;
     E.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
     Tables& T = h->T;
-    T.fat = h->fat; T.pv = h->pv; T.top = h->top; T.ofat = h->ofat;
+    T.fat = h->fat; T.pv = h->pv; T.top = h->top; T.pv8 = h->pv8; T.ofat = h->ofat;
     T.cdf = h->cdf; T.payload = h->payload; T.sketch = h->sketch; T.pivot = h->pivot; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
     T.obs_cdf = h->obs_cdf; T.max_ceil = h->max_ceil; T.tflags = h->tflags; T.raw_t = h->raw_t; T.n_real = h->n_real; T.tbits = h->tbits;
     T.n_pad = c.n_pad; T.na = c.na; T.no_pad = c.no_pad; T.d_o = c.n_obs_tok; T.d_a = c.n_act_tok; T.s0_pad = c.s0_pad;
@@ -819,7 +844,8 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
                                                   h->fat ? h->fat + (size_t)t0 * c.n_pad * c.na * h->T.tp_blocks * 8 : nullptr,
                                                   h->pv ? h->pv + (size_t)t0 * c.n_pad * c.na * h->T.tp_groups * 16 : nullptr,
                                                   h->top ? h->top + (size_t)t0 * c.n_pad * c.na * 16 : nullptr,
-                                                  h->T.tp_blocks, h->T.tp_groups, status_out);
+                                                  h->pv8 ? h->pv8 + (size_t)t0 * c.n_pad * c.na * h->T.tp_groups * 16 : nullptr,
+                                                  h->T.tp_blocks, h->T.tp_groups, h->T.tp_obs_bits, status_out);
     k_build_small<<<nblk(cnt, 128), 128, 0, st>>>(cnt, c.n_pad, c.s0_pad, state_mapping, n_real, is_terminal, s0_idx, s0_prob,
                                                   n_s0, max_steps, ns, h->sinfo + t0 * c.n_pad, h->s0_cdf + t0 * c.s0_pad,
                                                   h->s0_idx + t0 * c.s0_pad, h->max_ceil + t0, h->tflags + t0,

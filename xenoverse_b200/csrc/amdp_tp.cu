@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
     __shared__ unsigned long long sh_cnt[2][TP_TPB];              // ep_count, sum_len
     __shared__ double sh_s0c[TP_S0][TP_TPB];                         // the env's start-state CDF and states (s0_pad <= TP_S0):
     __shared__ int sh_s0i[TP_S0][TP_TPB];                            // a reset costs no global-memory round trip
+    __shared__ int sh_s0o[TP_S0][TP_TPB];                            // state_mapping of the start states (the observation of a reset)
     const int tx = threadIdx.x;
     const long long e = (long long)blockIdx.x * TP_TPB + tx;
     if (e >= E.n_envs) return;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
     for (int i = 0; i < TP_S0; ++i) {
         sh_s0c[i][tx] = (i < s0_pad) ? T.s0_cdf[t * s0_pad + i] : 2.0;
         sh_s0i[i][tx] = T.s0_idx[t * s0_pad + min(i, s0_pad - 1)];
+        sh_s0o[i][tx] = sinfo_t[sh_s0i[i][tx]] & 0x7fffffff;
     }
 
     // draws of one tick: words 0..3 of Philox block 0 (transition uniform = w.x, w.y; reset uniform = w.z, w.w), the reward
@@ -113,7 +115,8 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
     // the previous tick, settled one tick late (its payload / observation loads were issued at the end of that tick)
     float2 pay_p = make_float2(0.f, 0.f);
     float z_p = 0.f;
-    int si_p = 0, a_p = 0, done_p = 0, steps_p = 0;
+    int ob_p = 0, a_p = 0, done_p = 0, steps_p = 0;
+    const unsigned omask = (1u << T.tp_obs_bits) - 1u;          // state_mapping[j] sits in bits 1.. of the code word of entry j
     bool close_p = false;
     unsigned n_fallback = 0;
     // POMDP: the observation of tick k is a second two-level search (anymdp_env.py:153), taken off the chain: its pivots are
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
         const double rew = (double)pay_p.x + (double)pay_p.y * (double)z_p;
         ep_ret += rew;
         if (POMDP) { rew_q = (float)rew; rgt_q = pay_p.x; a_q = a_p; done_q = done_p; }
-        else write_rec(kp, si_p & 0x7fffffff, a_p, done_p, (float)rew, pay_p.x);
+        else write_rec(kp, ob_p, a_p, done_p, (float)rew, pay_p.x);
         if (close_p) {
             sh_cnt[0][tx] += 1; sh_cnt[1][tx] += (unsigned long long)steps_p;
             sh_stat[0][tx] += ep_ret; sh_stat[1][tx] += ep_ret * ep_ret;
@@ -201,7 +204,6 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
         int done_bits = 0;
         bool do_reset = pend;
         bool touched = pend;                                       // the tick stepped or reset: it has an observation
-        bool si_from_line = false;                                 // the state word of s' came with the block line
         if (valid) {
             // (3) next state = #{cdf <= u}  (numpy choice: searchsorted(cdf, u, 'right'))         anymdp_env.py:100
             const uint32_t v15 = code15_from_m21(cur.wx >> 11);
@@ -217,11 +219,40 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
             };
             int blk = 0;
             if (LEVELS == 3) {
+                // second level: the 16 block pivots of group g, 8 bits each, relative to the group's code range (lo15, hi15]
                 const int g = min(count16(), n_groups - 1);
+#ifdef AMDP_TP_PV8
+                uint4 p8[1];
+                ldg_words_keep<1>(T.pv8 + ((size_t)row * (unsigned)n_groups + (unsigned)g) * 16u, p8, pol_keep);
+                // in the shadow of that load: the group's range from the pivots in registers, and the code of u inside it
+                auto pick16 = [&](int idx) {                       // halfword idx of the 16 pivots (a tree of selects)
+                    const int wi = idx >> 1;
+                    const unsigned a0 = (wi & 1) ? lv[0].y : lv[0].x, a1 = (wi & 1) ? lv[0].w : lv[0].z;
+                    const unsigned a2 = (wi & 1) ? lv[1].y : lv[1].x, a3 = (wi & 1) ? lv[1].w : lv[1].z;
+                    const unsigned c0 = (wi & 2) ? a1 : a0, c1 = (wi & 2) ? a3 : a2;
+                    const unsigned d = (wi & 4) ? c1 : c0;
+                    return (idx & 1) ? (d >> 16) : (d & 0xffffu);
+                };
+                const uint32_t hi15 = pick16(g), lo15 = g ? pick16(g - 1) : 0x3ffu;
+                const unsigned vq2 = (0x0400u + code8_rel(v15, lo15, hi15)) * 0x00010001u;
+                int acc = 0;
+                const unsigned pw[4] = {p8[0].x, p8[0].y, p8[0].z, p8[0].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                      // bytes widened to normal fp16 patterns 0x0400 + b
+                    acc = h2_count_lt(__byte_perm(pw[i], 0x04040404u, 0x4140), vq2, acc);
+                    acc = h2_count_lt(__byte_perm(pw[i], 0x04040404u, 0x4342), vq2, acc);
+                }
+                blk = min(g * 16 - acc, n_blocks - 1);
+#else
+#ifdef AMDP_TP_PV_NOKEEP
+                ldg_words<2>(T.pv + (row * (unsigned)n_groups + (unsigned)g) * 16u, lv);
+#else
                 ldg_words_keep<2>(T.pv + (row * (unsigned)n_groups + (unsigned)g) * 16u, lv, pol_keep);
-                blk = g * 16;
+#endif
+                blk = min(g * 16 + count16(), n_blocks - 1);
+#endif
             }
-            if (LEVELS >= 2) blk = min(blk + count16(), n_blocks - 1);
+            if (LEVELS == 2) blk = min(count16(), n_blocks - 1);
             // code31(u) << 1; cmask = 0xfffffffe drops the is_terminal bit of the entries (tests coarsen it further to
             // exercise the float64 fallback)
             const unsigned ve = ((((cur.wx >> 5) << 4) | (cur.wy >> 28)) << 1) & cmask;
@@ -254,14 +285,16 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
                 const double u = u53(cur.wx, cur.wy);
                 const double* cr = T.cdf + row * (unsigned)n_pad;
                 while (nxt < n_pad - 1 && __ldg(cr + nxt) <= u) ++nxt;
-                term = sinfo_t[nxt] < 0;
+                const int siw = sinfo_t[nxt];
+                term = siw < 0;
+                if (!POMDP) ob_p = siw & 0x7fffffff;
                 n_fallback += 1;
                 // (4) payload (reward, noise) of (s, a, s')  (anymdp_env.py:103-104): consumed by settle() of the next tick
                 pay_p = ldg_stream_f32x2(T.payload + (row * (unsigned)n_pad + (unsigned)nxt));
             } else {
                 const char* line = reinterpret_cast<const char*>(frow + blk * 8);
                 pay_p = ldg_stream_f32x2(reinterpret_cast<const float2*>(line + 32) + lt);
-                if (!POMDP) { si_p = __ldg(reinterpret_cast<const int*>(line + 96) + lt); si_from_line = true; }
+                if (!POMDP) ob_p = (int)((mn >> 1) & omask);       // observation = state_mapping[s'] (anymdp_env.py:145-148)
             }
             // (5) state update, termination, truncation (anymdp_env.py:107-108,113-114)
             s = nxt;
@@ -275,6 +308,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
             }
         } else {
             pay_p = make_float2(0.f, 0.f);
+            if (!POMDP) ob_p = 0;
             if (!DRAW_EARLY) nx = draw(k + 1);
         }
         z_p = cur.z;
@@ -285,15 +319,13 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
             for (int i = 0; i < TP_S0; ++i) c += (sh_s0c[i][tx] <= ur);              // pad 2.0 is never <= ur
             c = min(c, s0_pad - 1);
             s = sh_s0i[0][tx];
+            int so = sh_s0o[0][tx];
 #pragma unroll
-            for (int i = 1; i < TP_S0; ++i) if (c == i) s = sh_s0i[i][tx];
+            for (int i = 1; i < TP_S0; ++i) if (c == i) { s = sh_s0i[i][tx]; so = sh_s0o[i][tx]; }
+            if (!POMDP) ob_p = so;                                 // the observation of the reset (anymdp_env.py:90)
             steps = 0;
             flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
         }
-        // observation = state_mapping[s] (anymdp_env.py:145-148): from the block line unless the env was reset / fell back
-        // (measured: issuing the state-word load right behind the payload load and selecting here is ~8 % faster than one
-        // deferred load from a selected address, which ptxas schedules after the reset logic)
-        if (!POMDP) { if (do_reset || !si_from_line) si_p = touched ? __ldg(sinfo_t + s) : 0; }
         if (POMDP) {
             if (k > 0) obs_stage2(k - 1);                          // the previous tick's record (its codes arrived long ago)
             // this tick's observation: drawn from the state after the step, or after the reset    anymdp_env.py:90,132
@@ -338,7 +370,8 @@ static void launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, boo
 
 void amdp_launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, bool pomdp, bool next, int coarse_bits, unsigned long long tick, int K,
                     const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
-    const unsigned cmask = 0xfffffffeu << coarse_bits;
+    const int low = 1 + T.tp_obs_bits + coarse_bits;            // is_terminal + state_mapping bits (+ bits the tests drop)
+    const unsigned cmask = 0xffffffffu << (low < 30 ? low : 30);
     if (T.tp_levels == 1) launch_tp<1>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
     else if (T.tp_levels == 2) launch_tp<2>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
     else launch_tp<3>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);

@@ -52,7 +52,7 @@ def task_geometry(tasks):
         s0_max = max(s0_max, len(numpy.atleast_1d(t["s_0"])))
         if tt != "MDP":
             no_max = max(no_max, int(t["no"]))
-    return {"task_type": tt, "na": na, "da": da, "do": do, "n_pad": round_up4(n_max),
+    return {"task_type": tt, "na": na, "da": da, "do": do, "n_pad": round_up4(n_max), "ns_max": max(int(t["ns"]) for t in tasks),
             "no_pad": round_up4(no_max) if tt != "MDP" else 0, "s0_pad": s0_max}
 
 
@@ -112,6 +112,7 @@ _STATUS_MSG = {
     _lib.TASK_NOT_NORMALISED: "probabilities do not sum to 1",                # numpy choice(), raised at step time by the reference
     _lib.TASK_NEGATIVE_P: "probabilities are not non-negative",               # numpy choice()
     _lib.TASK_S0_IN_SE: "a state is both a start state and a terminal state",  # anymdp_env.py:76
+    _lib.TASK_OBS_RANGE: "state_mapping value outside the observation space stated for the engine (geo['ns_max'])",
 }
 
 
@@ -133,7 +134,7 @@ class Engine:
         cfg = _lib.Config(device=self.device.index, task_type=_lib.TASK_TYPES[geo["task_type"]],
                           autoreset=_lib.AUTORESET[autoreset], na=geo["na"], n_pad=geo["n_pad"], no_pad=geo["no_pad"],
                           n_obs_tok=geo["do"], n_act_tok=geo["da"], s0_pad=geo["s0_pad"],
-                          reserved0=(1 if keep_transition else 0) | {"auto": 0, "one_level": 2, "two_level": 4, "thread": 8, "warp": 16, "warp_v1": 48}[search],
+                          reserved0=(1 if keep_transition else 0) | (self._obs_bits(geo) << 8) | {"auto": 0, "one_level": 2, "two_level": 4, "thread": 8, "warp": 16, "warp_v1": 48}[search],
                           n_envs=self.N, n_tasks=self.T,
                           seed=int(seed) & (2 ** 64 - 1), env_id_base=int(env_id_base))
         h = ctypes.c_void_p()
@@ -146,6 +147,13 @@ class Engine:
                 self._h = None
             raise AMDPError(f"amdp_create failed ({rc}): {msg}")
         self.n_slots = lib.amdp_n_slots(h)
+
+    @staticmethod
+    def _obs_bits(geo):
+        """bit_length(max ns - 1): how many bits of state_mapping the thread-per-env tables carry inside their CDF code
+        words (amdp_config.reserved0 bits 8-12; more than 15 keeps the engine off that kernel)."""
+        ns_max = max(int(geo.get("ns_max", 0)), int(geo["n_pad"]), 2)
+        return min(31, max(1, (ns_max - 1).bit_length()))
 
     # ---- plumbing -----------------------------------------------------------------------------
     def _ck(self, rc):
