@@ -326,14 +326,16 @@ def run_b200(args, name, envs, tasks, ns, na, no):
 
     others = None
     if world == 1 and not args.no_other:
-        # the other BASELINE.json configs at their per-GPU sizes (cfg4 with the 32 tasks one of 8 GPUs owns), plus the
-        # cfg2 tables with enough envs to fill the GPU: the regimes where the path is bound by DRAM, not by latency
+        # the other BASELINE.json configs at their per-GPU sizes (cfg4 with the 32 tasks one of 8 GPUs owns, also with the
+        # 131072 envs per GPU SURVEY.md §8d names as its saturating variant), plus the cfg2 tables with enough envs to
+        # fill the GPU: the regimes where the path is bound by DRAM, not by latency
         device_bytes = env.engine.device_bytes
         env.close()
         torch.cuda.empty_cache()
         others = {}
         for key, (wl, n_envs, n_tasks, tk) in {"cfg2_x65536_envs": ("cfg2", 65536, 4096, 128), "cfg3": ("cfg3", 65536, 4096, 64),
-                                               "cfg4_32_tasks": ("cfg4", 65536, 32, 64), "cfg5": ("cfg5", 131072, 131072, 128)}.items():
+                                               "cfg4_32_tasks": ("cfg4", 65536, 32, 64), "cfg4_32_tasks_x131072_envs": ("cfg4", 131072, 32, 64),
+                                               "cfg5": ("cfg5", 131072, 131072, 128)}.items():
             _, _, o_ns, o_na, o_no = WORKLOADS[wl]
             try:
                 others[key] = quick_measure(wl, n_envs, n_tasks, o_ns, o_na, o_no, tk, 10, dev, local)

@@ -320,7 +320,7 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
                              const int32_t* __restrict__ n_real, const uint8_t* __restrict__ is_terminal,
                              double* __restrict__ cdf, float2* __restrict__ payload, uint16_t* __restrict__ sketch,
                              uint16_t* __restrict__ pivot, const int32_t* __restrict__ state_mapping, uint4* __restrict__ fat,
-                             uint16_t* __restrict__ pv, uint16_t* __restrict__ top, uint8_t* __restrict__ pv8, int tp_blocks, int tp_groups,
+                             uint16_t* __restrict__ pv, uint16_t* __restrict__ top, int tp_blocks, int tp_groups,
                              int tp_obs_bits,
                              int32_t* __restrict__ status) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -343,7 +343,6 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
                 for (int i = 2; i < 8; ++i) line[i] = make_uint4(0u, 0u, 0u, 0u);
             }
             if (pv) for (int b = 0; b < tp_groups * 16; ++b) pv[r * tp_groups * 16 + b] = 0x7bff;
-            if (pv8) for (int b = 0; b < tp_groups * 16; ++b) pv8[r * tp_groups * 16 + b] = 255;
             if (top) for (int g = 0; g < 16; ++g) top[r * 16 + g] = 0x7bff;
         }
         return;
@@ -428,20 +427,6 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
             for (int g = 0; g < 16; ++g) {
                 const int last = 128 * g + 127;
                 top[r * 16 + g] = (g < tp_groups) ? (uint16_t)code15((last < n_pad) ? c[last] : 1.0) : (uint16_t)0x7bff;
-            }
-        }
-        if (pv8) {
-            // block pivots of a three-level row: 8 bits, relative to the code range of their group (lo15, hi15] — the two
-            // neighbouring entries of `top`, which the search has in registers when it needs them
-            uint32_t lo15 = 0x3ffu;
-            for (int g = 0; g < tp_groups; ++g) {
-                const int glast = 128 * g + 127;
-                const uint32_t hi15 = code15((glast < n_pad) ? c[glast] : 1.0);
-                for (int b = 16 * g; b < 16 * g + 16; ++b) {
-                    const int last = 8 * b + 7;
-                    pv8[r * tp_groups * 16 + b] = (b < tp_blocks) ? (uint8_t)code8_rel(code15((last < n_pad) ? c[last] : 1.0), lo15, hi15) : (uint8_t)255;
-                }
-                lo15 = hi15;
             }
         }
     }
@@ -644,7 +629,7 @@ struct amdp {
     bool wv2;              // MDP rollouts with same-step auto-reset run on k_rollout_w (one warp per env, REDUX.MIN search)
     int n_sm;              // multiprocessors of the device
     int tp_coarse_bits;    // debug: low bits of the 31-bit codes ignored by k_rollout_tp (0 in production)
-    uint4* fat; uint16_t* pv; uint16_t* top; uint8_t* pv8; uint32_t* ofat;   // its tables (see Tables)
+    uint4* fat; uint16_t* pv; uint16_t* top; uint32_t* ofat;   // its tables (see Tables)
     char err[512];
     char kname[64];
     // rollout_host staging
@@ -712,7 +697,7 @@ static int pick_group(int n_pad) {
 extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->ofat, h->fat, h->pv, h->pv8, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits,
+    void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
@@ -769,7 +754,6 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
         h->T.tp_groups = h->T.tp_levels == 3 ? (nb + 15) / 16 : 1;
         if ((rc = dalloc(h, &h->fat, rows * nb * 8))) return rc;
         if (h->T.tp_levels >= 2) { if ((rc = dalloc(h, &h->pv, rows * h->T.tp_groups * 16))) return rc; }
-        if (h->T.tp_levels == 3 && getenv("AMDP_TP_PV8")) { if ((rc = dalloc(h, &h->pv8, rows * h->T.tp_groups * 16))) return rc; }
         if (h->T.tp_levels == 3) { if ((rc = dalloc(h, &h->top, rows * 16))) return rc; }
         if (!mdp) {
             h->T.o_blocks = (c.no_pad + 7) / 8;
@@ -811,7 +795,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     E.task = h->env_task; E.faults = h->faults; E.counters = h->counters; E.n_envs = c.n_envs; E.env_id_base = c.env_id_base;
     E.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
     Tables& T = h->T;
-    T.fat = h->fat; T.pv = h->pv; T.top = h->top; T.pv8 = h->pv8; T.ofat = h->ofat;
+    T.fat = h->fat; T.pv = h->pv; T.top = h->top; T.ofat = h->ofat;
     T.cdf = h->cdf; T.payload = h->payload; T.sketch = h->sketch; T.pivot = h->pivot; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
     T.obs_cdf = h->obs_cdf; T.max_ceil = h->max_ceil; T.tflags = h->tflags; T.raw_t = h->raw_t; T.n_real = h->n_real; T.tbits = h->tbits;
     T.n_pad = c.n_pad; T.na = c.na; T.no_pad = c.no_pad; T.d_o = c.n_obs_tok; T.d_a = c.n_act_tok; T.s0_pad = c.s0_pad;
@@ -844,7 +828,6 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
                                                   h->fat ? h->fat + (size_t)t0 * c.n_pad * c.na * h->T.tp_blocks * 8 : nullptr,
                                                   h->pv ? h->pv + (size_t)t0 * c.n_pad * c.na * h->T.tp_groups * 16 : nullptr,
                                                   h->top ? h->top + (size_t)t0 * c.n_pad * c.na * 16 : nullptr,
-                                                  h->pv8 ? h->pv8 + (size_t)t0 * c.n_pad * c.na * h->T.tp_groups * 16 : nullptr,
                                                   h->T.tp_blocks, h->T.tp_groups, h->T.tp_obs_bits, status_out);
     k_build_small<<<nblk(cnt, 128), 128, 0, st>>>(cnt, c.n_pad, c.s0_pad, state_mapping, n_real, is_terminal, s0_idx, s0_prob,
                                                   n_s0, max_steps, ns, h->sinfo + t0 * c.n_pad, h->s0_cdf + t0 * c.s0_pad,
@@ -1156,10 +1139,12 @@ static int rollout_host_impl(amdp* h, int K, int chunk, const void* actions_host
     cudaStream_t s_in = h->st_stream[0], s_k = h->st_stream[1], s_out = h->st_stream[2];
     const size_t N = (size_t)c.n_envs;
     const size_t act_bytes = packed ? 1 : sizeof(int32_t);
-    int i = 0;
-    for (int k0 = 0; k0 < K; k0 += chunk, ++i) {
+    // the first chunk is a quarter of the others: nothing overlaps its kernel, so it sets the depth of the pipeline
+    int i = 0, kc = 0;
+    for (int k0 = 0; k0 < K; k0 += kc, ++i) {
         const int b = i & 1;
-        const int kc = (K - k0 < chunk) ? (K - k0) : chunk;
+        kc = (i == 0 && K > chunk && chunk >= 4) ? chunk / 4 : chunk;
+        if (K - k0 < kc) kc = K - k0;
         // buffer b is free once the copy-out of chunk i-2 has finished
         if (i >= 2) { CK(cudaStreamWaitEvent(s_in, h->st_ev_out[b], 0)); CK(cudaStreamWaitEvent(s_k, h->st_ev_out[b], 0)); }
         if (actions_host) {

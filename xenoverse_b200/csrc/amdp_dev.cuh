@@ -42,9 +42,6 @@ struct Tables {
                               //   block needs in ONE DRAM line and TWO sector requests (codes + observation + flag; payload)
     const uint16_t* pv;       // [T][n_pad][na][tp_groups][16] code15 of the LAST entry of each block of a group of 16; pad 0x7bff
     const uint16_t* top;      // [T][n_pad][na][16] code15 of the last entry of each group (three-level rows only)
-    const uint8_t*  pv8;      // three-level rows: [T][n_pad][na][tp_groups][16] code8_rel of the LAST entry of each block of a group,
-                              // relative to the group's code range (its neighbours in `top`); pad 255.  Half the bytes of 16-bit
-                              // pivots: 128 B per 1024-state row, so that this level stays L2-resident next to `top`
     int tp_levels, tp_groups, tp_blocks;
     int tp_obs_bits;          // bits of state_mapping carried in the code words (bit_length(max ns - 1) <= 15)
     const uint32_t* ofat;     // POMDP (do = 1): [T][n_pad][8 + 8 * o_blocks] words per observation row: 16 pivots (code15 of the last
@@ -119,15 +116,6 @@ __device__ __forceinline__ uint32_t code15_from_m21(uint32_t m21) {      // m21 
 }
 __device__ __forceinline__ uint32_t code15(double x) {
     return x >= 1.0 ? 0x7bffu : code15_from_m21((uint32_t)floor(x * 2097152.0));
-}
-
-// 8-bit code of a 15-bit code x15 inside a group whose codes lie in (lo15, hi15]: monotone in x15 and computed by the same
-// IEEE operations when the table is built and when it is searched, so  code8(c) < code8(u) => c < u  (equality is undecided and
-// resolved on the block below, like every other level).  Requires lo15 <= x15 <= hi15.
-__device__ __forceinline__ uint32_t code8_rel(uint32_t x15, uint32_t lo15, uint32_t hi15) {
-    const float s = __frcp_rn(__uint2float_rn(hi15 - lo15 + 1u));
-    const uint32_t q = __float2uint_rz(__fmul_rn(__uint2float_rn((x15 - lo15) << 8), s));
-    return q < 255u ? q : 255u;
 }
 
 // Source of the draws of one (env, tick): injected matrix row or Philox.

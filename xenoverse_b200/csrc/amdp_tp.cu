@@ -219,38 +219,10 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
             };
             int blk = 0;
             if (LEVELS == 3) {
-                // second level: the 16 block pivots of group g, 8 bits each, relative to the group's code range (lo15, hi15]
+                // second level: the 16 block pivots of group g
                 const int g = min(count16(), n_groups - 1);
-#ifdef AMDP_TP_PV8
-                uint4 p8[1];
-                ldg_words_keep<1>(T.pv8 + ((size_t)row * (unsigned)n_groups + (unsigned)g) * 16u, p8, pol_keep);
-                // in the shadow of that load: the group's range from the pivots in registers, and the code of u inside it
-                auto pick16 = [&](int idx) {                       // halfword idx of the 16 pivots (a tree of selects)
-                    const int wi = idx >> 1;
-                    const unsigned a0 = (wi & 1) ? lv[0].y : lv[0].x, a1 = (wi & 1) ? lv[0].w : lv[0].z;
-                    const unsigned a2 = (wi & 1) ? lv[1].y : lv[1].x, a3 = (wi & 1) ? lv[1].w : lv[1].z;
-                    const unsigned c0 = (wi & 2) ? a1 : a0, c1 = (wi & 2) ? a3 : a2;
-                    const unsigned d = (wi & 4) ? c1 : c0;
-                    return (idx & 1) ? (d >> 16) : (d & 0xffffu);
-                };
-                const uint32_t hi15 = pick16(g), lo15 = g ? pick16(g - 1) : 0x3ffu;
-                const unsigned vq2 = (0x0400u + code8_rel(v15, lo15, hi15)) * 0x00010001u;
-                int acc = 0;
-                const unsigned pw[4] = {p8[0].x, p8[0].y, p8[0].z, p8[0].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {                      // bytes widened to normal fp16 patterns 0x0400 + b
-                    acc = h2_count_lt(__byte_perm(pw[i], 0x04040404u, 0x4140), vq2, acc);
-                    acc = h2_count_lt(__byte_perm(pw[i], 0x04040404u, 0x4342), vq2, acc);
-                }
-                blk = min(g * 16 - acc, n_blocks - 1);
-#else
-#ifdef AMDP_TP_PV_NOKEEP
-                ldg_words<2>(T.pv + (row * (unsigned)n_groups + (unsigned)g) * 16u, lv);
-#else
                 ldg_words_keep<2>(T.pv + (row * (unsigned)n_groups + (unsigned)g) * 16u, lv, pol_keep);
-#endif
                 blk = min(g * 16 + count16(), n_blocks - 1);
-#endif
             }
             if (LEVELS == 2) blk = min(count16(), n_blocks - 1);
             // code31(u) << 1; cmask = 0xfffffffe drops the is_terminal bit of the entries (tests coarsen it further to
