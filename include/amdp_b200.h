@@ -28,7 +28,8 @@
  *     3 reset-observation uniform (token k < do)     anymdp_env.py:153,157 under reset()
  *     4 reward standard normal z  (token k < da)     anymdp_env.py:105
  *     5 uniform-random-policy action (token k < da)  (caller side in the reference)
- *     6,7 spare
+ *     6 exploration uniform of a device-side behaviour policy (token 0): (word3 >> 8) * 2^-24 of the kinds-4/5 block
+ *     7 spare
  * Slots come from Philox4x32-10 with counter (env_lo, block | env_hi << 16, tick_lo, tick_hi),
  * key (seed_lo, seed_hi); block b yields slots 2b (words 0,1) and 2b+1 (words 2,3) as 53-bit
  * doubles ((w0 >> 5) * 2^26 + (w1 >> 6)) / 2^53 — numpy's MT19937 double construction — except the
@@ -86,6 +87,7 @@ extern "C" {
 #define AMDP_SLOT_RESET_OBS  3
 #define AMDP_SLOT_Z          4
 #define AMDP_SLOT_ACTION     5
+#define AMDP_SLOT_EXPLORE    6
 
 typedef struct amdp amdp_t;
 
@@ -243,6 +245,13 @@ int amdp_get_mapped_state(amdp_t* h, int32_t* out, void* stream);
 /* Synchronises `stream`, returns the OR of AMDP_FAULT_* bits raised since the last poll in
  * *faults (HOST) and clears them. */
 int amdp_poll_errors(amdp_t* h, uint32_t* faults, void* stream);
+
+/* Device-side behaviour policy for rollouts and steps WITHOUT caller actions (replaces the Python loop
+ * `a = solver.policy(...); env.step(a)` of the reference's data collection, anymdp_solver_opt.py:41-51 with da == 1):
+ *     action = policy[task][inner state]   unless   (exploration draw, slot 6) < epsilon, then the uniform-random action (slot 5).
+ * policy: uint8 [n_tasks][n_pad] (device; e.g. argmax over the value matrix of AnyMDPSolverOpt), every entry < na — else
+ * AMDP_EINVAL; the handle keeps a copy.  NULL switches back to the uniform random policy.  Synchronises `stream`. */
+int amdp_set_policy(amdp_t* h, const uint8_t* policy, float epsilon, void* stream);
 
 /* Debug/verification: copy the built CDF row of (task, s, a) to out double [n_pad] (device). */
 int amdp_debug_cdf_row(amdp_t* h, int64_t task, int32_t s, int32_t a, double* out, void* stream);

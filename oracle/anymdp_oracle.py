@@ -39,6 +39,7 @@ SLOT_OBS = 2         # uniform for observation token k after the step           
 SLOT_RESET_OBS = 3   # uniform for observation token k after an (auto-)reset     (k < do)
 SLOT_Z = 4           # standard normal for the reward of action token k          (k < da)
 SLOT_ACTION = 5      # action of token k under the built-in uniform random policy (k < da)
+SLOT_EXPLORE = 6     # uniform (24 bit) of the epsilon-greedy choice of a device-side behaviour policy (k = 0)
 SLOT_SPARE0 = 6
 SLOT_SPARE1 = 7
 SLOTS_PER_TOKEN = 8
@@ -259,6 +260,16 @@ class OracleVecEnv:
         self.sum_length = numpy.zeros(self.N, dtype=numpy.int64)
         self.min_return = numpy.full(self.N, numpy.inf)
         self.max_return = numpy.full(self.N, -numpy.inf)
+        self.policy, self.epsilon = None, 0.0
+
+    def set_policy(self, policy, epsilon=0.0):
+        """Behaviour policy for `step(None, U)`: action = policy[task][inner state], except that with probability
+        `epsilon` (U[:, SLOT_EXPLORE] < epsilon) the uniform-random action of SLOT_ACTION is taken.  `policy` is a list of
+        per-task integer arrays indexed by INNER state, e.g. argmax(value_matrix, axis=1) of the reference's
+        AnyMDPSolverOpt (anymdp_solver_opt.py:41-46 with da == 1); None switches back to the uniform random policy."""
+        assert policy is None or self.da == 1
+        self.policy = None if policy is None else [numpy.asarray(p, dtype=numpy.int64) for p in policy]
+        self.epsilon = float(numpy.float32(epsilon))
 
     def _obs_array(self, obs):
         return numpy.asarray(obs, dtype=numpy.int64).reshape(self.N, -1)
@@ -302,7 +313,9 @@ class OracleVecEnv:
             "action": numpy.zeros((N, self.da), dtype=numpy.int64),
         }
         for i, e in enumerate(self.envs):
-            if actions is None:
+            if actions is None and self.policy is not None and not U[i, SLOT_EXPLORE] < self.epsilon:
+                act = numpy.array([int(self.policy[self.env_task[i]][e._state if getattr(e, "_state", None) is not None else 0])])
+            elif actions is None:
                 act = numpy.array([int(U[i, SLOT_ACTION + SLOTS_PER_TOKEN * k]) for k in range(self.da)])
             else:
                 act = numpy.asarray(actions[i]).reshape(-1)

@@ -80,4 +80,18 @@ def load_case(name):
 
 
 def list_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("policy_"))
+
+
+def list_policy_cases():
+    """Cases of tests/golden/make_policy_golden.py: the reference's optimal-solver policy driving its env."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("policy_"))
+
+
+def load_policy_case(name):
+    with numpy.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False) as z:
+        d = {k: z[k] for k in z.files}
+    tasks = unpack_tasks(d)
+    return {"tasks": tasks, "env_task": d["env_task"], "U": d["U"], "obs0": d["obs0"],
+            "value_matrix": [d[f"vm{t}"] for t in range(len(tasks))],
+            "out": {k[len("out_"):]: v for k, v in d.items() if k.startswith("out_")}}

@@ -1,0 +1,95 @@
+"""Device-side behaviour policies (amdp_set_policy) on the GPU, through the C ABI."""
+import numpy
+import pytest
+import torch
+
+import _golden_io as gio
+from oracle import anymdp_oracle as ao
+
+pytestmark = pytest.mark.gpu
+RTOL = ATOL = 1e-6        # rewards: fp32 payload vs the reference's float64 (BASELINE.json north_star)
+
+
+def _greedy(vm):
+    return numpy.argmax(vm, axis=1)
+
+
+@pytest.mark.parametrize("name", gio.list_policy_cases())
+def test_golden_reference_solver_loop_on_gpu(name):
+    """The reference's `a = AnyMDPSolverOpt.policy(); env.step(a)` loop, recorded from the live reference with injected
+    draws, reproduced by the engine with the policy table on the device and NO caller actions."""
+    from _engine_adapter import EngineVecEnv
+    c = gio.load_policy_case(name)
+    G = EngineVecEnv(c["tasks"], env_task=c["env_task"], autoreset="same_step")
+    n_pad = G.eng.geo["n_pad"]
+    tab = numpy.zeros((len(c["tasks"]), n_pad), dtype=numpy.uint8)
+    for t, vm in enumerate(c["value_matrix"]):
+        tab[t, :vm.shape[0]] = _greedy(vm)
+    G.eng.set_policy(tab, 0.0)
+    assert numpy.array_equal(G.reset(c["U"][0])[:, 0], numpy.asarray(c["obs0"]).reshape(-1))
+    for k in range(c["U"].shape[0] - 1):
+        o = G.step(None, c["U"][k + 1])
+        for key in ("obs", "state", "action", "terminated", "truncated"):
+            want = c["out"][key][k]
+            assert numpy.array_equal(numpy.asarray(o[key]).reshape(want.shape), want), (k, key)
+        for key in ("reward", "reward_gt"):
+            assert numpy.allclose(o[key], c["out"][key][k], rtol=RTOL, atol=ATOL), (k, key)
+    assert G.faults() == 0
+
+
+@pytest.mark.parametrize("ns,na,N,eps,mode,search", [
+    (16, 5, 200, 0.25, "same_step", "auto"), (32, 4, 96, 0.0, "next_step", "auto"), (64, 8, 130, 0.1, "same_step", "auto"),
+    (128, 5, 257, 0.3, "same_step", "auto"), (128, 5, 64, 1.0, "same_step", "warp_v1"), (40, 3, 100, 0.5, "same_step", "thread"),
+    (256, 3, 40, 0.05, "same_step", "thread"), (1000, 2, 24, 0.2, "next_step", "thread")])
+def test_policy_rollout_replays_through_oracle(ns, na, N, eps, mode, search):
+    """Self-RNG rollouts under an epsilon-greedy table policy (whatever kernel the engine picks): the dumped draws,
+    replayed through the CPU oracle with the same table, give the same actions, observations, flags and rewards."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    tasks = [synth_task(ns, na, 2100 + t) for t in range(4)]
+    if ns >= 200:
+        for t in tasks:
+            t["max_steps"] = 45
+    rng = numpy.random.default_rng(ns + na)
+    pol = [rng.integers(0, na, ns) for _ in tasks]
+    K = 60 if ns >= 200 else 150
+    env = AnyMDPVecEnv(N, seed=61, autoreset=mode, search=search)
+    env.set_task(tasks)
+    env.set_policy(pol, epsilon=eps)
+    obs0, _ = env.reset()
+    tr = env.rollout(K, policy="device", record=("obs", "action", "reward", "done"))
+    env.check()
+    draws = env.engine.dump_draws(0, K + 1).cpu().numpy()
+    orc = ao.OracleVecEnv(tasks, env_task=numpy.arange(N) % len(tasks), autoreset=mode)
+    orc.set_policy(pol, epsilon=eps)
+    assert numpy.array_equal(obs0.cpu().numpy(), orc.reset(draws[0])[:, 0])
+    n_table = 0
+    for k in range(K):
+        o = orc.step(None, draws[k + 1])
+        assert numpy.array_equal(tr["action"][k].cpu().numpy(), o["action"]), k
+        assert numpy.array_equal(tr["obs"][k].cpu().numpy(), o["obs"]), k
+        d = tr["done"][k].cpu().numpy()
+        assert numpy.array_equal((d & 1).astype(bool), o["terminated"]) and numpy.array_equal((d >> 1).astype(bool), o["truncated"])
+        assert numpy.allclose(tr["reward"][k].cpu().numpy(), o["reward"], rtol=RTOL, atol=ATOL)
+        n_table += int(numpy.sum(draws[k + 1][:, ao.SLOT_EXPLORE] >= numpy.float32(eps)))
+    if eps < 1.0:
+        assert n_table > 0
+    assert env.episode_stats()["episodes"] == orc.stats()["episodes"]
+    # back to the uniform random policy
+    env.set_policy(None)
+    tr2 = env.rollout(5, record=("action",))
+    d2 = env.engine.dump_draws(K + 1, 5).cpu().numpy()
+    assert numpy.array_equal(tr2["action"].cpu().numpy()[..., 0], d2[:, :, ao.SLOT_ACTION].astype(numpy.int64))
+
+
+def test_policy_argument_errors():
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv, AMDPError
+    env = AnyMDPVecEnv(8)
+    env.set_task([synth_task(16, 5, 1)])
+    with pytest.raises(AssertionError):
+        env.set_policy([numpy.full(16, 5)])
+    with pytest.raises(AMDPError):
+        env.engine.set_policy(torch.full((1, 16), 7, dtype=torch.uint8), 0.0)
+    with pytest.raises(AMDPError):
+        env.engine.set_policy(torch.zeros((1, 16), dtype=torch.uint8), 1.5)
+    with pytest.raises(ValueError):
+        env.engine.set_policy(torch.zeros((2, 16), dtype=torch.uint8), 0.0)

@@ -12,6 +12,7 @@ from .vec_env import AnyMDPVecEnv  # noqa: F401
 from .task_sampler import (AnyMDPTaskSampler, AnyPOMDPTaskSampler, MultiTokensAnyPOMDPTaskSampler,  # noqa: F401
                            GarnetTaskSampler)
 from .synth import synth_task, synth_packed, synth_geometry, packed_to_task  # noqa: F401
+from .solvers import greedy_policy, value_iteration, optimal_policy  # noqa: F401
 
 __version__ = "0.1.0"
 

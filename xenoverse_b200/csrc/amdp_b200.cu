@@ -107,7 +107,9 @@ __device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, lo
         int a_pol = 0;
         zs[k] = 0.0;
         if (!act_in || stepping) D.z_action(k, T.na, zs[k], a_pol);
-        const int a = act_in ? (active ? act_in[k] : 0) : a_pol;
+        int a = act_in ? (active ? act_in[k] : 0) : a_pol;
+        // device-side behaviour policy (da == 1): the table action of the env's inner state unless the tick explores
+        if (!act_in && T.policy && active && !D.explore(T.eps_thr, T.eps)) a = (int)T.policy[t * T.n_pad + R.state];
         act_used[k] = a;
         if (stepping && (a < 0 || a >= T.na)) fault |= AMDP_FAULT_BAD_ACTION;          // anymdp_env.py:97
     }
@@ -570,7 +572,11 @@ __global__ void k_dump_draws(EnvArrays E, unsigned long long tick0, int K, int n
     const long long k = i / ((long long)blocks * E.n_envs);
     double* o = out + (k * E.n_envs + e) * n_slots + 2 * b;
     const int kind = (2 * b) % AMDP_SLOTS_PER_TOKEN;
-    if (kind == 6) { o[0] = 0.0; o[1] = 0.0; return; }
+    if (kind == 6) {                                               // exploration uniform: word 3 of the z / action block
+        const uint4 wz = philox_block(E.env_id_base + (unsigned long long)e, (uint32_t)(b - 1), tick0 + (unsigned long long)k, E.key);
+        o[0] = (double)(wz.w >> 8) * 5.9604644775390625e-08; o[1] = 0.0;
+        return;
+    }
     const uint4 w = philox_block(E.env_id_base + (unsigned long long)e, (uint32_t)b, tick0 + (unsigned long long)k, E.key);
     if (kind == AMDP_SLOT_Z) { o[0] = (double)box_muller(w.x, w.y); o[1] = (double)__umulhi(w.z, (uint32_t)na); }
     else { o[0] = u53(w.x, w.y); o[1] = u53(w.z, w.w); }
@@ -613,6 +619,7 @@ struct amdp {
     // owned device memory
     double* cdf; float2* payload; uint16_t* sketch; uint16_t* pivot; int32_t* sinfo; double* s0_cdf; int32_t* s0_idx; double* obs_cdf;
     int32_t* max_ceil; uint8_t* tflags; double* raw_t; int32_t* n_real; uint32_t* tbits;
+    uint8_t* policy;       // copy of the behaviour-policy table (amdp_set_policy) or null
     int32_t* env_task;
     Stat6* stat_part;
     unsigned int* stat_ticket;
@@ -697,7 +704,7 @@ static int pick_group(int n_pad) {
 extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits,
+    void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits, h->policy,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
@@ -775,7 +782,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     if ((rc = dalloc(h, &h->tbits, (size_t)c.n_tasks * h->T.tb_words))) return rc;
     if ((rc = dalloc(h, &h->env_task, (size_t)c.n_envs))) return rc;
     if ((rc = dalloc(h, &h->stat_part, (size_t)STAT_BLOCKS))) return rc;
-    if ((rc = dalloc(h, &h->stat_ticket, 1))) return rc;
+    if ((rc = dalloc(h, &h->stat_ticket, 2))) return rc;          // [1]: scratch flag of amdp_set_policy
     if ((rc = dalloc(h, &h->faults, 1))) return rc;
     if ((rc = dalloc(h, &h->counters, 4))) return rc;
     EnvArrays& E = h->E;
@@ -926,7 +933,8 @@ extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const 
                      (h->cfg.task_type != AMDP_MDP && h->cfg.no_pad > (1 << 20))))
         return fail(h, AMDP_EINVAL, "packed records need do == da == 1, at most 2^20 observations and 1024 actions");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fast = (h->cfg.task_type == AMDP_MDP || (h->tp && h->cfg.task_type == AMDP_POMDP)) && !u_inject && !h->force_generic;
+    const bool policy_ok = !h->T.policy || actions;               // (kernels without policy support: the generic one runs)
+    const bool fast = (h->cfg.task_type == AMDP_MDP || (h->tp && h->cfg.task_type == AMDP_POMDP)) && !u_inject && !h->force_generic && policy_ok;
     if (fast) {
         launch_rollout_fast(h, K, actions, J, st);
     } else {
@@ -995,6 +1003,39 @@ extern "C" int amdp_get_tick(const amdp_t* h, uint64_t* tick) {
 extern "C" int amdp_set_tick(amdp_t* h, uint64_t tick) {
     if (!h) return AMDP_EINVAL;
     h->tick = tick;
+    return AMDP_OK;
+}
+
+__global__ void k_check_policy(const uint8_t* __restrict__ policy, long long n, int na, unsigned int* __restrict__ bad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && policy[i] >= na) atomicOr(bad, 1u);
+}
+
+extern "C" int amdp_set_policy(amdp_t* h, const uint8_t* policy, float epsilon, void* stream) {
+    if (!h) return AMDP_EINVAL;
+    const amdp_config& c = h->cfg;
+    CK(cudaSetDevice(c.device));
+    if (!policy) { h->T.policy = nullptr; h->T.eps_thr = 0; h->T.eps = 0.f; return AMDP_OK; }
+    if (c.n_act_tok != 1) return fail(h, AMDP_EINVAL, "device-side policies need one action token (da == 1)");
+    if (c.na > 256) return fail(h, AMDP_EINVAL, "device-side policies need na <= 256");
+    if (!(epsilon >= 0.f && epsilon <= 1.f)) return fail(h, AMDP_EINVAL, "epsilon must lie in [0, 1]");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)c.n_tasks * c.n_pad;
+    int rc;
+    if (!h->policy) { if ((rc = dalloc(h, &h->policy, n))) return rc; }
+    // out-of-range table entries are an argument error, checked here once instead of on every tick
+    unsigned int* bad = h->stat_ticket + 1;
+    CK(cudaMemsetAsync(bad, 0, sizeof(unsigned int), st));
+    k_check_policy<<<nblk((long long)n, 256), 256, 0, st>>>(policy, (long long)n, c.na, bad);
+    unsigned int hb = 0;
+    CK(cudaMemcpyAsync(&hb, bad, sizeof(hb), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->policy, policy, n, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    h->launches += 1;
+    if (hb) return fail(h, AMDP_EINVAL, "policy table holds an action >= na");
+    h->T.policy = h->policy;
+    h->T.eps = epsilon;
+    h->T.eps_thr = (uint32_t)ceil((double)epsilon * 16777216.0);
     return AMDP_OK;
 }
 

@@ -48,6 +48,11 @@ struct Tables {
                               // entry of each 8-entry block; pad 0x7bff), then o_blocks x 8 codes (floor(cdf * 2^31) << 1)
     int o_blocks;
     int n_pad, na, no_pad, d_o, d_a, s0_pad, task_type, autoreset;
+    // device-side behaviour policy (amdp_set_policy): action = policy[task][inner state] unless the 24-bit
+    // exploration draw of the tick is below eps_thr (then the uniform-random action of the tick); null = uniform random
+    const uint8_t* policy;    // [T][n_pad]
+    uint32_t eps_thr;         // ceil(epsilon * 2^24)
+    float eps;
 };
 
 struct EnvArrays {
@@ -128,6 +133,11 @@ struct Draws {
         const uint4 w = philox_block(env, (uint32_t)block, tick, key);
         a = u53(w.x, w.y);
         b = u53(w.z, w.w);
+    }
+    // epsilon-greedy choice of the behaviour policy (slot 6 of token 0): 24 bits of word 3 of the z / action block
+    __device__ __forceinline__ bool explore(uint32_t eps_thr, float eps) const {
+        if (row) return row[AMDP_SLOT_EXPLORE] < (double)eps;
+        return (philox_block(env, (uint32_t)(AMDP_SLOT_Z >> 1), tick, key).w >> 8) < eps_thr;
     }
     __device__ __forceinline__ void z_action(int tok, int na, double& z, int& act) const {  // slots 4,5 of token
         const int s = AMDP_SLOT_Z + AMDP_SLOTS_PER_TOKEN * tok;

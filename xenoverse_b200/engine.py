@@ -216,6 +216,18 @@ class Engine:
         self._ck(lib.amdp_debug_counters(self._h, out))
         return {"exact_fallbacks": int(out[0])}
 
+    def set_policy(self, policy, epsilon=0.0):
+        """Device-side behaviour policy for rollouts / steps without caller actions: uint8 [T, n_pad] (action of every
+        inner state of every task) or None for the uniform random policy; `epsilon` = probability of a random action."""
+        with torch.cuda.device(self.device):
+            if policy is None:
+                self._ck(lib.amdp_set_policy(self._h, None, 0.0, _stream()))
+                return
+            p = self._dev(policy, torch.uint8)
+            if tuple(p.shape) != (self.T, self.geo["n_pad"]):
+                raise ValueError(f"policy must have shape {(self.T, self.geo['n_pad'])}, got {tuple(p.shape)}")
+            self._ck(lib.amdp_set_policy(self._h, _ptr(p), float(epsilon), _stream()))
+
     def set_seed(self, seed):
         self._ck(lib.amdp_set_seed(self._h, int(seed) & (2 ** 64 - 1)))
 

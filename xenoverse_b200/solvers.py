@@ -1,0 +1,44 @@
+"""Host-side helpers for the device-side behaviour policies.
+
+The reference collects data with a Python loop `a = solver.policy(...); env.step(a)` around one env
+(anymdp_solver_opt.py:41-51, test_utils.py:42-60).  Here the policy is a per-task table indexed by the INNER state,
+uploaded once with `AnyMDPVecEnv.set_policy`, and evaluated inside the rollout kernels.  The table of the reference's
+optimal solver is `greedy_policy(AnyMDPSolverOpt(env).value_matrix)`; `value_iteration` restates its solver for callers
+that do not have the reference installed.
+"""
+import numpy
+
+
+def greedy_policy(value_matrix):
+    """argmax over actions, first maximum wins (numpy.argmax, as anymdp_solver_opt.py:45 / anymdp_solver_q.py:54)."""
+    return numpy.argmax(numpy.asarray(value_matrix), axis=1).astype(numpy.uint8)
+
+
+def value_iteration(task, gamma=0.99, tol=1.0e-4, max_sweeps=10000):
+    """Q-values [n, na] of a task dict by the reference's damped in-place sweeps (solver.py:57-80, is_greedy=True):
+    every (s, a) is updated in place from the current matrix, `alpha` decays 1.0 -> 0.5 by 0.8 per sweep, and the
+    iteration stops when the RMS change of a sweep is <= 1e-4.  (The sum over next states is a numpy dot instead of
+    the reference's sequential loop: values agree to rounding.)"""
+    t_mat = numpy.asarray(task["transition"], dtype=numpy.float64)
+    r_mat = numpy.asarray(task["reward"], dtype=numpy.float64)
+    n, na, _ = r_mat.shape
+    er = (t_mat * r_mat).sum(axis=2)                 # expected immediate reward of (s, a)
+    vm = numpy.zeros((n, na))
+    vmax = vm.max(axis=1)
+    alpha, diff, sweeps = 1.0, 1.0, 0
+    while diff > tol and sweeps < max_sweeps:
+        sweeps += 1
+        old = vm.copy()
+        for s in range(n):
+            for a in range(na):
+                exp_q = er[s, a] + gamma * float(t_mat[s, a] @ vmax)
+                vm[s, a] += alpha * (exp_q - vm[s, a])
+                vmax[s] = vm[s].max()                # later (s, a) of the same sweep see the update
+        diff = float(numpy.sqrt(numpy.mean((old - vm) ** 2)))
+        alpha = max(0.80 * alpha, 0.50)
+    return vm
+
+
+def optimal_policy(task, gamma=0.99):
+    """uint8 [n]: the greedy policy of `value_iteration` (what AnyMDPSolverOpt.policy() plays from inner state s)."""
+    return greedy_policy(value_iteration(task, gamma))

@@ -120,6 +120,27 @@ class AnyMDPVecEnv:
         """Raise the reference's exception for any per-env fault recorded since the last check (synchronises)."""
         raise_faults(self.engine.poll_errors())
 
+    # ---- device-side behaviour policy ------------------------------------------------------------
+    def set_policy(self, policy, epsilon=0.0):
+        """Behaviour policy of `rollout()` / `step(None)`: a list with one integer array per task (action of every INNER
+        state, e.g. `solvers.greedy_policy(AnyMDPSolverOpt(env).value_matrix)`), a [T, n_pad] array, or None for the
+        uniform random policy.  With probability `epsilon` a tick plays the uniform random action instead
+        (anymdp_solver_opt.py:41-51 is epsilon = 0)."""
+        self._require_task()
+        if policy is None:
+            self.engine.set_policy(None)
+            return
+        n_pad = self.geo["n_pad"]
+        if isinstance(policy, (list, tuple)):
+            tab = numpy.zeros((len(policy), n_pad), dtype=numpy.uint8)
+            for i, p in enumerate(policy):
+                p = numpy.asarray(p)
+                if p.min(initial=0) < 0 or p.max(initial=0) >= self.na:
+                    raise AssertionError(f"policy of task {i} holds an action outside [0, {self.na})")
+                tab[i, :len(p)] = p
+            policy = tab
+        self.engine.set_policy(policy, epsilon)
+
     # ---- K steps per launch ---------------------------------------------------------------------
     def rollout(self, K, actions=None, policy="uniform", record=("obs", "action", "reward", "done"), u_inject=None,
                 out=None):
@@ -127,8 +148,8 @@ class AnyMDPVecEnv:
         actions int tensor [K, N(, da)] or None with policy="uniform".  Returns a dict of [K, N(, w)]
         tensors for the requested fields (`done`: bit0 terminated, bit1 truncated)."""
         self._require_task()
-        if actions is None and policy != "uniform":
-            raise ValueError("policy must be 'uniform' when no actions are given")
+        if actions is None and policy not in ("uniform", "device"):
+            raise ValueError("without actions the policy is 'uniform' or the table given to set_policy ('device')")
         if actions is not None and isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8:
             a = actions.to(self.device).reshape(K, self.num_envs, self.da).contiguous()
         else:
