@@ -159,7 +159,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def quick_measure(name, envs, tasks, ns, na, no, ticks, steps, dev, local, search="auto"):
+def table_policy(env, tasks, n_pad, na, dev, epsilon):
+    """A synthetic behaviour-policy table (uniform random action per inner state, fixed seed) on the device: the rollout
+    kernels then play policy[task][state] with probability 1 - epsilon (amdp_set_policy)."""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    env.engine.set_policy(torch.randint(0, na, (tasks, n_pad), dtype=torch.uint8, device=dev, generator=g), epsilon)
+
+
+def quick_measure(name, envs, tasks, ns, na, no, ticks, steps, dev, local, search="auto", epsilon=None):
     """Device-timed rollouts of another workload on this GPU (same method as the headline: CUDA events around `steps`
     launches after 3 warm-ups, tables >> L2) — reported under "other_workloads", never as the headline value."""
     import torch
@@ -170,6 +179,8 @@ def quick_measure(name, envs, tasks, ns, na, no, ticks, steps, dev, local, searc
     chunk = max(1, min(tasks, (768 << 20) // per_task))
     env.set_task(None, packed=(geo, tasks, ((t0, synth_packed(ns, na, min(chunk, tasks - t0), seed=1000 + t0, device=dev, no=no))
                                             for t0 in range(0, tasks, chunk))))
+    if epsilon is not None:
+        table_policy(env, tasks, geo["n_pad"], na, dev, epsilon)
     env.reset()
     traj = {"obs": torch.empty((ticks, envs, 1), dtype=torch.int32, device=dev),
             "action": torch.empty((ticks, envs, 1), dtype=torch.int32, device=dev),
@@ -186,7 +197,10 @@ def quick_measure(name, envs, tasks, ns, na, no, ticks, steps, dev, local, searc
     torch.cuda.synchronize()
     env.check()
     ms = t0.elapsed_time(t1) / steps
-    out = {"workload": describe(name, envs, tasks, ns, na, no, ticks), "value": envs * ticks / (ms * 1e-3), "unit": "env-steps/s",
+    wl = describe(name, envs, tasks, ns, na, no, ticks)
+    if epsilon is not None:
+        wl = wl.replace("uniform random policy", f"device-side table policy, epsilon = {epsilon}")
+    out = {"workload": wl, "value": envs * ticks / (ms * 1e-3), "unit": "env-steps/s",
            "ms_per_launch": ms, "kernel": env.engine.rollout_kernel, "table_bytes": env.engine.device_bytes,
            "algorithmic_bytes_per_env_step": b_alg(ns, no)}
     env.close()
@@ -233,6 +247,8 @@ def run_b200(args, name, envs, tasks, ns, na, no):
     env.set_task(None, packed=(geo, tasks, batches()))
     torch.cuda.synchronize()
     t_up = time.time() - t_up
+    if args.policy == "table":
+        table_policy(env, tasks, geo["n_pad"], na, dev, args.epsilon)
     env.reset()
     N = envs
     traj = {"obs": torch.empty((ticks, N, 1), dtype=torch.int32, device=dev),
@@ -335,10 +351,13 @@ def run_b200(args, name, envs, tasks, ns, na, no):
         others = {}
         for key, (wl, n_envs, n_tasks, tk) in {"cfg2_x65536_envs": ("cfg2", 65536, 4096, 128), "cfg3": ("cfg3", 65536, 4096, 64),
                                                "cfg4_32_tasks": ("cfg4", 65536, 32, 64), "cfg4_32_tasks_x131072_envs": ("cfg4", 131072, 32, 64),
-                                               "cfg5": ("cfg5", 131072, 131072, 128)}.items():
+                                               "cfg5": ("cfg5", 131072, 131072, 128),
+                                               # the same workloads driven by a device-side behaviour policy
+                                               "cfg2_table_policy": ("cfg2", 4096, 4096, 512), "cfg5_table_policy": ("cfg5", 131072, 131072, 128)}.items():
             _, _, o_ns, o_na, o_no = WORKLOADS[wl]
             try:
-                others[key] = quick_measure(wl, n_envs, n_tasks, o_ns, o_na, o_no, tk, 10, dev, local)
+                others[key] = quick_measure(wl, n_envs, n_tasks, o_ns, o_na, o_no, tk, 10, dev, local,
+                                            epsilon=0.1 if key.endswith("_table_policy") else None)
             except Exception as ex:           # never lose the headline line to an extra
                 others[key] = {"error": str(ex)[:200]}
     else:
@@ -363,7 +382,9 @@ def run_b200(args, name, envs, tasks, ns, na, no):
             "metric": "AnyMDP env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": describe(name, envs, tasks, ns, na, no, ticks), "envs_per_gpu": N, "tasks_per_gpu": tasks,
+            "config": {"workload": describe(name, envs, tasks, ns, na, no, ticks) if args.policy == "uniform" else
+                       describe(name, envs, tasks, ns, na, no, ticks).replace("uniform random policy", f"device-side table policy, epsilon = {args.epsilon}"),
+                       "envs_per_gpu": N, "tasks_per_gpu": tasks,
                        "ticks_per_step": ticks, "table_bytes_per_gpu": device_bytes,
                        "l2": "inputs larger than L2 (tables >> 126 MB; no flush needed)" if device_bytes > (1 << 30)
                              else "tables may be L2 resident", "parallelism": f"env-sharded dp{world}",
@@ -402,6 +423,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other workloads (N = 1 only)")
     ap.add_argument("--ref-steps-per-worker", type=int, default=20000)
+    ap.add_argument("--policy", default="uniform", choices=["uniform", "table"],
+                    help="behaviour policy of the device rollouts: the engine's uniform random one (BASELINE.json) or a table (amdp_set_policy)")
+    ap.add_argument("--epsilon", type=float, default=0.1)
     ap.add_argument("--search", default="auto", choices=["auto", "one_level", "two_level", "thread", "warp", "warp_v1"],
                     help="row-search / kernel selection of the engine (see Engine)")
     args = ap.parse_args()

@@ -933,7 +933,7 @@ extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const 
                      (h->cfg.task_type != AMDP_MDP && h->cfg.no_pad > (1 << 20))))
         return fail(h, AMDP_EINVAL, "packed records need do == da == 1, at most 2^20 observations and 1024 actions");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool policy_ok = !h->T.policy || actions;               // (kernels without policy support: the generic one runs)
+    const bool policy_ok = !h->T.policy || actions || h->tp || h->wv2;   // (k_rollout_mdp has no table policy: the generic kernel runs)
     const bool fast = (h->cfg.task_type == AMDP_MDP || (h->tp && h->cfg.task_type == AMDP_POMDP)) && !u_inject && !h->force_generic && policy_ok;
     if (fast) {
         launch_rollout_fast(h, K, actions, J, st);

@@ -20,13 +20,15 @@
 //     -> next pivots; payload and state word of tick k are consumed in the shadow of tick k+1's loads.
 //   * LEVELS = 1 (n_pad <= 8), 2 (<= 128) or 3 (<= 2048).
 // ------------------------------------------------------------------------------------------------
-template <int LEVELS, int MINB, bool GIVEN, bool POMDP>
+// ACT: where the actions come from: 0 the engine's uniform random policy, 1 the caller (`actions`), 2 the behaviour-policy
+// table of amdp_set_policy (policy[task][inner state], epsilon-greedy; one L1-resident byte load at the top of a tick).
+template <int LEVELS, int MINB, int ACT, bool POMDP>
 __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
                                                        const int32_t* __restrict__ actions, const amdp_traj J, int next, unsigned cmask) {
     // GIVEN is a template parameter on purpose: with a runtime flag the (predicated-off) action load still owns a
     // scoreboard slot, which ptxas shares with the deferred payload / state-word loads, and the first use of the action at
     // the top of a tick then waits for those loads BEFORE the tick's first search load is issued (ncu: +15 % time).
-    constexpr bool given = GIVEN;
+    constexpr bool given = ACT == 1, table = ACT == 2;
     __shared__ double sh_stat[4][TP_TPB];                         // closed-episode statistics: sum_ret, sum_ret_sq, min, max
     __shared__ unsigned long long sh_cnt[2][TP_TPB];              // ep_count, sum_len
     __shared__ double sh_s0c[TP_S0][TP_TPB];                         // the env's start-state CDF and states (s0_pad <= TP_S0):
@@ -71,7 +73,11 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
         for (int k = 0; k < K; ++k) {
             int a;
             if (given) a = load_action(actions, (long long)k * N + e, J.actions_u8);
-            else a = (int)__umulhi(philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key).z, (uint32_t)na);
+            else {
+                const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key);
+                a = (int)__umulhi(w2.z, (uint32_t)na);
+                if (table && !((w2.w >> 8) < T.eps_thr)) a = (int)T.policy[t * n_pad + s];
+            }
             write_rec(k, 0, a, 0, 0.f, 0.f);
         }
         atomicOr(E.faults, fault);
@@ -94,7 +100,8 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
     // draws of one tick: words 0..3 of Philox block 0 (transition uniform = w.x, w.y; reset uniform = w.z, w.w), the reward
     // normal and the action (given or uniform random policy)
     // POMDP: also block 1 = (observation uniform, reset-observation uniform)           anymdp_env.py:153 under step / reset
-    struct Draw { uint32_t wx, wy, wz, ww; float z; int a; uint32_t ox, oy, rx, ry; };
+    struct Draw { uint32_t wx, wy, wz, ww; float z; int a; uint32_t ox, oy, rx, ry; bool ex; };
+    const uint8_t* __restrict__ pol_t = table ? T.policy + t * n_pad : nullptr;
     auto draw = [&](int k) {
         Draw d;
         const unsigned long long tk = tick0 + (unsigned long long)k;
@@ -108,6 +115,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
         } else { d.ox = d.oy = d.rx = d.ry = 0; }
         if (given) d.a = (k < K) ? load_action(actions, (long long)k * N + e, J.actions_u8) : 0;
         else d.a = (int)__umulhi(w2.z, (uint32_t)na);
+        d.ex = !table || (w2.w >> 8) < T.eps_thr;                  // the tick plays the uniform random action
         return d;
     };
     Draw cur = draw(0);
@@ -186,6 +194,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
     };
     for (int k = 0; k < K; ++k) {
         const bool pend = next && (flags & FLAG_PENDING);          // next_step mode: this tick only performs the reset
+        if (table && !cur.ex) cur.a = (int)__ldg(pol_t + s);       // behaviour policy: the table action of the inner state
         const bool a_ok = !given || (unsigned)cur.a < (unsigned)na;
         const bool valid = !pend && a_ok;
         if (given && !pend && !a_ok) fault |= AMDP_FAULT_BAD_ACTION;                          // :97
@@ -331,12 +340,16 @@ static void launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, boo
     // AMDP_TP_MINB=lo selects the large one for experiments.  The POMDP variant carries the observation search as well.
     bool hi = !pomdp;                                 // (the POMDP variant spills at 72 registers)
     if (const char* o = getenv("AMDP_TP_MINB")) hi = (o[0] == 'h');
-#define TP_LAUNCH(MINB, GIVEN, POMDP) k_rollout_tp<LEVELS, MINB, GIVEN, POMDP><<<blocks, TP_TPB, 0, st>>>(T, E, tick, K, actions, J, next, cmask)
+#define TP_LAUNCH(MINB, ACT, POMDP) k_rollout_tp<LEVELS, MINB, ACT, POMDP><<<blocks, TP_TPB, 0, st>>>(T, E, tick, K, actions, J, next, cmask)
+    if (!actions && T.policy) {                       // table policy: one register budget per task type
+        if (pomdp) TP_LAUNCH(TP_MINB_LO, 2, true); else TP_LAUNCH(TP_MINB_HI, 2, false);
+        return;
+    }
     if (pomdp) {
-        if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, true, true); else TP_LAUNCH(TP_MINB_LO, true, true); }
-        else { if (hi) TP_LAUNCH(TP_MINB_HI, false, true); else TP_LAUNCH(TP_MINB_LO, false, true); }
-    } else if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, true, false); else TP_LAUNCH(TP_MINB_LO, true, false); }
-    else { if (hi) TP_LAUNCH(TP_MINB_HI, false, false); else TP_LAUNCH(TP_MINB_LO, false, false); }
+        if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, 1, true); else TP_LAUNCH(TP_MINB_LO, 1, true); }
+        else { if (hi) TP_LAUNCH(TP_MINB_HI, 0, true); else TP_LAUNCH(TP_MINB_LO, 0, true); }
+    } else if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, 1, false); else TP_LAUNCH(TP_MINB_LO, 1, false); }
+    else { if (hi) TP_LAUNCH(TP_MINB_HI, 0, false); else TP_LAUNCH(TP_MINB_LO, 0, false); }
 #undef TP_LAUNCH
 }
 

@@ -56,9 +56,15 @@ __device__ __forceinline__ float2 ldg_f32x2_hint(const float2* p, uint64_t pol) 
     return v;
 }
 
-template <int EPL, bool GIVEN>
+// ACT: where the actions come from: 0 the engine's uniform random policy, 1 the caller (`actions`), 2 the behaviour-policy
+// table of amdp_set_policy.  The table costs the chain one select and one IMAD: the lane that owns the next state also owns
+// its table action (a register with the actions of the lane's own entries) and sends it along in the REDUX operand; the
+// action after a reset and the explore / exploit choice are made with the draws.
+template <int EPL, int ACT>
 __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
                                                       const int32_t* __restrict__ actions, const amdp_traj J) {
+    constexpr bool GIVEN = ACT == 1, TABLE = ACT == 2;
+    constexpr int ISH = TABLE ? 13 : 5;                           // where the state index sits in the REDUX operand
     constexpr int NW = EPL / 2;                                   // 32-bit words of filter codes per lane
     constexpr int N_PAD = 32 * EPL;
     constexpr unsigned ROW_BYTES = 2u * N_PAD;
@@ -85,6 +91,13 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
     // is_terminal of this lane's own EPL entries (ns < 2: every state terminates, anymdp_env.py:108)
     unsigned myterm = (T.tbits[t * T.tb_words + ((lane * EPL) >> 5)] >> ((lane * EPL) & 31)) & ((1u << EPL) - 1u);
     if (always_term) myterm = (1u << EPL) - 1u;
+    // table actions of this lane's own entries, 8 bits each
+    const uint8_t* __restrict__ pol_t = TABLE ? T.policy + t * N_PAD : nullptr;
+    unsigned long long mypol = 0;
+    if (TABLE) {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) mypol |= (unsigned long long)pol_t[lane * EPL + i] << (8 * i);
+    }
 
     int s = E.state[e], steps = E.steps[e];
     const int flags = E.flags[e];
@@ -120,7 +133,11 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
             int a = 0;
             if (k < K) {
                 if (GIVEN) a = load_action(actions, (long long)k * N + e, J.actions_u8);
-                else a = (int)__umulhi(philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key).z, (uint32_t)na);
+                else {
+                    const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick0 + (unsigned long long)k, E.key);
+                    a = (int)__umulhi(w2.z, (uint32_t)na);
+                    if (TABLE && !((w2.w >> 8) < T.eps_thr)) a = (int)pol_t[s];
+                }
             }
             st_ad = a & 0x0fffffff;
             flush(kb, min(32, K - kb));
@@ -151,7 +168,8 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
     };
 
     // Draws of one tick, packed: bits 0-14 code15(u_transition), 15-22 action (engine policy), 23-30 the state a reset in
-    // this tick leads to, 31 given action out of range.  Lane L of a batch holds tick kb + L + 1.
+    // this tick leads to, 31 given action out of range.  Lane L of a batch holds tick kb + L + 1.  With a policy table `act`
+    // holds: bits 0-7 the table action of that reset state, bit 8 the tick explores (plays the uniform random action).
     unsigned b_pk = 0;
     float b_z = 0.f;
     int b_act = 0;
@@ -168,6 +186,7 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
         } else {
             act = 0;
             pk |= __umulhi(w2.z, (uint32_t)na) << 15;
+            if (TABLE) act = (int)pol_t[pk >> 23] | (((w2.w >> 8) < T.eps_thr) ? 0x100 : 0);
         }
     };
     unsigned pk;
@@ -177,6 +196,7 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
     make(lane + 1, b_pk, b_z, b_act);
     if (GIVEN && (pk >> 31)) fault |= AMDP_FAULT_BAD_ACTION;                                  // :97
     int a = GIVEN ? ((pk >> 31) ? 0 : a_raw) : (int)((pk >> 15) & 0xffu);
+    if (TABLE && !(a_raw & 0x100)) a = (int)pol_t[s];
     unsigned sa = (unsigned)(s * na + a);                         // row (s, a) inside the task
     unsigned v2 = (pk & 0x7fffu) * 0x00010001u;
     // What is in flight between two ticks: the filter row of tick k, and the payload / state word of tick k - 1 (settled
@@ -217,7 +237,7 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_norm));
 #endif
     // loop-invariant pieces of the REDUX operand, kept in registers (ptxas would re-derive them from %tid every tick)
-    unsigned lane_base32 = (unsigned)(lane * EPL) << 5;
+    unsigned lane_base32 = (unsigned)(lane * EPL) << ISH;
     unsigned myterm16 = myterm << 4;
     asm volatile("" : "+r"(lane_base32), "+r"(myterm16));
     const float2* pay_row = pay_t + (unsigned long long)sa * N_PAD;   // payload row of (s, a)
@@ -228,9 +248,11 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
         const unsigned npk = __shfl_sync(FULL, b_pk, j);
         const float nz = __shfl_sync(FULL, b_z, j);
         int na_raw = 0;
-        if (GIVEN) na_raw = __shfl_sync(FULL, b_act, j);
-        const int n_a = GIVEN ? ((npk >> 31) ? 0 : na_raw) : (int)((npk >> 15) & 0xffu);
-        const char* nbase = sk_lane + (unsigned)n_a * ROW_BYTES;
+        if (GIVEN || TABLE) na_raw = __shfl_sync(FULL, b_act, j);
+        int n_a = GIVEN ? ((npk >> 31) ? 0 : na_raw) : (int)((npk >> 15) & 0xffu);
+        // table policy: the next action if this tick ends the episode (the table action of the reset state, or the random one)
+        const int n_a_reset = (na_raw & 0x100) ? n_a : (a_raw & 0xff);
+        const char* nbase = TABLE ? sk_lane : sk_lane + (unsigned)n_a * ROW_BYTES;
         asm volatile("" : "+l"(nbase));                           // one IMAD.WIDE from the next row address
         const unsigned nv2 = (npk & 0x7fffu) * 0x00010001u;
         const bool valid = !GIVEN || !(pk >> 31);                 // a tick with a bad action does not step
@@ -244,15 +266,22 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
 #pragma unroll
         for (int i = 0; i < NW; ++i) { lt = h2_count_lt_pos(cur.q.w[i], v2, lt); le = h2_count_lt_pos(cur.q.w[i], v2le, le); }
         // (index of the first entry not below u) << 5 | is_terminal[it] << 4 | entries sharing u's code (undecided)
-        unsigned val = lane_base32 + ((unsigned)lt << 5) + (unsigned)(le - lt) + ((myterm16 >> lt) & 16u);
+        unsigned val = lane_base32 + ((unsigned)lt << ISH) + (unsigned)(le - lt) + ((myterm16 >> lt) & 16u);
+        if (TABLE) val += ((unsigned)(mypol >> ((8 * lt) & 63)) & 0xffu) << 5;   // ... | table action of that entry << 5
         if (lt == EPL) val = FULL;                                // all below: the boundary is in a later lane
         unsigned r = __reduce_min_sync(FULL, val);
         unsigned nxt, s_next;
         auto advance = [&]() {
-            nxt = r >> 5;
+            nxt = r >> ISH;
             const bool done = ((r | trunc16) & 16u) != 0;         // anymdp_env.py:108,114
             s_next = done ? sreset : nxt;                         // same-step auto-reset (anymdp_env.py:81-90)
             if (GIVEN && !valid) s_next = (unsigned)s;
+            if (TABLE) {
+                const int a_table = (na_raw & 0x100) ? (int)((npk >> 15) & 0xffu) : (int)((r >> 5) & 0xffu);
+                n_a = done ? n_a_reset : a_table;
+            }
+            const unsigned long long roff = TABLE ? (unsigned long long)(s_next * (unsigned)na + (unsigned)n_a) * ROW_BYTES
+                                                  : (unsigned long long)(s_next * (unsigned long long)srow);
             // payload (reward, noise) of (s, a, s') (anymdp_env.py:103-104), the next row, the state word of the observation
             // (anymdp_env.py:145-148; after a reset: of the start state).  Issued together: ptxas puts loads of one kind on
             // one barrier, and a payload load issued later than the row would make the chain wait for it.
@@ -262,9 +291,9 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
             nxf.pay = ldg_stream_f32x2(pay_row + nxt);
 #endif
 #if AMDP_W_HINT & 2
-            nxf.q = ldg_row_hint<NW>(nbase + (unsigned long long)(s_next * (unsigned long long)srow), done ? pol_keep : pol_norm);
+            nxf.q = ldg_row_hint<NW>(nbase + roff, done ? pol_keep : pol_norm);
 #else
-            nxf.q = ldg_row<NW>(nbase + (unsigned long long)(s_next * (unsigned long long)srow));
+            nxf.q = ldg_row<NW>(nbase + roff);
 #endif
             nxf.si = __ldg(sinfo_t + s_next);
         };
@@ -283,7 +312,8 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
             cnt = min(cnt, N_PAD - 1);
-            r = ((unsigned)cnt << 5) | ((sinfo_t[cnt] < 0 || always_term) ? 16u : 0u);
+            r = ((unsigned)cnt << ISH) | ((sinfo_t[cnt] < 0 || always_term) ? 16u : 0u);
+            if (TABLE) r |= (unsigned)pol_t[cnt] << 5;
             n_fallback += 1;
             advance();
         }
@@ -329,8 +359,9 @@ __global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvA
 void amdp_launch_w(const Tables& T, const EnvArrays& E, long long n_envs, unsigned long long tick, int K, const int32_t* actions,
                    const amdp_traj& J, cudaStream_t st) {
     const unsigned int blocks = nblk(n_envs, 4);
-#define WV2(epl) { if (actions) k_rollout_w<epl, true><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); \
-                   else k_rollout_w<epl, false><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); }
+#define WV2(epl) { if (actions) k_rollout_w<epl, 1><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); \
+                   else if (T.policy) k_rollout_w<epl, 2><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); \
+                   else k_rollout_w<epl, 0><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); }
     if (T.n_pad == 64) WV2(2) else if (T.n_pad == 128) WV2(4) else WV2(8)
 #undef WV2
 }
