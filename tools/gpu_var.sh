@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_gpu_var.sh "<bench args>" name1 name2 ...   (name "base" = the in-tree library)
+# usage: tools/gpu_var.sh "<bench args>" name1 name2 ...   (name "base" = the in-tree library)
 mkdir -p gpurun_out
 args=$1; shift
 for v in "$@"; do

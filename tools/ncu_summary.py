@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep: key raw metrics + the hottest SASS lines of the loop body.
-usage: tools_ncu_summary.py <report.ncu-rep> [ticks_per_launch*warps]"""
+usage: tools/ncu_summary.py <report.ncu-rep> [ticks_per_launch*warps]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
 per = float(sys.argv[2]) if len(sys.argv) > 2 else None
