@@ -610,6 +610,10 @@ __global__ void k_transition_gt(Tables T, EnvArrays E, const int32_t* __restrict
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// staging sets of the host-buffer rollouts: with four the rollout kernels run up to three chunks ahead of the device-to-host
+// copies, so the copy engine never waits for a kernel (with two, every cross-stream hand-over was a bubble on the PCIe link)
+#define ST_NBUF 4
+
 struct amdp {
     amdp_config cfg;
     int n_slots;
@@ -640,10 +644,10 @@ struct amdp {
     char err[512];
     char kname[64];
     // rollout_host staging
-    int32_t* st_act[2]; int32_t* st_obs[2]; float* st_rew[2]; uint8_t* st_done[2]; unsigned long long* st_rec[2];
+    int32_t* st_act[ST_NBUF]; int32_t* st_obs[ST_NBUF]; float* st_rew[ST_NBUF]; uint8_t* st_done[ST_NBUF]; unsigned long long* st_rec[ST_NBUF];
     int st_chunk;
     cudaStream_t st_stream[3];
-    cudaEvent_t st_ev_in[2], st_ev_k[2], st_ev_out[2];
+    cudaEvent_t st_ev_in[ST_NBUF], st_ev_k[ST_NBUF], st_ev_out[ST_NBUF];
     bool st_ready;
 };
 
@@ -707,12 +711,15 @@ extern "C" int amdp_destroy(amdp_t* h) {
     void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits, h->policy,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
-                    h->st_act[0], h->st_act[1], h->st_obs[0], h->st_obs[1], h->st_rew[0], h->st_rew[1],
-                    h->st_done[0], h->st_done[1], h->st_rec[0], h->st_rec[1]};
+                    };
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < ST_NBUF; ++i) {
+        void* st[] = {h->st_act[i], h->st_obs[i], h->st_rew[i], h->st_done[i], h->st_rec[i]};
+        for (void* p : st) if (p) cudaFree(p);
+    }
     if (h->st_ready) {
         for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->st_stream[i]);
-        for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->st_ev_in[i]); cudaEventDestroy(h->st_ev_k[i]); cudaEventDestroy(h->st_ev_out[i]); }
+        for (int i = 0; i < ST_NBUF; ++i) { cudaEventDestroy(h->st_ev_in[i]); cudaEventDestroy(h->st_ev_k[i]); cudaEventDestroy(h->st_ev_out[i]); }
     }
     delete h;
     return AMDP_OK;
@@ -1140,13 +1147,13 @@ static int staging_init(amdp* h, int chunk) {
     const amdp_config& c = h->cfg;
     if (h->st_ready && h->st_chunk >= chunk) return AMDP_OK;
     if (h->st_ready) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < ST_NBUF; ++i) {
             cudaFree(h->st_act[i]); cudaFree(h->st_obs[i]); cudaFree(h->st_rew[i]); cudaFree(h->st_done[i]); cudaFree(h->st_rec[i]);
             h->st_act[i] = nullptr; h->st_obs[i] = nullptr; h->st_rew[i] = nullptr; h->st_done[i] = nullptr; h->st_rec[i] = nullptr;
         }
     } else {
         for (int i = 0; i < 3; ++i) CK(cudaStreamCreateWithFlags(&h->st_stream[i], cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < ST_NBUF; ++i) {
             CK(cudaEventCreateWithFlags(&h->st_ev_in[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->st_ev_k[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->st_ev_out[i], cudaEventDisableTiming));
@@ -1155,7 +1162,7 @@ static int staging_init(amdp* h, int chunk) {
     }
     const size_t per = (size_t)chunk * c.n_envs;
     int rc;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ST_NBUF; ++i) {
         if ((rc = dalloc(h, &h->st_act[i], per * c.n_act_tok))) return rc;
         if ((rc = dalloc(h, &h->st_obs[i], per * c.n_obs_tok))) return rc;
         if ((rc = dalloc(h, &h->st_rew[i], per))) return rc;
@@ -1167,7 +1174,8 @@ static int staging_init(amdp* h, int chunk) {
 }
 
 // actions in / trajectory out through pinned host memory, `chunk` ticks at a time on three streams (copy-in, kernel,
-// copy-out) with two staging buffers, so that PCIe traffic in both directions overlaps the rollout kernel.
+// copy-out) with ST_NBUF staging sets, so that PCIe traffic in both directions overlaps the rollout kernels and the
+// device-to-host link (the bound of this path: 8 bytes per env-step) never waits for a kernel.
 static int rollout_host_impl(amdp* h, int K, int chunk, const void* actions_host, bool packed, int32_t* obs_host,
                              float* reward_host, uint8_t* done_host, unsigned long long* rec_host) {
     if (!h || K < 1) return AMDP_EINVAL;
@@ -1183,11 +1191,11 @@ static int rollout_host_impl(amdp* h, int K, int chunk, const void* actions_host
     // the first chunk is a quarter of the others: nothing overlaps its kernel, so it sets the depth of the pipeline
     int i = 0, kc = 0;
     for (int k0 = 0; k0 < K; k0 += kc, ++i) {
-        const int b = i & 1;
+        const int b = i % ST_NBUF;
         kc = (i == 0 && K > chunk && chunk >= 4) ? chunk / 4 : chunk;
         if (K - k0 < kc) kc = K - k0;
-        // buffer b is free once the copy-out of chunk i-2 has finished
-        if (i >= 2) { CK(cudaStreamWaitEvent(s_in, h->st_ev_out[b], 0)); CK(cudaStreamWaitEvent(s_k, h->st_ev_out[b], 0)); }
+        // set b is free once the copy-out of chunk i - ST_NBUF has finished
+        if (i >= ST_NBUF) { CK(cudaStreamWaitEvent(s_in, h->st_ev_out[b], 0)); CK(cudaStreamWaitEvent(s_k, h->st_ev_out[b], 0)); }
         if (actions_host) {
             CK(cudaMemcpyAsync(h->st_act[b], (const char*)actions_host + (size_t)k0 * N * c.n_act_tok * act_bytes,
                                act_bytes * kc * N * c.n_act_tok, cudaMemcpyHostToDevice, s_in));
