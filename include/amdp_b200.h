@@ -253,6 +253,14 @@ int amdp_poll_errors(amdp_t* h, uint32_t* faults, void* stream);
  * AMDP_EINVAL; the handle keeps a copy.  NULL switches back to the uniform random policy.  Synchronises `stream`. */
 int amdp_set_policy(amdp_t* h, const uint8_t* policy, float epsilon, void* stream);
 
+/* Batched value iteration over the resident tables (the reference's update_value_matrix(is_greedy=True),
+ * solver.py:57-80, as used by AnyMDPSolverOpt, anymdp_solver_opt.py:32-36 — here as synchronous sweeps over ALL tasks of
+ * the handle at once, stopped when max |dQ| <= tol or after max_sweeps):  q_out double [n_tasks][n_pad][na] (device, or NULL),
+ * policy_out uint8 [n_tasks][n_pad] = first argmax_a Q (device, or NULL; the table amdp_set_policy takes), sweeps_out HOST
+ * int32 (or NULL).  Rows of terminal and padding states are 0.  Synchronises `stream` every 8 sweeps. */
+int amdp_value_iteration(amdp_t* h, double gamma, double tol, int32_t max_sweeps, double* q_out, uint8_t* policy_out,
+                         int32_t* sweeps_out, void* stream);
+
 /* Debug/verification: copy the built CDF row of (task, s, a) to out double [n_pad] (device). */
 int amdp_debug_cdf_row(amdp_t* h, int64_t task, int32_t s, int32_t a, double* out, void* stream);
 

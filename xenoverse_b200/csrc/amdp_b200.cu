@@ -624,6 +624,7 @@ struct amdp {
     double* cdf; float2* payload; uint16_t* sketch; uint16_t* pivot; int32_t* sinfo; double* s0_cdf; int32_t* s0_idx; double* obs_cdf;
     int32_t* max_ceil; uint8_t* tflags; double* raw_t; int32_t* n_real; uint32_t* tbits;
     uint8_t* policy;       // copy of the behaviour-policy table (amdp_set_policy) or null
+    double* vi_q; double* vi_v; double* vi_er; unsigned long long* vi_diff;   // amdp_value_iteration work space
     int32_t* env_task;
     Stat6* stat_part;
     unsigned int* stat_ticket;
@@ -708,7 +709,7 @@ static int pick_group(int n_pad) {
 extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits, h->policy,
+    void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits, h->policy, h->vi_q, h->vi_v, h->vi_er, h->vi_diff,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     };
@@ -1043,6 +1044,32 @@ extern "C" int amdp_set_policy(amdp_t* h, const uint8_t* policy, float epsilon, 
     h->T.policy = h->policy;
     h->T.eps = epsilon;
     h->T.eps_thr = (uint32_t)ceil((double)epsilon * 16777216.0);
+    return AMDP_OK;
+}
+
+extern "C" int amdp_value_iteration(amdp_t* h, double gamma, double tol, int32_t max_sweeps, double* q_out, uint8_t* policy_out,
+                                    int32_t* sweeps_out, void* stream) {
+    if (!h || max_sweeps < 1 || !(gamma >= 0.0 && gamma < 1.0) || !(tol >= 0.0)) return AMDP_EINVAL;
+    if (!h->uploaded) return fail(h, AMDP_ESTATE, "value_iteration before upload_tasks");
+    const amdp_config& c = h->cfg;
+    if (c.n_act_tok != 1) return fail(h, AMDP_EINVAL, "value iteration needs one action token (da == 1)");
+    CK(cudaSetDevice(c.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t states = (size_t)c.n_tasks * c.n_pad, rows = states * c.na;
+    int rc;
+    if (!h->vi_q) {
+        if ((rc = dalloc(h, &h->vi_q, rows))) return rc;
+        if ((rc = dalloc(h, &h->vi_v, states))) return rc;
+        if ((rc = dalloc(h, &h->vi_er, rows))) return rc;
+        if ((rc = dalloc(h, &h->vi_diff, 1))) return rc;
+    }
+    int sweeps = 0;
+    long long launches = 0;
+    if (amdp_vi_run(h->T, c.n_tasks, gamma, tol, max_sweeps, h->vi_q, h->vi_v, h->vi_er, h->vi_diff, policy_out, &sweeps, &launches, st))
+        return fail(h, AMDP_ECUDA, "value iteration failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->launches += launches;
+    if (q_out) CK(cudaMemcpyAsync(q_out, h->vi_q, sizeof(double) * rows, cudaMemcpyDeviceToDevice, st));
+    if (sweeps_out) *sweeps_out = sweeps;
     return AMDP_OK;
 }
 

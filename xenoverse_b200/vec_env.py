@@ -141,6 +141,16 @@ class AnyMDPVecEnv:
             policy = tab
         self.engine.set_policy(policy, epsilon)
 
+    def solve_policy(self, gamma=0.99, tol=1.0e-4, max_sweeps=10000, epsilon=None):
+        """Greedy policy of every resident task by batched value iteration on the GPU (what AnyMDPSolverOpt computes per
+        env on the CPU, anymdp_solver_opt.py:32-36).  Returns (Q, policy, sweeps); with `epsilon` given the policy also
+        becomes the behaviour policy of the following rollouts."""
+        self._require_task()
+        q, pol, sweeps = self.engine.value_iteration(gamma, tol, max_sweeps)
+        if epsilon is not None:
+            self.engine.set_policy(pol, epsilon)
+        return q, pol, sweeps
+
     # ---- K steps per launch ---------------------------------------------------------------------
     def rollout(self, K, actions=None, policy="uniform", record=("obs", "action", "reward", "done"), u_inject=None,
                 out=None):
