@@ -209,6 +209,34 @@ def quick_measure(name, envs, tasks, ns, na, no, ticks, steps, dev, local, searc
     return out
 
 
+def measure_vi(name, tasks, ns, na, dev, local, sweeps=64):
+    """Batched value iteration (amdp_value_iteration) over `tasks` resident synthetic tasks: a fixed
+    number of sweeps (tol = 0), device time; HBM roofline = the float64 CDF rows streamed once per sweep."""
+    import torch
+    from xenoverse_b200 import AnyMDPVecEnv, synth_packed, synth_geometry
+    geo = synth_geometry(ns, na, None)
+    env = AnyMDPVecEnv(64, device=local, seed=0, search="warp")
+    per_task = 3 * 8 * geo["n_pad"] * na * geo["n_pad"]
+    chunk = max(1, min(tasks, (768 << 20) // per_task))
+    env.set_task(None, packed=(geo, tasks, ((t0, synth_packed(ns, na, min(chunk, tasks - t0), seed=1000 + t0, device=dev))
+                                            for t0 in range(0, tasks, chunk))))
+    env.engine.value_iteration(0.99, 0.0, 8, want_q=False)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    _, _, done = env.engine.value_iteration(0.99, 0.0, sweeps, want_q=False)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    bytes_per_sweep = 8 * tasks * geo["n_pad"] * na * geo["n_pad"]
+    out = {"workload": f"{name}: value iteration, {tasks} tasks ns={ns} na={na}, {done} Jacobi sweeps (gamma 0.99, tol 0)",
+           "ms_per_sweep": ms / done, "task_sweeps_per_s": tasks * done / (ms * 1e-3), "kernel": "k_vi_sweep",
+           "algorithmic_bytes_per_sweep": bytes_per_sweep, "achieved_GBps": bytes_per_sweep * done / (ms * 1e-3) / 1e9}
+    env.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # the B200 arm
 # --------------------------------------------------------------------------------------------------
@@ -360,6 +388,12 @@ def run_b200(args, name, envs, tasks, ns, na, no):
                                             epsilon=0.1 if key.endswith("_table_policy") else None)
             except Exception as ex:           # never lose the headline line to an extra
                 others[key] = {"error": str(ex)[:200]}
+        for key, (wl, n_tasks) in {"value_iteration_cfg2": ("cfg2", 4096), "value_iteration_cfg5": ("cfg5", 131072)}.items():
+            _, _, o_ns, o_na, _ = WORKLOADS[wl]
+            try:
+                others[key] = measure_vi(wl, n_tasks, o_ns, o_na, dev, local)
+            except Exception as ex:
+                others[key] = {"error": str(ex)[:200]}
     else:
         device_bytes = env.engine.device_bytes
     if rank == 0:
@@ -401,6 +435,8 @@ def run_b200(args, name, envs, tasks, ns, na, no):
             for o in others.values():
                 if "value" in o:
                     o["roofline_frac"] = o["algorithmic_bytes_per_env_step"] * o["value"] / 1e9 / peak
+                if "achieved_GBps" in o:
+                    o["roofline_frac"] = o["achieved_GBps"] / peak
             line["other_workloads"] = others
         print(json.dumps(line), flush=True)
     if world > 1:

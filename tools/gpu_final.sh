@@ -13,6 +13,6 @@ for k,v in d['other_workloads'].items():
     print(k, '%.3e'%v['value'], v['kernel'], 'frac %.3f'%v['roofline_frac']) if 'value' in v else print(k, v)
 print(d['clocks'])
 PY
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other > gpurun_out/b_ncu.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other > gpurun_out/b_ncu.log 2>&1
 grep -c k_rollout gpurun_out/launches.csv
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 | cut -c1-400
