@@ -102,3 +102,32 @@ def test_invalid_tasks_rejected_at_set_task():
     bad["task_type"] = "XYZ"
     with pytest.raises(NotImplementedError):
         env.set_task(bad)
+
+
+@pytest.mark.gpu
+def test_trajectory_writer_shards_equal_device_rollout(tmp_path):
+    """TrajectoryWriter (pinned host records -> env-major .npy shards, worker thread) == one device rollout of the same
+    engine state."""
+    import json
+    import numpy
+    from xenoverse_b200 import AnyMDPVecEnv, TrajectoryWriter, load_shard, synth_task, optimal_policy
+    tasks = [synth_task(32, 5, 900 + t) for t in range(6)]
+    N, K = 200, 150
+
+    def fresh():
+        env = AnyMDPVecEnv(N, seed=9)
+        env.set_task(tasks)
+        env.set_policy([optimal_policy(t) for t in tasks], epsilon=0.2)
+        env.reset()
+        return env
+    ref = fresh().rollout(K, policy="device", record=("obs", "action", "reward", "done"))
+    env = fresh()
+    w = TrajectoryWriter(env, str(tmp_path / "data"), ticks_per_shard=64, chunk=20)
+    assert w.collect(K) == N * K
+    w.close(env_task=numpy.arange(N) % len(tasks))
+    man = json.load(open(tmp_path / "data" / "manifest.json"))
+    assert man["shards"] == 3 and man["num_envs"] == N
+    parts = [load_shard(str(tmp_path / "data" / f"shard_{i:05d}")) for i in range(3)]
+    for key, want in (("observations", ref["obs"][..., 0]), ("actions", ref["action"][..., 0]), ("rewards", ref["reward"]), ("dones", ref["done"])):
+        got = numpy.concatenate([p[key] for p in parts], axis=1)
+        assert numpy.array_equal(got, want.cpu().numpy().T), key

@@ -13,6 +13,7 @@ from .task_sampler import (AnyMDPTaskSampler, AnyPOMDPTaskSampler, MultiTokensAn
                            GarnetTaskSampler)
 from .synth import synth_task, synth_packed, synth_geometry, packed_to_task  # noqa: F401
 from .solvers import greedy_policy, value_iteration, optimal_policy  # noqa: F401
+from .writer import TrajectoryWriter, dump_task, load_task, load_shard, records_to_arrays  # noqa: F401
 
 __version__ = "0.1.0"
 
