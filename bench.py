@@ -209,6 +209,32 @@ def quick_measure(name, envs, tasks, ns, na, no, ticks, steps, dev, local, searc
     return out
 
 
+def measure_dropin(local, steps=4000):
+    """cfg1 (BASELINE.json configs[0]): the single-env gymnasium drop-in, `make("anymdp-v0")` -> set_task -> reset -> step
+    with a pre-drawn random policy; wall clock, every step a kernel launch and one read-back (API parity, not throughput)."""
+    import numpy
+    import xenoverse_b200 as xb
+    task = xb.synth_task(16, 5, 1000)
+    task["max_steps"] = 5000
+    env = xb.make("anymdp-v0", max_steps=5000, device=local, seed=0)
+    env.set_task(task)
+    acts = numpy.random.default_rng(0).integers(0, 5, steps)
+    env.reset()
+    for a in acts[:200]:
+        _, _, term, trunc, _ = env.step(int(a))
+        if term or trunc:
+            env.reset()
+    t0 = time.perf_counter()
+    for a in acts:
+        _, _, term, trunc, _ = env.step(int(a))
+        if term or trunc:
+            env.reset()
+    dt = time.perf_counter() - t0
+    env.close()
+    return {"workload": "cfg1: anymdp-v0 single env drop-in, ns=16 na=5, max_steps=5000, pre-drawn random policy, reset on done",
+            "value": steps / dt, "unit": "env-steps/s", "us_per_step": 1e6 * dt / steps, "kernel": "k_step<G=4>"}
+
+
 def measure_vi(name, tasks, ns, na, dev, local, sweeps=64):
     """Batched value iteration (amdp_value_iteration) over `tasks` resident synthetic tasks: a fixed
     number of sweeps (tol = 0), device time; HBM roofline = the float64 CDF rows streamed once per sweep."""
@@ -388,6 +414,10 @@ def run_b200(args, name, envs, tasks, ns, na, no):
                                             epsilon=0.1 if key.endswith("_table_policy") else None)
             except Exception as ex:           # never lose the headline line to an extra
                 others[key] = {"error": str(ex)[:200]}
+        try:
+            others["cfg1_single_env_dropin"] = measure_dropin(local)
+        except Exception as ex:
+            others["cfg1_single_env_dropin"] = {"error": str(ex)[:200]}
         for key, (wl, n_tasks) in {"value_iteration_cfg2": ("cfg2", 4096), "value_iteration_cfg5": ("cfg5", 131072)}.items():
             _, _, o_ns, o_na, _ = WORKLOADS[wl]
             try:
@@ -433,7 +463,7 @@ def run_b200(args, name, envs, tasks, ns, na, no):
         }
         if others:
             for o in others.values():
-                if "value" in o:
+                if "value" in o and "algorithmic_bytes_per_env_step" in o:
                     o["roofline_frac"] = o["algorithmic_bytes_per_env_step"] * o["value"] / 1e9 / peak
                 if "achieved_GBps" in o:
                     o["roofline_frac"] = o["achieved_GBps"] / peak

@@ -261,6 +261,18 @@ int amdp_set_policy(amdp_t* h, const uint8_t* policy, float epsilon, void* strea
 int amdp_value_iteration(amdp_t* h, double gamma, double tol, int32_t max_sweeps, double* q_out, uint8_t* policy_out,
                          int32_t* sweeps_out, void* stream);
 
+/* One whole reset / step per call from HOST memory, for engines driven one tick at a time by a Python loop (the single-env
+ * gymnasium drop-in: anymdp_env.py:81-90 / :112-132 become one library call each).  Both run on a stream owned by the
+ * handle and synchronise.  actions_host: int32 [n_envs][da].  result_host: int32 [n_envs][16] (pinned memory preferred):
+ * words 0-7 observation tokens, 8 reward (fp32 bits), 9 reward_gt (fp32 bits), 10 terminated, 11 truncated, 12 info["steps"],
+ * 13 inner state, 14 the engine's sticky fault word (AMDP_FAULT_*; cleared once reported), 15 zero; reset fills 0-7, 13, 14. */
+int amdp_reset_host(amdp_t* h, int32_t* result_host);
+int amdp_step_host(amdp_t* h, const int32_t* actions_host, int32_t* result_host);
+
+/* Asynchronous look at the sticky fault word: copies it (device to device, no synchronisation, not cleared) to out_dev, so
+ * that a caller that reads its results back anyway sees the faults in the same transfer (the single-env drop-in does). */
+int amdp_peek_errors(amdp_t* h, uint32_t* out_dev, void* stream);
+
 /* Debug/verification: copy the built CDF row of (task, s, a) to out double [n_pad] (device). */
 int amdp_debug_cdf_row(amdp_t* h, int64_t task, int32_t s, int32_t a, double* out, void* stream);
 

@@ -64,6 +64,9 @@ _SIGNATURES = {
     "amdp_set_state": (ctypes.c_int, [_P] * 6),
     "amdp_get_mapped_state": (ctypes.c_int, [_P, _P, _P]),
     "amdp_poll_errors": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32), _P]),
+    "amdp_peek_errors": (ctypes.c_int, [_P, _P, _P]),
+    "amdp_reset_host": (ctypes.c_int, [_P, _P]),
+    "amdp_step_host": (ctypes.c_int, [_P, _P, _P]),
     "amdp_debug_cdf_row": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P]),
     "amdp_debug_force_generic": (ctypes.c_int, [_P, ctypes.c_int]),
     "amdp_debug_tp_coarse_bits": (ctypes.c_int, [_P, ctypes.c_int]),

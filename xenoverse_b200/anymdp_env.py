@@ -11,12 +11,14 @@ Differences, all deliberate:
   * rows that numpy's choice() would reject at step time ("probabilities do not sum to 1") are
     rejected at `set_task`.
 """
+import ctypes
 import os
 
 import numpy
 import torch
 
 from . import _lib
+from ._lib import lib
 from .engine import Engine, task_geometry
 from .gym_compat import Env, spaces
 from .vec_env import raise_faults
@@ -73,8 +75,16 @@ class AnyMDPEnv(Env):
                 raise Exception(f"State {inter} is {self.s_0} and {self.s_e}")
             raise
         self._engine.assign(numpy.zeros(1, dtype=numpy.int32))
-        self._buf = self._engine.new_buffers()
-        self._act = torch.zeros((1, geo["da"]), dtype=torch.int32, device=self._engine.device)
+        # One library call per reset / step (amdp_reset_host / amdp_step_host): actions go in and a 16-word result record
+        # comes back through pinned host memory: words 0-7 obs, 8 reward, 9 reward_gt, 10 terminated, 11 truncated,
+        # 12 steps, 13 inner state, 14 fault word
+        self._res = torch.zeros(16, dtype=torch.int32).pin_memory()
+        self._hnp = self._res.numpy()
+        self._hf = self._hnp.view(numpy.float32)
+        self._act_host = torch.zeros(geo["da"], dtype=torch.int32).pin_memory()
+        self._anp = self._act_host.numpy()
+        self._p_res = ctypes.c_void_p(self._res.data_ptr())
+        self._p_act = ctypes.c_void_p(self._act_host.data_ptr())
         self._geo = geo
         self._gt = None
         self._last_obs = None
@@ -113,12 +123,19 @@ class AnyMDPEnv(Env):
         if seed is not None:
             self._engine.set_seed(seed)
             self._engine.tick = 0
-        self._engine.reset(self._buf["obs"])
+        self._engine._ck(lib.amdp_reset_host(self._engine._h, self._p_res))
         self.steps = 0
         self.need_reset = False
-        self._last_obs = self._obs_value(self._buf["obs"].cpu().numpy()[0])
-        self._state = int(self._engine.get_state()["state"][0])
+        h = self._check()
+        self._last_obs = self._obs_value(h[0:self._geo["do"]].copy())
         return self._last_obs, {"steps": self.steps}
+
+    def _check(self):
+        h = self._hnp
+        self._state = int(h[13])
+        if h[14]:
+            raise_faults(int(h[14]))
+        return h
 
     # anymdp_env.py:112-132 (+ single_step :92-110)
     def step(self, action):
@@ -132,18 +149,17 @@ class AnyMDPEnv(Env):
         for a in acts:
             assert a < self.na, f"Action {a} is out of range"
         assert len(acts) == self._geo["da"], f"Action {action} is out of range"
-        self._act.copy_(torch.tensor([acts], dtype=torch.int32))
-        b = self._buf
-        self._engine.step(self._act, b)
-        raise_faults(self._engine.poll_errors())
+        self._anp[:] = acts
+        self._engine._ck(lib.amdp_step_host(self._engine._h, self._p_act, self._p_res))
+        h = self._check()                                        # raises the engine's faults (:94, :96, :97)
         self.steps += 1
-        reward = float(b["reward"][0])
-        terminated = bool(b["terminated"][0])
-        truncated = bool(b["truncated"][0])
-        self._state = int(self._engine.get_state()["state"][0])
-        info = {"steps": self.steps, "reward_gt": float(b["reward_gt"][0])}
+        f = self._hf
+        reward = float(f[8])
+        terminated = bool(h[10] & 0xff)
+        truncated = bool(h[11] & 0xff)
+        info = {"steps": self.steps, "reward_gt": float(f[9])}
         info["transition_gt"] = self.transition_obs[self.state, action]      # :130 (post-transition state)
-        self._last_obs = self._obs_value(b["obs"].cpu().numpy()[0])
+        self._last_obs = self._obs_value(h[0:self._geo["do"]].copy())
         return self._last_obs, reward, terminated, truncated, info
 
     @property

@@ -625,6 +625,9 @@ struct amdp {
     int32_t* max_ceil; uint8_t* tflags; double* raw_t; int32_t* n_real; uint32_t* tbits;
     uint8_t* policy;       // copy of the behaviour-policy table (amdp_set_policy) or null
     double* vi_q; double* vi_v; double* vi_er; unsigned long long* vi_diff;   // amdp_value_iteration work space
+    // amdp_step_host / amdp_reset_host: device staging and the handle's own stream
+    int32_t* hs_act; int32_t* hs_obs; float* hs_rew; float* hs_rgt; uint8_t* hs_term; uint8_t* hs_trunc; int32_t* hs_steps; int32_t* hs_out;
+    cudaStream_t hs_stream;
     int32_t* env_task;
     Stat6* stat_part;
     unsigned int* stat_ticket;
@@ -710,6 +713,7 @@ extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
     void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits, h->policy, h->vi_q, h->vi_v, h->vi_er, h->vi_diff,
+                    h->hs_act, h->hs_obs, h->hs_rew, h->hs_rgt, h->hs_term, h->hs_trunc, h->hs_steps, h->hs_out,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
                     };
@@ -718,6 +722,7 @@ extern "C" int amdp_destroy(amdp_t* h) {
         void* st[] = {h->st_act[i], h->st_obs[i], h->st_rew[i], h->st_done[i], h->st_rec[i]};
         for (void* p : st) if (p) cudaFree(p);
     }
+    if (h->hs_stream) cudaStreamDestroy(h->hs_stream);
     if (h->st_ready) {
         for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->st_stream[i]);
         for (int i = 0; i < ST_NBUF; ++i) { cudaEventDestroy(h->st_ev_in[i]); cudaEventDestroy(h->st_ev_k[i]); cudaEventDestroy(h->st_ev_out[i]); }
@@ -1156,6 +1161,75 @@ extern "C" int amdp_poll_errors(amdp_t* h, uint32_t* faults, void* stream) {
     CK(cudaStreamSynchronize(st));
     if (v) CK(cudaMemsetAsync(h->faults, 0, sizeof(v), st));
     *faults = v;
+    return AMDP_OK;
+}
+
+// ---- whole step / reset in ONE call from host memory (the single-env gymnasium drop-in) ---------------------------------
+// result record per env: 16 words: 0-7 obs tokens, 8 reward (fp32 bits), 9 reward_gt, 10 terminated, 11 truncated, 12 steps,
+// 13 inner state, 14 sticky fault word of the engine, 15 zero
+__global__ void k_pack_result(EnvArrays E, int d_o, const int32_t* __restrict__ obs, const float* __restrict__ rew,
+                              const float* __restrict__ rgt, const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc,
+                              const int32_t* __restrict__ steps, int with_step, int32_t* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E.n_envs) return;
+    int32_t* o = out + e * 16;
+    for (int k = 0; k < 8; ++k) o[k] = k < d_o ? obs[e * d_o + k] : 0;
+    o[8] = with_step ? __float_as_int(rew[e]) : 0; o[9] = with_step ? __float_as_int(rgt[e]) : 0;
+    o[10] = with_step ? term[e] : 0; o[11] = with_step ? trunc[e] : 0; o[12] = with_step ? steps[e] : 0;
+    o[13] = E.state[e]; o[14] = (int32_t)*E.faults; o[15] = 0;
+}
+
+static int host_step_init(amdp* h) {
+    if (h->hs_stream) return AMDP_OK;
+    const amdp_config& c = h->cfg;
+    const size_t n = (size_t)c.n_envs;
+    int rc;
+    if ((rc = dalloc(h, &h->hs_act, n * c.n_act_tok))) return rc;
+    if ((rc = dalloc(h, &h->hs_obs, n * c.n_obs_tok))) return rc;
+    if ((rc = dalloc(h, &h->hs_rew, n))) return rc;
+    if ((rc = dalloc(h, &h->hs_rgt, n))) return rc;
+    if ((rc = dalloc(h, &h->hs_term, n))) return rc;
+    if ((rc = dalloc(h, &h->hs_trunc, n))) return rc;
+    if ((rc = dalloc(h, &h->hs_steps, n))) return rc;
+    if ((rc = dalloc(h, &h->hs_out, n * 16))) return rc;
+    CK(cudaStreamCreateWithFlags(&h->hs_stream, cudaStreamNonBlocking));
+    return AMDP_OK;
+}
+
+static int host_result(amdp* h, int with_step, int32_t* result_host) {
+    const amdp_config& c = h->cfg;
+    k_pack_result<<<nblk(c.n_envs, 128), 128, 0, h->hs_stream>>>(h->E, c.n_obs_tok, h->hs_obs, h->hs_rew, h->hs_rgt, h->hs_term, h->hs_trunc,
+                                                                 h->hs_steps, with_step, h->hs_out);
+    h->launches += 1;
+    CK(cudaMemcpyAsync(result_host, h->hs_out, sizeof(int32_t) * 16 * (size_t)c.n_envs, cudaMemcpyDeviceToHost, h->hs_stream));
+    CK(cudaStreamSynchronize(h->hs_stream));
+    if (result_host[14]) CK(cudaMemsetAsync(h->faults, 0, sizeof(unsigned int), h->hs_stream));   // reported: clear (as amdp_poll_errors)
+    return AMDP_OK;
+}
+
+extern "C" int amdp_reset_host(amdp_t* h, int32_t* result_host) {
+    if (!h || !result_host) return AMDP_EINVAL;
+    int rc = host_step_init(h);
+    if (rc) return rc;
+    if ((rc = amdp_reset(h, nullptr, h->hs_obs, nullptr, h->hs_stream))) return rc;
+    return host_result(h, 0, result_host);
+}
+
+extern "C" int amdp_step_host(amdp_t* h, const int32_t* actions_host, int32_t* result_host) {
+    if (!h || !actions_host || !result_host) return AMDP_EINVAL;
+    int rc = host_step_init(h);
+    if (rc) return rc;
+    const amdp_config& c = h->cfg;
+    CK(cudaMemcpyAsync(h->hs_act, actions_host, sizeof(int32_t) * (size_t)c.n_envs * c.n_act_tok, cudaMemcpyHostToDevice, h->hs_stream));
+    if ((rc = amdp_step(h, h->hs_act, h->hs_obs, nullptr, h->hs_rew, h->hs_rgt, h->hs_term, h->hs_trunc, nullptr, h->hs_steps, nullptr, h->hs_stream)))
+        return rc;
+    return host_result(h, 1, result_host);
+}
+
+extern "C" int amdp_peek_errors(amdp_t* h, uint32_t* out_dev, void* stream) {
+    if (!h || !out_dev) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(out_dev, h->faults, sizeof(unsigned int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return AMDP_OK;
 }
 

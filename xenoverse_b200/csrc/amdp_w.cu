@@ -1,6 +1,9 @@
 // amdp_w.cu — k_rollout_w: warp-per-env rollout kernel with the shortest dependent chain; see amdp_dev.cuh / amdp_b200.cu.
 #include "amdp_dev.cuh"
 
+#ifndef AMDP_W_MINB
+#define AMDP_W_MINB 7      // resident blocks per SM the register budget is sized for (7 x 4 warps x 148 SMs >= 4096 envs)
+#endif
 #ifndef AMDP_W_HINT
 #define AMDP_W_HINT 0      // L2 eviction hints: 1 payload evict_first, 2 rows of reset states evict_last (measured: both lose)
 #endif
@@ -61,7 +64,7 @@ __device__ __forceinline__ float2 ldg_f32x2_hint(const float2* p, uint64_t pol) 
 // its table action (a register with the actions of the lane's own entries) and sends it along in the REDUX operand; the
 // action after a reset and the explore / exploit choice are made with the draws.
 template <int EPL, int ACT>
-__global__ void __launch_bounds__(128, 7) k_rollout_w(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
+__global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
                                                       const int32_t* __restrict__ actions, const amdp_traj J) {
     constexpr bool GIVEN = ACT == 1, TABLE = ACT == 2;
     constexpr int ISH = TABLE ? 13 : 5;                           // where the state index sits in the REDUX operand

@@ -357,6 +357,16 @@ class Engine:
             self._ck(lib.amdp_poll_errors(self._h, ctypes.byref(v), _stream()))
         return int(v.value)
 
+    def peek_errors(self, out_dev):
+        """Copy the sticky fault word into a uint32 device tensor on the current stream (no synchronisation)."""
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_peek_errors(self._h, _ptr(out_dev), _stream()))
+
+    def state_into(self, state_dev):
+        """Copy the inner states into an int32 device tensor on the current stream (no synchronisation)."""
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_get_state(self._h, _ptr(state_dev), None, None, None, _stream()))
+
     def dump_draws(self, tick0, K):
         out = torch.empty((K, self.N, self.n_slots), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
