@@ -105,7 +105,7 @@ typedef struct amdp_config {
     int32_t  n_act_tok;     /* `da` (1 unless MTPOMDP) */
     int32_t  s0_pad;        /* max len(s_0) over tasks */
     int32_t  reserved0;     /* flags: 1 keep a copy of `transition` (amdp_gather_transition_gt); 8 / 16 force / forbid the thread-per-env rollout
-                               kernel (default: used from 16384 envs); 2 / 4 force the one- / two-level
+                               kernel (default: used from 4096 envs, from 12288 where k_rollout_w applies); 2 / 4 force the one- / two-level
                                row search of the fast rollout kernel (default: chosen from n_pad and n_envs); 32 keeps MDP engines
                                off k_rollout_w (the REDUX.MIN warp-per-env kernel for rows of 64 / 128 / 256 states);
                                bits 8-12: bit_length(max ns - 1) over all tasks (0 = not stated, 15 assumed): the thread-per-env tables

@@ -10,7 +10,7 @@ import json
 d=json.loads(open('gpurun_out/bench_default.json').read().strip().splitlines()[-1])
 print('value %.3e frac %.3f kernel %s e2e %.3e cpu %.3e launches %d' % (d['value'], d['roofline']['frac'], d['roofline']['kernel'], d['e2e']['value'], d['cpu_baseline']['value'], d['gpu_launches']))
 for k,v in d['other_workloads'].items():
-    print(k, '%.3e'%v['value'], v['kernel'], 'frac %.3f'%v['roofline_frac']) if 'value' in v else print(k, v)
+    print(k, '%.3e' % v['value'], v.get('kernel'), 'frac %.3f' % v.get('roofline_frac', float('nan'))) if 'value' in v else print(k, {a: b for a, b in v.items() if a != 'workload'})
 print(d['clocks'])
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other > gpurun_out/b_ncu.log 2>&1

@@ -766,7 +766,13 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     // (0 = not stated: 15 is assumed and larger mappings are rejected at upload)
     const int obs_bits = ((c.reserved0 >> 8) & 31) ? ((c.reserved0 >> 8) & 31) : 15;
     h->T.tp_obs_bits = obs_bits;
-    h->tp = tp_kind && obs_bits <= 15 && c.n_pad <= 2048 && c.s0_pad <= TP_S0 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= 16384));
+    // From how many envs the thread-per-env kernel wins (measured, tools/gpu_threshold.sh): against k_rollout_w (same-step MDP,
+    // rows of 64 / 128 / 256 states) from ~12k envs (cfg2 tables: 8192 envs 4.1e9 vs 5.8e9, 16384 envs 8.2e9 vs 6.1e9); against
+    // k_rollout_mdp already at 4096 (ns=1024: 1.27e9 vs 1.14e9; ns=32 at 8192 envs: 4.2e9 vs 3.7e9).
+    const bool wv2_ok = mdp && !(c.reserved0 & 32) && c.autoreset == AMDP_AUTORESET_SAME_STEP &&
+                        (c.n_pad == 64 || c.n_pad == 128 || c.n_pad == 256) && c.na <= 256 && c.s0_pad <= TP_S0;
+    const long long tp_from = wv2_ok ? 12288 : 4096;
+    h->tp = tp_kind && obs_bits <= 15 && c.n_pad <= 2048 && c.s0_pad <= TP_S0 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= tp_from));
     if (h->tp) {
         const int nb = (c.n_pad + 7) / 8;
         h->T.tp_blocks = nb;
@@ -781,8 +787,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
         }
     }
     // one warp per env, shortest dependent chain: rows of exactly 64 / 128 / 256 states (flag 32 keeps the older k_rollout_mdp)
-    h->wv2 = mdp && !h->tp && !h->two_level && !(c.reserved0 & 32) && c.autoreset == AMDP_AUTORESET_SAME_STEP &&
-             (c.n_pad == 64 || c.n_pad == 128 || c.n_pad == 256) && c.na <= 256 && c.s0_pad <= TP_S0;
+    h->wv2 = wv2_ok && !h->tp && !h->two_level;
     if (c.reserved0 & 1) { if ((rc = dalloc(h, &h->raw_t, rows * c.n_pad))) return rc; }
     if ((rc = dalloc(h, &h->sinfo, (size_t)c.n_tasks * c.n_pad))) return rc;
     if ((rc = dalloc(h, &h->s0_cdf, (size_t)c.n_tasks * c.s0_pad))) return rc;

@@ -120,7 +120,7 @@ class Engine:
     def __init__(self, num_envs, num_tasks, geo, device=0, seed=0, autoreset="same_step", env_id_base=0,
                  keep_transition=False, search="auto"):
         """search: how MDP rollouts search a CDF row.  "thread": the thread-per-env throughput kernel (pivots + one
-        8/16-entry block of 31-bit codes; auto picks it for >= 16384 envs); "one_level" / "two_level": the warp-per-env
+        8/16-entry block of 31-bit codes; auto picks it from 12288 envs where k_rollout_w applies, else from 4096); "one_level" / "two_level": the warp-per-env
         latency kernel streaming the 16-bit filter row / reading 32 pivots + one 32-entry block (auto: two_level for
         n_pad >= 512); "warp": auto without the thread-per-env kernel; "warp_v1": additionally without k_rollout_w (the
         REDUX.MIN warp-per-env kernel auto picks for same-step MDP engines with rows of 64 / 128 / 256 states)."""
