@@ -324,12 +324,14 @@ def run_b200(args, name, envs, tasks, ns, na, no):
         if ev:
             ev[1].record()
         env.engine.stats_tensor(buf)
-        if world > 1:
+        if world > 1 and args.allreduce == "side":
             done = torch.cuda.Event()
             done.record()
             with torch.cuda.stream(side):
                 side.wait_event(done)
                 dist.all_reduce(buf[:4], op=dist.ReduceOp.SUM)
+        elif world > 1:
+            dist.all_reduce(buf[:4], op=dist.ReduceOp.SUM)        # in line: between two rollout launches
 
     for _ in range(W):
         one_step()
@@ -489,6 +491,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other workloads (N = 1 only)")
     ap.add_argument("--ref-steps-per-worker", type=int, default=20000)
+    ap.add_argument("--allreduce", default="side", choices=["side", "main"],
+                    help="N > 1: the per-iteration NCCL all-reduce of the episode statistics on a side stream (overlapping the next "
+                         "rollout) or in line on the main stream")
     ap.add_argument("--policy", default="uniform", choices=["uniform", "table"],
                     help="behaviour policy of the device rollouts: the engine's uniform random one (BASELINE.json) or a table (amdp_set_policy)")
     ap.add_argument("--epsilon", type=float, default=0.1)
