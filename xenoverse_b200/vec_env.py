@@ -114,7 +114,8 @@ class AnyMDPVecEnv:
         if check:
             raise_faults(self.engine.poll_errors())
         info = {"steps": b["steps"], "reward_gt": b["reward_gt"], "final_obs": self._squeeze(b["final_obs"]), "action": self._squeeze(b["action"])}
-        return self._squeeze(b["obs"]), b["reward"], b["terminated"].bool(), b["truncated"].bool(), info
+        # (the flags are 0 / 1 bytes: a bool VIEW costs no kernel launch)
+        return self._squeeze(b["obs"]), b["reward"], b["terminated"].view(torch.bool), b["truncated"].view(torch.bool), info
 
     def check(self):
         """Raise the reference's exception for any per-env fault recorded since the last check (synchronises)."""
