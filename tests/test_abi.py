@@ -77,3 +77,13 @@ def test_synth_task_is_valid_for_the_oracle():
     term = numpy.zeros(32, dtype=bool)
     term[t["s_e"]] = True
     assert numpy.allclose(s[~term], 1.0) and (s[term] == 0).all()
+
+
+def test_observation_bits_of_the_engine_config():
+    """Engine._obs_bits: bit_length(max ns - 1), what amdp_config.reserved0 bits 8-12 carry (no GPU needed)."""
+    from xenoverse_b200.engine import Engine
+    assert Engine._obs_bits({"n_pad": 128, "ns_max": 128}) == 7
+    assert Engine._obs_bits({"n_pad": 128, "ns_max": 129}) == 8
+    assert Engine._obs_bits({"n_pad": 16}) == 4
+    assert Engine._obs_bits({"n_pad": 4, "ns_max": 1}) == 2
+    assert Engine._obs_bits({"n_pad": 1024, "ns_max": 1 << 20}) == 20      # > 15: the engine stays off the thread-per-env kernel

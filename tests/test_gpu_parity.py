@@ -649,3 +649,34 @@ def test_warp_per_env_redux_kernel_faults_and_oracle_replay():
         assert numpy.array_equal((d & 1).astype(bool), o["terminated"]) and numpy.array_equal((d >> 1).astype(bool), o["truncated"])
         assert numpy.allclose(tr["reward"][k].cpu().numpy(), o["reward"], rtol=1e-6, atol=1e-6)
     assert env.episode_stats()["episodes"] == orc.stats()["episodes"]
+
+
+@pytest.mark.parametrize("search,N", [("thread", 300), ("warp", 300), ("auto", 5000)])
+def test_ragged_tasks_in_one_engine_fast_kernels_equal_generic(search, N):
+    """Tasks with DIFFERENT numbers of states (and observable spaces larger than their state count) padded into one
+    engine: the fast kernels must treat the padding like the generic kernel does (pad CDF entries 1.0, pad rows never hit)."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    tasks = []
+    for t, ns in enumerate((20, 28, 32, 9, 32, 17)):
+        task = synth_task(ns, 4, 2500 + t)
+        task["ns"] = 40                                           # min_state_space-style: ns > len(state_mapping)
+        task["state_mapping"] = numpy.random.default_rng(t).permutation(40)[:ns]
+        tasks.append(task)
+    K = 200
+    outs = []
+    for generic in (False, True):
+        env = AnyMDPVecEnv(N, seed=67, search=search)
+        env.set_task(tasks)
+        env.engine.force_generic(generic)
+        env.reset()
+        tr = env.rollout(K, record=("obs", "action", "reward", "reward_gt", "done"))
+        env.check()
+        outs.append((tr, env.engine.get_state(), env.episode_stats(), env.engine.rollout_kernel))
+    (a, sa, ea, ka), (b, sb, eb, kb) = outs
+    assert ("k_rollout_tp" in ka) == (search != "warp")
+    for key in ("obs", "action", "done", "reward", "reward_gt"):
+        assert torch.equal(a[key], b[key]), key
+    for key in ("state", "steps", "flags", "ep_return"):
+        assert torch.equal(sa[key], sb[key]), key
+    assert ea == eb and ea["episodes"] > 0
+    assert int(a["obs"].max()) >= 32                              # observations beyond n_pad: state_mapping, not state indices
