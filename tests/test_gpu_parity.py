@@ -680,3 +680,49 @@ def test_ragged_tasks_in_one_engine_fast_kernels_equal_generic(search, N):
         assert torch.equal(sa[key], sb[key]), key
     assert ea == eb and ea["episodes"] > 0
     assert int(a["obs"].max()) >= 32                              # observations beyond n_pad: state_mapping, not state indices
+
+
+@pytest.mark.parametrize("ns,na,mode", [(32, 5, "same_step"), (128, 5, "next_step"), (16, 3, "disabled"), (1000, 2, "same_step"), (8, 4, "next_step")])
+def test_thread_per_env_step_kernel_equals_generic_step(ns, na, mode):
+    """amdp_step on an engine with the thread-per-env tables (k_step_tp) vs the generic k_step: every output of every tick
+    (obs, final_obs, reward, reward_gt, flags, info steps, action), env state, statistics and faults; caller actions,
+    engine policy and table policy; virgin envs and a bad action are reported, not stepped."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    tasks = [synth_task(ns, na, 2700 + t) for t in range(5)]
+    for t in tasks:
+        t["max_steps"] = 37.5
+    N, K = 300, 90
+    g = torch.Generator().manual_seed(ns)
+    acts = torch.randint(0, na, (K, N), dtype=torch.int32, generator=g).cuda()
+    pol = [numpy.random.default_rng(ns + i).integers(0, na, ns) for i in range(len(tasks))]
+    outs = []
+    for generic in (False, True):
+        env = AnyMDPVecEnv(N, seed=71, autoreset=mode, search="thread")
+        env.set_task(tasks)
+        env.engine.force_generic(generic)
+        log = []
+        env.step(acts[0])                                          # before any reset: every env faults
+        with pytest.raises(Exception, match="reset"):
+            env.check()
+        env.reset()
+        for k in range(K):
+            if k == 30:
+                env.set_policy(pol, epsilon=0.3)
+            a = acts[k].clone() if k % 3 else None                 # every third tick: the engine's / the table policy
+            if a is not None and k == 50:
+                a[7] = na                                          # out of range
+            if mode == "disabled" and k % 9 == 8:
+                env.reset()                                        # (no auto-reset: restart everything now and then)
+            obs, rew, term, trunc, info = env.step(a)
+            log.append([x.clone() for x in (obs, rew, term, trunc, info["steps"], info["reward_gt"], info["final_obs"], info["action"])])
+        faults = env.engine.poll_errors()
+        outs.append((log, env.engine.get_state(), env.episode_stats(), faults))
+    (la, sa, ea, fa), (lb, sb, eb, fb) = outs
+    for k, (x, y) in enumerate(zip(la, lb)):
+        for i, (u, v) in enumerate(zip(x, y)):
+            assert torch.equal(u, v), (k, i)
+    for key in ("state", "steps", "flags", "ep_return"):
+        assert torch.equal(sa[key], sb[key]), key
+    assert str(ea) == str(eb) and fa == fb and (fa & 4)           # (str: mean_length is nan when no episode closed)
+    if mode != "disabled":
+        assert ea["episodes"] > 0

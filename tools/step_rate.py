@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, ".")
 import xenoverse_b200 as xb  # noqa: E402
 
-for N, ns, na, T in ((4096, 128, 5, 256), (65536, 128, 5, 256), (65536, 32, 5, 1024), (262144, 32, 5, 1024)):
+for N, ns, na, T in ((4096, 128, 5, 256), (65536, 128, 5, 256), (65536, 32, 5, 1024), (262144, 32, 5, 1024), (65536, 1024, 16, 8)):
     geo = xb.synth_geometry(ns, na)
     env = xb.AnyMDPVecEnv(N, device=0, seed=0)
     env.set_task(None, packed=(geo, T, ((0, xb.synth_packed(ns, na, T, seed=1000, device=torch.device("cuda", 0))),)))

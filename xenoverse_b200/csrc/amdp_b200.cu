@@ -912,6 +912,16 @@ extern "C" int amdp_step(amdp_t* h, const int32_t* actions, int32_t* obs, int32_
     if (!h->assigned) return fail(h, AMDP_ESTATE, "Must \"set_task\" and \"reset\" before doing any actions");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->tp && h->cfg.task_type == AMDP_MDP && !u_inject && !h->force_generic) {
+        // engines that own the thread-per-env tables: one thread per env instead of G lanes streaming the float64 row
+        amdp_launch_step_tp(h->T, h->E, h->cfg.n_envs, h->tp_coarse_bits, h->tick, actions, obs, final_obs, reward, reward_gt,
+                            terminated, truncated, actions_out, steps_out, st);
+        h->launches += 1;
+        h->tick += 1;
+        h->total_steps += (double)h->cfg.n_envs;
+        CK(cudaGetLastError());
+        return AMDP_OK;
+    }
     switch (h->G) {
 #define CASE(g) case g: launch_step<g>(h, actions, obs, final_obs, reward, reward_gt, terminated, truncated, actions_out, steps_out, u_inject, st); break;
         CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)

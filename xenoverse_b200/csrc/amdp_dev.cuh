@@ -253,6 +253,9 @@ void amdp_launch_mdp(const Tables& T, const EnvArrays& E, long long n_envs, int 
                      const int32_t* actions, const amdp_traj& J, cudaStream_t st);
 void amdp_launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, bool pomdp, bool next, int coarse_bits, unsigned long long tick, int K,
                     const int32_t* actions, const amdp_traj& J, cudaStream_t st);
+void amdp_launch_step_tp(const Tables& T, const EnvArrays& E, long long n_envs, int coarse_bits, unsigned long long tick,
+                         const int32_t* actions, int32_t* obs, int32_t* final_obs, float* reward, float* reward_gt, uint8_t* terminated,
+                         uint8_t* truncated, int32_t* actions_out, int32_t* steps_out, cudaStream_t st);
 void amdp_launch_w(const Tables& T, const EnvArrays& E, long long n_envs, unsigned long long tick, int K, const int32_t* actions,
                    const amdp_traj& J, cudaStream_t st);
 int amdp_vi_run(const Tables& T, long long n_tasks, double gamma, double tol, int max_sweeps, double* Q, double* V, double* er,

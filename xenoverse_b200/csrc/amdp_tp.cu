@@ -361,3 +361,151 @@ void amdp_launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, bool 
     else if (T.tp_levels == 2) launch_tp<2>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
     else launch_tp<3>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
 }
+
+// ------------------------------------------------------------------------------------------------
+// One tick, one thread per env (k_step_tp): amdp_step() for MDP engines that own the thread-per-env tables — the per-tick
+// API an RL training loop drives (obs -> policy network -> action, every tick).  Same arithmetic and the same outputs as the
+// generic k_step (env_tick in amdp_b200.cu): all three auto-reset modes, faults, final_obs, info["steps"], reward_gt;
+// the transition is searched like in k_rollout_tp ([top ->] pivots -> 8-entry block line, float64 row when undecided).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tp_count16(const uint4 (&lv)[2], unsigned v2) {
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        acc = h2_count_lt(lv[i].x, v2, acc); acc = h2_count_lt(lv[i].y, v2, acc);
+        acc = h2_count_lt(lv[i].z, v2, acc); acc = h2_count_lt(lv[i].w, v2, acc);
+    }
+    return -acc;
+}
+
+__global__ void __launch_bounds__(128) k_step_tp(const Tables T, const EnvArrays E, unsigned long long tick, unsigned cmask,
+                                                 const int32_t* __restrict__ actions, int32_t* __restrict__ obs_out,
+                                                 int32_t* __restrict__ final_obs_out, float* __restrict__ reward,
+                                                 float* __restrict__ reward_gt, uint8_t* __restrict__ terminated,
+                                                 uint8_t* __restrict__ truncated, int32_t* __restrict__ actions_out,
+                                                 int32_t* __restrict__ steps_out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E.n_envs) return;
+    const int n_pad = T.n_pad, na = T.na;
+    const long long t = E.task[e];
+    const int32_t* __restrict__ sinfo_t = T.sinfo + t * n_pad;
+    int s = E.state[e], steps = E.steps[e], flags = E.flags[e];
+    double ep_ret = E.ep_return[e];
+    const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
+    const uint4 w0 = philox_block(env_id, 0u, tick, E.key);                       // transition uniform, reset uniform
+    const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick, E.key);   // reward normal, action, exploration
+    const bool pending = T.autoreset == AMDP_AUTORESET_NEXT_STEP && (flags & FLAG_PENDING);
+    const bool stepping = !pending;
+    const bool always_term = (T.tflags[t] & 1) != 0;
+    int a = (int)__umulhi(w2.z, (uint32_t)na);
+    if (actions) a = actions[e];
+    else if (T.policy && !((w2.w >> 8) < T.eps_thr)) a = (int)T.policy[t * n_pad + s];
+    unsigned fault = 0;
+    if (stepping) {
+        if (a < 0 || a >= na) fault |= AMDP_FAULT_BAD_ACTION;                          // anymdp_env.py:97
+        if (flags & FLAG_VIRGIN) fault |= AMDP_FAULT_NEED_RESET;                       // :93-94
+        else if (sinfo_t[s] < 0 && !always_term) fault |= AMDP_FAULT_TERMINAL_STATE;   // :95-96
+    }
+    const bool ok = stepping && fault == 0;                       // faulted envs are left untouched
+    float rew = 0.f, rgt = 0.f;
+    int term = 0, trunc = 0, obs = 0;
+    if (ok) {
+        steps += 1;                                                                    // :113-114
+        trunc = steps >= T.max_ceil[t];
+        const unsigned long long row = ((unsigned long long)t * n_pad + (unsigned)s) * (unsigned)na + (unsigned)a;
+        const uint32_t v15 = code15_from_m21(w0.x >> 11);
+        const unsigned v2 = v15 | (v15 << 16);
+        const int n_blocks = T.tp_blocks, n_groups = T.tp_groups;
+        int blk = 0;
+        uint4 lv[2];
+        if (T.tp_levels == 3) {
+            ldg_words<2>(T.top + row * 16u, lv);
+            const int g = min(tp_count16(lv, v2), n_groups - 1);
+            ldg_words<2>(T.pv + (row * (unsigned)n_groups + (unsigned)g) * 16u, lv);
+            blk = min(g * 16 + tp_count16(lv, v2), n_blocks - 1);
+        } else if (T.tp_levels == 2) {
+            ldg_words<2>(T.pv + row * 16u, lv);
+            blk = min(tp_count16(lv, v2), n_blocks - 1);
+        }
+        const unsigned ve = ((((w0.x >> 5) << 4) | (w0.y >> 28)) << 1) & cmask;       // code31(u) << 1, comparable bits
+        const uint4* frow = T.fat + row * (unsigned)n_blocks * 8u;
+        int lt, le;
+        unsigned mn;
+        for (;;) {
+            uint4 bw[2];
+            ldg_words<2>(frow + blk * 8, bw);
+            lt = 0; le = 0; mn = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const unsigned x[4] = {bw[i].x, bw[i].y, bw[i].z, bw[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned xm = x[j] & cmask;
+                    lt += (xm < ve); le += (xm <= ve);
+                    mn = min(mn, xm >= ve ? x[j] : 0xffffffffu);
+                }
+            }
+            if (lt < 8 || blk >= n_blocks - 1) break;
+            ++blk;
+        }
+        int nxt = blk * 8 + lt;
+        float2 pay;
+        if (le != lt) {                                            // undecided on the codes: the float64 row (anymdp_env.py:100)
+            const double u = u53(w0.x, w0.y);
+            const double* cr = T.cdf + row * (unsigned)n_pad;
+            while (nxt < n_pad - 1 && __ldg(cr + nxt) <= u) ++nxt;
+            const int siw = sinfo_t[nxt];
+            term = siw < 0; obs = siw & 0x7fffffff;
+            pay = ldg_stream_f32x2(T.payload + (row * (unsigned)n_pad + (unsigned)nxt));
+            atomicAdd(E.counters, 1ull);
+        } else {
+            term = (int)(mn & 1u);
+            obs = (int)((mn >> 1) & ((1u << T.tp_obs_bits) - 1u));
+            pay = ldg_stream_f32x2(reinterpret_cast<const float2*>(reinterpret_cast<const char*>(frow + blk * 8) + 32) + lt);
+        }
+        if (always_term) term = 1;                                                     // :108
+        const double r = (double)pay.x + (double)pay.y * (double)box_muller(w2.x, w2.y);   // :103-105
+        rew = (float)r; rgt = pay.x;
+        ep_ret += r;
+        s = nxt;
+    }
+    int steps_info = steps, final_obs = obs;
+    const bool done = ok && (term || trunc);
+    bool do_reset = pending;
+    if (done && T.autoreset != AMDP_AUTORESET_DISABLED) {          // close the episode (statistics of closed episodes only)
+        E.ep_count[e] += 1; E.sum_len[e] += (unsigned long long)steps;
+        E.sum_ret[e] += ep_ret; E.sum_ret_sq[e] += ep_ret * ep_ret;
+        E.min_ret[e] = fmin(E.min_ret[e], ep_ret); E.max_ret[e] = fmax(E.max_ret[e], ep_ret);
+        ep_ret = 0.0;
+        if (T.autoreset == AMDP_AUTORESET_SAME_STEP) do_reset = true; else flags |= FLAG_PENDING;
+    }
+    if (do_reset) {                                                // anymdp_env.py:81-90
+        const double ur = u53(w0.z, w0.w);
+        int c = 0;
+        for (int i = 0; i < T.s0_pad; ++i) c += (T.s0_cdf[t * T.s0_pad + i] <= ur);
+        s = T.s0_idx[t * T.s0_pad + min(c, T.s0_pad - 1)];
+        steps = 0;
+        flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
+        obs = sinfo_t[s] & 0x7fffffff;
+        if (pending) { steps_info = 0; final_obs = obs; }
+    }
+    E.state[e] = s; E.steps[e] = steps; E.flags[e] = (uint8_t)flags; E.ep_return[e] = ep_ret;
+    obs_out[e] = obs;
+    if (final_obs_out) final_obs_out[e] = final_obs;
+    reward[e] = rew;
+    if (reward_gt) reward_gt[e] = rgt;
+    terminated[e] = (uint8_t)term;
+    truncated[e] = (uint8_t)trunc;
+    if (actions_out) actions_out[e] = a;
+    if (steps_out) steps_out[e] = steps_info;
+    if (fault) atomicOr(E.faults, fault);
+}
+
+void amdp_launch_step_tp(const Tables& T, const EnvArrays& E, long long n_envs, int coarse_bits, unsigned long long tick,
+                         const int32_t* actions, int32_t* obs, int32_t* final_obs, float* reward, float* reward_gt, uint8_t* terminated,
+                         uint8_t* truncated, int32_t* actions_out, int32_t* steps_out, cudaStream_t st) {
+    const int low = 1 + T.tp_obs_bits + coarse_bits;
+    const unsigned cmask = 0xffffffffu << (low < 30 ? low : 30);
+    k_step_tp<<<nblk(n_envs, 128), 128, 0, st>>>(T, E, tick, cmask, actions, obs, final_obs, reward, reward_gt, terminated, truncated,
+                                                 actions_out, steps_out);
+}
