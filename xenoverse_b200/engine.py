@@ -315,6 +315,18 @@ class Engine:
                                    _ptr(out["truncated"]), _ptr(out.get("action")), _ptr(out.get("steps")), _ptr(u_inject),
                                    _stream()))
 
+    def make_stepper(self, out):
+        """A closure `f(actions_or_None)` that runs amdp_step into the fixed buffers `out` with every pointer converted once:
+        the per-tick API is host-bound (~25 us per call), so the 12 ctypes conversions of `step()` are worth caching."""
+        ptrs = [_ptr(out["obs"]), _ptr(out.get("final_obs")), _ptr(out["reward"]), _ptr(out.get("reward_gt")),
+                _ptr(out["terminated"]), _ptr(out["truncated"]), _ptr(out.get("action")), _ptr(out.get("steps"))]
+        h, fn, ck, dev = self._h, lib.amdp_step, self._ck, self.device
+
+        def f(actions):
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            ck(fn(h, None if actions is None else ctypes.c_void_p(actions.data_ptr()), *ptrs, None, st))
+        return f
+
     def rollout(self, K, actions=None, traj=None, u_inject=None, env_major=False):
         """traj: dict with optional tensors obs [K,N,do], action [K,N,da], reward, reward_gt, done [K,N]
         (or [N,K,...] when env_major)."""

@@ -79,6 +79,7 @@ class AnyMDPVecEnv:
         self.task_type, self.na, self.da, self.do = geo["task_type"], geo["na"], geo["da"], geo["do"]
         self.device = self.engine.device
         self._buf = self.engine.new_buffers()
+        self._stepper = None
         self._stats = torch.empty(8, dtype=torch.float64, device=self.device)
         self.task_set = True
 
@@ -110,7 +111,12 @@ class AnyMDPVecEnv:
         if actions is not None:
             a = self.engine._dev(actions, torch.int32).reshape(self.num_envs, self.da)
         b = self._buf
-        self.engine.step(a, b, u_inject=u_inject)
+        if u_inject is None:
+            if self._stepper is None:
+                self._stepper = self.engine.make_stepper(b)
+            self._stepper(a)
+        else:
+            self.engine.step(a, b, u_inject=u_inject)
         if check:
             raise_faults(self.engine.poll_errors())
         info = {"steps": b["steps"], "reward_gt": b["reward_gt"], "final_obs": self._squeeze(b["final_obs"]), "action": self._squeeze(b["action"])}
