@@ -726,3 +726,47 @@ def test_thread_per_env_step_kernel_equals_generic_step(ns, na, mode):
     assert str(ea) == str(eb) and fa == fb and (fa & 4)           # (str: mean_length is nan when no episode closed)
     if mode != "disabled":
         assert ea["episodes"] > 0
+
+
+def _fuzz_cases(n=28, seed=2025):
+    rng = numpy.random.default_rng(seed)
+    cases = []
+    for i in range(n):
+        ns = int(rng.choice([4, 7, 8, 16, 31, 32, 33, 64, 100, 128, 129, 256, 300]))
+        cases.append((i, ns, int(rng.integers(2, 10)), int(rng.choice([33, 64, 257, 1000, 4100, 6000])),
+                      str(rng.choice(["same_step", "next_step"])), str(rng.choice(["uniform", "given", "table"])),
+                      str(rng.choice(["auto", "thread", "warp", "warp_v1"])), int(rng.choice([1, 31, 32, 33, 64, 130]))))
+    return cases
+
+
+@pytest.mark.parametrize("i,ns,na,N,mode,act,search,K", _fuzz_cases())
+def test_fuzz_fast_rollout_kernels_equal_generic(i, ns, na, N, mode, act, search, K):
+    """Random shapes / modes / action sources / kernel selections: whatever fast kernel the engine picks must reproduce the
+    generic per-tick kernel bit for bit (records, env state, statistics), over two consecutive launches."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    rng = numpy.random.default_rng(1000 + i)
+    tasks = [synth_task(ns, na, 3000 + 10 * i + t) for t in range(3)]
+    for t in tasks:
+        t["max_steps"] = float(rng.integers(5, 60)) + 0.5
+    acts = torch.from_numpy(rng.integers(0, na, (K, N)).astype(numpy.int32)).cuda() if act == "given" else None
+    pol = [rng.integers(0, na, ns) for _ in tasks]
+    outs = []
+    for generic in (False, True):
+        env = AnyMDPVecEnv(N, seed=100 + i, autoreset=mode, search=search)
+        env.set_task(tasks)
+        if act == "table":
+            env.set_policy(pol, epsilon=0.25)
+        env.engine.force_generic(generic)
+        env.reset()
+        tr = env.rollout(K, actions=acts, policy="device" if act == "table" else "uniform",
+                         record=("obs", "action", "reward", "reward_gt", "done"))
+        tr2 = env.rollout(K, actions=acts, policy="device" if act == "table" else "uniform", record=("packed",))
+        env.check()
+        outs.append((tr, tr2, env.engine.get_state(), env.episode_stats()))
+    (a, a2, sa, ea), (b, b2, sb, eb) = outs
+    for key in ("obs", "action", "done", "reward", "reward_gt"):
+        assert torch.equal(a[key], b[key]), key
+    assert torch.equal(a2["packed"], b2["packed"])
+    for key in ("state", "steps", "flags", "ep_return"):
+        assert torch.equal(sa[key], sb[key]), key
+    assert str(ea) == str(eb)
