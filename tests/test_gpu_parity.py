@@ -682,13 +682,15 @@ def test_ragged_tasks_in_one_engine_fast_kernels_equal_generic(search, N):
     assert int(a["obs"].max()) >= 32                              # observations beyond n_pad: state_mapping, not state indices
 
 
-@pytest.mark.parametrize("ns,na,mode", [(32, 5, "same_step"), (128, 5, "next_step"), (16, 3, "disabled"), (1000, 2, "same_step"), (8, 4, "next_step")])
-def test_thread_per_env_step_kernel_equals_generic_step(ns, na, mode):
+@pytest.mark.parametrize("ns,na,mode,no", [(32, 5, "same_step", None), (128, 5, "next_step", None), (16, 3, "disabled", None),
+                                           (1000, 2, "same_step", None), (8, 4, "next_step", None), (64, 8, "same_step", 64),
+                                           (30, 3, "next_step", 100), (16, 4, "disabled", 12)])
+def test_thread_per_env_step_kernel_equals_generic_step(ns, na, mode, no):
     """amdp_step on an engine with the thread-per-env tables (k_step_tp) vs the generic k_step: every output of every tick
     (obs, final_obs, reward, reward_gt, flags, info steps, action), env state, statistics and faults; caller actions,
     engine policy and table policy; virgin envs and a bad action are reported, not stepped."""
     from xenoverse_b200 import synth_task, AnyMDPVecEnv
-    tasks = [synth_task(ns, na, 2700 + t) for t in range(5)]
+    tasks = [synth_task(ns, na, 2700 + t, no=no) for t in range(5)]
     for t in tasks:
         t["max_steps"] = 37.5
     N, K = 300, 90

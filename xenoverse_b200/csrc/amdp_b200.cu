@@ -912,7 +912,7 @@ extern "C" int amdp_step(amdp_t* h, const int32_t* actions, int32_t* obs, int32_
     if (!h->assigned) return fail(h, AMDP_ESTATE, "Must \"set_task\" and \"reset\" before doing any actions");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (h->tp && h->cfg.task_type == AMDP_MDP && !u_inject && !h->force_generic) {
+    if (h->tp && !u_inject && !h->force_generic) {               // (tp: MDP, or POMDP with one observation token)
         // engines that own the thread-per-env tables: one thread per env instead of G lanes streaming the float64 row
         amdp_launch_step_tp(h->T, h->E, h->cfg.n_envs, h->tp_coarse_bits, h->tick, actions, obs, final_obs, reward, reward_gt,
                             terminated, truncated, actions_out, steps_out, st);

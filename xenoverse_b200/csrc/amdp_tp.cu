@@ -378,6 +378,38 @@ __device__ __forceinline__ int tp_count16(const uint4 (&lv)[2], unsigned v2) {
     return -acc;
 }
 
+// observation of a POMDP state (anymdp_env.py:153): pivots -> 8-entry block of 31-bit codes -> float64 row when undecided
+__device__ __forceinline__ int tp_observe(const Tables& T, const EnvArrays& E, long long t, int s, uint32_t ux, uint32_t uy, unsigned cmask) {
+    const int o_blocks = T.o_blocks;
+    const uint32_t* orow = T.ofat + (unsigned long long)(t * T.n_pad + s) * (unsigned)(8 + 8 * o_blocks);
+    uint4 pv[2], cd[2];
+    ldg_words<2>(orow, pv);
+    const uint32_t v15 = code15_from_m21(ux >> 11);
+    int blk = min(tp_count16(pv, v15 | (v15 << 16)), o_blocks - 1);
+    const unsigned ve = ((((ux >> 5) << 4) | (uy >> 28)) << 1) & cmask;
+    int lt, le;
+    for (;;) {
+        ldg_words<2>(orow + 8 + 8 * blk, cd);
+        lt = 0; le = 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const unsigned x[4] = {cd[i].x, cd[i].y, cd[i].z, cd[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const unsigned xm = x[j] & cmask; lt += (xm < ve); le += (xm <= ve); }
+        }
+        if (lt < 8 || blk >= o_blocks - 1) break;
+        ++blk;
+    }
+    int obs = blk * 8 + lt;
+    if (le != lt) {
+        const double u = u53(ux, uy);
+        const double* cr = T.obs_cdf + (t * T.n_pad + s) * (long long)T.no_pad;
+        while (obs < T.no_pad - 1 && __ldg(cr + obs) <= u) ++obs;
+        atomicAdd(E.counters, 1ull);
+    }
+    return obs;
+}
+
 __global__ void __launch_bounds__(128) k_step_tp(const Tables T, const EnvArrays E, unsigned long long tick, unsigned cmask,
                                                  const int32_t* __restrict__ actions, int32_t* __restrict__ obs_out,
                                                  int32_t* __restrict__ final_obs_out, float* __restrict__ reward,
@@ -394,6 +426,9 @@ __global__ void __launch_bounds__(128) k_step_tp(const Tables T, const EnvArrays
     const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
     const uint4 w0 = philox_block(env_id, 0u, tick, E.key);                       // transition uniform, reset uniform
     const uint4 w2 = philox_block(env_id, (uint32_t)(AMDP_SLOT_Z >> 1), tick, E.key);   // reward normal, action, exploration
+    const bool pomdp = T.task_type == AMDP_POMDP;
+    uint4 w1 = make_uint4(0u, 0u, 0u, 0u);                         // POMDP: observation uniform, reset-observation uniform
+    if (pomdp) w1 = philox_block(env_id, (uint32_t)(AMDP_SLOT_OBS >> 1), tick, E.key);
     const bool pending = T.autoreset == AMDP_AUTORESET_NEXT_STEP && (flags & FLAG_PENDING);
     const bool stepping = !pending;
     const bool always_term = (T.tflags[t] & 1) != 0;
@@ -468,6 +503,7 @@ __global__ void __launch_bounds__(128) k_step_tp(const Tables T, const EnvArrays
         rew = (float)r; rgt = pay.x;
         ep_ret += r;
         s = nxt;
+        if (pomdp) obs = tp_observe(T, E, t, s, w1.x, w1.y, cmask);                    // :132,153 (drawn from the new state)
     }
     int steps_info = steps, final_obs = obs;
     const bool done = ok && (term || trunc);
@@ -486,7 +522,7 @@ __global__ void __launch_bounds__(128) k_step_tp(const Tables T, const EnvArrays
         s = T.s0_idx[t * T.s0_pad + min(c, T.s0_pad - 1)];
         steps = 0;
         flags &= ~(FLAG_PENDING | FLAG_VIRGIN);
-        obs = sinfo_t[s] & 0x7fffffff;
+        obs = pomdp ? tp_observe(T, E, t, s, w1.z, w1.w, cmask) : (sinfo_t[s] & 0x7fffffff);   // :90
         if (pending) { steps_info = 0; final_obs = obs; }
     }
     E.state[e] = s; E.steps[e] = steps; E.flags[e] = (uint8_t)flags; E.ep_return[e] = ep_ret;
