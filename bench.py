@@ -330,7 +330,7 @@ def run_b200(args, name, envs, tasks, ns, na, no):
             with torch.cuda.stream(side):
                 side.wait_event(done)
                 dist.all_reduce(buf[:4], op=dist.ReduceOp.SUM)
-        elif world > 1:
+        elif world > 1 and args.allreduce == "main":
             dist.all_reduce(buf[:4], op=dist.ReduceOp.SUM)        # in line: between two rollout launches
 
     for _ in range(W):
@@ -491,7 +491,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other workloads (N = 1 only)")
     ap.add_argument("--ref-steps-per-worker", type=int, default=20000)
-    ap.add_argument("--allreduce", default="side", choices=["side", "main"],
+    ap.add_argument("--allreduce", default="side", choices=["side", "main", "none"],
                     help="N > 1: the per-iteration NCCL all-reduce of the episode statistics on a side stream (overlapping the next "
                          "rollout) or in line on the main stream")
     ap.add_argument("--policy", default="uniform", choices=["uniform", "table"],
