@@ -257,9 +257,10 @@ int amdp_set_policy(amdp_t* h, const uint8_t* policy, float epsilon, void* strea
  * solver.py:57-80, as used by AnyMDPSolverOpt, anymdp_solver_opt.py:32-36 — here as synchronous sweeps over ALL tasks of
  * the handle at once, stopped when max |dQ| <= tol or after max_sweeps):  q_out double [n_tasks][n_pad][na] (device, or NULL),
  * policy_out uint8 [n_tasks][n_pad] = first argmax_a Q (device, or NULL; the table amdp_set_policy takes), sweeps_out HOST
- * int32 (or NULL).  Rows of terminal and padding states are 0.  Synchronises `stream` every 8 sweeps. */
-int amdp_value_iteration(amdp_t* h, double gamma, double tol, int32_t max_sweeps, double* q_out, uint8_t* policy_out,
-                         int32_t* sweeps_out, void* stream);
+ * int32 (or NULL).  greedy != 0: the optimal values (max backup); greedy == 0: the values of the uniform random policy
+ * (mean backup, is_greedy=False, solver.py:73-74 — the other half of the reference's task-quality check, solver.py:113-126).  Rows of terminal and padding states are 0.  Synchronises `stream` every 8 sweeps. */
+int amdp_value_iteration(amdp_t* h, int32_t greedy, double gamma, double tol, int32_t max_sweeps, double* q_out,
+                         uint8_t* policy_out, int32_t* sweeps_out, void* stream);
 
 /* One whole reset / step per call from HOST memory, for engines driven one tick at a time by a Python loop (the single-env
  * gymnasium drop-in: anymdp_env.py:81-90 / :112-132 become one library call each).  Both run on a stream owned by the

@@ -144,3 +144,19 @@ def test_batched_value_iteration_vs_reference_value_matrix(name):
     env.rollout(400, policy="device")
     solved = env.episode_stats()
     assert solved["sum_return"] > uniform["sum_return"] + 100.0, (solved, uniform)
+
+
+def test_batched_value_iteration_random_policy_values():
+    """greedy=False: the values of the uniform random policy (update_value_matrix(is_greedy=False), solver.py:73-74) — with
+    the optimal values the two halves of the reference's task-quality check (solver.py:113-126)."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv, value_iteration
+    tasks = [synth_task(16, 5, 2900 + t) for t in range(4)]
+    env = AnyMDPVecEnv(8)
+    env.set_task(tasks)
+    q_rnd, _, _ = env.engine.value_iteration(gamma=0.9, tol=1e-11, max_sweeps=4000, greedy=False)
+    q_opt, _, _ = env.engine.value_iteration(gamma=0.9, tol=1e-11, max_sweeps=4000, greedy=True)
+    q_rnd, q_opt = q_rnd.cpu().numpy(), q_opt.cpu().numpy()
+    for t, task in enumerate(tasks):
+        vm = value_iteration(task, gamma=0.9, tol=1e-12, greedy=False)
+        assert numpy.allclose(q_rnd[t, :16], vm, rtol=1e-5, atol=1e-5)
+    assert (q_opt >= q_rnd - 1e-6).all() and (q_opt.max(axis=2) > q_rnd.mean(axis=2) + 1e-3).any()

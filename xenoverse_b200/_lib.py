@@ -59,7 +59,8 @@ _SIGNATURES = {
     "amdp_set_tick": (ctypes.c_int, [_P, ctypes.c_uint64]),
     "amdp_set_seed": (ctypes.c_int, [_P, ctypes.c_uint64]),
     "amdp_set_policy": (ctypes.c_int, [_P, _P, ctypes.c_float, _P]),
-    "amdp_value_iteration": (ctypes.c_int, [_P, ctypes.c_double, ctypes.c_double, ctypes.c_int32, _P, _P, ctypes.POINTER(ctypes.c_int32), _P]),
+    "amdp_value_iteration": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_int32, _P, _P,
+                                            ctypes.POINTER(ctypes.c_int32), _P]),
     "amdp_get_state": (ctypes.c_int, [_P] * 6),
     "amdp_set_state": (ctypes.c_int, [_P] * 6),
     "amdp_get_mapped_state": (ctypes.c_int, [_P, _P, _P]),

@@ -1067,8 +1067,8 @@ extern "C" int amdp_set_policy(amdp_t* h, const uint8_t* policy, float epsilon, 
     return AMDP_OK;
 }
 
-extern "C" int amdp_value_iteration(amdp_t* h, double gamma, double tol, int32_t max_sweeps, double* q_out, uint8_t* policy_out,
-                                    int32_t* sweeps_out, void* stream) {
+extern "C" int amdp_value_iteration(amdp_t* h, int32_t greedy, double gamma, double tol, int32_t max_sweeps, double* q_out,
+                                    uint8_t* policy_out, int32_t* sweeps_out, void* stream) {
     if (!h || max_sweeps < 1 || !(gamma >= 0.0 && gamma < 1.0) || !(tol >= 0.0)) return AMDP_EINVAL;
     if (!h->uploaded) return fail(h, AMDP_ESTATE, "value_iteration before upload_tasks");
     const amdp_config& c = h->cfg;
@@ -1085,7 +1085,7 @@ extern "C" int amdp_value_iteration(amdp_t* h, double gamma, double tol, int32_t
     }
     int sweeps = 0;
     long long launches = 0;
-    if (amdp_vi_run(h->T, c.n_tasks, gamma, tol, max_sweeps, h->vi_q, h->vi_v, h->vi_er, h->vi_diff, policy_out, &sweeps, &launches, st))
+    if (amdp_vi_run(h->T, c.n_tasks, greedy ? 1 : 0, gamma, tol, max_sweeps, h->vi_q, h->vi_v, h->vi_er, h->vi_diff, policy_out, &sweeps, &launches, st))
         return fail(h, AMDP_ECUDA, "value iteration failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->launches += launches;
     if (q_out) CK(cudaMemcpyAsync(q_out, h->vi_q, sizeof(double) * rows, cudaMemcpyDeviceToDevice, st));

@@ -258,6 +258,6 @@ void amdp_launch_step_tp(const Tables& T, const EnvArrays& E, long long n_envs, 
                          uint8_t* truncated, int32_t* actions_out, int32_t* steps_out, cudaStream_t st);
 void amdp_launch_w(const Tables& T, const EnvArrays& E, long long n_envs, unsigned long long tick, int K, const int32_t* actions,
                    const amdp_traj& J, cudaStream_t st);
-int amdp_vi_run(const Tables& T, long long n_tasks, double gamma, double tol, int max_sweeps, double* Q, double* V, double* er,
+int amdp_vi_run(const Tables& T, long long n_tasks, int greedy, double gamma, double tol, int max_sweeps, double* Q, double* V, double* er,
                 unsigned long long* maxdiff, uint8_t* policy_out, int* sweeps_out, long long* launches, cudaStream_t st);
 static inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }

@@ -99,21 +99,24 @@ __global__ void __launch_bounds__(256) k_vi_sweep(Tables T, long long rows, cons
     }
 }
 
-// V[s] = max_a Q[s,a], greedy policy = first maximum (numpy.argmax); one thread per (task, state)
-__global__ void k_vi_max(Tables T, long long states, const double* __restrict__ Q, double* __restrict__ V, uint8_t* __restrict__ policy) {
+// V[s] = max_a Q[s,a] (greedy backup) or mean_a Q[s,a] (the value of the uniform random policy: update_value_matrix with
+// is_greedy=False, solver.py:73-74), greedy policy = first maximum (numpy.argmax); one thread per (task, state)
+__global__ void k_vi_max(Tables T, long long states, const double* __restrict__ Q, double* __restrict__ V, uint8_t* __restrict__ policy,
+                         int greedy) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= states) return;
-    double best = Q[i * T.na];
+    double best = Q[i * T.na], sum = best;
     int arg = 0;
     for (int a = 1; a < T.na; ++a) {
         const double q = Q[i * T.na + a];
+        sum += q;
         if (q > best) { best = q; arg = a; }
     }
-    V[i] = best;
+    V[i] = greedy ? best : sum / (double)T.na;
     if (policy) policy[i] = (uint8_t)arg;
 }
 
-int amdp_vi_run(const Tables& T, long long n_tasks, double gamma, double tol, int max_sweeps, double* Q, double* V, double* er,
+int amdp_vi_run(const Tables& T, long long n_tasks, int greedy, double gamma, double tol, int max_sweeps, double* Q, double* V, double* er,
                 unsigned long long* maxdiff, uint8_t* policy_out, int* sweeps_out, long long* launches, cudaStream_t st) {
     const long long states = n_tasks * T.n_pad, rows = states * T.na;
     cudaMemsetAsync(Q, 0, sizeof(double) * rows, st);
@@ -133,7 +136,7 @@ int amdp_vi_run(const Tables& T, long long n_tasks, double gamma, double tol, in
     while (sweep < max_sweeps) {
         cudaMemsetAsync(maxdiff, 0, sizeof(unsigned long long), st);
         VI_DISPATCH(k_vi_sweep, T, rows, er, V, Q, gamma, alpha, maxdiff);
-        k_vi_max<<<nblk(states, 256), 256, 0, st>>>(T, states, Q, V, nullptr);
+        k_vi_max<<<nblk(states, 256), 256, 0, st>>>(T, states, Q, V, nullptr, greedy);
         *launches += 2;
         ++sweep;
         alpha = fmax(0.80 * alpha, 0.50);
@@ -146,7 +149,7 @@ int amdp_vi_run(const Tables& T, long long n_tasks, double gamma, double tol, in
             if (d <= tol) break;
         }
     }
-    if (policy_out) { k_vi_max<<<nblk(states, 256), 256, 0, st>>>(T, states, Q, V, policy_out); *launches += 1; }
+    if (policy_out) { k_vi_max<<<nblk(states, 256), 256, 0, st>>>(T, states, Q, V, policy_out, greedy); *launches += 1; }
     if (sweeps_out) *sweeps_out = sweep;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -228,15 +228,16 @@ class Engine:
                 raise ValueError(f"policy must have shape {(self.T, self.geo['n_pad'])}, got {tuple(p.shape)}")
             self._ck(lib.amdp_set_policy(self._h, _ptr(p), float(epsilon), _stream()))
 
-    def value_iteration(self, gamma=0.99, tol=1.0e-4, max_sweeps=10000, want_q=True):
+    def value_iteration(self, gamma=0.99, tol=1.0e-4, max_sweeps=10000, want_q=True, greedy=True):
         """Batched value iteration over every resident task (amdp_value_iteration).  Returns (Q float64 [T, n_pad, na] or
-        None, greedy policy uint8 [T, n_pad], sweeps); the policy tensor can go straight into `set_policy`."""
+        None, greedy policy uint8 [T, n_pad], sweeps); the policy tensor can go straight into `set_policy`.
+        greedy=False evaluates the uniform random policy instead (mean backup, solver.py:73-74)."""
         with torch.cuda.device(self.device):
             n_pad, na = self.geo["n_pad"], self.geo["na"]
             q = torch.empty((self.T, n_pad, na), dtype=torch.float64, device=self.device) if want_q else None
             pol = torch.empty((self.T, n_pad), dtype=torch.uint8, device=self.device)
             sweeps = ctypes.c_int32(0)
-            self._ck(lib.amdp_value_iteration(self._h, float(gamma), float(tol), int(max_sweeps), _ptr(q), _ptr(pol),
+            self._ck(lib.amdp_value_iteration(self._h, 1 if greedy else 0, float(gamma), float(tol), int(max_sweeps), _ptr(q), _ptr(pol),
                                               ctypes.byref(sweeps), _stream()))
             torch.cuda.current_stream().synchronize()
         return q, pol, int(sweeps.value)

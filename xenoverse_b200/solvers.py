@@ -14,7 +14,7 @@ def greedy_policy(value_matrix):
     return numpy.argmax(numpy.asarray(value_matrix), axis=1).astype(numpy.uint8)
 
 
-def value_iteration(task, gamma=0.99, tol=1.0e-4, max_sweeps=10000):
+def value_iteration(task, gamma=0.99, tol=1.0e-4, max_sweeps=10000, greedy=True):
     """Q-values [n, na] of a task dict by the reference's damped in-place sweeps (solver.py:57-80, is_greedy=True):
     every (s, a) is updated in place from the current matrix, `alpha` decays 1.0 -> 0.5 by 0.8 per sweep, and the
     iteration stops when the RMS change of a sweep is <= 1e-4.  (The sum over next states is a numpy dot instead of
@@ -24,7 +24,8 @@ def value_iteration(task, gamma=0.99, tol=1.0e-4, max_sweeps=10000):
     n, na, _ = r_mat.shape
     er = (t_mat * r_mat).sum(axis=2)                 # expected immediate reward of (s, a)
     vm = numpy.zeros((n, na))
-    vmax = vm.max(axis=1)
+    back = (lambda q: q.max()) if greedy else (lambda q: q.mean())     # solver.py:71-74 is_greedy
+    vmax = numpy.array([back(vm[s]) for s in range(n)])
     alpha, diff, sweeps = 1.0, 1.0, 0
     while diff > tol and sweeps < max_sweeps:
         sweeps += 1
@@ -33,7 +34,7 @@ def value_iteration(task, gamma=0.99, tol=1.0e-4, max_sweeps=10000):
             for a in range(na):
                 exp_q = er[s, a] + gamma * float(t_mat[s, a] @ vmax)
                 vm[s, a] += alpha * (exp_q - vm[s, a])
-                vmax[s] = vm[s].max()                # later (s, a) of the same sweep see the update
+                vmax[s] = back(vm[s])                # later (s, a) of the same sweep see the update
         diff = float(numpy.sqrt(numpy.mean((old - vm) ** 2)))
         alpha = max(0.80 * alpha, 0.50)
     return vm
