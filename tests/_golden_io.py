@@ -80,7 +80,7 @@ def load_case(name):
 
 
 def list_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("policy_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("policy_", "filter_")))
 
 
 def list_policy_cases():
@@ -95,3 +95,10 @@ def load_policy_case(name):
     return {"tasks": tasks, "env_task": d["env_task"], "U": d["U"], "obs0": d["obs0"],
             "value_matrix": [d[f"vm{t}"] for t in range(len(tasks))],
             "out": {k[len("out_"):]: v for k, v in d.items() if k.startswith("out_")}}
+
+
+def load_filter_case(name):
+    """Cases of tests/golden/make_filter_golden.py: raw candidate tasks and the reference's quality-filter quantities."""
+    with numpy.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False) as z:
+        d = {k: z[k] for k in z.files}
+    return {"tasks": unpack_tasks(d), "accept": d["accept"], "min_gap": d["min_gap"], "gini": d["gini"], "entropy": d["entropy"]}

@@ -160,3 +160,43 @@ def test_batched_value_iteration_random_policy_values():
         vm = value_iteration(task, gamma=0.9, tol=1e-12, greedy=False)
         assert numpy.allclose(q_rnd[t, :16], vm, rtol=1e-5, atol=1e-5)
     assert (q_opt >= q_rnd - 1e-6).all() and (q_opt.max(axis=2) > q_rnd.mean(axis=2) + 1e-3).any()
+
+
+def test_task_quality_filter_matches_reference_check_valuefunction():
+    """check_valuefunction_batch (two batched value iterations + batched matrix powers on the GPU) against the quantities
+    and decisions of the LIVE reference's solver.check_valuefunction on raw candidates of its own generator
+    (tests/golden/make_filter_golden.py).  The reference stops its value iteration at an RMS change of 1e-4, so values agree
+    to its stopping error and decisions wherever no threshold is within that error."""
+    from xenoverse_b200 import check_valuefunction_batch
+    c = gio.load_filter_case("filter_mdp16")
+    out = check_valuefunction_batch(c["tasks"])
+    gap_scale = numpy.array([(1.0 - 2.0 ** (-1.0 / 16)) * t["max_steps"] for t in c["tasks"]])
+    assert numpy.all(numpy.abs(out["min_gap"] - c["min_gap"]) < 0.05 * gap_scale + 1e-3 * numpy.abs(c["min_gap"]))
+    same_policy = (numpy.abs(out["gini"] - c["gini"]) < 1e-6)
+    assert same_policy.sum() >= len(same_policy) - 2             # (a near-tie in the value matrix may flip one greedy action)
+    assert numpy.allclose(out["entropy"][same_policy], c["entropy"][same_policy], atol=1e-6)
+    clear = (numpy.abs(c["min_gap"] - 2.0) > 0.3) & (numpy.abs(c["gini"] - 0.70) > 0.02) & (numpy.abs(c["entropy"] - 0.35) > 0.02) & same_policy
+    assert clear.sum() >= 8
+    assert numpy.array_equal(out["accept"][clear], c["accept"][clear])
+    assert out["accept"].any() and not out["accept"].all()
+
+
+def test_batch_task_sampler_gpu_filter():
+    """AnyMDPTaskSamplerBatch: CPU candidates, quality filter on the GPU; every returned task passes the filter again, has
+    the sampler's schema and runs in the engine."""
+    import time
+    from xenoverse_b200 import AnyMDPTaskSamplerBatch, AnyMDPVecEnv, check_valuefunction_batch
+    t0 = time.time()
+    tasks = AnyMDPTaskSamplerBatch(12, state_space=16, action_space=5, seed=7, batch=48)
+    dt = time.time() - t0
+    assert len(tasks) == 12 and dt < 120
+    for t in tasks:
+        assert t["transition"].shape == (16, 5, 16) and t["task_type"] == "MDP" and 100 <= t["max_steps"] <= 129
+        assert set(("ns", "na", "s_0", "s_0_prob", "s_e", "reward", "reward_noise", "state_mapping")) <= set(t)
+    assert check_valuefunction_batch(tasks)["accept"].all()
+    env = AnyMDPVecEnv(64, seed=1)
+    env.set_task(tasks)
+    env.reset()
+    env.rollout(50)
+    env.check()
+    assert tuple(AnyMDPTaskSamplerBatch(3, 16, 5, seed=7, batch=48)[0]["transition"].shape) == (16, 5, 16)

@@ -10,9 +10,9 @@ from .engine import Engine, AMDPError, task_geometry, pack_tasks, unpack_records
 from .anymdp_env import AnyMDPEnv  # noqa: F401
 from .vec_env import AnyMDPVecEnv  # noqa: F401
 from .task_sampler import (AnyMDPTaskSampler, AnyPOMDPTaskSampler, MultiTokensAnyPOMDPTaskSampler,  # noqa: F401
-                           GarnetTaskSampler)
+                           GarnetTaskSampler, AnyMDPTaskSamplerBatch)
 from .synth import synth_task, synth_packed, synth_geometry, packed_to_task  # noqa: F401
-from .solvers import greedy_policy, value_iteration, optimal_policy  # noqa: F401
+from .solvers import greedy_policy, value_iteration, optimal_policy, check_valuefunction_batch  # noqa: F401
 from .writer import TrajectoryWriter, dump_task, load_task, load_shard, records_to_arrays  # noqa: F401
 
 __version__ = "0.1.0"

@@ -11,7 +11,7 @@ across numpy versions either).  Task sampling is host-side set-up work, outside 
 import numpy
 
 __all__ = ["AnyMDPTaskSampler", "AnyPOMDPTaskSampler", "MultiTokensAnyPOMDPTaskSampler", "GarnetTaskSampler",
-           "value_iteration"]
+           "AnyMDPTaskSamplerBatch", "value_iteration"]
 
 
 def _rng(seed):
@@ -219,6 +219,41 @@ def AnyMDPTaskSampler(state_space: int = 64, action_space: int = 5, min_state_sp
     if best is None:
         raise RuntimeError("could not sample a valid MDP")
     return best
+
+
+def AnyMDPTaskSamplerBatch(count, state_space: int = 64, action_space: int = 5, seed=None, device=0, batch=None,
+                           max_rounds=50, verbose=False):
+    """`count` MDP tasks at once.  The reference samples one task at a time and runs two value iterations
+    per CANDIDATE on the CPU (task_sampler.py:52-63 -> solver.check_valuefunction), 0.2-50 s per accepted task.  Here
+    candidates are generated on the CPU without any value iteration and the whole quality filter (value gap of every start
+    state, Gini impurity and entropy of the optimal policy's long-run distribution; solver.py:105-148) runs for a batch of
+    candidates on the GPU (`solvers.check_valuefunction_batch`).  Returns a list of `count` task dicts (schema of
+    AnyMDPTaskSampler)."""
+    from .solvers import check_valuefunction_batch
+    assert state_space >= 8, "State Space must be at least 8"
+    rng = _rng(seed)
+    batch = batch or max(16, min(1024, 2 * count))
+    out = []
+    for rnd in range(max_rounds):
+        cands = []
+        while len(cands) < batch:
+            max_steps = _max_steps(rng, state_space)
+            state_mapping, n = _state_subset(rng, state_space, None)
+            s_0, s_0_prob, terminal, goal_terminates, transition = _sample_structure(rng, n, action_space)
+            rewards = _sample_rewards(rng, n, action_space, terminal, goal_terminates, transition, s_0)
+            if rewards is None:
+                continue
+            cands.append({"ns": state_space, "na": action_space, "max_steps": max_steps, "state_mapping": state_mapping,
+                          "task_type": "MDP", "s_0": s_0, "s_0_prob": s_0_prob, "s_e": numpy.nonzero(terminal)[0],
+                          "transition": transition, "reward": rewards[0], "reward_noise": rewards[1],
+                          "final_goal_terminate": goal_terminates})
+        res = check_valuefunction_batch(cands, device=device)
+        out.extend(c for c, ok in zip(cands, res["accept"]) if ok)
+        if verbose:
+            print(f"round {rnd}: {int(res['accept'].sum())} of {batch} candidates accepted, {len(out)} / {count}")
+        if len(out) >= count:
+            return out[:count]
+    raise RuntimeError(f"only {len(out)} of {count} tasks passed the quality filter in {max_rounds} rounds")
 
 
 def _observation_matrix(rng, n, observation_space, density, maximum_distribution):
