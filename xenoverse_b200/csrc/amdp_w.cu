@@ -4,6 +4,9 @@
 #ifndef AMDP_W_MINB
 #define AMDP_W_MINB 7      // resident blocks per SM the register budget is sized for (7 x 4 warps x 148 SMs >= 4096 envs)
 #endif
+#ifndef AMDP_W_HOIST
+#define AMDP_W_HOIST 1     // force the next tick's input shuffles in front of the wait for the row (measured: +0.5 %)
+#endif
 #ifndef AMDP_W_HINT
 #define AMDP_W_HINT 0      // L2 eviction hints: 1 payload evict_first, 2 rows of reset states evict_last (measured: both lose)
 #endif
@@ -266,8 +269,13 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
         // (B) the chain: row -> count below code15(u) -> REDUX.MIN -> next state -> next row address
         const unsigned v2le = v2 + 0x00010001u;                   // entries <= code15(u): below the next code
         int lt = 0, le = 0;                                       // this lane's entries below u / not above u
+        RowW<NW> q = cur.q;
+#if AMDP_W_HOIST
+        // everything of (A) is issued BEFORE the row is waited for: the asm ties the first row word to the next tick's inputs
+        { unsigned nv2_ = nv2; asm volatile("" : "+r"(q.w[0]), "+l"(nbase), "+r"(nv2_)); }
+#endif
 #pragma unroll
-        for (int i = 0; i < NW; ++i) { lt = h2_count_lt_pos(cur.q.w[i], v2, lt); le = h2_count_lt_pos(cur.q.w[i], v2le, le); }
+        for (int i = 0; i < NW; ++i) { lt = h2_count_lt_pos(q.w[i], v2, lt); le = h2_count_lt_pos(q.w[i], v2le, le); }
         // (index of the first entry not below u) << 5 | is_terminal[it] << 4 | entries sharing u's code (undecided)
         unsigned val = lane_base32 + ((unsigned)lt << ISH) + (unsigned)(le - lt) + ((myterm16 >> lt) & 16u);
         if (TABLE) val += ((unsigned)(mypol >> ((8 * lt) & 63)) & 0xffu) << 5;   // ... | table action of that entry << 5
