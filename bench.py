@@ -497,7 +497,7 @@ def main():
     ap.add_argument("--policy", default="uniform", choices=["uniform", "table"],
                     help="behaviour policy of the device rollouts: the engine's uniform random one (BASELINE.json) or a table (amdp_set_policy)")
     ap.add_argument("--epsilon", type=float, default=0.1)
-    ap.add_argument("--search", default="auto", choices=["auto", "one_level", "two_level", "thread", "warp", "warp_v1"],
+    ap.add_argument("--search", default="auto", choices=["auto", "one_level", "two_level", "thread", "warp", "warp_v1", "sparse"],
                     help="row-search / kernel selection of the engine (see Engine)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

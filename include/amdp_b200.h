@@ -78,6 +78,7 @@ extern "C" {
 #define AMDP_TASK_NOT_NORMALISED 2  /* numpy choice(): 'probabilities do not sum to 1' (|kahan_sum(p)-1| > sqrt(eps)) */
 #define AMDP_TASK_NEGATIVE_P    3   /* numpy choice(): 'probabilities are not non-negative' */
 #define AMDP_TASK_S0_IN_SE      4   /* anymdp_env.py:74-76 a start state is also terminal */
+#define AMDP_TASK_NOT_SPARSE    6   /* the handle was created for sparse rows (reserved0 flag 64) and a row has more than 8 non-zero successors */
 #define AMDP_TASK_OBS_RANGE     5   /* a state_mapping value does not fit the observation bits stated in amdp_config.reserved0 (bits 8-12) */
 
 #define AMDP_SLOTS_PER_TOKEN 8
@@ -108,6 +109,8 @@ typedef struct amdp_config {
                                kernel (default: used from 4096 envs, from 12288 where k_rollout_w applies); 2 / 4 force the one- / two-level
                                row search of the fast rollout kernel (default: chosen from n_pad and n_envs); 32 keeps MDP engines
                                off k_rollout_w (the REDUX.MIN warp-per-env kernel for rows of 64 / 128 / 256 states);
+                               64: SPARSE rows — every (s, a) of every task has at most 8 non-zero successors (Garnet tasks,
+                               task_sampler.py:120-159): one 128-byte line per row, no pivot levels, the thread-per-env kernel at any size;
                                bits 8-12: bit_length(max ns - 1) over all tasks (0 = not stated, 15 assumed): the thread-per-env tables
                                carry state_mapping in that many low bits of their CDF code words; more than 15 disables that kernel */
     int64_t  n_envs;        /* envs owned by this handle (this GPU's shard) */

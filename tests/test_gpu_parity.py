@@ -772,3 +772,57 @@ def test_fuzz_fast_rollout_kernels_equal_generic(i, ns, na, N, mode, act, search
     for key in ("state", "steps", "flags", "ep_return"):
         assert torch.equal(sa[key], sb[key]), key
     assert str(ea) == str(eb)
+
+
+@pytest.mark.parametrize("ns,na,b,N,mode,act", [(16, 5, 2, 300, "same_step", "uniform"), (128, 5, 3, 257, "next_step", "given"),
+                                                (128, 4, 8, 1000, "same_step", "table"), (300, 3, 5, 64, "same_step", "uniform"),
+                                                (64, 8, 1, 100, "next_step", "uniform"), (1000, 2, 4, 40, "same_step", "given")])
+def test_sparse_rows_garnet_equal_generic(ns, na, b, N, mode, act):
+    """Garnet tasks (exactly b non-zero successors per (s, a), task_sampler.py:120-159): the engine picks the sparse row format
+    (ONE 128-byte line per row: codes of the non-zero successors with their state index, mapping and terminal flag in the
+    low bits, payloads) — rollouts and per-tick steps must equal the generic kernels on the dense tables bit for bit."""
+    from xenoverse_b200 import GarnetTaskSampler, AnyMDPVecEnv
+    tasks = [GarnetTaskSampler(ns, na, b=b, seed=3100 + t) for t in range(4)]
+    for i, t in enumerate(tasks):
+        t["max_steps"] = 41.5
+        t["s_e"] = numpy.array([ns - 1 - i, ns // 2])             # some terminal states (Garnet itself has none)
+        t["transition"][t["s_e"]] = 0.0
+        t["reward_noise"] = numpy.abs(t["reward"]) * 0.3
+    K = 130
+    rng = numpy.random.default_rng(ns + b)
+    acts = torch.from_numpy(rng.integers(0, na, (K, N)).astype(numpy.int32)).cuda() if act == "given" else None
+    pol = [rng.integers(0, na, ns) for _ in tasks]
+    outs = []
+    for generic in (False, True):
+        env = AnyMDPVecEnv(N, seed=77, autoreset=mode)
+        env.set_task(tasks)
+        fits = 1 + 2 * (ns - 1).bit_length() <= 19               # flag + mapping + state index must leave >= 12 code bits
+        assert env.engine.rollout_kernel.endswith("sparse>") == fits, env.engine.rollout_kernel
+        if act == "table":
+            env.set_policy(pol, epsilon=0.2)
+        env.engine.force_generic(generic)
+        env.reset()
+        tr = env.rollout(K, actions=acts, policy="device" if act == "table" else "uniform",
+                         record=("obs", "action", "reward", "reward_gt", "done"))
+        steps = []
+        for k in range(12):                                       # the per-tick kernel on the same tables
+            o, r, te, tu, info = env.step(None if acts is None else acts[k])
+            steps.append([x.clone() for x in (o, r, te, tu, info["steps"], info["final_obs"])])
+        env.check()
+        outs.append((tr, steps, env.engine.get_state(), env.episode_stats()))
+    (a, xa, sa, ea), (b_, xb_, sb, eb) = outs
+    for key in ("obs", "action", "done", "reward", "reward_gt"):
+        assert torch.equal(a[key], b_[key]), key
+    for k, (x, y) in enumerate(zip(xa, xb_)):
+        for u, v in zip(x, y):
+            assert torch.equal(u, v), k
+    for key in ("state", "steps", "flags", "ep_return"):
+        assert torch.equal(sa[key], sb[key]), key
+    assert str(ea) == str(eb) and ea["episodes"] > 0
+
+
+def test_sparse_rows_reject_dense_tasks():
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    env = AnyMDPVecEnv(8, search="sparse")
+    with pytest.raises(Exception, match="non-zero successors"):
+        env.set_task([synth_task(32, 4, 1)])

@@ -16,7 +16,7 @@ MDP, POMDP, MTPOMDP = 0, 1, 2
 TASK_TYPES = {"MDP": MDP, "POMDP": POMDP, "MTPOMDP": MTPOMDP}
 AUTORESET = {"same_step": 0, "next_step": 1, "disabled": 2}
 FAULT_NEED_RESET, FAULT_TERMINAL_STATE, FAULT_BAD_ACTION = 1, 2, 4
-TASK_OK, TASK_BAD_ROW_SUM, TASK_NOT_NORMALISED, TASK_NEGATIVE_P, TASK_S0_IN_SE, TASK_OBS_RANGE = 0, 1, 2, 3, 4, 5
+TASK_OK, TASK_BAD_ROW_SUM, TASK_NOT_NORMALISED, TASK_NEGATIVE_P, TASK_S0_IN_SE, TASK_OBS_RANGE, TASK_NOT_SPARSE = 0, 1, 2, 3, 4, 5, 6
 SLOTS_PER_TOKEN = 8
 SLOT_TRANS, SLOT_RESET, SLOT_OBS, SLOT_RESET_OBS, SLOT_Z, SLOT_ACTION = 0, 1, 2, 3, 4, 5
 ABI_VERSION = 1

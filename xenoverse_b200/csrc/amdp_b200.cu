@@ -323,7 +323,7 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
                              double* __restrict__ cdf, float2* __restrict__ payload, uint16_t* __restrict__ sketch,
                              uint16_t* __restrict__ pivot, const int32_t* __restrict__ state_mapping, uint4* __restrict__ fat,
                              uint16_t* __restrict__ pv, uint16_t* __restrict__ top, int tp_blocks, int tp_groups,
-                             int tp_obs_bits,
+                             int tp_obs_bits, int tp_nxt_bits,
                              int32_t* __restrict__ status) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long rows = cnt * n_pad * na;
@@ -400,8 +400,33 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
         // and the kernel reads its flag as the minimum over the entries not below u.
         // The low 1 + tp_obs_bits bits of a code word carry is_terminal[j] and state_mapping[j] (the observation of a
         // transition into j), so that the search needs no state-word request; the search compares the remaining high bits.
-        const uint32_t hmask = 0xffffffffu << (1 + tp_obs_bits);
+        const uint32_t hmask = 0xffffffffu << (1 + tp_obs_bits + tp_nxt_bits);
         uint32_t prev_code = 1u, prev_f = 0;                       // (1: not a masked code)
+        if (tp_nxt_bits) {
+            // SPARSE row: the (at most 8) successors with non-zero probability, in state order, with their entries of the
+            // dense CDF (adding a zero changes no partial sum: the first entry above u is always one of them) and their
+            // state index above the mapping bits.  More than 8: the task does not fit this format.
+            uint32_t* line = reinterpret_cast<uint32_t*>(fat + r * 8);
+            int k = 0;
+            for (int j = 0; j < n; ++j) {
+                if (p[j] == 0.0) continue;
+                if (k == 8) { if (status) atomicMax(status + t, AMDP_TASK_NOT_SPARSE); break; }
+                const uint32_t code = (code31(c[j]) << 1) & hmask;
+                const uint32_t is_t = is_terminal[t * n_pad + j] ? 1u : 0u;
+                uint32_t f = is_t | (((uint32_t)state_mapping[t * n_pad + j] << 1) | ((uint32_t)j << (1 + tp_obs_bits))) & ~hmask;
+                if (((uint32_t)state_mapping[t * n_pad + j] >> tp_obs_bits) && status) atomicMax(status + t, AMDP_TASK_OBS_RANGE);
+                if (code == prev_code) f = prev_f;
+                line[k] = code | f;
+                prev_code = code; prev_f = f;
+                line[8 + 2 * k] = __float_as_uint(pl[j].x);
+                line[8 + 2 * k + 1] = __float_as_uint(pl[j].y);
+                ++k;
+            }
+            // padding entries share the code of 1.0 with the last successor: like every run of equal codes they carry the
+            // low bits of the run's first entry (the search reads the minimum over the entries not below u)
+            for (; k < 8; ++k) { line[k] = hmask | (prev_code == hmask ? prev_f : 0u); line[8 + 2 * k] = 0u; line[8 + 2 * k + 1] = 0u; }
+            for (int i = 24; i < 32; ++i) line[i] = 0u;
+        } else
         for (int b = 0; b < tp_blocks; ++b) {
             uint32_t* line = reinterpret_cast<uint32_t*>(fat + (r * tp_blocks + b) * 8);
             for (int i = 0; i < 8; ++i) {
@@ -772,9 +797,16 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     const bool wv2_ok = mdp && !(c.reserved0 & 32) && c.autoreset == AMDP_AUTORESET_SAME_STEP &&
                         (c.n_pad == 64 || c.n_pad == 128 || c.n_pad == 256) && c.na <= 256 && c.s0_pad <= TP_S0;
     const long long tp_from = wv2_ok ? 12288 : 4096;
-    h->tp = tp_kind && obs_bits <= 15 && c.n_pad <= 2048 && c.s0_pad <= TP_S0 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= tp_from));
+    // flag 64: SPARSE rows (every (s, a) of every task has at most 8 non-zero successors; Garnet tasks): the thread-per-env
+    // kernel with ONE 128-byte line per row and no pivot levels, for any number of envs
+    int nxt_bits = 0;
+    while ((1 << nxt_bits) < c.n_pad) ++nxt_bits;
+    const bool sparse = mdp && (c.reserved0 & 64) && !(c.reserved0 & 16) && obs_bits <= 15 && 1 + obs_bits + nxt_bits <= 19 &&
+                        c.s0_pad <= TP_S0;
+    h->T.tp_nxt_bits = sparse ? (nxt_bits > 0 ? nxt_bits : 1) : 0;
+    h->tp = sparse || (tp_kind && obs_bits <= 15 && c.n_pad <= 2048 && c.s0_pad <= TP_S0 && !(c.reserved0 & 16) && ((c.reserved0 & 8) || (!(c.reserved0 & 6) && c.n_envs >= tp_from)));
     if (h->tp) {
-        const int nb = (c.n_pad + 7) / 8;
+        const int nb = sparse ? 1 : (c.n_pad + 7) / 8;
         h->T.tp_blocks = nb;
         h->T.tp_levels = nb == 1 ? 1 : (nb <= 16 ? 2 : 3);
         h->T.tp_groups = h->T.tp_levels == 3 ? (nb + 15) / 16 : 1;
@@ -853,7 +885,7 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
                                                   h->fat ? h->fat + (size_t)t0 * c.n_pad * c.na * h->T.tp_blocks * 8 : nullptr,
                                                   h->pv ? h->pv + (size_t)t0 * c.n_pad * c.na * h->T.tp_groups * 16 : nullptr,
                                                   h->top ? h->top + (size_t)t0 * c.n_pad * c.na * 16 : nullptr,
-                                                  h->T.tp_blocks, h->T.tp_groups, h->T.tp_obs_bits, status_out);
+                                                  h->T.tp_blocks, h->T.tp_groups, h->T.tp_obs_bits, h->T.tp_nxt_bits, status_out);
     k_build_small<<<nblk(cnt, 128), 128, 0, st>>>(cnt, c.n_pad, c.s0_pad, state_mapping, n_real, is_terminal, s0_idx, s0_prob,
                                                   n_s0, max_steps, ns, h->sinfo + t0 * c.n_pad, h->s0_cdf + t0 * c.s0_pad,
                                                   h->s0_idx + t0 * c.s0_pad, h->max_ceil + t0, h->tflags + t0,
@@ -1112,7 +1144,8 @@ extern "C" const char* amdp_rollout_kernel(amdp_t* h) {
     const amdp_config& c = h->cfg;
     const bool fast = (c.task_type == AMDP_MDP || (h->tp && c.task_type == AMDP_POMDP)) && !h->force_generic;
     if (!fast) snprintf(h->kname, sizeof(h->kname), "k_rollout<G=%d>", h->G);
-    else if (h->tp) snprintf(h->kname, sizeof(h->kname), "k_rollout_tp<levels=%d,%s>", h->T.tp_levels, c.task_type == AMDP_POMDP ? "POMDP" : "MDP");
+    else if (h->tp) snprintf(h->kname, sizeof(h->kname), "k_rollout_tp<levels=%d,%s%s>", h->T.tp_levels, c.task_type == AMDP_POMDP ? "POMDP" : "MDP",
+                             h->T.tp_nxt_bits ? ",sparse" : "");
     else if (h->two_level) snprintf(h->kname, sizeof(h->kname), "k_rollout_mdp<G=8,two-level>");
     else if (h->wv2) snprintf(h->kname, sizeof(h->kname), "k_rollout_w<EPL=%d>", c.n_pad / 32);
     else snprintf(h->kname, sizeof(h->kname), "k_rollout_mdp<G=%d>", h->G);

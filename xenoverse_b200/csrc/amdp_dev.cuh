@@ -44,6 +44,8 @@ struct Tables {
     const uint16_t* top;      // [T][n_pad][na][16] code15 of the last entry of each group (three-level rows only)
     int tp_levels, tp_groups, tp_blocks;
     int tp_obs_bits;          // bits of state_mapping carried in the code words (bit_length(max ns - 1) <= 15)
+    int tp_nxt_bits;          // > 0: SPARSE rows (every (s, a) has at most 8 non-zero successors, e.g. Garnet tasks): a row is ONE
+                              // line whose 8 entries are its non-zero successors; their state indices sit above the mapping bits
     const uint32_t* ofat;     // POMDP (do = 1): [T][n_pad][8 + 8 * o_blocks] words per observation row: 16 pivots (code15 of the last
                               // entry of each 8-entry block; pad 0x7bff), then o_blocks x 8 codes (floor(cdf * 2^31) << 1)
     int o_blocks;

@@ -260,6 +260,9 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
                 ++blk;                                             // the whole block is below u (its pivot shared u's 15-bit cell)
             }
             int nxt = blk * 8 + lt;
+            // sparse rows (one line per row, LEVELS == 1): the state index of the entry sits above its mapping bits
+            const bool sparse = LEVELS == 1 && T.tp_nxt_bits > 0;
+            if (sparse) nxt = (le != lt) ? 0 : (int)((mn >> (1 + T.tp_obs_bits)) & ((1u << T.tp_nxt_bits) - 1u));
             bool term = (mn & 1u) != 0;                            // is_terminal[nxt] (bit 0 of the first entry not below u)
             if (le != lt) {
                 // code31(cdf[j]) == code31(u) for some j: decide those entries on the float64 row
@@ -355,7 +358,7 @@ static void launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, boo
 
 void amdp_launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, bool pomdp, bool next, int coarse_bits, unsigned long long tick, int K,
                     const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
-    const int low = 1 + T.tp_obs_bits + coarse_bits;            // is_terminal + state_mapping bits (+ bits the tests drop)
+    const int low = 1 + T.tp_obs_bits + T.tp_nxt_bits + coarse_bits;   // is_terminal + state_mapping (+ sparse: state index) bits (+ bits the tests drop)
     const unsigned cmask = 0xffffffffu << (low < 30 ? low : 30);
     if (T.tp_levels == 1) launch_tp<1>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
     else if (T.tp_levels == 2) launch_tp<2>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
@@ -484,6 +487,7 @@ __global__ void __launch_bounds__(128) k_step_tp(const Tables T, const EnvArrays
             ++blk;
         }
         int nxt = blk * 8 + lt;
+        if (T.tp_nxt_bits) nxt = (le != lt) ? 0 : (int)((mn >> (1 + T.tp_obs_bits)) & ((1u << T.tp_nxt_bits) - 1u));   // sparse rows
         float2 pay;
         if (le != lt) {                                            // undecided on the codes: the float64 row (anymdp_env.py:100)
             const double u = u53(w0.x, w0.y);
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(128) k_step_tp(const Tables T, const EnvArrays
 void amdp_launch_step_tp(const Tables& T, const EnvArrays& E, long long n_envs, int coarse_bits, unsigned long long tick,
                          const int32_t* actions, int32_t* obs, int32_t* final_obs, float* reward, float* reward_gt, uint8_t* terminated,
                          uint8_t* truncated, int32_t* actions_out, int32_t* steps_out, cudaStream_t st) {
-    const int low = 1 + T.tp_obs_bits + coarse_bits;
+    const int low = 1 + T.tp_obs_bits + T.tp_nxt_bits + coarse_bits;
     const unsigned cmask = 0xffffffffu << (low < 30 ? low : 30);
     k_step_tp<<<nblk(n_envs, 128), 128, 0, st>>>(T, E, tick, cmask, actions, obs, final_obs, reward, reward_gt, terminated, truncated,
                                                  actions_out, steps_out);

@@ -42,8 +42,9 @@ def task_geometry(tasks):
     na = int(t0["na"])
     da = int(t0.get("da", 1)) if tt == "MTPOMDP" else 1
     do = int(t0.get("do", 1)) if tt == "MTPOMDP" else 1
-    n_max, no_max, s0_max = 1, 1, 1
+    n_max, no_max, s0_max, nnz_max = 1, 1, 1, 0
     for t in tasks:
+        nnz_max = max(nnz_max, int((numpy.asarray(t["transition"]) != 0).sum(axis=-1).max()))
         if t["task_type"] != tt or int(t["na"]) != na:
             raise ValueError("all tasks of one engine must share task_type and na")
         if tt == "MTPOMDP" and (int(t["da"]) != da or int(t["do"]) != do):
@@ -52,7 +53,7 @@ def task_geometry(tasks):
         s0_max = max(s0_max, len(numpy.atleast_1d(t["s_0"])))
         if tt != "MDP":
             no_max = max(no_max, int(t["no"]))
-    return {"task_type": tt, "na": na, "da": da, "do": do, "n_pad": round_up4(n_max), "ns_max": max(int(t["ns"]) for t in tasks),
+    return {"task_type": tt, "na": na, "da": da, "do": do, "n_pad": round_up4(n_max), "ns_max": max(int(t["ns"]) for t in tasks), "max_nnz": nnz_max,
             "no_pad": round_up4(no_max) if tt != "MDP" else 0, "s0_pad": s0_max}
 
 
@@ -113,6 +114,7 @@ _STATUS_MSG = {
     _lib.TASK_NEGATIVE_P: "probabilities are not non-negative",               # numpy choice()
     _lib.TASK_S0_IN_SE: "a state is both a start state and a terminal state",  # anymdp_env.py:76
     _lib.TASK_OBS_RANGE: "state_mapping value outside the observation space stated for the engine (geo['ns_max'])",
+    _lib.TASK_NOT_SPARSE: "a transition row has more than 8 non-zero successors (engine created for sparse rows)",
 }
 
 
@@ -123,7 +125,9 @@ class Engine:
         8/16-entry block of 31-bit codes; auto picks it from 12288 envs where k_rollout_w applies, else from 4096); "one_level" / "two_level": the warp-per-env
         latency kernel streaming the 16-bit filter row / reading 32 pivots + one 32-entry block (auto: two_level for
         n_pad >= 512); "warp": auto without the thread-per-env kernel; "warp_v1": additionally without k_rollout_w (the
-        REDUX.MIN warp-per-env kernel auto picks for same-step MDP engines with rows of 64 / 128 / 256 states)."""
+        REDUX.MIN warp-per-env kernel auto picks for same-step MDP engines with rows of 64 / 128 / 256 states); "sparse":
+        one 128-byte line per (s, a) row for tasks whose rows have at most 8 non-zero successors (Garnet); auto picks it
+        when `geo["max_nnz"] <= 8`."""
         if not torch.cuda.is_available():
             raise AMDPError("xenoverse_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
@@ -131,10 +135,13 @@ class Engine:
         self.N, self.T = int(num_envs), int(num_tasks)
         self.da, self.do = geo["da"], geo["do"]
         self.autoreset = autoreset
+        # sparse rows (Garnet tasks: at most 8 non-zero successors per (s, a)): one line per row in the thread-per-env kernel
+        sparse = (geo["task_type"] == "MDP" and search in ("auto", "sparse") and 0 < int(geo.get("max_nnz", 0)) <= 8
+                  and geo["n_pad"] > 8) or (search == "sparse" and geo["task_type"] == "MDP")
         cfg = _lib.Config(device=self.device.index, task_type=_lib.TASK_TYPES[geo["task_type"]],
                           autoreset=_lib.AUTORESET[autoreset], na=geo["na"], n_pad=geo["n_pad"], no_pad=geo["no_pad"],
                           n_obs_tok=geo["do"], n_act_tok=geo["da"], s0_pad=geo["s0_pad"],
-                          reserved0=(1 if keep_transition else 0) | (self._obs_bits(geo) << 8) | {"auto": 0, "one_level": 2, "two_level": 4, "thread": 8, "warp": 16, "warp_v1": 48}[search],
+                          reserved0=(1 if keep_transition else 0) | (self._obs_bits(geo) << 8) | {"auto": 0, "one_level": 2, "two_level": 4, "thread": 8, "warp": 16, "warp_v1": 48, "sparse": 64}[search] | (64 if sparse else 0),
                           n_envs=self.N, n_tasks=self.T,
                           seed=int(seed) & (2 ** 64 - 1), env_id_base=int(env_id_base))
         h = ctypes.c_void_p()
