@@ -235,6 +235,36 @@ def measure_dropin(local, steps=4000):
             "value": steps / dt, "unit": "env-steps/s", "us_per_step": 1e6 * dt / steps, "kernel": "k_step<G=4>"}
 
 
+def measure_garnet(local, dev, envs=65536, tasks=64, ns=128, na=5, b=3, ticks=128, steps=10):
+    """Garnet tasks (GarnetTaskSampler: exactly b non-zero successors per (s, a)) in the sparse row format:
+    one 128-byte line per row, no pivot levels; same timing method as the other workloads."""
+    import torch
+    from xenoverse_b200 import AnyMDPVecEnv, GarnetTaskSampler
+    env = AnyMDPVecEnv(envs, device=local, seed=0)
+    env.set_task([GarnetTaskSampler(ns, na, b=b, seed=4000 + t) for t in range(tasks)])
+    env.reset()
+    traj = {"obs": torch.empty((ticks, envs, 1), dtype=torch.int32, device=dev), "action": torch.empty((ticks, envs, 1), dtype=torch.int32, device=dev),
+            "reward": torch.empty((ticks, envs), dtype=torch.float32, device=dev), "done": torch.empty((ticks, envs), dtype=torch.uint8, device=dev)}
+    for _ in range(3):
+        env.rollout(ticks, out=traj)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        env.rollout(ticks, out=traj)
+    t1.record()
+    torch.cuda.synchronize()
+    env.check()
+    ms = t0.elapsed_time(t1) / steps
+    out = {"workload": f"garnet: AnyMDP Garnet MDP batch {envs} envs x ns={ns} na={na} b={b}, {tasks} tasks shared round-robin "
+                       f"(rows L2-resident), uniform random policy, {ticks} ticks per rollout launch",
+           "value": envs * ticks / (ms * 1e-3), "unit": "env-steps/s", "ms_per_launch": ms, "kernel": env.engine.rollout_kernel,
+           "table_bytes": env.engine.device_bytes, "algorithmic_bytes_per_env_step": b_alg(ns, None)}
+    env.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def measure_vi(name, tasks, ns, na, dev, local, sweeps=64):
     """Batched value iteration (amdp_value_iteration) over `tasks` resident synthetic tasks: a fixed
     number of sweeps (tol = 0), device time; HBM roofline = the float64 CDF rows streamed once per sweep."""
@@ -416,6 +446,10 @@ def run_b200(args, name, envs, tasks, ns, na, no):
                                             epsilon=0.1 if key.endswith("_table_policy") else None)
             except Exception as ex:           # never lose the headline line to an extra
                 others[key] = {"error": str(ex)[:200]}
+        try:
+            others["garnet128_b3_sparse_rows"] = measure_garnet(local, dev)
+        except Exception as ex:
+            others["garnet128_b3_sparse_rows"] = {"error": str(ex)[:200]}
         try:
             others["cfg1_single_env_dropin"] = measure_dropin(local)
         except Exception as ex:
