@@ -127,22 +127,29 @@ class ClockSampler:
         except Exception as e:
             self.err = str(e)
 
-    def _run(self):
+    def sample_once(self):
+        """One sample (also called from the timed loop itself every 32 steps: the background thread can be starved of the
+        GIL by the launching loop, and a timed region without clock samples proves nothing)."""
+        if not self.ok:
+            return
         nv = self.nv
         bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-        while not self._stop.is_set():
+        try:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
             try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for name, bit in bits.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self.sample_once()
             time.sleep(0.0005)
 
     def start(self):
@@ -378,6 +385,8 @@ def run_b200(args, name, envs, tasks, ns, na, no):
     t0.record()
     for i in range(K):
         one_step(evs[i])
+        if rank == 0 and (i & 31) == 16:
+            clocks.sample_once()
     if side is not None:
         torch.cuda.current_stream().wait_stream(side)      # the timed region ends when the last all-reduce has landed
     t1.record()
