@@ -128,8 +128,8 @@ class ClockSampler:
             self.err = str(e)
 
     def sample_once(self):
-        """One sample (also called from the timed loop itself every 32 steps: the background thread can be starved of the
-        GIL by the launching loop, and a timed region without clock samples proves nothing)."""
+        """One sample.  (NVML calls take milliseconds now and then: never call this from the timed loop itself — measured: six
+        calls in 200 steps halved the throughput.  The background thread does the sampling.)"""
         if not self.ok:
             return
         nv = self.nv
@@ -385,8 +385,6 @@ def run_b200(args, name, envs, tasks, ns, na, no):
     t0.record()
     for i in range(K):
         one_step(evs[i])
-        if rank == 0 and (i & 31) == 16:
-            clocks.sample_once()
     if side is not None:
         torch.cuda.current_stream().wait_stream(side)      # the timed region ends when the last all-reduce has landed
     t1.record()
