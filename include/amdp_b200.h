@@ -111,6 +111,8 @@ typedef struct amdp_config {
                                off k_rollout_w (the REDUX.MIN warp-per-env kernel for rows of 64 / 128 / 256 states);
                                64: SPARSE rows — every (s, a) of every task has at most 8 non-zero successors (Garnet tasks,
                                task_sampler.py:120-159): one 128-byte line per row, no pivot levels, the thread-per-env kernel at any size;
+                               128: SPARSE observation rows — every state of every POMDP task observes at most 8 different observations
+                               (task_sampler.py:81-87 makes ~4): one 32-byte sector per state in the thread-per-env kernels;
                                bits 8-12: bit_length(max ns - 1) over all tasks (0 = not stated, 15 assumed): the thread-per-env tables
                                carry state_mapping in that many low bits of their CDF code words; more than 15 disables that kernel */
     int64_t  n_envs;        /* envs owned by this handle (this GPU's shard) */

@@ -496,7 +496,7 @@ __global__ void k_build_small(int64_t cnt, int n_pad, int s0_pad, const int32_t*
 
 // observation CDF rows: one thread per (task, token, state)
 __global__ void k_build_obs(int64_t rows, int n_pad, int no_pad, const double* __restrict__ obs_t, double* __restrict__ obs_cdf,
-                            uint32_t* __restrict__ ofat, int o_blocks) {
+                            uint32_t* __restrict__ ofat, int o_blocks, int o_sparse_bits, int rows_per_task, int32_t* __restrict__ status) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const double* p = obs_t + r * no_pad;
@@ -506,7 +506,24 @@ __global__ void k_build_obs(int64_t rows, int n_pad, int no_pad, const double* _
     // zero padding leaves the tail at the final partial sum, i.e. 1.0 after the divide
     if (acc > 0.0) for (int i = 0; i < no_pad; ++i) { double v = __ddiv_rn(c[i], acc); c[i] = (v == 0.0) ? 0.0 : v; }
     else for (int i = 0; i < no_pad; ++i) c[i] = 1.0;
-    if (ofat) {
+    if (ofat && o_sparse_bits) {
+        // sparse observation row: the (at most 8) observations with non-zero probability, in index order, with their entries
+        // of the dense CDF and their index in the low bits; padding carries the low bits of the last entry (a run of equal codes)
+        const uint32_t hmask = 0xffffffffu << (1 + o_sparse_bits);
+        uint32_t* o = ofat + r * 8;
+        uint32_t prev_code = 1u, prev_f = 0;
+        int k = 0;
+        for (int i = 0; i < no_pad; ++i) {
+            if (p[i] == 0.0) continue;
+            if (k == 8) { if (status) atomicMax(status + r / rows_per_task, AMDP_TASK_NOT_SPARSE); break; }
+            const uint32_t code = (code31(c[i]) << 1) & hmask;
+            uint32_t f = ((uint32_t)i << 1) & ~hmask;
+            if (code == prev_code) f = prev_f;
+            o[k++] = code | f;
+            prev_code = code; prev_f = f;
+        }
+        for (; k < 8; ++k) o[k] = hmask | (prev_code == hmask ? prev_f : 0u);
+    } else if (ofat) {
         // thread-per-env observation row (do = 1): 16 pivots, then the 31-bit codes block by block
         uint32_t* o = ofat + r * (8 + 8 * o_blocks);
         uint16_t* pvt = reinterpret_cast<uint16_t*>(o);
@@ -814,7 +831,11 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
         if (h->T.tp_levels >= 2) { if ((rc = dalloc(h, &h->pv, rows * h->T.tp_groups * 16))) return rc; }
         if (h->T.tp_levels == 3) { if ((rc = dalloc(h, &h->top, rows * 16))) return rc; }
         if (!mdp) {
-            h->T.o_blocks = (c.no_pad + 7) / 8;
+            // flag 128: sparse observation rows (at most 8 non-zero observations per state)
+            int ob = 0;
+            while ((1 << ob) < c.no_pad) ++ob;
+            h->T.o_sparse_bits = (c.reserved0 & 128) ? (ob > 0 ? ob : 1) : 0;
+            h->T.o_blocks = h->T.o_sparse_bits ? 0 : (c.no_pad + 7) / 8;
             if ((rc = dalloc(h, &h->ofat, (size_t)c.n_tasks * c.n_pad * (8 + 8 * h->T.o_blocks)))) return rc;
         }
     }
@@ -896,7 +917,7 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
         k_build_obs<<<nblk(orows, 128), 128, 0, st>>>(orows, c.n_pad, c.no_pad, obs_transition,
                                                       h->obs_cdf + (size_t)t0 * c.n_obs_tok * c.n_pad * c.no_pad,
                                                       h->ofat ? h->ofat + (size_t)t0 * c.n_pad * (8 + 8 * h->T.o_blocks) : nullptr,
-                                                      h->T.o_blocks);
+                                                      h->T.o_blocks, h->T.o_sparse_bits, c.n_obs_tok * c.n_pad, status_out);
         h->launches += 1;
     }
     if (h->raw_t) CK(cudaMemcpyAsync(h->raw_t + t0 * per_task, transition, per_task * cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));

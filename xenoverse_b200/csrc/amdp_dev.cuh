@@ -49,6 +49,9 @@ struct Tables {
     const uint32_t* ofat;     // POMDP (do = 1): [T][n_pad][8 + 8 * o_blocks] words per observation row: 16 pivots (code15 of the last
                               // entry of each 8-entry block; pad 0x7bff), then o_blocks x 8 codes (floor(cdf * 2^31) << 1)
     int o_blocks;
+    int o_sparse_bits;        // > 0: SPARSE observation rows (at most 8 non-zero observations per state, as the reference's POMDP
+                              // sampler makes them, task_sampler.py:81-87): an `ofat` row is ONE 32-byte sector of 8 code words
+                              // code31(cdf) << 1 whose low bits carry the observation index << 1; o_blocks = 0
     int n_pad, na, no_pad, d_o, d_a, s0_pad, task_type, autoreset;
     // device-side behaviour policy (amdp_set_policy): action = policy[task][inner state] unless the 24-bit
     // exploration draw of the tick is below eps_thr (then the uniform-random action of the tick); null = uniform random

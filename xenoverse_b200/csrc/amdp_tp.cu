@@ -137,8 +137,11 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
     const uint32_t* orow = nullptr;            // its row in T.ofat (null: the tick has no observation)
     int oblk = 0, so_p = 0;
     const int o_blocks = T.o_blocks;
+    const unsigned ocmask = cmask & (0xffffffffu << (1 + T.o_sparse_bits));   // sparse observation rows: index bits are not code
+    const bool osparse = T.o_sparse_bits > 0;
     auto obs_stage1 = [&]() {                  // pivots -> block; request the block's codes
-        if (orow) {
+        if (orow && osparse) { ocd[0] = opv[0]; ocd[1] = opv[1]; oblk = 0; }       // the sector that came IS the row
+        else if (orow) {
             const uint32_t v15 = code15_from_m21(oux >> 11);
             const unsigned v2 = v15 | (v15 << 16);
             int acc = 0;
@@ -154,21 +157,27 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
     auto obs_stage2 = [&](int kp) {            // codes -> observation; write the record of tick kp
         int obs = 0;
         if (orow) {
-            const unsigned ve = ((((oux >> 5) << 4) | (ouy >> 28)) << 1) & cmask;
+            const unsigned ve = ((((oux >> 5) << 4) | (ouy >> 28)) << 1) & ocmask;
             int lt, le;
+            unsigned mn;
             for (;;) {
-                lt = 0; le = 0;
+                lt = 0; le = 0; mn = 0xffffffffu;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const unsigned x[4] = {ocd[i].x, ocd[i].y, ocd[i].z, ocd[i].w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { const unsigned xm = x[j] & cmask; lt += (xm < ve); le += (xm <= ve); }
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned xm = x[j] & ocmask;
+                        lt += (xm < ve); le += (xm <= ve);
+                        mn = min(mn, xm >= ve ? x[j] : 0xffffffffu);
+                    }
                 }
                 if (lt < 8 || oblk >= o_blocks - 1) break;
                 ++oblk;
                 ldg_words<2>(orow + 8 + 8 * oblk, ocd);
             }
             obs = oblk * 8 + lt;
+            if (osparse) obs = (le != lt) ? 0 : (int)((mn >> 1) & ((1u << T.o_sparse_bits) - 1u));
             if (le != lt) {
                 const double u = u53(oux, ouy);
                 const double* cr = T.obs_cdf + (t * n_pad + so_p) * (long long)T.no_pad;
@@ -387,23 +396,31 @@ __device__ __forceinline__ int tp_observe(const Tables& T, const EnvArrays& E, l
     const uint32_t* orow = T.ofat + (unsigned long long)(t * T.n_pad + s) * (unsigned)(8 + 8 * o_blocks);
     uint4 pv[2], cd[2];
     ldg_words<2>(orow, pv);
+    const bool osparse = T.o_sparse_bits > 0;
+    cmask &= 0xffffffffu << (1 + T.o_sparse_bits);                 // sparse observation rows: index bits are not code
     const uint32_t v15 = code15_from_m21(ux >> 11);
-    int blk = min(tp_count16(pv, v15 | (v15 << 16)), o_blocks - 1);
+    int blk = osparse ? 0 : min(tp_count16(pv, v15 | (v15 << 16)), o_blocks - 1);
     const unsigned ve = ((((ux >> 5) << 4) | (uy >> 28)) << 1) & cmask;
     int lt, le;
+    unsigned mn;
     for (;;) {
-        ldg_words<2>(orow + 8 + 8 * blk, cd);
-        lt = 0; le = 0;
+        if (osparse) { cd[0] = pv[0]; cd[1] = pv[1]; } else ldg_words<2>(orow + 8 + 8 * blk, cd);
+        lt = 0; le = 0; mn = 0xffffffffu;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const unsigned x[4] = {cd[i].x, cd[i].y, cd[i].z, cd[i].w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { const unsigned xm = x[j] & cmask; lt += (xm < ve); le += (xm <= ve); }
+            for (int j = 0; j < 4; ++j) {
+                const unsigned xm = x[j] & cmask;
+                lt += (xm < ve); le += (xm <= ve);
+                mn = min(mn, xm >= ve ? x[j] : 0xffffffffu);
+            }
         }
         if (lt < 8 || blk >= o_blocks - 1) break;
         ++blk;
     }
     int obs = blk * 8 + lt;
+    if (osparse) obs = (le != lt) ? 0 : (int)((mn >> 1) & ((1u << T.o_sparse_bits) - 1u));
     if (le != lt) {
         const double u = u53(ux, uy);
         const double* cr = T.obs_cdf + (t * T.n_pad + s) * (long long)T.no_pad;

@@ -42,9 +42,11 @@ def task_geometry(tasks):
     na = int(t0["na"])
     da = int(t0.get("da", 1)) if tt == "MTPOMDP" else 1
     do = int(t0.get("do", 1)) if tt == "MTPOMDP" else 1
-    n_max, no_max, s0_max, nnz_max = 1, 1, 1, 0
+    n_max, no_max, s0_max, nnz_max, onnz_max = 1, 1, 1, 0, 0
     for t in tasks:
         nnz_max = max(nnz_max, int((numpy.asarray(t["transition"]) != 0).sum(axis=-1).max()))
+        if tt == "POMDP":
+            onnz_max = max(onnz_max, int((numpy.asarray(t["observation_transition"]) != 0).sum(axis=-1).max()))
         if t["task_type"] != tt or int(t["na"]) != na:
             raise ValueError("all tasks of one engine must share task_type and na")
         if tt == "MTPOMDP" and (int(t["da"]) != da or int(t["do"]) != do):
@@ -53,7 +55,7 @@ def task_geometry(tasks):
         s0_max = max(s0_max, len(numpy.atleast_1d(t["s_0"])))
         if tt != "MDP":
             no_max = max(no_max, int(t["no"]))
-    return {"task_type": tt, "na": na, "da": da, "do": do, "n_pad": round_up4(n_max), "ns_max": max(int(t["ns"]) for t in tasks), "max_nnz": nnz_max,
+    return {"task_type": tt, "na": na, "da": da, "do": do, "n_pad": round_up4(n_max), "ns_max": max(int(t["ns"]) for t in tasks), "max_nnz": nnz_max, "max_obs_nnz": onnz_max,
             "no_pad": round_up4(no_max) if tt != "MDP" else 0, "s0_pad": s0_max}
 
 
@@ -138,10 +140,12 @@ class Engine:
         # sparse rows (Garnet tasks: at most 8 non-zero successors per (s, a)): one line per row in the thread-per-env kernel
         sparse = (geo["task_type"] == "MDP" and search in ("auto", "sparse") and 0 < int(geo.get("max_nnz", 0)) <= 8
                   and geo["n_pad"] > 8) or (search == "sparse" and geo["task_type"] == "MDP")
+        # sparse observation rows (POMDP tasks whose states observe at most 8 different observations)
+        osparse = geo["task_type"] == "POMDP" and 0 < int(geo.get("max_obs_nnz", 0)) <= 8 and search != "warp_v1"
         cfg = _lib.Config(device=self.device.index, task_type=_lib.TASK_TYPES[geo["task_type"]],
                           autoreset=_lib.AUTORESET[autoreset], na=geo["na"], n_pad=geo["n_pad"], no_pad=geo["no_pad"],
                           n_obs_tok=geo["do"], n_act_tok=geo["da"], s0_pad=geo["s0_pad"],
-                          reserved0=(1 if keep_transition else 0) | (self._obs_bits(geo) << 8) | {"auto": 0, "one_level": 2, "two_level": 4, "thread": 8, "warp": 16, "warp_v1": 48, "sparse": 64}[search] | (64 if sparse else 0),
+                          reserved0=(1 if keep_transition else 0) | (self._obs_bits(geo) << 8) | {"auto": 0, "one_level": 2, "two_level": 4, "thread": 8, "warp": 16, "warp_v1": 48, "sparse": 64}[search] | (64 if sparse else 0) | (128 if osparse else 0),
                           n_envs=self.N, n_tasks=self.T,
                           seed=int(seed) & (2 ** 64 - 1), env_id_base=int(env_id_base))
         h = ctypes.c_void_p()

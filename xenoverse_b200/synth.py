@@ -71,7 +71,7 @@ def synth_task(ns, na, seed, term_frac=0.10, no=None, task_type=None, do=1, da=1
 
 
 def synth_geometry(ns, na, no=None):
-    return {"task_type": "MDP" if no is None else "POMDP", "na": int(na), "da": 1, "do": 1, "n_pad": round_up4(ns), "ns_max": int(ns),
+    return {"task_type": "MDP" if no is None else "POMDP", "na": int(na), "da": 1, "do": 1, "n_pad": round_up4(ns), "ns_max": int(ns), "max_obs_nnz": 0 if no is None else min(4, int(no)),
             "no_pad": round_up4(no) if no is not None else 0, "s0_pad": min(3, int(ns))}
 
 
