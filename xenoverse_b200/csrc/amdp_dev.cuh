@@ -40,7 +40,9 @@ struct Tables {
                               //   bytes 0-31 8 words  code31(cdf[j]) << 1 (low 1 + tp_obs_bits bits replaced by) | state_mapping[j] << 1 |
                               //   is_terminal[j];  32-95 8 x (reward, noise) fp32;  96-127 unused — everything a transition into the
                               //   block needs in ONE DRAM line and TWO sector requests (codes + observation + flag; payload)
-    const uint16_t* pv;       // [T][n_pad][na][tp_groups][16] code15 of the LAST entry of each block of a group of 16; pad 0x7bff
+    const uint16_t* pv;       // three-level rows: [T][n_pad][na][tp_groups][16] code15 of the LAST entry of each block of a group of 16; pad
+                              // 0x7bff; also two-level rows of more than 4 blocks.  Rows of 2..4 blocks (<= 32 states) keep their pivots in
+                              // bytes 96-127 of the row's first block line instead (pv == null)
     const uint16_t* top;      // [T][n_pad][na][16] code15 of the last entry of each group (three-level rows only)
     int tp_levels, tp_groups, tp_blocks;
     int tp_obs_bits;          // bits of state_mapping carried in the code words (bit_length(max ns - 1) <= 15)

@@ -211,7 +211,10 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
         // (1) first level of the search tree of row (s, a)                                      anymdp_env.py:99
         uint4 lv[2];                                               // 16 pivots (15-bit codes)
         if (LEVELS == 3 && valid) ldg_words_keep<2>(T.top + row * 16u, lv, pol_keep);
-        if (LEVELS == 2 && valid) ldg_words_keep<2>(T.pv + row * 16u, lv, pol_keep);
+        if (LEVELS == 2 && valid) {
+            if (T.pv) ldg_words_keep<2>(T.pv + row * 16u, lv, pol_keep);
+            else ldg_words<2>(T.fat + row * (unsigned)n_blocks * 8u + 6, lv);      // rows of <= 4 blocks: spare sector of the first block line
+        }
         // (2) in the shadow of that load: the previous tick's reward / record
         if (k > 0) { settle(k - 1); if (POMDP) obs_stage1(); }
         // the next tick's draws: in the shadow of the block load, or (small register budget) here, before the search data
@@ -479,7 +482,8 @@ __global__ void __launch_bounds__(128) k_step_tp(const Tables T, const EnvArrays
             ldg_words<2>(T.pv + (row * (unsigned)n_groups + (unsigned)g) * 16u, lv);
             blk = min(g * 16 + tp_count16(lv, v2), n_blocks - 1);
         } else if (T.tp_levels == 2) {
-            ldg_words<2>(T.pv + row * 16u, lv);
+            if (T.pv) ldg_words<2>(T.pv + row * 16u, lv);
+            else ldg_words<2>(T.fat + row * (unsigned)n_blocks * 8u + 6, lv);            // rows of <= 4 blocks: spare sector of the first block line
             blk = min(tp_count16(lv, v2), n_blocks - 1);
         }
         const unsigned ve = ((((w0.x >> 5) << 4) | (w0.y >> 28)) << 1) & cmask;       // code31(u) << 1, comparable bits
