@@ -2,23 +2,27 @@
 #include "amdp_dev.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// Throughput path: ONE THREAD PER ENV (MDP, one action token, engine Philox draws, auto-reset on), for engines with
-// enough envs to fill the machine (>= 16k per GPU).  The warp-per-env kernel above keeps at most ~4k envs in flight
-// per GPU (one row per warp); here every resident thread is an env, so 60k-95k dependent chains are in flight and
-// the path is bound by DRAM lines instead of by latency x residency.
+// Throughput path: ONE THREAD PER ENV (MDP and single-token POMDP, one action token, engine Philox draws, auto-reset on),
+// for engines with enough envs to fill the machine (from 4096 per GPU; from 12288 where k_rollout_w applies).  The
+// warp-per-env kernels keep at most ~4k envs in flight per GPU (one row per warp); here every resident thread is an env,
+// so 60k-130k dependent chains are in flight and the path is bound by DRAM lines / requests instead of latency x residency.
 //   Measured on B200 (profiles/r1_gather_microbench.txt, r1_tp_*): every L2 miss fetches its whole 128-byte line from
 //   DRAM whatever the request size, and what the kernel pays for is (a) DRAM lines and (b) 32-byte sector requests.
-//   Hence the layout: a row is cut into 8-entry blocks, and ONE 128-byte line per block holds the 8 CDF codes, the 8
-//   (reward, noise) payloads and the 8 state words (mapping | terminal) — a transition touches exactly one DRAM line
-//   below the pivots, with 3 sector requests (codes; payload entry; state word — the last two hit L2).
+//   Hence the layout: a row is cut into 8-entry blocks, and ONE 128-byte line per block holds the 8 CDF code words — whose
+//   low bits carry is_terminal and state_mapping of the entry — and the 8 (reward, noise) payloads: a transition touches
+//   exactly one DRAM line below the pivots, with 2 sector requests (codes; payload entry — the second hits L2).
 //   * search = a 1..3-level tree, one 32-byte request per level: [top: <= 16 groups] -> [pivots: <= 16 blocks of the
 //     group] -> [block: 8 codes].  Pivots are 15-bit fp16-ordered codes of the LAST entry of a block / group, counted
-//     with packed HSET2 compares; block entries are 31-bit codes.  All levels are exact; the only undecided case is
-//     code31(cdf[j]) == code31(u) (~n * 2^-31 of the ticks), which reads the float64 row.  (A 16-bit filter would
-//     send n/65536 of the ticks to the float64 row, which at 32 envs per warp stalls most warps when n = 1024.)
-//   * is_terminal[s'] rides in bit 0 of the block codes, so the dependent chain per tick is  [top ->] pivots -> codes
-//     -> next pivots; payload and state word of tick k are consumed in the shadow of tick k+1's loads.
-//   * LEVELS = 1 (n_pad <= 8), 2 (<= 128) or 3 (<= 2048).
+//     with packed HSET2 compares; block entries are (31 - 1 - b_obs)-bit codes.  All levels are exact; the only undecided
+//     case is equal truncated codes of cdf[j] and u (~n * 2^-20 of the ticks at worst), which reads the float64 row.
+//   * is_terminal[s'] and the observation state_mapping[s'] ride in the low bits of the block's code words, so the
+//     dependent chain per tick is  [top ->] pivots -> codes -> next pivots  and nothing else is requested but the
+//     payload, consumed in the shadow of tick k+1's loads.
+//   * LEVELS = 1 (n_pad <= 8, or SPARSE rows: one line per row whose 8 entries are the row's non-zero successors with
+//     their state index in the low bits), 2 (<= 128; rows of <= 32 states keep the pivots in the spare sector of their
+//     first block line) or 3 (<= 2048).
+//   * POMDP: observation rows are pivots + 8-entry code blocks, or ONE sector of 8 code words with the observation index
+//     in the low bits when no state has more than 8 possible observations.
 // ------------------------------------------------------------------------------------------------
 // ACT: where the actions come from: 0 the engine's uniform random policy, 1 the caller (`actions`), 2 the behaviour-policy
 // table of amdp_set_policy (policy[task][inner state], epsilon-greedy; one L1-resident byte load at the top of a tick).
