@@ -184,12 +184,9 @@ def test_task_quality_filter_matches_reference_check_valuefunction():
 def test_batch_task_sampler_gpu_filter():
     """AnyMDPTaskSamplerBatch: CPU candidates, quality filter on the GPU; every returned task passes the filter again, has
     the sampler's schema and runs in the engine."""
-    import time
     from xenoverse_b200 import AnyMDPTaskSamplerBatch, AnyMDPVecEnv, check_valuefunction_batch
-    t0 = time.time()
     tasks = AnyMDPTaskSamplerBatch(12, state_space=16, action_space=5, seed=7, batch=48)
-    dt = time.time() - t0
-    assert len(tasks) == 12 and dt < 120
+    assert len(tasks) == 12
     for t in tasks:
         assert t["transition"].shape == (16, 5, 16) and t["task_type"] == "MDP" and 100 <= t["max_steps"] <= 129
         assert set(("ns", "na", "s_0", "s_0_prob", "s_e", "reward", "reward_noise", "state_mapping")) <= set(t)
