@@ -81,6 +81,10 @@ extern "C" {
 #define AMDP_TASK_NOT_SPARSE    6   /* the handle was created for sparse rows (reserved0 flag 64) and a row has more than 8 non-zero successors */
 #define AMDP_TASK_OBS_RANGE     5   /* a state_mapping value does not fit the observation bits stated in amdp_config.reserved0 (bits 8-12) */
 
+/* action value for tokens k >= 1 of a multi-token step: the step ends before this token (anymdp_env.py:127-128: step() with
+ * a scalar action on an MTPOMDP task performs one single_step) */
+#define AMDP_NO_ACTION (-2147483647 - 1)
+
 #define AMDP_SLOTS_PER_TOKEN 8
 #define AMDP_SLOT_TRANS      0
 #define AMDP_SLOT_RESET      1
@@ -244,6 +248,15 @@ int amdp_set_seed(amdp_t* h, uint64_t seed);
 int amdp_get_state(amdp_t* h, int32_t* state, int32_t* steps, uint8_t* flags, double* ep_return, void* stream);
 int amdp_set_state(amdp_t* h, const int32_t* state, const int32_t* steps, const uint8_t* flags,
                    const double* ep_return, void* stream);
+/* The rest of a checkpoint ("episode counters/returns"): the per-env accumulators of CLOSED episodes that
+ * amdp_stats reduces — ep_count, sum_len uint64 [n_envs]; sum_ret, sum_ret_sq, min_ret, max_ret double [n_envs] (DEVICE, any
+ * may be NULL) — and the handle's total step count (HOST double).  No reference equivalent (the reference keeps no
+ * statistics; its callers average returns in Python, test_utils.py:60). */
+int amdp_get_episode_accumulators(amdp_t* h, uint64_t* ep_count, uint64_t* sum_len, double* sum_ret, double* sum_ret_sq,
+                                  double* min_ret, double* max_ret, double* total_steps_host, void* stream);
+int amdp_set_episode_accumulators(amdp_t* h, const uint64_t* ep_count, const uint64_t* sum_len, const double* sum_ret,
+                                  const double* sum_ret_sq, const double* min_ret, const double* max_ret,
+                                  double total_steps, void* stream);
 /* mapped (observable) state of every env: state_mapping[_state] (anymdp_env.py:134-136) */
 int amdp_get_mapped_state(amdp_t* h, int32_t* out, void* stream);
 
@@ -306,6 +319,9 @@ int64_t amdp_launch_count(const amdp_t* h);
  * Host-buffer convenience for end-to-end use from non-CUDA callers: K-step rollout with HOST
  * (preferably pinned) action input and trajectory output; the library stages through device
  * buffers it owns, in chunks, overlapping copies with the rollout kernel.  Synchronises.
+ * Like amdp_reset_host / amdp_step_host it runs on streams the handle owns; those streams first wait for the last
+ * asynchronous call made on this handle (amdp_reset, amdp_assign, amdp_set_state, ...) on the caller's stream, so
+ * `amdp_reset(h, ..., stream); amdp_rollout_host(h, ...)` needs no synchronisation in between.
  *   actions_host  int32 [K][n_envs][da] or NULL (uniform policy)
  *   obs_host int32 [K][n_envs][do], reward_host float [K][n_envs], done_host uint8 [K][n_envs]
  *   (any output may be NULL)

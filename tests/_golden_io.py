@@ -80,7 +80,7 @@ def load_case(name):
 
 
 def list_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("policy_", "filter_")))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("policy_", "filter_", "tasks_", "sampler_")))
 
 
 def list_policy_cases():

@@ -1,0 +1,146 @@
+"""Parity of the EXACT kernels and workloads bench.py measures (VERDICT r1 "What's weak" 1): every BASELINE.json config shape is
+built the way bench.py builds it — `synth_packed` tasks generated on the GPU, uploaded in chunks, `search="auto"` — the
+kernel `amdp_rollout` picks is asserted to be the one the bench line names, and a sample of envs is replayed through the CPU
+oracle from the engine's dumped Philox draws (`amdp_dump_draws`): observations, actions, done flags, step counters bit-exact,
+rewards to rtol = atol = 1e-6 (fp32 payload vs the reference's float64; BASELINE.json north_star).
+
+    cfg2  4096 envs x ns=128 na=5, one task per env        -> k_rollout_w<EPL=4>   (device rollout AND the e2e host path)
+    cfg3  POMDP ns=64 na=8 no=64, 4096 tasks round-robin   -> k_rollout_tp<levels=2,POMDP>
+    cfg4  ns=1024 na=16                                     -> k_rollout_tp<levels=3,MDP>
+    cfg5  ns=32 na=5, one task per env (pivots in the line) -> k_rollout_tp<levels=2,MDP>
+"""
+import numpy
+import pytest
+import torch
+
+from oracle import anymdp_oracle as ao
+
+pytestmark = pytest.mark.gpu
+
+RTOL = ATOL = 1e-6
+
+
+def _build(ns, na, no, envs, tasks, seed, search="auto", **kw):
+    """An engine on synth_packed tasks, uploaded exactly as bench.run_b200 / quick_measure do."""
+    from xenoverse_b200 import AnyMDPVecEnv, synth_packed, synth_geometry
+    dev = torch.device("cuda", 0)
+    geo = synth_geometry(ns, na, no)
+    per_task = 3 * 8 * geo["n_pad"] * na * geo["n_pad"]
+    chunk = max(1, min(tasks, (768 << 20) // per_task))
+    env = AnyMDPVecEnv(envs, device=0, seed=seed, search=search, **kw)
+    env.set_task(None, packed=(geo, tasks, ((t0, synth_packed(ns, na, min(chunk, tasks - t0), seed=1000 + t0, device=dev, no=no))
+                                            for t0 in range(0, tasks, chunk))))
+    return env, chunk
+
+
+def _oracle_tasks(ns, na, no, tasks, chunk, wanted):
+    """Reference-schema dicts of the tasks in `wanted`, regenerated chunk by chunk with the generator seeds of `_build`."""
+    from xenoverse_b200 import synth_packed
+    from xenoverse_b200.synth import packed_to_task
+    dev = torch.device("cuda", 0)
+    out = {}
+    for t0 in sorted({(t // chunk) * chunk for t in wanted}):
+        batch = synth_packed(ns, na, min(chunk, tasks - t0), seed=1000 + t0, device=dev, no=no)
+        for t in wanted:
+            if t0 <= t < t0 + chunk:
+                out[t] = packed_to_task(batch, t - t0, no=no)
+        del batch
+    torch.cuda.empty_cache()
+    return out
+
+
+def _replay(env, obs0, tr, draws, sel, task_dicts, env_task, K, actions=None):
+    """Replay envs `sel` through OracleVecEnv from the dumped draws; compare every tick."""
+    order = sorted(set(int(t) for t in env_task))
+    index = {t: i for i, t in enumerate(order)}
+    orc = ao.OracleVecEnv([task_dicts[t] for t in order], env_task=[index[int(t)] for t in env_task])
+    U = draws[:, sel]
+    o0 = orc.reset(U[0])
+    assert numpy.array_equal(obs0[sel], o0[:, 0])
+    for k in range(K):
+        a = None if actions is None else actions[k][sel].reshape(-1, 1)
+        o = orc.step(a, U[k + 1])
+        assert numpy.array_equal(tr["obs"][k][sel], o["obs"][:, 0]), f"tick {k}: obs"
+        assert numpy.array_equal(tr["action"][k][sel], o["action"][:, 0]), f"tick {k}: action"
+        assert numpy.array_equal(tr["terminated"][k][sel], o["terminated"]), f"tick {k}: terminated"
+        assert numpy.array_equal(tr["truncated"][k][sel], o["truncated"]), f"tick {k}: truncated"
+        assert numpy.allclose(tr["reward"][k][sel], o["reward"], rtol=RTOL, atol=ATOL), f"tick {k}: reward"
+        if "reward_gt" in tr:
+            assert numpy.allclose(tr["reward_gt"][k][sel], o["reward_gt"], rtol=RTOL, atol=ATOL), f"tick {k}: reward_gt"
+    return orc
+
+
+def _host_traj(tr):
+    d = tr["done"].cpu().numpy()
+    out = {"obs": tr["obs"][..., 0].cpu().numpy(), "action": tr["action"][..., 0].cpu().numpy(),
+           "terminated": (d & 1).astype(bool), "truncated": (d >> 1).astype(bool), "reward": tr["reward"].cpu().numpy()}
+    if "reward_gt" in tr:
+        out["reward_gt"] = tr["reward_gt"].cpu().numpy()
+    return out
+
+
+CASES = {
+    #        ns    na  no    envs    tasks  K    kernel                              sampled envs
+    "cfg2": (128,  5,  None, 4096,   4096,  96,  "k_rollout_w<EPL=4>",               256),
+    "cfg3": (64,   8,  64,   65536,  4096,  48,  "k_rollout_tp<levels=2,POMDP>",     256),
+    "cfg4": (1024, 16, None, 8192,   4,     40,  "k_rollout_tp<levels=3,MDP>",       96),
+    "cfg5": (32,   5,  None, 131072, 131072, 64, "k_rollout_tp<levels=2,MDP>",       384),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_bench_workload_kernel_replays_through_oracle(name):
+    ns, na, no, envs, tasks, K, kernel, n_sel = CASES[name]
+    env, chunk = _build(ns, na, no, envs, tasks, seed=17)
+    assert env.engine.rollout_kernel == kernel, env.engine.rollout_kernel
+    obs0, _ = env.reset()
+    obs0 = obs0.cpu().numpy().copy()
+    tr = env.rollout(K, record=("obs", "action", "reward", "reward_gt", "done"))
+    env.check()
+    st_dev = env.episode_stats()
+    rng = numpy.random.default_rng(5)
+    if name == "cfg4":
+        # two of the four 400 MB tasks (host memory): envs of tasks 1 and 2
+        pool = numpy.nonzero(numpy.isin(numpy.arange(envs) % tasks, (1, 2)))[0]
+        sel = numpy.sort(rng.choice(pool, n_sel, replace=False))
+    else:
+        sel = numpy.sort(rng.choice(envs, n_sel, replace=False))
+    if name != "cfg4":
+        sel[0] = 0                                                 # always include the first env of the engine
+    env_task = sel % tasks
+    task_dicts = _oracle_tasks(ns, na, no, tasks, chunk, sorted(set(int(t) for t in env_task)))
+    draws = env.engine.dump_draws(0, K + 1)[:, torch.as_tensor(sel, device=env.device)].cpu().numpy()
+    # (the trajectory is indexed by `sel` here, the draws are already restricted to it)
+    trh = _host_traj(tr)
+    trs = {k: v[:, sel] for k, v in trh.items()}
+    orc = _replay(env, obs0[sel], trs, draws, slice(None), task_dicts, env_task, K)
+    assert st_dev["total_steps"] == envs * K and st_dev["episodes"] > 0
+    # per-env episode statistics of the sampled envs
+    est = env.engine.get_state()
+    assert numpy.array_equal(est["state"].cpu().numpy()[sel], [e._state for e in orc.envs])
+    assert numpy.array_equal(est["steps"].cpu().numpy()[sel], [e.steps for e in orc.envs])
+    assert numpy.allclose(est["ep_return"].cpu().numpy()[sel], orc.ep_return, rtol=1e-5, atol=1e-5)
+    env.close()
+
+
+def test_cfg2_end_to_end_host_path_replays_through_oracle():
+    """The e2e leg of the bench line: amdp_rollout_host_packed at the cfg2 shape (uint8 host actions in, 8-byte host records
+    out, chunked on the library's own streams) — k_rollout_w<EPL=4> with caller actions — against the oracle."""
+    from xenoverse_b200 import unpack_records
+    ns, na, no, envs, tasks, K, kernel, n_sel = CASES["cfg2"]
+    env, chunk = _build(ns, na, no, envs, tasks, seed=23)
+    assert env.engine.rollout_kernel == kernel
+    obs0, _ = env.reset()
+    obs0 = obs0.cpu().numpy().copy()
+    acts = torch.randint(0, na, (K, envs), dtype=torch.uint8, generator=torch.Generator().manual_seed(9)).pin_memory()
+    rec = torch.empty((K, envs), dtype=torch.int64).pin_memory()
+    env.engine.rollout_host_packed(K, 40, acts, rec)                # 40 does not divide 96: ragged last chunk
+    env.check()
+    r = unpack_records(rec)
+    sel = numpy.sort(numpy.random.default_rng(6).choice(envs, n_sel, replace=False))
+    env_task = sel % tasks
+    task_dicts = _oracle_tasks(ns, na, no, tasks, chunk, sorted(set(int(t) for t in env_task)))
+    draws = env.engine.dump_draws(0, K + 1)[:, torch.as_tensor(sel, device=env.device)].cpu().numpy()
+    trs = {k: r[k][:, sel] for k in ("obs", "action", "terminated", "truncated", "reward")}
+    _replay(env, obs0[sel], trs, draws, slice(None), task_dicts, env_task, K, actions=acts.numpy().astype(numpy.int64)[:, sel])
+    env.close()

@@ -1,0 +1,157 @@
+"""GPU tests of the round-2 fixes to the vector / drop-in surface:
+`transition_gt` width and mapping with `min_state_space` tasks, host entry points ordered behind the caller's stream,
+seeded reset + checkpoint, checkpoint of the episode-statistics accumulators, scalar action on an MTPOMDP task."""
+import os
+
+import numpy
+import pytest
+import torch
+
+from oracle import anymdp_oracle as ao
+import _golden_io as gio
+
+pytestmark = pytest.mark.gpu
+
+
+def _tasks(name):
+    with numpy.load(os.path.join(gio.GOLDEN_DIR, name + ".npz"), allow_pickle=False) as z:
+        return gio.unpack_tasks({k: z[k] for k in z.files})
+
+
+def test_transition_gt_min_state_space_matches_oracle():
+    """info["transition_gt"] (anymdp_env.py:130) has length task["ns"] and is indexed by MAPPED state: with
+    `min_state_space` tasks (n_real = 53 of ns = 64) mapped states reach beyond n_pad and must not be dropped."""
+    from xenoverse_b200 import AnyMDPVecEnv
+    tasks = _tasks("tasks_minss64")
+    assert len(tasks[0]["state_mapping"]) < tasks[0]["ns"] and int(numpy.max(tasks[0]["state_mapping"])) >= len(tasks[0]["state_mapping"])
+    N = 48
+    env = AnyMDPVecEnv(N, seed=5, keep_transition=True)
+    env.set_task(tasks)
+    env.reset()
+    orc = ao.OracleVecEnv(tasks, env_task=numpy.arange(N) % len(tasks))
+    draws = env.engine.dump_draws(0, 13).cpu().numpy()
+    orc.reset(draws[0])
+    rng = numpy.random.default_rng(0)
+    for k in range(12):
+        acts = rng.integers(0, tasks[0]["na"], N)
+        env.step(torch.as_tensor(acts, dtype=torch.int32))
+        orc.step(acts.reshape(N, 1), draws[k + 1])
+        gt = env.transition_gt(torch.as_tensor(acts, dtype=torch.int32)).cpu().numpy()
+        assert gt.shape == (N, 1, tasks[0]["ns"])
+        for i, e in enumerate(orc.envs):
+            want = e.transition_gt(int(acts[i]))
+            assert numpy.array_equal(gt[i, 0], want), (k, i)
+        # a terminal (all-zero) row has no mass; every other row keeps all of it
+        s = gt[:, 0].sum(axis=1)
+        assert numpy.all((numpy.abs(s - 1.0) < 1e-9) | (s == 0.0))
+
+
+def test_host_rollout_is_ordered_behind_the_callers_stream():
+    """`env.reset(); engine.rollout_host*()` with no synchronisation in between: the library's own (non-blocking) streams
+    must wait for the k_reset the caller queued on torch's current stream — else envs fault with NEED_RESET or start from
+    torn state.  A large memset in front of the reset keeps the caller's stream busy while the host call is issued."""
+    from xenoverse_b200 import AnyMDPVecEnv, synth_task, unpack_records
+    tasks = [synth_task(32, 5, 3000 + t) for t in range(16)]
+    N, K = 8192, 24
+    ref = AnyMDPVecEnv(N, seed=11)
+    ref.set_task(tasks)
+    ref.reset()
+    want = ref.rollout(K, record=("packed",))["packed"].cpu()
+    ballast = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    for trial in range(3):
+        env = AnyMDPVecEnv(N, seed=11)
+        env.set_task(tasks)
+        rec = torch.empty((K, N), dtype=torch.int64).pin_memory()
+        torch.cuda.synchronize()
+        for _ in range(8):
+            ballast.zero_()                                       # ~1 ms of queued work on the caller's stream
+        env.reset()                                               # asynchronous, behind the memsets
+        env.engine.rollout_host_packed(K, 8, None, rec)           # handle-owned streams
+        env.check()
+        assert torch.equal(rec, want), trial
+        env.close()
+    r = unpack_records(want)
+    assert r["terminated"].any()
+
+
+def test_seeded_reset_restarts_the_stream_and_checkpoints():
+    from xenoverse_b200 import AnyMDPVecEnv, synth_task
+    tasks = [synth_task(16, 5, 90 + t) for t in range(8)]
+    a = AnyMDPVecEnv(64, seed=3)
+    a.set_task(tasks)
+    a.reset()
+    a.rollout(10)
+    o1, _ = a.reset(seed=77)
+    o1 = o1.clone()
+    t1 = a.rollout(30)
+    o2, _ = a.reset(seed=77)                                      # twice the same seed: twice the same trajectories
+    assert torch.equal(o1, o2)
+    t2 = a.rollout(30)
+    for key in ("obs", "reward", "done", "action"):
+        assert torch.equal(t1[key], t2[key]), key
+    ck = a.state_dict()
+    assert ck["seed"] == 77
+    want = a.rollout(25)
+    b = AnyMDPVecEnv(64, seed=1)
+    b.set_task(tasks)
+    b.load_state_dict(ck)
+    got = b.rollout(25)
+    for key in ("obs", "reward", "done", "action"):
+        assert torch.equal(want[key], got[key]), key
+
+
+def test_checkpoint_carries_episode_statistics():
+    from xenoverse_b200 import AnyMDPVecEnv, synth_task
+    tasks = [synth_task(16, 5, 90 + t) for t in range(8)]
+    a = AnyMDPVecEnv(96, seed=4)
+    a.set_task(tasks)
+    a.reset()
+    a.rollout(80)
+    ck = a.state_dict()
+    assert a.episode_stats()["episodes"] > 0
+    a.rollout(60)
+    want = a.episode_stats()
+    b = AnyMDPVecEnv(96, seed=999)
+    b.set_task(tasks)
+    b.load_state_dict(ck)
+    b.rollout(60)
+    got = b.episode_stats()
+    assert got == want, (got, want)                               # incl. total_steps, min / max and the sums, bit for bit
+
+
+def test_scalar_action_on_mtpomdp_is_one_single_step():
+    """anymdp_env.py:127-128: step() with a scalar action performs ONE single_step even on a multi-token task."""
+    import xenoverse_b200 as xb
+    task = _tasks("tasks_mtpomdp32")[0]
+    env = xb.AnyMDPEnv(max_steps=5000, seed=21)
+    env.set_task(task)
+    orc = ao.OracleEnv(task)
+    S = ao.n_slots(task["da"], task["do"])
+    eng = env._engine
+    draws = eng.dump_draws(0, 80).cpu().numpy()[:, 0]
+    obs, _ = env.reset()
+    o0, _ = orc.reset(draws[0][ao.SLOT_RESET], [draws[0][ao.SLOT_RESET_OBS + 8 * k] for k in range(task["do"])])
+    assert numpy.array_equal(obs, o0)
+    tick = 1
+    rng = numpy.random.default_rng(2)
+    for k in range(60):
+        U = draws[tick]
+        u_obs = [U[ao.SLOT_OBS + 8 * j] for j in range(task["do"])]
+        if k % 2:
+            a = int(rng.integers(0, task["na"]))
+            want = orc.step(a, [U[ao.SLOT_TRANS]], [U[ao.SLOT_Z]], u_obs)
+        else:
+            a = rng.integers(0, task["na"], task["da"])
+            want = orc.step(a, [U[ao.SLOT_TRANS + 8 * j] for j in range(task["da"])], [U[ao.SLOT_Z + 8 * j] for j in range(task["da"])], u_obs)
+        got = env.step(a)
+        tick += 1
+        assert numpy.array_equal(got[0], want[0]) and got[2] == want[2] and got[3] == want[3], k
+        assert abs(got[1] - want[1]) <= 1e-6 * max(1.0, abs(want[1])) + 1e-6
+        assert got[4]["steps"] == want[4]["steps"] and env.inner_state == orc.inner_state
+        assert S == eng.n_slots
+        if got[2] or got[3]:
+            U = draws[tick]
+            obs, _ = env.reset()
+            o0, _ = orc.reset(U[ao.SLOT_RESET], [U[ao.SLOT_RESET_OBS + 8 * j] for j in range(task["do"])])
+            assert numpy.array_equal(obs, o0)
+            tick += 1

@@ -94,3 +94,18 @@ def test_mtpomdp(ref):
 def test_bandit_and_min_state_space(ref):
     _differential([ref.AnyMDPTaskSampler(1, 3, seed=106)], "same_step", 30, 6)
     _differential([ref.AnyMDPTaskSampler(24, 4, min_state_space=8, seed=107)], "same_step", 150, 7)
+
+
+def test_task_fixtures_are_what_the_live_sampler_produces(ref):
+    """tests/golden/tasks_*.npz (make_task_golden.py) — the reference-sampled tasks the GPU tests push through the fast
+    kernels — are bit-identical to a fresh call of the live sampler with the recorded seed, and step identically through
+    the live reference and the restated oracle."""
+    import os
+    import _golden_io as gio
+    with numpy.load(os.path.join(gio.GOLDEN_DIR, "tasks_mdp64.npz"), allow_pickle=False) as z:
+        stored = gio.unpack_tasks({k: z[k] for k in z.files})
+    fresh = ref.AnyMDPTaskSampler(64, 5, seed=100)
+    for key in ("transition", "reward", "reward_noise", "state_mapping", "s_0", "s_0_prob", "s_e"):
+        assert numpy.array_equal(numpy.asarray(stored[0][key]), numpy.asarray(fresh[key])), key
+    assert stored[0]["max_steps"] == fresh["max_steps"]
+    _differential(stored[:2], "same_step", 120, 8)

@@ -20,6 +20,7 @@ TASK_OK, TASK_BAD_ROW_SUM, TASK_NOT_NORMALISED, TASK_NEGATIVE_P, TASK_S0_IN_SE, 
 SLOTS_PER_TOKEN = 8
 SLOT_TRANS, SLOT_RESET, SLOT_OBS, SLOT_RESET_OBS, SLOT_Z, SLOT_ACTION = 0, 1, 2, 3, 4, 5
 ABI_VERSION = 1
+NO_ACTION = -2 ** 31      # AMDP_NO_ACTION: tokens after the first of a multi-token step that ends early
 
 
 class Config(ctypes.Structure):
@@ -64,6 +65,8 @@ _SIGNATURES = {
     "amdp_get_state": (ctypes.c_int, [_P] * 6),
     "amdp_set_state": (ctypes.c_int, [_P] * 6),
     "amdp_get_mapped_state": (ctypes.c_int, [_P, _P, _P]),
+    "amdp_get_episode_accumulators": (ctypes.c_int, [_P] * 7 + [ctypes.POINTER(ctypes.c_double), _P]),
+    "amdp_set_episode_accumulators": (ctypes.c_int, [_P] * 7 + [ctypes.c_double, _P]),
     "amdp_poll_errors": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32), _P]),
     "amdp_peek_errors": (ctypes.c_int, [_P, _P, _P]),
     "amdp_reset_host": (ctypes.c_int, [_P, _P]),

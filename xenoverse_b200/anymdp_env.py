@@ -145,14 +145,14 @@ class AnyMDPEnv(Env):
             assert numpy.shape(action) == (self.da,), f"Action {action} is out of range"
             acts = [int(a) for a in action]
         else:
-            acts = [int(action)]
+            acts = [int(action)]                                 # :127-128: a scalar action is ONE single_step, also on MTPOMDP
         for a in acts:
             assert a < self.na, f"Action {a} is out of range"
-        assert len(acts) == self._geo["da"], f"Action {action} is out of range"
+        acts = acts + [_lib.NO_ACTION] * (self._geo["da"] - len(acts))
         self._anp[:] = acts
+        self.steps += 1                                          # :113 (before single_step can raise)
         self._engine._ck(lib.amdp_step_host(self._engine._h, self._p_act, self._p_res))
         h = self._check()                                        # raises the engine's faults (:94, :96, :97)
-        self.steps += 1
         f = self._hf
         reward = float(f[8])
         terminated = bool(h[10] & 0xff)

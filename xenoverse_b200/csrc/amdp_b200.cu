@@ -111,7 +111,9 @@ __device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, lo
         // device-side behaviour policy (da == 1): the table action of the env's inner state unless the tick explores
         if (!act_in && T.policy && active && !D.explore(T.eps_thr, T.eps)) a = (int)T.policy[t * T.n_pad + R.state];
         act_used[k] = a;
-        if (stepping && (a < 0 || a >= T.na)) fault |= AMDP_FAULT_BAD_ACTION;          // anymdp_env.py:97
+        // AMDP_NO_ACTION in a token after the first: the step ends before that token (the reference's step() with a scalar
+        // action on a multi-token task performs ONE single_step, anymdp_env.py:127-128)
+        if (stepping && (a < 0 || a >= T.na) && !(k > 0 && a == AMDP_NO_ACTION)) fault |= AMDP_FAULT_BAD_ACTION;   // anymdp_env.py:97
     }
     if (stepping) {
         if (R.flags & FLAG_VIRGIN) fault |= AMDP_FAULT_NEED_RESET;                     // anymdp_env.py:93-94
@@ -119,14 +121,15 @@ __device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, lo
     }
     const bool ok = stepping && fault == 0;     // faulted envs are left untouched
     int s = R.state;
-    bool term = false;
+    bool term = false, term_stop = false;
     double rew = 0.0, rew_gt = 0.0;
     if (ok) {
         R.steps += 1;                                                                   // anymdp_env.py:113-114
         O.trunc = R.steps >= T.max_ceil[t];
     }
     for (int k = 0; k < da; ++k) {
-        const bool live = ok && !term;                                                  // :120-126 break on termination
+        if (k > 0 && act_used[k] == AMDP_NO_ACTION) term_stop = true;
+        const bool live = ok && !term && !term_stop;                                    // :120-126 break on termination
         double u;
         if (k == 0) u = u_trans0; else { double u1; D.pair((AMDP_SLOT_TRANS + AMDP_SLOTS_PER_TOKEN * k) >> 1, u, u1); }
         const long long rowi = ((t * T.n_pad + s) * T.na + (live ? act_used[k] : 0)) * (long long)T.n_pad;
@@ -706,6 +709,10 @@ struct amdp {
     cudaStream_t st_stream[3];
     cudaEvent_t st_ev_in[ST_NBUF], st_ev_k[ST_NBUF], st_ev_out[ST_NBUF];
     bool st_ready;
+    // ordering of the host-buffer entry points (which run on streams the handle owns) after work the caller queued on ITS
+    // stream through the asynchronous entry points: the last such enqueue is marked with an event the handle's streams wait for
+    cudaEvent_t ev_caller;
+    bool ev_caller_set;
 };
 
 static int fail(amdp* h, int code, const char* fmt, const char* a = "") {
@@ -737,6 +744,19 @@ static int dalloc(amdp* h, Tp** p, size_t count) {
     return AMDP_OK;
 }
 
+
+// Asynchronous entry points that touch env state or tables call this after their last enqueue on the caller's stream `st`
+// (not for the handle's own streams): amdp_reset_host / amdp_step_host / amdp_rollout_host* then order themselves behind it.
+static void mark_caller_stream(amdp* h, cudaStream_t st) {
+    if (st == h->hs_stream && h->hs_stream) return;
+    if (h->st_ready && (st == h->st_stream[0] || st == h->st_stream[1] || st == h->st_stream[2])) return;
+    if (!h->ev_caller && cudaEventCreateWithFlags(&h->ev_caller, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaEventRecord(h->ev_caller, st) == cudaSuccess) h->ev_caller_set = true; else cudaGetLastError();
+}
+
+static void wait_caller_stream(amdp* h, cudaStream_t own) {
+    if (h->ev_caller_set) cudaStreamWaitEvent(own, h->ev_caller, 0);
+}
 
 extern "C" int amdp_abi_version(void) { return AMDP_ABI_VERSION; }
 
@@ -776,6 +796,7 @@ extern "C" int amdp_destroy(amdp_t* h) {
         for (void* p : st) if (p) cudaFree(p);
     }
     if (h->hs_stream) cudaStreamDestroy(h->hs_stream);
+    if (h->ev_caller) cudaEventDestroy(h->ev_caller);
     if (h->st_ready) {
         for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->st_stream[i]);
         for (int i = 0; i < ST_NBUF; ++i) { cudaEventDestroy(h->st_ev_in[i]); cudaEventDestroy(h->st_ev_k[i]); cudaEventDestroy(h->st_ev_out[i]); }
@@ -935,6 +956,7 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
     }
     if (h->raw_t) CK(cudaMemcpyAsync(h->raw_t + t0 * per_task, transition, per_task * cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CK(cudaGetLastError());
+    mark_caller_stream(h, st);
     h->uploaded = true;
     return AMDP_OK;
 }
@@ -946,6 +968,7 @@ extern "C" int amdp_assign(amdp_t* h, const int32_t* env_task, void* stream) {
     k_assign<<<nblk(h->cfg.n_envs, 256), 256, 0, (cudaStream_t)stream>>>(h->E, h->env_task, env_task);
     h->launches += 1;
     CK(cudaGetLastError());
+    mark_caller_stream(h, (cudaStream_t)stream);
     h->assigned = true;
     h->total_steps = 0;
     return AMDP_OK;
@@ -959,6 +982,7 @@ extern "C" int amdp_reset(amdp_t* h, const uint8_t* mask, int32_t* obs_out, cons
     h->launches += 1;
     h->tick += 1;
     CK(cudaGetLastError());
+    mark_caller_stream(h, (cudaStream_t)stream);
     return AMDP_OK;
 }
 
@@ -986,6 +1010,7 @@ extern "C" int amdp_step(amdp_t* h, const int32_t* actions, int32_t* obs, int32_
         h->tick += 1;
         h->total_steps += (double)h->cfg.n_envs;
         CK(cudaGetLastError());
+        mark_caller_stream(h, st);
         return AMDP_OK;
     }
     switch (h->G) {
@@ -998,6 +1023,7 @@ extern "C" int amdp_step(amdp_t* h, const int32_t* actions, int32_t* obs, int32_
     h->tick += 1;
     h->total_steps += (double)h->cfg.n_envs;
     CK(cudaGetLastError());
+    mark_caller_stream(h, st);
     return AMDP_OK;
 }
 
@@ -1043,6 +1069,7 @@ extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const 
     h->tick += (unsigned long long)K;
     h->total_steps += (double)h->cfg.n_envs * K;
     CK(cudaGetLastError());
+    mark_caller_stream(h, st);
     return AMDP_OK;
 }
 
@@ -1054,6 +1081,7 @@ extern "C" int amdp_stats(amdp_t* h, double* out8, void* stream) {
     k_stats<<<STAT_BLOCKS, STAT_THREADS, 0, st>>>(h->E, h->stat_part, h->stat_ticket, h->total_steps, out8);
     h->launches += 1;
     CK(cudaGetLastError());
+    mark_caller_stream(h, st);
     return AMDP_OK;
 }
 
@@ -1064,6 +1092,7 @@ extern "C" int amdp_clear_stats(amdp_t* h, void* stream) {
     h->launches += 1;
     h->total_steps = 0;
     CK(cudaGetLastError());
+    mark_caller_stream(h, (cudaStream_t)stream);
     return AMDP_OK;
 }
 
@@ -1207,6 +1236,7 @@ extern "C" int amdp_get_state(amdp_t* h, int32_t* state, int32_t* steps, uint8_t
     if (steps) CK(cudaMemcpyAsync(steps, h->E.steps, n * 4, cudaMemcpyDeviceToDevice, st));
     if (flags) CK(cudaMemcpyAsync(flags, h->E.flags, n, cudaMemcpyDeviceToDevice, st));
     if (ep_return) CK(cudaMemcpyAsync(ep_return, h->E.ep_return, n * 8, cudaMemcpyDeviceToDevice, st));
+    mark_caller_stream(h, st);
     return AMDP_OK;
 }
 
@@ -1221,6 +1251,45 @@ extern "C" int amdp_set_state(amdp_t* h, const int32_t* state, const int32_t* st
     if (steps) CK(cudaMemcpyAsync(h->E.steps, steps, n * 4, cudaMemcpyDeviceToDevice, st));
     if (flags) CK(cudaMemcpyAsync(h->E.flags, flags, n, cudaMemcpyDeviceToDevice, st));
     if (ep_return) CK(cudaMemcpyAsync(h->E.ep_return, ep_return, n * 8, cudaMemcpyDeviceToDevice, st));
+    mark_caller_stream(h, st);
+    return AMDP_OK;
+}
+
+// per-env episode-statistics accumulators (closed episodes only) + the handle's total step count: the part of a checkpoint
+// that amdp_get_state / amdp_set_state do not cover (episode counters belong to the checkpoint)
+extern "C" int amdp_get_episode_accumulators(amdp_t* h, uint64_t* ep_count, uint64_t* sum_len, double* sum_ret, double* sum_ret_sq,
+                                             double* min_ret, double* max_ret, double* total_steps_host, void* stream) {
+    if (!h) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->cfg.n_envs * 8;
+    if (ep_count) CK(cudaMemcpyAsync(ep_count, h->E.ep_count, n, cudaMemcpyDeviceToDevice, st));
+    if (sum_len) CK(cudaMemcpyAsync(sum_len, h->E.sum_len, n, cudaMemcpyDeviceToDevice, st));
+    if (sum_ret) CK(cudaMemcpyAsync(sum_ret, h->E.sum_ret, n, cudaMemcpyDeviceToDevice, st));
+    if (sum_ret_sq) CK(cudaMemcpyAsync(sum_ret_sq, h->E.sum_ret_sq, n, cudaMemcpyDeviceToDevice, st));
+    if (min_ret) CK(cudaMemcpyAsync(min_ret, h->E.min_ret, n, cudaMemcpyDeviceToDevice, st));
+    if (max_ret) CK(cudaMemcpyAsync(max_ret, h->E.max_ret, n, cudaMemcpyDeviceToDevice, st));
+    if (total_steps_host) *total_steps_host = h->total_steps;
+    mark_caller_stream(h, st);
+    return AMDP_OK;
+}
+
+extern "C" int amdp_set_episode_accumulators(amdp_t* h, const uint64_t* ep_count, const uint64_t* sum_len, const double* sum_ret,
+                                             const double* sum_ret_sq, const double* min_ret, const double* max_ret,
+                                             double total_steps, void* stream) {
+    if (!h) return AMDP_EINVAL;
+    if (!h->assigned) return fail(h, AMDP_ESTATE, "set_episode_accumulators before assign");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->cfg.n_envs * 8;
+    if (ep_count) CK(cudaMemcpyAsync(h->E.ep_count, ep_count, n, cudaMemcpyDeviceToDevice, st));
+    if (sum_len) CK(cudaMemcpyAsync(h->E.sum_len, sum_len, n, cudaMemcpyDeviceToDevice, st));
+    if (sum_ret) CK(cudaMemcpyAsync(h->E.sum_ret, sum_ret, n, cudaMemcpyDeviceToDevice, st));
+    if (sum_ret_sq) CK(cudaMemcpyAsync(h->E.sum_ret_sq, sum_ret_sq, n, cudaMemcpyDeviceToDevice, st));
+    if (min_ret) CK(cudaMemcpyAsync(h->E.min_ret, min_ret, n, cudaMemcpyDeviceToDevice, st));
+    if (max_ret) CK(cudaMemcpyAsync(h->E.max_ret, max_ret, n, cudaMemcpyDeviceToDevice, st));
+    h->total_steps = total_steps;
+    mark_caller_stream(h, st);
     return AMDP_OK;
 }
 
@@ -1293,6 +1362,7 @@ extern "C" int amdp_reset_host(amdp_t* h, int32_t* result_host) {
     if (!h || !result_host) return AMDP_EINVAL;
     int rc = host_step_init(h);
     if (rc) return rc;
+    wait_caller_stream(h, h->hs_stream);
     if ((rc = amdp_reset(h, nullptr, h->hs_obs, nullptr, h->hs_stream))) return rc;
     return host_result(h, 0, result_host);
 }
@@ -1302,6 +1372,7 @@ extern "C" int amdp_step_host(amdp_t* h, const int32_t* actions_host, int32_t* r
     int rc = host_step_init(h);
     if (rc) return rc;
     const amdp_config& c = h->cfg;
+    wait_caller_stream(h, h->hs_stream);
     CK(cudaMemcpyAsync(h->hs_act, actions_host, sizeof(int32_t) * (size_t)c.n_envs * c.n_act_tok, cudaMemcpyHostToDevice, h->hs_stream));
     if ((rc = amdp_step(h, h->hs_act, h->hs_obs, nullptr, h->hs_rew, h->hs_rgt, h->hs_term, h->hs_trunc, nullptr, h->hs_steps, nullptr, h->hs_stream)))
         return rc;
@@ -1369,6 +1440,9 @@ static int rollout_host_impl(amdp* h, int K, int chunk, const void* actions_host
     int rc = staging_init(h, chunk);
     if (rc) return rc;
     cudaStream_t s_in = h->st_stream[0], s_k = h->st_stream[1], s_out = h->st_stream[2];
+    // behind whatever the caller queued on its own stream (amdp_reset, amdp_assign, ...): the handle's streams are
+    // non-blocking and would otherwise start before those kernels have written the env state
+    wait_caller_stream(h, s_k);
     const size_t N = (size_t)c.n_envs;
     const size_t act_bytes = packed ? 1 : sizeof(int32_t);
     // the first chunk is a quarter of the others: nothing overlaps its kernel, so it sets the depth of the pipeline

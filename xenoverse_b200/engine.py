@@ -413,6 +413,25 @@ class Engine:
             self._ck(lib.amdp_set_state(self._h, *[_ptr(b) for b in bufs], _stream()))
             torch.cuda.current_stream().synchronize()
 
+    _ACC = (("ep_count", torch.int64), ("sum_len", torch.int64), ("sum_ret", torch.float64), ("sum_ret_sq", torch.float64),
+            ("min_ret", torch.float64), ("max_ret", torch.float64))
+
+    def get_accumulators(self):
+        """Per-env accumulators of closed episodes (what `stats_tensor` reduces) + the total step count: the part of a
+        checkpoint `get_state` does not cover."""
+        acc = {k: torch.empty(self.N, dtype=dt, device=self.device) for k, dt in self._ACC}
+        total = ctypes.c_double(0.0)
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_get_episode_accumulators(self._h, *[_ptr(acc[k]) for k, _ in self._ACC], ctypes.byref(total), _stream()))
+        acc["total_steps"] = float(total.value)
+        return acc
+
+    def set_accumulators(self, acc):
+        with torch.cuda.device(self.device):
+            bufs = [self._dev(acc[k], dt) for k, dt in self._ACC]
+            self._ck(lib.amdp_set_episode_accumulators(self._h, *[_ptr(b) for b in bufs], float(acc["total_steps"]), _stream()))
+            torch.cuda.current_stream().synchronize()
+
     def mapped_state(self):
         out = torch.empty(self.N, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):

@@ -96,7 +96,11 @@ class AnyMDPVecEnv:
         Returns (obs int32 [N] or [N, do], {"steps": int32 zeros}); unselected envs report -1."""
         self._require_task()
         if seed is not None:
-            self.engine.set_seed(seed)
+            # a seeded reset restarts the draw stream: same seed => same trajectories (the single-env drop-in does the same);
+            # the seed is remembered so that state_dict() / load_state_dict() resume THIS stream
+            self.seed = int(seed)
+            self.engine.set_seed(self.seed)
+            self.engine.tick = 0
         m = None if mask is None else self.engine._dev(mask, torch.uint8)
         self.engine.reset(self._buf["obs"], mask=m, u_inject=u_inject)
         return self._squeeze(self._buf["obs"]), {"steps": torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)}
@@ -216,19 +220,23 @@ class AnyMDPVecEnv:
 
     def transition_gt(self, actions):
         """info["transition_gt"] (anymdp_env.py:130) for every env: float64 [N, da, ns]; needs keep_transition=True."""
-        ns = max(int(x) for x in numpy.atleast_1d(self.geo.get("ns_out", self.geo["n_pad"])))
-        return self.engine.transition_gt(actions, ns)
+        ns = int(self.geo.get("ns_max") or self.geo["n_pad"])   # width of the observable state space (task["ns"]), not n_pad:
+        return self.engine.transition_gt(actions, ns)          # the row is indexed by MAPPED state (anymdp_env.py:61-63,130)
 
     # ---- checkpoint / resume (bit-exact: counter-based RNG) --------------------------------------
     def state_dict(self):
         st = {k: v.cpu() for k, v in self.engine.get_state().items()}
         st["tick"] = self.engine.tick
         st["seed"] = self.seed
+        # closed-episode accumulators: without them a resumed job reports different episode_stats() (SURVEY.md §5)
+        st["accumulators"] = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in self.engine.get_accumulators().items()}
         return st
 
     def load_state_dict(self, st):
         self._require_task()
         self.engine.set_state(st)
+        if "accumulators" in st:
+            self.engine.set_accumulators(st["accumulators"])
         self.engine.tick = st["tick"]
         self.seed = int(st["seed"])
         self.engine.set_seed(self.seed)
