@@ -71,6 +71,7 @@ extern "C" {
 #define AMDP_FAULT_NEED_RESET     1  /* anymdp_env.py:93-94 'Must "set_task" and "reset" before doing any actions' */
 #define AMDP_FAULT_TERMINAL_STATE 2  /* anymdp_env.py:95-96 'Unexpected Error: given an terminated state' */
 #define AMDP_FAULT_BAD_ACTION     4  /* anymdp_env.py:97 assert action < na */
+#define AMDP_FAULT_PEER_TIMEOUT   8  /* amdp_stats_exchange: a peer rank did not post its statistics within ~4 s */
 
 /* per-task upload status written by amdp_upload_tasks() */
 #define AMDP_TASK_OK            0
@@ -226,6 +227,33 @@ int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const amdp_traj* 
  */
 int amdp_stats(amdp_t* h, double* out8, void* stream);
 int amdp_clear_stats(amdp_t* h, void* stream);
+
+/*
+ * Multi-GPU: the per-iteration exchange of the statistics vector over PEER MEMORY (NVLink / NVSwitch), fused into the tail
+ * of the statistics kernel — the all-reduce SURVEY.md §8e names, without a collective library on the path.  No reference
+ * equivalent (the reference is single-process; its callers average returns in Python, test_utils.py:60).
+ *   amdp_xchg_create   allocates this rank's exchange buffer (8 slots x 16 ranks x (flag + 8 doubles)); returns its
+ *                      cudaIpcMemHandle_t (64 bytes, HOST, may be NULL) and / or its device pointer (HOST void**, may be NULL).
+ *   amdp_xchg_open_ipc handles: HOST [world][64], rank-ordered, as gathered from amdp_xchg_create of every rank (one process
+ *                      per GPU); opens the peers with cudaIpcOpenMemHandle.
+ *   amdp_xchg_open_ptrs the same for ranks that live in ONE process: HOST void* [world] device pointers (peer access enabled).
+ *   amdp_stats_exchange one launch = amdp_stats (local vector to local_out8, may be NULL) + post it as iteration i (1, 2, ...)
+ *                      into every rank's buffer + combine iteration i - lag of ALL ranks into global_out8 (sums in rank
+ *                      order, min, max; [7] = the iteration number combined; untouched while i <= lag).  lag in 0..3:
+ *                      0 waits for every rank inside the kernel (a blocking all-reduce); lag >= 1 never waits for ranks
+ *                      that are less than `lag` iterations behind.
+ *   amdp_stats_exchange_flush combines the LAST posted iteration (waits for every rank): the end of a job.
+ * Every rank must call amdp_stats_exchange the same number of times.  A peer that does not show up within ~4 s raises
+ * AMDP_FAULT_PEER_TIMEOUT instead of hanging the GPU.
+ */
+int amdp_xchg_create(amdp_t* h, int32_t world, int32_t rank, void* ipc_handle_out, void** local_ptr_out);
+int amdp_xchg_open_ipc(amdp_t* h, const void* handles);
+int amdp_xchg_open_ptrs(amdp_t* h, void* const* ptrs);
+/* Unmaps the peers' buffers (cudaIpcCloseMemHandle).  Every rank must have called this before any rank destroys its handle
+ * (an exported buffer must not be freed while a peer still has it mapped). */
+int amdp_xchg_close(amdp_t* h);
+int amdp_stats_exchange(amdp_t* h, double* local_out8, double* global_out8, int32_t lag, void* stream);
+int amdp_stats_exchange_flush(amdp_t* h, double* global_out8, void* stream);
 
 /* info["transition_gt"] (anymdp_env.py:130): out double [n_envs][da][ns_out]: row of the
  * observation-indexed transition table at (state_mapping[current state], action[k]).

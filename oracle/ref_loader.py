@@ -4,9 +4,11 @@ This module is part of the oracle: only `tests/`, `tests/golden/make_golden.py`,
 `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline leg may import it.  The product
 package (`xenoverse_b200`) never does.
 
-The reference tree (`/root/reference`, read-only) exists only in the build container;
-GPU boxes do not have it, so `available()` is False there and callers fall back to the
-restated oracle (`oracle/anymdp_oracle.py`) plus the committed golden vectors.
+The reference tree (`/root/reference`, read-only) exists only in the build container.  GPU boxes
+do not have it; they may have `baseline/_ref/` (the offline `pip install --target` of the same
+tree, git-ignored), which bench.py's reference arm times as the CPU baseline (kind "reference").
+Where neither exists `available()` is False and callers fall back to the restated oracle
+(`oracle/anymdp_oracle.py`), the port (`oracle/reference_loop.py`) and the committed golden vectors.
 
 What is loaded: `xenoverse/anymdp/__init__.py:15-30` and everything it pulls in
 (`anymdp_env.py`, `task_sampler.py`, `task_sampler_utils.py`, `solver.py`, solvers).
@@ -20,7 +22,9 @@ import sys
 import tempfile
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_CANDIDATE_ROOTS = ("/root/reference",)
+# /root/reference: the read-only tree of the build container.  baseline/_ref: `pip install --no-deps --target baseline/_ref` of
+# that tree (git-ignored, travels to the GPU box with the snapshot) — there only bench.py's reference arm / CPU baseline use it.
+_CANDIDATE_ROOTS = ("/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref"))
 
 _loaded = None
 

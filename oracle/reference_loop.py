@@ -7,8 +7,10 @@ this class makes the same numpy calls per step as `AnyMDPEnv` does
 (xenoverse/anymdp/anymdp_env.py:81-132): `numpy.copy(transition[s, a])`, `random.choice(n, p=row)`
 (validation + cumsum + normalise + searchsorted every step), `random.normal(mu, sigma)`,
 two `in s_e` membership tests, the `transition_obs[...]` fancy-index for `info`, and the
-wall-clock reseed at every reset (`utils/random_nn.py:9-16`).  The reference itself is Python and
-lives only in the build container, so this port is what travels to the GPU box (kind = "port").
+wall-clock reseed at every reset (`utils/random_nn.py:9-16`).  The reference itself is Python; where its
+tree is present (`/root/reference` in the build container, `baseline/_ref` = its offline pip install, which travels to
+the GPU box) `make_env("reference", ...)` times the UNMODIFIED `AnyMDPEnv` instead (kind = "reference") and this port is
+the fallback (kind = "port").
 Parity unpinned by the reference's tests; pinned instead by tests/test_reference_loop.py against
 the live reference where it exists.
 """
@@ -97,8 +99,20 @@ def run_steps(env, actions):
     return done, ret
 
 
+def make_env(impl, task):
+    """One env on `task`: impl "reference" = the UNMODIFIED AnyMDPEnv (gym.make("anymdp-v0") under the import shim,
+    oracle/ref_loader.py), "port" = RefPortEnv."""
+    if impl == "reference":
+        from oracle import ref_loader
+        env = ref_loader.make_env(5000)
+    else:
+        env = RefPortEnv()
+    env.set_task(task)
+    return env
+
+
 def _worker(args):
-    ns, na, no, seed, n_steps, n_rounds, warm = args
+    ns, na, no, seed, n_steps, n_rounds, warm, impl = args
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     if root not in sys.path:
@@ -106,8 +120,7 @@ def _worker(args):
     # task generator only (schema + numpy arrays); nothing of the CUDA library is used
     from xenoverse_b200.synth import synth_task
     task = synth_task(ns, na, seed, no=no)
-    env = RefPortEnv()
-    env.set_task(task)
+    env = make_env(impl, task)
     env.reset()
     rng = numpy.random.default_rng(seed)
     out = []
@@ -119,12 +132,46 @@ def _worker(args):
     return out[warm:]
 
 
-def timed_pool(ns, na, no, workers, n_steps, n_rounds, warm=1, seed0=1000):
+def timed_pool(ns, na, no, workers, n_steps, n_rounds, warm=1, seed0=1000, impl="port"):
     """`workers` processes, one env each on its own synthetic task; every round = n_steps env-steps
     per worker.  Returns per-round wall time (max over workers) — the workers run concurrently."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     with ctx.Pool(workers) as pool:
-        res = pool.map(_worker, [(ns, na, no, seed0 + w, n_steps, n_rounds, warm) for w in range(workers)])
+        res = pool.map(_worker, [(ns, na, no, seed0 + w, n_steps, n_rounds, warm, impl) for w in range(workers)])
     per_round = [max(r[i] for r in res) for i in range(n_rounds)]
     return per_round
+
+
+def _single(args):
+    ns, na, no, seed, n_steps, impl = args
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from xenoverse_b200.synth import synth_task
+    env = make_env(impl, synth_task(ns, na, seed, no=no))
+    env.reset()
+    rng = numpy.random.default_rng(seed)
+    run_steps(env, rng.integers(0, na, min(n_steps, 2000)))          # warm-up (numba JIT of set_task is already done)
+    acts = rng.integers(0, na, n_steps)
+    t_step, resets = 0.0, 0
+    t0 = time.perf_counter()
+    for a in acts:
+        s0 = time.perf_counter()
+        obs, r, term, trunc, info = env.step(int(a))
+        t_step += time.perf_counter() - s0
+        if term or trunc:
+            env.reset()
+            resets += 1
+    wall = time.perf_counter() - t0
+    return {"steps_per_s": n_steps / wall, "step_only_us": 1e6 * t_step / n_steps, "episodes": resets,
+            "reset_share": 1.0 - t_step / wall}
+
+
+def single_core(ns, na, no, n_steps, seed=1000, impl="port"):
+    """ONE process, one env: steps/s of the whole loop (step + reset on done) over a fixed window of
+    `n_steps`, and the time inside `env.step()` alone (us per call).  Runs in a child process like the pool workers."""
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(1) as pool:
+        return pool.map(_single, [(ns, na, no, seed, n_steps, impl)])[0]

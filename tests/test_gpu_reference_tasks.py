@@ -22,7 +22,11 @@ RTOL = ATOL = 1e-6
 
 def _tasks(name):
     with numpy.load(os.path.join(gio.GOLDEN_DIR, name + ".npz"), allow_pickle=False) as z:
-        return gio.unpack_tasks({k: z[k] for k in z.files})
+        tasks = gio.unpack_tasks({k: z[k] for k in z.files})
+    for i, t in enumerate(tasks):
+        if i % 2 == 0:
+            t["max_steps"] = 57.5          # the sampler's own max_steps is 256..500: make truncation (and resets) happen
+    return tasks
 
 
 def _rollout(tasks, N, K, search, generic, acts, mode="same_step", coarse=0, seed=91):

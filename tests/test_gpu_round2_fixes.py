@@ -155,3 +155,64 @@ def test_scalar_action_on_mtpomdp_is_one_single_step():
             o0, _ = orc.reset(U[ao.SLOT_RESET], [U[ao.SLOT_RESET_OBS + 8 * j] for j in range(task["do"])])
             assert numpy.array_equal(obs, o0)
             tick += 1
+
+
+@pytest.mark.parametrize("lag", [1, 2, 0])
+def test_peer_memory_stats_exchange_three_ranks_in_one_process(lag):
+    """amdp_stats_exchange: three engines (ranks) on one GPU, wired by device pointers.  Iteration i's combined vector
+    (sums in rank order, min, max) must equal the combination of the three LOCAL vectors of iteration i - lag, bit for bit;
+    lag 0 (every rank waits for every rank inside the kernel) runs the ranks on separate streams."""
+    from xenoverse_b200 import AnyMDPVecEnv, synth_task
+    from xenoverse_b200.distributed import PeerStatsExchange
+    tasks = [synth_task(16, 5, 90 + t) for t in range(8)]
+    envs = []
+    for r, n in enumerate((64, 200, 33)):
+        e = AnyMDPVecEnv(n, seed=3, env_id_base=1000 * r)
+        e.set_task(tasks)
+        e.reset()
+        envs.append(e)
+    engines = [e.engine for e in envs]
+    ex = [PeerStatsExchange(g, engines=engines, lag=lag) for g in engines[:1]]
+    ex += [PeerStatsExchange.__new__(PeerStatsExchange) for _ in engines[1:]]
+    for r in (1, 2):                                               # the first constructor wired all three
+        ex[r].engine, ex[r].lag, ex[r].world, ex[r].rank = engines[r], lag, 3, r
+        ex[r].global_out = torch.zeros(8, dtype=torch.float64, device="cuda")
+        ex[r].local_out = torch.zeros(8, dtype=torch.float64, device="cuda")
+    streams = [torch.cuda.Stream() for _ in engines]
+    locals_, globals_ = [], []
+    torch.cuda.synchronize()
+    for it in range(1, 12):
+        glo = []
+        for r, e in enumerate(envs):
+            with torch.cuda.stream(streams[r]):
+                e.rollout(9 + r, record=("done",))
+                g = ex[r].step(global_out=torch.zeros(8, dtype=torch.float64, device="cuda"),
+                               local_out=torch.zeros(8, dtype=torch.float64, device="cuda"))
+                glo.append(g)
+        torch.cuda.synchronize()
+        locals_.append([e.episode_stats_tensor().cpu().numpy().copy() for e in envs])
+        globals_.append([g.cpu().numpy() for g in glo])
+    for e in envs:
+        e.check()                                                 # no AMDP_FAULT_PEER_TIMEOUT
+    for it in range(1, 12):
+        src = it - lag
+        for r in range(3):
+            g = globals_[it - 1][r]
+            if src < 1:
+                assert not g.any()
+                continue
+            L = locals_[src - 1]
+            want = numpy.zeros(8)
+            for i in (0, 1, 2, 3, 6):
+                acc = 0.0
+                for rr in range(3):
+                    acc = acc + L[rr][i]
+                want[i] = acc
+            want[4] = min(x[4] for x in L)
+            want[5] = max(x[5] for x in L)
+            want[7] = src
+            assert numpy.array_equal(g, want), (it, r, g, want)
+    # flush: the last iteration, on every rank
+    for r in range(3):
+        f = ex[r].flush(global_out=torch.zeros(8, dtype=torch.float64, device="cuda")).cpu().numpy()
+        assert f[7] == 11 and f[0] == sum(x[0] for x in locals_[-1])

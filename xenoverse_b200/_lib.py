@@ -15,7 +15,7 @@ OK, EINVAL, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4
 MDP, POMDP, MTPOMDP = 0, 1, 2
 TASK_TYPES = {"MDP": MDP, "POMDP": POMDP, "MTPOMDP": MTPOMDP}
 AUTORESET = {"same_step": 0, "next_step": 1, "disabled": 2}
-FAULT_NEED_RESET, FAULT_TERMINAL_STATE, FAULT_BAD_ACTION = 1, 2, 4
+FAULT_NEED_RESET, FAULT_TERMINAL_STATE, FAULT_BAD_ACTION, FAULT_PEER_TIMEOUT = 1, 2, 4, 8
 TASK_OK, TASK_BAD_ROW_SUM, TASK_NOT_NORMALISED, TASK_NEGATIVE_P, TASK_S0_IN_SE, TASK_OBS_RANGE, TASK_NOT_SPARSE = 0, 1, 2, 3, 4, 5, 6
 SLOTS_PER_TOKEN = 8
 SLOT_TRANS, SLOT_RESET, SLOT_OBS, SLOT_RESET_OBS, SLOT_Z, SLOT_ACTION = 0, 1, 2, 3, 4, 5
@@ -54,6 +54,12 @@ _SIGNATURES = {
     "amdp_rollout": (ctypes.c_int, [_P, ctypes.c_int32, _P, ctypes.POINTER(Traj), _P, _P]),
     "amdp_stats": (ctypes.c_int, [_P, _P, _P]),
     "amdp_clear_stats": (ctypes.c_int, [_P, _P]),
+    "amdp_xchg_create": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P, ctypes.POINTER(_P)]),
+    "amdp_xchg_open_ipc": (ctypes.c_int, [_P, _P]),
+    "amdp_xchg_open_ptrs": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
+    "amdp_xchg_close": (ctypes.c_int, [_P]),
+    "amdp_stats_exchange": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
+    "amdp_stats_exchange_flush": (ctypes.c_int, [_P, _P, _P]),
     "amdp_gather_transition_gt": (ctypes.c_int, [_P, _P, ctypes.c_int32, _P, _P]),
     "amdp_dump_draws": (ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_int32, _P, _P]),
     "amdp_get_tick": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),

@@ -586,10 +586,70 @@ __device__ __forceinline__ Stat6 stat_block_reduce(Stat6 v) {
     return sh[0];
 }
 
+// ---- multi-GPU: fused reduce + exchange of the per-iteration statistics over peer memory (NVLink / NVSwitch) -----------
+// Replaces the per-iteration ncclAllReduce of 4-8 doubles.  Every rank owns ONE buffer that all ranks can
+// address (cudaIpc, or plain device pointers inside one process):
+//     flag [XG_DEPTH][XG_MAX_RANKS] uint64     iteration number last posted by rank r into slot d
+//     data [XG_DEPTH][XG_MAX_RANKS][8] double  the amdp_stats vector of rank r for that iteration
+// In iteration `seq` the tail of k_stats (its last block) stores this rank's vector into slot seq % XG_DEPTH of EVERY rank
+// (one thread per peer, 64 bytes over NVLink), fences, then publishes `seq` in the flag; it then combines iteration
+// seq - lag from its OWN buffer (flags polled with acquire loads; rank order, so the result is deterministic and identical
+// on every rank).  With lag >= 1 a rank never waits for a peer that is less than `lag` iterations behind, so the ranks are
+// not coupled per iteration the way a blocking collective couples them; there is no extra kernel, no CTA slot to find
+// while the rollout owns the GPU, no host involvement.  Slot reuse is safe for XG_DEPTH >= 2 * lag + 2 (a writer of
+// iteration i + XG_DEPTH has seen every rank post i + XG_DEPTH - lag - 1, i.e. finish the kernel that combined i).
+#define XG_DEPTH 8
+#define XG_MAX_RANKS 16
+#define XG_MAX_LAG 3
+struct Xchg {
+    void* const* peers;        // [world] base pointer of every rank's buffer (device array)
+    int world, rank, lag;      // world == 0: no exchange
+    unsigned long long seq;    // this iteration (1, 2, ...)
+    double* global_out8;       // combined vector of iteration seq - lag (device; untouched while seq <= lag)
+};
+#define XG_BYTES (sizeof(unsigned long long) * XG_DEPTH * XG_MAX_RANKS + sizeof(double) * XG_DEPTH * XG_MAX_RANKS * 8)
+
+__device__ __forceinline__ unsigned long long* xg_flag(void* base, unsigned long long seq, int r) {
+    return reinterpret_cast<unsigned long long*>(base) + (seq % XG_DEPTH) * XG_MAX_RANKS + r;
+}
+__device__ __forceinline__ double* xg_data(void* base, unsigned long long seq, int r) {
+    return reinterpret_cast<double*>(reinterpret_cast<unsigned long long*>(base) + XG_DEPTH * XG_MAX_RANKS) + ((seq % XG_DEPTH) * XG_MAX_RANKS + r) * 8;
+}
+
+// combine iteration `g` from this rank's own buffer: sums in rank order, min / max; waits (bounded) for late peers
+__device__ void xg_combine(const Xchg& X, unsigned long long g, unsigned int* faults, double (*sh)[8]) {
+    void* mine = X.peers[X.rank];
+    if ((int)threadIdx.x < X.world) {
+        const unsigned long long* f = xg_flag(mine, g, threadIdx.x);
+        unsigned long long v;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= g) break;
+            if (clock64() - t0 > 8000000000ll) { atomicOr(faults, AMDP_FAULT_PEER_TIMEOUT); break; }   // ~4 s: a peer died
+            __nanosleep(200);
+        }
+        const double* d = xg_data(mine, g, threadIdx.x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sh[threadIdx.x][i] = __ldcv(d + i);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double o[8] = {0, 0, 0, 0, INFINITY, -INFINITY, 0, 0};
+        for (int r = 0; r < X.world; ++r) {
+            o[0] += sh[r][0]; o[1] += sh[r][1]; o[2] += sh[r][2]; o[3] += sh[r][3];
+            o[4] = fmin(o[4], sh[r][4]); o[5] = fmax(o[5], sh[r][5]); o[6] += sh[r][6];
+        }
+        o[7] = (double)g;                                          // which iteration this is
+        for (int i = 0; i < 8; ++i) X.global_out8[i] = o[i];
+    }
+}
+
 // One launch: every block reduces a strided slice of the envs into part[blockIdx]; the block that finishes last
 // (device-wide ticket) combines the 148 partials in index order, so the result does not depend on scheduling.
+// With X.world > 0 that block also posts the vector to every peer and combines iteration X.seq - X.lag (above).
 __global__ void __launch_bounds__(STAT_THREADS) k_stats(EnvArrays E, Stat6* __restrict__ part, unsigned int* __restrict__ ticket,
-                                                        double total_steps, double* __restrict__ out8) {
+                                                        double total_steps, double* __restrict__ out8, Xchg X) {
     Stat6 v = {0, 0, 0, 0, INFINITY, -INFINITY};
     for (long long e = (long long)blockIdx.x * STAT_THREADS + threadIdx.x; e < E.n_envs; e += (long long)STAT_BLOCKS * STAT_THREADS) {
         Stat6 w = {(double)E.ep_count[e], E.sum_ret[e], E.sum_ret_sq[e], (double)E.sum_len[e], E.min_ret[e], E.max_ret[e]};
@@ -597,6 +657,8 @@ __global__ void __launch_bounds__(STAT_THREADS) k_stats(EnvArrays E, Stat6* __re
     }
     v = stat_block_reduce(v);
     __shared__ bool last;
+    __shared__ double sh_x[XG_MAX_RANKS][8];
+    __shared__ double sh_mine[8];
     if (threadIdx.x == 0) {
         part[blockIdx.x] = v;
         __threadfence();
@@ -610,10 +672,28 @@ __global__ void __launch_bounds__(STAT_THREADS) k_stats(EnvArrays E, Stat6* __re
     __syncthreads();
     f = stat_block_reduce(f);
     if (threadIdx.x == 0) {
-        out8[0] = f.n; out8[1] = f.sr; out8[2] = f.sq; out8[3] = f.sl; out8[4] = f.mn; out8[5] = f.mx;
-        out8[6] = total_steps; out8[7] = 0.0;
+        sh_mine[0] = f.n; sh_mine[1] = f.sr; sh_mine[2] = f.sq; sh_mine[3] = f.sl; sh_mine[4] = f.mn; sh_mine[5] = f.mx;
+        sh_mine[6] = total_steps; sh_mine[7] = 0.0;
+        if (out8) for (int i = 0; i < 8; ++i) out8[i] = sh_mine[i];
         *ticket = 0;
     }
+    if (X.world == 0) return;
+    __syncthreads();
+    if ((int)threadIdx.x < X.world) {                              // post: one thread per peer (64 bytes + the flag)
+        void* peer = X.peers[threadIdx.x];
+        double* d = xg_data(peer, X.seq, X.rank);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = sh_mine[i];
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(xg_flag(peer, X.seq, X.rank)), "l"(X.seq) : "memory");
+    }
+    if (X.seq > (unsigned long long)X.lag) xg_combine(X, X.seq - X.lag, E.faults, sh_x);
+}
+
+// combine the latest posted iteration without posting (the flush at the end of a job: lag 0)
+__global__ void __launch_bounds__(32) k_xchg_flush(Xchg X, unsigned int* faults) {
+    __shared__ double sh_x[XG_MAX_RANKS][8];
+    xg_combine(X, X.seq, faults, sh_x);
 }
 
 // ---- introspection -----------------------------------------------------------------------------
@@ -713,6 +793,14 @@ struct amdp {
     // stream through the asynchronous entry points: the last such enqueue is marked with an event the handle's streams wait for
     cudaEvent_t ev_caller;
     bool ev_caller_set;
+    // statistics exchange over peer memory (amdp_xchg_*): this rank's buffer, every rank's base pointer, iteration counter
+    void* xg_buf;
+    void* xg_peer[XG_MAX_RANKS];
+    bool xg_opened[XG_MAX_RANKS];        // opened with cudaIpcOpenMemHandle (to be closed)
+    void** xg_peers_dev;
+    int xg_world, xg_rank;
+    unsigned long long xg_seq;
+    bool xg_ready;
 };
 
 static int fail(amdp* h, int code, const char* fmt, const char* a = "") {
@@ -797,6 +885,9 @@ extern "C" int amdp_destroy(amdp_t* h) {
     }
     if (h->hs_stream) cudaStreamDestroy(h->hs_stream);
     if (h->ev_caller) cudaEventDestroy(h->ev_caller);
+    for (int r = 0; r < XG_MAX_RANKS; ++r) if (h->xg_opened[r] && h->xg_peer[r]) cudaIpcCloseMemHandle(h->xg_peer[r]);
+    if (h->xg_buf) cudaFree(h->xg_buf);
+    if (h->xg_peers_dev) cudaFree(h->xg_peers_dev);
     if (h->st_ready) {
         for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->st_stream[i]);
         for (int i = 0; i < ST_NBUF; ++i) { cudaEventDestroy(h->st_ev_in[i]); cudaEventDestroy(h->st_ev_k[i]); cudaEventDestroy(h->st_ev_out[i]); }
@@ -1078,10 +1169,107 @@ extern "C" int amdp_stats(amdp_t* h, double* out8, void* stream) {
     if (!h->assigned) return fail(h, AMDP_ESTATE, "stats before assign");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    k_stats<<<STAT_BLOCKS, STAT_THREADS, 0, st>>>(h->E, h->stat_part, h->stat_ticket, h->total_steps, out8);
+    Xchg none;
+    memset(&none, 0, sizeof(none));
+    k_stats<<<STAT_BLOCKS, STAT_THREADS, 0, st>>>(h->E, h->stat_part, h->stat_ticket, h->total_steps, out8, none);
     h->launches += 1;
     CK(cudaGetLastError());
     mark_caller_stream(h, st);
+    return AMDP_OK;
+}
+
+// ---- statistics exchange over peer memory -------------------------------------------------------------------------------
+extern "C" int amdp_xchg_create(amdp_t* h, int32_t world, int32_t rank, void* ipc_handle_out, void** local_ptr_out) {
+    if (!h || world < 1 || world > XG_MAX_RANKS || rank < 0 || rank >= world) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->xg_buf) {
+        int rc;
+        char* p = nullptr;
+        if ((rc = dalloc(h, &p, XG_BYTES))) return rc;
+        h->xg_buf = p;
+        void** pd = nullptr;
+        if ((rc = dalloc(h, &pd, (size_t)XG_MAX_RANKS))) return rc;
+        h->xg_peers_dev = pd;
+    }
+    CK(cudaMemset(h->xg_buf, 0, XG_BYTES));
+    h->xg_world = world; h->xg_rank = rank; h->xg_seq = 0; h->xg_ready = false;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t hd;
+        CK(cudaIpcGetMemHandle(&hd, h->xg_buf));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+        memcpy(ipc_handle_out, &hd, sizeof(hd));
+    }
+    if (local_ptr_out) *local_ptr_out = h->xg_buf;
+    return AMDP_OK;
+}
+
+static int xchg_finish(amdp* h) {
+    CK(cudaMemcpy(h->xg_peers_dev, h->xg_peer, sizeof(void*) * XG_MAX_RANKS, cudaMemcpyHostToDevice));
+    h->xg_ready = true;
+    return AMDP_OK;
+}
+
+extern "C" int amdp_xchg_open_ipc(amdp_t* h, const void* handles) {
+    if (!h || !handles) return AMDP_EINVAL;
+    if (!h->xg_buf) return fail(h, AMDP_ESTATE, "xchg_open before xchg_create");
+    CK(cudaSetDevice(h->cfg.device));
+    for (int r = 0; r < h->xg_world; ++r) {
+        if (r == h->xg_rank) { h->xg_peer[r] = h->xg_buf; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char*)handles + 64 * r, sizeof(hd));
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        h->xg_peer[r] = p;
+        h->xg_opened[r] = true;
+    }
+    return xchg_finish(h);
+}
+
+extern "C" int amdp_xchg_open_ptrs(amdp_t* h, void* const* ptrs) {
+    if (!h || !ptrs) return AMDP_EINVAL;
+    if (!h->xg_buf) return fail(h, AMDP_ESTATE, "xchg_open before xchg_create");
+    CK(cudaSetDevice(h->cfg.device));
+    for (int r = 0; r < h->xg_world; ++r) h->xg_peer[r] = (r == h->xg_rank) ? h->xg_buf : ptrs[r];
+    return xchg_finish(h);
+}
+
+extern "C" int amdp_xchg_close(amdp_t* h) {
+    if (!h) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaDeviceSynchronize());
+    for (int r = 0; r < XG_MAX_RANKS; ++r) {
+        if (h->xg_opened[r] && h->xg_peer[r]) cudaIpcCloseMemHandle(h->xg_peer[r]);
+        h->xg_opened[r] = false;
+        h->xg_peer[r] = nullptr;
+    }
+    h->xg_ready = false;
+    return AMDP_OK;
+}
+
+extern "C" int amdp_stats_exchange(amdp_t* h, double* local_out8, double* global_out8, int32_t lag, void* stream) {
+    if (!h || !global_out8 || lag < 0 || lag > XG_MAX_LAG) return AMDP_EINVAL;
+    if (!h->assigned) return fail(h, AMDP_ESTATE, "stats before assign");
+    if (!h->xg_ready) return fail(h, AMDP_ESTATE, "stats_exchange before xchg_open");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Xchg X;
+    X.peers = h->xg_peers_dev; X.world = h->xg_world; X.rank = h->xg_rank; X.lag = lag; X.seq = ++h->xg_seq; X.global_out8 = global_out8;
+    k_stats<<<STAT_BLOCKS, STAT_THREADS, 0, st>>>(h->E, h->stat_part, h->stat_ticket, h->total_steps, local_out8, X);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    mark_caller_stream(h, st);
+    return AMDP_OK;
+}
+
+extern "C" int amdp_stats_exchange_flush(amdp_t* h, double* global_out8, void* stream) {
+    if (!h || !global_out8) return AMDP_EINVAL;
+    if (!h->xg_ready || h->xg_seq == 0) return fail(h, AMDP_ESTATE, "stats_exchange_flush before stats_exchange");
+    CK(cudaSetDevice(h->cfg.device));
+    Xchg X;
+    X.peers = h->xg_peers_dev; X.world = h->xg_world; X.rank = h->xg_rank; X.lag = 0; X.seq = h->xg_seq; X.global_out8 = global_out8;
+    k_xchg_flush<<<1, 32, 0, (cudaStream_t)stream>>>(X, h->faults);
+    h->launches += 1;
+    CK(cudaGetLastError());
     return AMDP_OK;
 }
 

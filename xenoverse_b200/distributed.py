@@ -57,3 +57,56 @@ def stats_dict(v):
             "min_return": float(v[4]), "max_return": float(v[5]), "total_steps": int(v[6]),
             "mean_return": float(v[1] / n) if n else float("nan"),
             "mean_length": float(v[3] / n) if n else float("nan")}
+
+
+class PeerStatsExchange:
+    """Per-iteration all-reduce of the episode statistics WITHOUT a collective library on the path: every rank's statistics
+    kernel stores its 8-double vector straight into every peer's exchange buffer over NVLink (`amdp_stats_exchange`, fused
+    into the tail of the reduction) and combines the vectors of iteration `i - lag` from its own buffer, in rank order.
+
+    One process per GPU: the buffers are shared through cudaIpc handles, gathered once with `all_gather_object` (the only
+    use of torch.distributed here; gloo or nccl).  `engines` (a list) instead wires ranks that live in ONE process.
+
+        ex = PeerStatsExchange(env.engine, group=None, lag=2)
+        for it in range(...):
+            env.rollout(K, ...)
+            g = ex.step()            # float64[8] on the device: combined statistics of iteration it - lag ([7] = its number)
+        final = ex.flush()           # every iteration up to the last one, all ranks
+    """
+
+    def __init__(self, engine, group=None, lag=2, engines=None):
+        self.engine, self.lag = engine, int(lag)
+        if engines is not None:                       # same-process ranks (tests; single process driving several GPUs)
+            created = [e.xchg_create(len(engines), r) for r, e in enumerate(engines)]
+            for e in engines:
+                e.xchg_open_ptrs([p for _, p in created])
+            self.world, self.rank = len(engines), engines.index(engine)
+        else:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            handle, _ = engine.xchg_create(self.world, self.rank)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle, group=group)
+            engine.xchg_open_ipc(handles)
+            self._group = group
+            dist.barrier(group=group)                 # nobody posts before everybody has mapped everybody
+        self.global_out = torch.zeros(8, dtype=torch.float64, device=engine.device)
+        self.local_out = torch.zeros(8, dtype=torch.float64, device=engine.device)
+
+    def close(self):
+        """Unmap the peers' buffers, then wait for every rank to have done so: only then may an engine (the owner of a
+        buffer) be closed — freeing exported memory that a peer still has mapped is undefined (cudaIpc rules)."""
+        self.engine.xchg_close()
+        if hasattr(self, "_group"):
+            import torch.distributed as dist
+            dist.barrier(group=self._group)
+
+    def step(self, global_out=None, local_out=None):
+        g = self.global_out if global_out is None else global_out
+        self.engine.stats_exchange(g, self.local_out if local_out is None else local_out, self.lag)
+        return g
+
+    def flush(self, global_out=None):
+        g = self.global_out if global_out is None else global_out
+        self.engine.stats_exchange_flush(g)
+        return g

@@ -371,6 +371,43 @@ class Engine:
             self._ck(lib.amdp_stats(self._h, _ptr(out), _stream()))
         return out
 
+    # ---- statistics exchange over peer memory (multi-GPU; see distributed.PeerStatsExchange) ------------------------------
+    def xchg_create(self, world, rank):
+        """-> (64-byte cudaIpc handle, device pointer) of this rank's exchange buffer."""
+        hd = (ctypes.c_ubyte * 64)()
+        ptr = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_xchg_create(self._h, int(world), int(rank), hd, ctypes.byref(ptr)))
+        return bytes(hd), int(ptr.value)
+
+    def xchg_open_ipc(self, handles):
+        """handles: list of the 64-byte handles of every rank, in rank order (one process per GPU)."""
+        blob = b"".join(handles)
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_xchg_open_ipc(self._h, buf))
+
+    def xchg_open_ptrs(self, ptrs):
+        """ptrs: device pointers of every rank's buffer, in rank order (ranks inside one process)."""
+        arr = (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(p)) for p in ptrs])
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_xchg_open_ptrs(self._h, arr))
+
+    def xchg_close(self):
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()
+            self._ck(lib.amdp_xchg_close(self._h))
+
+    def stats_exchange(self, global_out, local_out=None, lag=2):
+        """amdp_stats + post to every rank + combine iteration (i - lag) of all ranks into `global_out` (float64[8], device),
+        in ONE launch on the current stream."""
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_stats_exchange(self._h, _ptr(local_out), _ptr(global_out), int(lag), _stream()))
+
+    def stats_exchange_flush(self, global_out):
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_stats_exchange_flush(self._h, _ptr(global_out), _stream()))
+
     def clear_stats(self):
         with torch.cuda.device(self.device):
             self._ck(lib.amdp_clear_stats(self._h, _stream()))

@@ -16,6 +16,7 @@ _FAULT_MSG = (
     (_lib.FAULT_NEED_RESET, Exception, "Must \"set_task\" and \"reset\" before doing any actions"),   # anymdp_env.py:94
     (_lib.FAULT_TERMINAL_STATE, Exception, "Unexpected Error: given an terminated state"),             # anymdp_env.py:96
     (_lib.FAULT_BAD_ACTION, AssertionError, "Action is out of range"),                                # anymdp_env.py:97
+    (_lib.FAULT_PEER_TIMEOUT, RuntimeError, "statistics exchange: a peer rank did not post its vector in time"),
 )
 
 
