@@ -449,6 +449,70 @@ def measure_vi(name, tasks, ns, na, dev, local, sweeps=64):
     return out
 
 
+def measure_e2e(env, args, N, na, K, world, rank, local, dev):
+    """The same metric through the reference-facing C ABI with HOST buffers (copies inside the timed region).  One step = one
+    amdp_rollout_host_compact call: `--e2e-ticks` ticks x N envs with the caller's uint8 actions copied in from pinned host
+    memory and the trajectory copied out as COMPACT records (uint16 observation + done bits, fp32 reward: 6 bytes per
+    env-step; the action is the caller's own and is not echoed).  The collector alternates two sets of host buffers: it
+    submits step i + 1 before it waits for step i, so the copy engines stay busy across calls (every step's H2D and D2H are
+    inside the timed region; the wall clock stops when the last step has landed).  The round-1 path — synchronous calls,
+    8-byte packed records — is timed next to it for comparison."""
+    import numpy
+    import torch
+    import torch.distributed as dist
+    from xenoverse_b200 import HostBuffer, bind_to_gpu_numa_node
+    eK = args.e2e_ticks
+    numa = bind_to_gpu_numa_node(local) if not args.no_numa_bind else {"bound": False, "skipped": True}
+    rng = numpy.random.default_rng(rank)
+    sets = []
+    for _ in range(2):
+        ha, ho, hr = HostBuffer(eK * N), HostBuffer(eK * N * 2, args.e2e_wc), HostBuffer(eK * N * 4, args.e2e_wc)
+        a, o, r = ha.view(numpy.uint8, (eK, N)), ho.view(numpy.uint16, (eK, N)), hr.view(numpy.float32, (eK, N))
+        a[:] = rng.integers(0, na, (eK, N), dtype=numpy.uint8)
+        sets.append((a, o, r, ha, ho, hr))
+    reps = max(20, min(K, 100))
+    eng = env.engine
+    for i in range(3):
+        eng.rollout_host_compact(eK, args.e2e_chunk, *sets[i % 2][:3])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    w0 = time.perf_counter()
+    eng.rollout_host_compact(eK, args.e2e_chunk, *sets[0][:3], wait=False)
+    for i in range(1, reps):
+        eng.rollout_host_compact(eK, args.e2e_chunk, *sets[i % 2][:3], wait=False)
+        eng.rollout_host_wait(pending=1)                 # step i - 1 has landed in its host buffers (the collector consumes it here)
+    eng.rollout_host_wait(0)
+    w = max_over_ranks(time.perf_counter() - w0, world, dev)
+    env.check()
+    out = {"value": world * N * eK * reps / w, "unit": "env-steps/s",
+           "h2d_bytes_per_step": int(eK * N), "d2h_bytes_per_step": int(eK * N * 6),
+           "step": f"one amdp_rollout_host_compact call = {eK} ticks x {N} envs: pinned uint8 host actions in, 6-byte host records "
+                   f"(uint16 obs | done bits, fp32 reward) out, chunks of {args.e2e_chunk} ticks on 3 streams with 4 staging sets; two "
+                   f"host buffer sets, step i + 1 submitted before step i is waited for; wall clock around {reps} steps (max over ranks)",
+           "ms_per_step": 1e3 * w / reps, "d2h_GBps_per_gpu": eK * N * 6 * reps / w / 1e9,
+           "host_buffers": {"write_combined": bool(args.e2e_wc), "numa": numa}}
+    # round-1 path for comparison: synchronous calls, 8-byte packed records, torch-pinned buffers
+    acts_h = torch.from_numpy(sets[0][0].copy()).pin_memory()
+    rec_h = torch.empty((eK, N), dtype=torch.int64).pin_memory()
+    for _ in range(3):
+        eng.rollout_host_packed(eK, args.e2e_chunk, acts_h, rec_h)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    w0 = time.perf_counter()
+    for _ in range(reps):
+        eng.rollout_host_packed(eK, args.e2e_chunk, acts_h, rec_h)   # synchronous
+    w = max_over_ranks(time.perf_counter() - w0, world, dev)
+    out["packed8_synchronous"] = {"value": world * N * eK * reps / w, "ms_per_step": 1e3 * w / reps,
+                                  "d2h_bytes_per_step": int(eK * N * 8), "d2h_GBps_per_gpu": eK * N * 8 * reps / w / 1e9}
+    env.check()
+    for st in sets:
+        for hb in st[3:]:
+            hb.close()
+    return out
+
+
 def other_workloads(world, rank, dev, local, args):
     """The other BASELINE.json configs.  N = 1: per-GPU sizes (cfg4 with the 32 tasks one of 8 GPUs owns, also with the 131072
     envs per GPU SURVEY.md §8d names as its saturating variant) plus cfg2 tables with enough envs to fill the GPU, the table
@@ -569,32 +633,10 @@ def run_b200(args, name, envs, tasks, ns, na, no):
         exchange_check = {"episodes_peer_exchange": int(g[0]), "episodes_all_reduce": int(ep["episodes"]),
                           "equal": bool(int(g[0]) == int(ep["episodes"]) and abs(g[1] - ep["sum_return"]) <= 1e-9 * max(1.0, abs(ep["sum_return"])))}
 
-    # ---- end to end through the C ABI with HOST buffers (amdp_rollout_host_packed) ---------------
+    # ---- end to end through the C ABI with HOST buffers (amdp_rollout_host_compact) --------------
     e2e = None
     if not args.no_e2e:
-        # compact wire format: uint8 actions in, one 8-byte record (obs, action, done, reward) per env-step out; pinned host
-        # buffers; copies inside the timed region
-        eK = args.e2e_ticks
-        g = torch.Generator().manual_seed(rank)
-        acts_h = torch.randint(0, na, (eK, N), dtype=torch.uint8, generator=g).pin_memory()
-        rec_h = torch.empty((eK, N), dtype=torch.int64).pin_memory()
-        reps = max(3, min(K, 20))
-        for _ in range(3):
-            env.engine.rollout_host_packed(eK, args.e2e_chunk, acts_h, rec_h)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        w0 = time.perf_counter()
-        for _ in range(reps):
-            env.engine.rollout_host_packed(eK, args.e2e_chunk, acts_h, rec_h)   # synchronous
-        w = max_over_ranks(time.perf_counter() - w0, world, dev)
-        e2e = {"value": world * N * eK * reps / w, "unit": "env-steps/s",
-               "h2d_bytes_per_step": int(acts_h.numel()), "d2h_bytes_per_step": int(rec_h.numel() * 8),
-               "step": f"one amdp_rollout_host_packed call = {eK} ticks x {N} envs: pinned uint8 host actions in, 8-byte host "
-                       f"records (obs, action, done, fp32 reward) out, chunks of {args.e2e_chunk} ticks on 3 streams with 4 staging "
-                       f"sets; wall clock around {reps} synchronous calls (max over ranks)",
-               "ms_per_step": 1e3 * w / reps, "d2h_GBps_per_gpu": rec_h.numel() * 8 * reps / w / 1e9}
-        env.check()
+        e2e = measure_e2e(env, args, N, na, K, world, rank, local, dev)
 
     device_bytes = env.engine.device_bytes
     stats.close()
@@ -682,8 +724,10 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--tasks", type=int, default=0, help="override tasks per GPU")
     ap.add_argument("--e2e-ticks", type=int, default=512)
-    ap.add_argument("--e2e-chunk", type=int, default=128)
+    ap.add_argument("--e2e-chunk", type=int, default=512)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-wc", action="store_true", help="e2e: write-combined pinned host buffers for the records")
+    ap.add_argument("--no-numa-bind", action="store_true", help="e2e: do not bind the process to the GPU's NUMA node before allocating host buffers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other workloads")
     ap.add_argument("--ref-steps-per-worker", type=int, default=20000)

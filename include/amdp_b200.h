@@ -43,12 +43,13 @@
 #define AMDP_B200_H
 
 #include <stdint.h>
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define AMDP_ABI_VERSION 1
+#define AMDP_ABI_VERSION 2
 
 /* status codes */
 #define AMDP_OK       0
@@ -210,9 +211,13 @@ typedef struct amdp_traj {
     int64_t  env_stride;
     uint64_t* packed;       /* or NULL.  When set, the five arrays above are ignored and ONE 8-byte record per
                                (tick, env) is written: bits 0-19 obs, 20-29 action, 30 terminated, 31 truncated,
-                               32-63 the fp32 reward.  Needs do == da == 1, ns <= 2^20, na <= 1024. */
+                               32-63 the fp32 reward.  Needs do == da == 1, ns <= 2^20, na <= 1024.  `reward_gt`, when also set,
+                               receives info["reward_gt"] (anymdp_env.py:129) as a separate fp32 plane: records with labels. */
     int32_t  actions_u8;    /* non-zero: `actions` points to uint8 [K][n_envs][da] instead of int32 */
     int32_t  reserved;
+    uint16_t* obs_done;     /* or NULL.  COMPACT records: with `reward` (and `packed` NULL) 6 bytes per (tick, env): bits 0-13 the
+                               observation, 14 terminated, 15 truncated.  Needs do == 1 and at most 2^14 observations.  The action is
+                               not echoed: this format is for rollouts whose actions the caller supplied (or does not need). */
 } amdp_traj;
 
 int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const amdp_traj* traj,
@@ -360,6 +365,24 @@ int amdp_rollout_host(amdp_t* h, int32_t K, int32_t chunk, const int32_t* action
 /* Same, in the compact wire format: uint8 actions in (1 byte per env-step over PCIe), packed 8-byte records out
  * (see amdp_traj.packed).  actions_host uint8 [K][n_envs] or NULL; records_host uint64 [K][n_envs]. */
 int amdp_rollout_host_packed(amdp_t* h, int32_t K, int32_t chunk, const uint8_t* actions_host, uint64_t* records_host);
+
+/* Same, in the COMPACT wire format (see amdp_traj.obs_done): uint8 actions in, 6 bytes per env-step out as two planes —
+ * obs_done_host uint16 [K][n_envs] (bits 0-13 observation, 14 terminated, 15 truncated) and reward_host float [K][n_envs].
+ * wait != 0: synchronises like the calls above.  wait == 0: SUBMITS the rollout and returns; the host buffers belong to the
+ * library until amdp_rollout_host_wait() says the submission has landed.  Several submissions may be in flight (they run in order), which keeps
+ * the copy engines busy across calls: a data collector alternates two sets of host buffers, submitting rollout i + 1 before
+ * it waits for (and then consumes) rollout i. */
+int amdp_rollout_host_compact(amdp_t* h, int32_t K, int32_t chunk, const uint8_t* actions_host, uint16_t* obs_done_host,
+                              float* reward_host, int32_t wait);
+/* Waits until at most `pending` (0..7) of the rollouts submitted with wait == 0 are still in flight; 0 = all have landed.
+ * `submit(i + 1); wait(1); consume(i)` keeps one rollout in flight behind the one being consumed. */
+int amdp_rollout_host_wait(amdp_t* h, int32_t pending);
+
+/* Page-locked host memory for the host-buffer entry points (cudaHostAlloc; HOST pointer in *out), zero-filled by the calling
+ * thread (first touch: bind the thread to the GPU's NUMA node first).  write_combined != 0: cudaHostAllocWriteCombined —
+ * PCIe writes are not snooped by the CPU caches, but CPU reads of the buffer are slow unless they are streaming loads. */
+int amdp_host_alloc(size_t bytes, int32_t write_combined, void** out);
+int amdp_host_free(void* p);
 
 #ifdef __cplusplus
 }

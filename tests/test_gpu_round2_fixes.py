@@ -216,3 +216,61 @@ def test_peer_memory_stats_exchange_three_ranks_in_one_process(lag):
     for r in range(3):
         f = ex[r].flush(global_out=torch.zeros(8, dtype=torch.float64, device="cuda")).cpu().numpy()
         assert f[7] == 11 and f[0] == sum(x[0] for x in locals_[-1])
+
+
+@pytest.mark.parametrize("search,N", [("auto", 300), ("thread", 4200), ("warp_v1", 200)])
+def test_compact_host_records_equal_device_rollout(search, N):
+    """amdp_rollout_host_compact (6 bytes per env-step: uint16 obs | done bits + fp32 reward), synchronous and pipelined
+    (submit i + 1, wait for i) with two host buffer sets, against the device rollout with the same actions; and the
+    reward_gt label plane next to packed 8-byte records."""
+    from xenoverse_b200 import AnyMDPVecEnv, synth_task, unpack_compact, unpack_records, HostBuffer
+    tasks = [synth_task(64, 5, 3300 + t) for t in range(7)]
+    K, calls = 50, 5
+    acts = torch.randint(0, 5, (calls, K, N), dtype=torch.uint8, generator=torch.Generator().manual_seed(8))
+
+    def fresh():
+        e = AnyMDPVecEnv(N, seed=19, search=search)
+        e.set_task(tasks)
+        e.reset()
+        return e
+    ref = fresh()
+    want = [ref.rollout(K, actions=acts[c].cuda(), record=("obs", "reward", "reward_gt", "done")) for c in range(calls)]
+    want = [{k: v.cpu().numpy() for k, v in w.items()} for w in want]
+    for pipelined in (False, True):
+        env = fresh()
+        sets = []
+        for _ in range(2):
+            hb = [HostBuffer(K * N), HostBuffer(K * N * 2), HostBuffer(K * N * 4)]
+            sets.append((hb[0].view(numpy.uint8, (K, N)), hb[1].view(numpy.uint16, (K, N)), hb[2].view(numpy.float32, (K, N)), hb))
+        got = []
+        for c in range(calls):
+            a, o, r, _ = sets[c % 2]
+            if pipelined and c >= 2:
+                env.engine.rollout_host_wait(pending=1)              # call c - 1 may still fly; c - 2 (this buffer set) has landed
+                got.append(unpack_compact(sets[c % 2][1].copy(), sets[c % 2][2].copy()))
+            a[:] = acts[c].numpy()
+            env.engine.rollout_host_compact(K, 16, a, o, r, wait=not pipelined)
+            if not pipelined:
+                got.append(unpack_compact(o.copy(), r.copy()))
+        if pipelined:
+            env.engine.rollout_host_wait(0)
+            for c in (calls - 2, calls - 1):
+                got.append(unpack_compact(sets[c % 2][1].copy(), sets[c % 2][2].copy()))
+        env.check()
+        assert len(got) == calls
+        for c in range(calls):
+            assert numpy.array_equal(got[c]["obs"], want[c]["obs"][..., 0]), (pipelined, c)
+            assert numpy.array_equal(got[c]["terminated"], (want[c]["done"] & 1).astype(bool))
+            assert numpy.array_equal(got[c]["truncated"], (want[c]["done"] >> 1).astype(bool))
+            assert numpy.array_equal(got[c]["reward"], want[c]["reward"])
+        for st in sets:
+            for hb in st[3]:
+                hb.close()
+        env.close()
+    # labels: packed records + the reward_gt plane (info["reward_gt"], anymdp_env.py:129)
+    env = fresh()
+    rec = torch.empty((K, N), dtype=torch.int64, device="cuda")
+    rgt = torch.empty((K, N), dtype=torch.float32, device="cuda")
+    env.engine.rollout(K, actions=acts[0].cuda(), traj={"packed": rec, "reward_gt": rgt})
+    assert numpy.array_equal(rgt.cpu().numpy(), want[0]["reward_gt"])
+    assert numpy.array_equal(unpack_records(rec)["reward"], want[0]["reward"])

@@ -6,7 +6,8 @@ reference (xenoverse/anymdp/__init__.py:24-30).  The CUDA library is loaded eage
 """
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
 from .gym_compat import register, make, spaces, HAVE_GYMNASIUM  # noqa: F401
-from .engine import Engine, AMDPError, task_geometry, pack_tasks, unpack_records  # noqa: F401
+from .engine import (Engine, AMDPError, task_geometry, pack_tasks, unpack_records, unpack_compact, HostBuffer,  # noqa: F401
+                     bind_to_gpu_numa_node)
 from .anymdp_env import AnyMDPEnv  # noqa: F401
 from .vec_env import AnyMDPVecEnv  # noqa: F401
 from .task_sampler import (AnyMDPTaskSampler, AnyPOMDPTaskSampler, MultiTokensAnyPOMDPTaskSampler,  # noqa: F401

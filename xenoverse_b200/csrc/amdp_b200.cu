@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(256) k_rollout(Tables T, EnvArrays E, unsigned
             if (J.reward) J.reward[o] = O.reward;
             if (J.reward_gt) J.reward_gt[o] = O.reward_gt;
             if (J.done) J.done[o] = (uint8_t)(O.term | (O.trunc << 1));
+            if (J.obs_done) J.obs_done[o] = (uint16_t)(((unsigned)obs[0] & 0x3fffu) | ((unsigned)(O.term | (O.trunc << 1)) << 14));
         }
     }
     if (active && lane == 0) { store_regs(E, e, R); store_stats(E, e, R); }
@@ -749,6 +750,7 @@ __global__ void k_transition_gt(Tables T, EnvArrays E, const int32_t* __restrict
 // staging sets of the host-buffer rollouts: with four the rollout kernels run up to three chunks ahead of the device-to-host
 // copies, so the copy engine never waits for a kernel (with two, every cross-stream hand-over was a bubble on the PCIe link)
 #define ST_NBUF 4
+#define ST_NSUB 8
 
 struct amdp {
     amdp_config cfg;
@@ -785,7 +787,12 @@ struct amdp {
     char kname[64];
     // rollout_host staging
     int32_t* st_act[ST_NBUF]; int32_t* st_obs[ST_NBUF]; float* st_rew[ST_NBUF]; uint8_t* st_done[ST_NBUF]; unsigned long long* st_rec[ST_NBUF];
+    uint16_t* st_od[ST_NBUF];
     int st_chunk;
+    long long st_i;        // chunks submitted so far (the staging ring keeps turning across submissions)
+    bool st_busy;          // work submitted and not yet waited for
+    long long sub_n;       // submissions so far; submission n records sub_ev[n % ST_NSUB] after its last copy-out
+    cudaEvent_t sub_ev[8];
     cudaStream_t st_stream[3];
     cudaEvent_t st_ev_in[ST_NBUF], st_ev_k[ST_NBUF], st_ev_out[ST_NBUF];
     bool st_ready;
@@ -880,7 +887,7 @@ extern "C" int amdp_destroy(amdp_t* h) {
                     };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < ST_NBUF; ++i) {
-        void* st[] = {h->st_act[i], h->st_obs[i], h->st_rew[i], h->st_done[i], h->st_rec[i]};
+        void* st[] = {h->st_act[i], h->st_obs[i], h->st_rew[i], h->st_done[i], h->st_rec[i], h->st_od[i]};
         for (void* p : st) if (p) cudaFree(p);
     }
     if (h->hs_stream) cudaStreamDestroy(h->hs_stream);
@@ -891,6 +898,7 @@ extern "C" int amdp_destroy(amdp_t* h) {
     if (h->st_ready) {
         for (int i = 0; i < 3; ++i) cudaStreamDestroy(h->st_stream[i]);
         for (int i = 0; i < ST_NBUF; ++i) { cudaEventDestroy(h->st_ev_in[i]); cudaEventDestroy(h->st_ev_k[i]); cudaEventDestroy(h->st_ev_out[i]); }
+        for (int i = 0; i < ST_NSUB; ++i) cudaEventDestroy(h->sub_ev[i]);
     }
     delete h;
     return AMDP_OK;
@@ -1143,6 +1151,11 @@ extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const 
     if (J.packed && (h->cfg.n_obs_tok != 1 || h->cfg.n_act_tok != 1 || h->cfg.n_pad > (1 << 20) || h->cfg.na > 1024 ||
                      (h->cfg.task_type != AMDP_MDP && h->cfg.no_pad > (1 << 20))))
         return fail(h, AMDP_EINVAL, "packed records need do == da == 1, at most 2^20 observations and 1024 actions");
+    if (J.obs_done) {
+        const int ob = (h->cfg.reserved0 >> 8) & 31;               // bit_length(max ns - 1), stated by the caller
+        if (h->cfg.n_obs_tok != 1 || (h->cfg.task_type == AMDP_MDP ? (ob == 0 || ob > 14) : h->cfg.no_pad > (1 << 14)))
+            return fail(h, AMDP_EINVAL, "compact records (obs_done) need do == 1 and at most 2^14 observations (state the observation bits in amdp_config.reserved0)");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const bool policy_ok = !h->T.policy || actions || h->tp || h->wv2;   // (k_rollout_mdp has no table policy: the generic kernel runs)
     const bool fast = (h->cfg.task_type == AMDP_MDP || (h->tp && h->cfg.task_type == AMDP_POMDP)) && !u_inject && !h->force_generic && policy_ok;
@@ -1590,8 +1603,8 @@ static int staging_init(amdp* h, int chunk) {
     if (h->st_ready && h->st_chunk >= chunk) return AMDP_OK;
     if (h->st_ready) {
         for (int i = 0; i < ST_NBUF; ++i) {
-            cudaFree(h->st_act[i]); cudaFree(h->st_obs[i]); cudaFree(h->st_rew[i]); cudaFree(h->st_done[i]); cudaFree(h->st_rec[i]);
-            h->st_act[i] = nullptr; h->st_obs[i] = nullptr; h->st_rew[i] = nullptr; h->st_done[i] = nullptr; h->st_rec[i] = nullptr;
+            cudaFree(h->st_act[i]); cudaFree(h->st_obs[i]); cudaFree(h->st_rew[i]); cudaFree(h->st_done[i]); cudaFree(h->st_rec[i]); cudaFree(h->st_od[i]);
+            h->st_act[i] = nullptr; h->st_obs[i] = nullptr; h->st_rew[i] = nullptr; h->st_done[i] = nullptr; h->st_rec[i] = nullptr; h->st_od[i] = nullptr;
         }
     } else {
         for (int i = 0; i < 3; ++i) CK(cudaStreamCreateWithFlags(&h->st_stream[i], cudaStreamNonBlocking));
@@ -1600,6 +1613,7 @@ static int staging_init(amdp* h, int chunk) {
             CK(cudaEventCreateWithFlags(&h->st_ev_k[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->st_ev_out[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < ST_NSUB; ++i) CK(cudaEventCreateWithFlags(&h->sub_ev[i], cudaEventDisableTiming));
         h->st_ready = true;
     }
     const size_t per = (size_t)chunk * c.n_envs;
@@ -1610,21 +1624,42 @@ static int staging_init(amdp* h, int chunk) {
         if ((rc = dalloc(h, &h->st_rew[i], per))) return rc;
         if ((rc = dalloc(h, &h->st_done[i], per))) return rc;
         if ((rc = dalloc(h, &h->st_rec[i], per))) return rc;
+        if ((rc = dalloc(h, &h->st_od[i], per))) return rc;
     }
     h->st_chunk = chunk;
+    h->st_i = 0;
     return AMDP_OK;
 }
 
 // actions in / trajectory out through pinned host memory, `chunk` ticks at a time on three streams (copy-in, kernel,
 // copy-out) with ST_NBUF staging sets, so that PCIe traffic in both directions overlaps the rollout kernels and the
-// device-to-host link (the bound of this path: 8 bytes per env-step) never waits for a kernel.
-static int rollout_host_impl(amdp* h, int K, int chunk, const void* actions_host, bool packed, int32_t* obs_host,
-                             float* reward_host, uint8_t* done_host, unsigned long long* rec_host) {
+// device-to-host link (the bound of this path: 6-8 bytes per env-step) never waits for a kernel.
+struct HostOut {
+    int format;                    // 0 separate arrays, 1 packed 8-byte records, 2 compact (uint16 obs_done + fp32 reward)
+    int32_t* obs; float* reward; uint8_t* done; unsigned long long* rec; uint16_t* obs_done;
+};
+
+// waits until at most `pending` of the submissions made so far are still in flight (0: everything has landed)
+static int host_wait(amdp* h, int pending = 0) {
+    if (!h->st_ready) return AMDP_OK;
+    if (pending > 0) {
+        const long long n = h->sub_n - 1 - pending;                // the newest submission that must be complete
+        if (n >= 0) CK(cudaEventSynchronize(h->sub_ev[n % ST_NSUB]));
+        return AMDP_OK;
+    }
+    CK(cudaStreamSynchronize(h->st_stream[2]));
+    CK(cudaStreamSynchronize(h->st_stream[1]));
+    h->st_busy = false;
+    return AMDP_OK;
+}
+
+static int rollout_host_impl(amdp* h, int K, int chunk, const void* actions_host, const HostOut& O, bool wait) {
     if (!h || K < 1) return AMDP_EINVAL;
     if (!h->assigned) return fail(h, AMDP_ESTATE, "Must \"set_task\" and \"reset\" before doing any actions");
     const amdp_config& c = h->cfg;
     CK(cudaSetDevice(c.device));
     if (chunk < 1 || chunk > K) chunk = K;
+    if (h->st_ready && h->st_chunk < chunk && h->st_busy) { int rc0 = host_wait(h); if (rc0) return rc0; }   // staging is about to be re-allocated
     int rc = staging_init(h, chunk);
     if (rc) return rc;
     cudaStream_t s_in = h->st_stream[0], s_k = h->st_stream[1], s_out = h->st_stream[2];
@@ -1632,15 +1667,19 @@ static int rollout_host_impl(amdp* h, int K, int chunk, const void* actions_host
     // non-blocking and would otherwise start before those kernels have written the env state
     wait_caller_stream(h, s_k);
     const size_t N = (size_t)c.n_envs;
-    const size_t act_bytes = packed ? 1 : sizeof(int32_t);
-    // the first chunk is a quarter of the others: nothing overlaps its kernel, so it sets the depth of the pipeline
-    int i = 0, kc = 0;
-    for (int k0 = 0; k0 < K; k0 += kc, ++i) {
-        const int b = i % ST_NBUF;
-        kc = (i == 0 && K > chunk && chunk >= 4) ? chunk / 4 : chunk;
+    const bool u8 = O.format != 0;
+    const size_t act_bytes = u8 ? 1 : sizeof(int32_t);
+    // the first chunk of a call into an idle pipeline is a quarter of the others: nothing overlaps its kernel, so it sets the
+    // depth of the pipeline
+    const bool idle = !h->st_busy;
+    int kc = 0;
+    bool first = true;
+    for (int k0 = 0; k0 < K; k0 += kc, ++h->st_i, first = false) {
+        const int b = (int)(h->st_i % ST_NBUF);
+        kc = (first && idle && K > chunk && chunk >= 4) ? chunk / 4 : chunk;
         if (K - k0 < kc) kc = K - k0;
         // set b is free once the copy-out of chunk i - ST_NBUF has finished
-        if (i >= ST_NBUF) { CK(cudaStreamWaitEvent(s_in, h->st_ev_out[b], 0)); CK(cudaStreamWaitEvent(s_k, h->st_ev_out[b], 0)); }
+        if (h->st_i >= ST_NBUF) { CK(cudaStreamWaitEvent(s_in, h->st_ev_out[b], 0)); CK(cudaStreamWaitEvent(s_k, h->st_ev_out[b], 0)); }
         if (actions_host) {
             CK(cudaMemcpyAsync(h->st_act[b], (const char*)actions_host + (size_t)k0 * N * c.n_act_tok * act_bytes,
                                act_bytes * kc * N * c.n_act_tok, cudaMemcpyHostToDevice, s_in));
@@ -1649,39 +1688,80 @@ static int rollout_host_impl(amdp* h, int K, int chunk, const void* actions_host
         }
         amdp_traj J;
         memset(&J, 0, sizeof(J));
-        if (packed) {
+        if (O.format == 1) {
             J.packed = (uint64_t*)h->st_rec[b];
-            J.actions_u8 = 1;
+        } else if (O.format == 2) {
+            J.obs_done = h->st_od[b];
+            J.reward = h->st_rew[b];
         } else {
-            J.obs = obs_host ? h->st_obs[b] : nullptr;
-            J.reward = reward_host ? h->st_rew[b] : nullptr;
-            J.done = done_host ? h->st_done[b] : nullptr;
+            J.obs = O.obs ? h->st_obs[b] : nullptr;
+            J.reward = O.reward ? h->st_rew[b] : nullptr;
+            J.done = O.done ? h->st_done[b] : nullptr;
         }
+        J.actions_u8 = u8 ? 1 : 0;
         J.step_stride = (int64_t)N; J.env_stride = 1;
         rc = amdp_rollout(h, kc, actions_host ? h->st_act[b] : nullptr, &J, nullptr, s_k);
         if (rc) return rc;
         CK(cudaEventRecord(h->st_ev_k[b], s_k));
         CK(cudaStreamWaitEvent(s_out, h->st_ev_k[b], 0));
-        if (packed) {
-            if (rec_host) CK(cudaMemcpyAsync(rec_host + (size_t)k0 * N, h->st_rec[b], sizeof(unsigned long long) * kc * N, cudaMemcpyDeviceToHost, s_out));
+        if (O.format == 1) {
+            if (O.rec) CK(cudaMemcpyAsync(O.rec + (size_t)k0 * N, h->st_rec[b], sizeof(unsigned long long) * kc * N, cudaMemcpyDeviceToHost, s_out));
+        } else if (O.format == 2) {
+            if (O.obs_done) CK(cudaMemcpyAsync(O.obs_done + (size_t)k0 * N, h->st_od[b], sizeof(uint16_t) * kc * N, cudaMemcpyDeviceToHost, s_out));
+            if (O.reward) CK(cudaMemcpyAsync(O.reward + (size_t)k0 * N, h->st_rew[b], sizeof(float) * kc * N, cudaMemcpyDeviceToHost, s_out));
         } else {
-            if (obs_host) CK(cudaMemcpyAsync(obs_host + (size_t)k0 * N * c.n_obs_tok, h->st_obs[b], sizeof(int32_t) * kc * N * c.n_obs_tok, cudaMemcpyDeviceToHost, s_out));
-            if (reward_host) CK(cudaMemcpyAsync(reward_host + (size_t)k0 * N, h->st_rew[b], sizeof(float) * kc * N, cudaMemcpyDeviceToHost, s_out));
-            if (done_host) CK(cudaMemcpyAsync(done_host + (size_t)k0 * N, h->st_done[b], (size_t)kc * N, cudaMemcpyDeviceToHost, s_out));
+            if (O.obs) CK(cudaMemcpyAsync(O.obs + (size_t)k0 * N * c.n_obs_tok, h->st_obs[b], sizeof(int32_t) * kc * N * c.n_obs_tok, cudaMemcpyDeviceToHost, s_out));
+            if (O.reward) CK(cudaMemcpyAsync(O.reward + (size_t)k0 * N, h->st_rew[b], sizeof(float) * kc * N, cudaMemcpyDeviceToHost, s_out));
+            if (O.done) CK(cudaMemcpyAsync(O.done + (size_t)k0 * N, h->st_done[b], (size_t)kc * N, cudaMemcpyDeviceToHost, s_out));
         }
         CK(cudaEventRecord(h->st_ev_out[b], s_out));
     }
-    CK(cudaStreamSynchronize(s_out));
-    CK(cudaStreamSynchronize(s_k));
+    if (h->sub_n >= ST_NSUB) CK(cudaEventSynchronize(h->sub_ev[h->sub_n % ST_NSUB]));      // (at most ST_NSUB submissions in flight)
+    CK(cudaEventRecord(h->sub_ev[h->sub_n % ST_NSUB], s_out));
+    h->sub_n += 1;
+    h->st_busy = true;
+    if (wait) return host_wait(h);
     return AMDP_OK;
 }
 
 extern "C" int amdp_rollout_host(amdp_t* h, int32_t K, int32_t chunk, const int32_t* actions_host, int32_t* obs_host,
                                  float* reward_host, uint8_t* done_host) {
-    return rollout_host_impl(h, K, chunk, actions_host, false, obs_host, reward_host, done_host, nullptr);
+    HostOut O = {0, obs_host, reward_host, done_host, nullptr, nullptr};
+    return rollout_host_impl(h, K, chunk, actions_host, O, true);
 }
 
 extern "C" int amdp_rollout_host_packed(amdp_t* h, int32_t K, int32_t chunk, const uint8_t* actions_host, uint64_t* records_host) {
     if (h && (h->cfg.na > 256)) return fail(h, AMDP_EINVAL, "uint8 actions need na <= 256");
-    return rollout_host_impl(h, K, chunk, actions_host, true, nullptr, nullptr, nullptr, (unsigned long long*)records_host);
+    HostOut O = {1, nullptr, nullptr, nullptr, (unsigned long long*)records_host, nullptr};
+    return rollout_host_impl(h, K, chunk, actions_host, O, true);
+}
+
+extern "C" int amdp_rollout_host_compact(amdp_t* h, int32_t K, int32_t chunk, const uint8_t* actions_host, uint16_t* obs_done_host,
+                                         float* reward_host, int32_t wait) {
+    if (h && (h->cfg.na > 256)) return fail(h, AMDP_EINVAL, "uint8 actions need na <= 256");
+    HostOut O = {2, nullptr, reward_host, nullptr, nullptr, obs_done_host};
+    return rollout_host_impl(h, K, chunk, actions_host, O, wait != 0);
+}
+
+extern "C" int amdp_rollout_host_wait(amdp_t* h, int32_t pending) {
+    if (!h || pending < 0 || pending >= ST_NSUB) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    return host_wait(h, pending);
+}
+
+// pinned host buffers for the host-buffer entry points: page-locked, optionally write-combined (not snooped by the CPU
+// caches while the GPU writes them over PCIe; slow for the CPU to READ except with streaming loads), allocated on the NUMA
+// node of the calling thread (first touch): bind the thread to the GPU's node before calling.
+extern "C" int amdp_host_alloc(size_t bytes, int32_t write_combined, void** out) {
+    if (!out || bytes == 0) return AMDP_EINVAL;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return AMDP_ENOMEM; }
+    memset(*out, 0, bytes);                                        // first touch on the caller's NUMA node
+    return AMDP_OK;
+}
+
+extern "C" int amdp_host_free(void* p) {
+    if (!p) return AMDP_OK;
+    return cudaFreeHost(p) == cudaSuccess ? AMDP_OK : AMDP_ECUDA;
 }

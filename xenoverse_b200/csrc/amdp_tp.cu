@@ -65,8 +65,9 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
             if (J.actions_out) J.actions_out[o] = a & 0x0fffffff;
             if (J.done) J.done[o] = (uint8_t)done;
             if (J.reward) J.reward[o] = rew;
-            if (J.reward_gt) J.reward_gt[o] = rgt;
+            if (J.obs_done) J.obs_done[o] = (uint16_t)(((unsigned)obs & 0x3fffu) | ((unsigned)done << 14));
         }
+        if (J.reward_gt) J.reward_gt[o] = rgt;                     // the label travels with either record format (anymdp_env.py:129)
     };
 
     unsigned fault = 0;

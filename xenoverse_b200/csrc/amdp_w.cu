@@ -124,8 +124,9 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
                 if (J.actions_out) J.actions_out[o] = st_ad & 0x0fffffff;
                 if (J.done) J.done[o] = (uint8_t)((unsigned)st_ad >> 28);
                 if (J.reward) J.reward[o] = st_rew;
-                if (J.reward_gt) J.reward_gt[o] = st_rgt;
+                if (J.obs_done) J.obs_done[o] = (uint16_t)(((unsigned)st_obs & 0x3fffu) | (((unsigned)st_ad >> 28) << 14));
             }
+            if (J.reward_gt) J.reward_gt[o] = st_rgt;         // the label travels with either record format (anymdp_env.py:129)
         }
     };
 

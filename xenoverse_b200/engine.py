@@ -22,6 +22,15 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def _hptr(t):
+    """Host pointer of a CPU torch tensor / numpy array / HostBuffer view (or None)."""
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t.ctypes.data)
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -347,6 +356,7 @@ class Engine:
         J.obs, J.actions_out = _ptr(traj.get("obs")), _ptr(traj.get("action"))
         J.reward, J.reward_gt, J.done = _ptr(traj.get("reward")), _ptr(traj.get("reward_gt")), _ptr(traj.get("done"))
         J.packed = _ptr(traj.get("packed"))
+        J.obs_done = _ptr(traj.get("obs_done"))          # compact records: uint16 [K, N] (with "reward")
         J.actions_u8 = 1 if (actions is not None and actions.dtype == torch.uint8) else 0
         if env_major:
             J.step_stride, J.env_stride = 1, int(K)
@@ -362,6 +372,16 @@ class Engine:
     def rollout_host_packed(self, K, chunk, actions_u8=None, records=None):
         """Compact wire format: uint8 actions [K, N] in, uint64 records [K, N] out (CPU, pinned); synchronous."""
         self._ck(lib.amdp_rollout_host_packed(self._h, int(K), int(chunk), _ptr(actions_u8), _ptr(records)))
+
+    def rollout_host_compact(self, K, chunk, actions_u8=None, obs_done=None, reward=None, wait=True):
+        """Compact wire format (6 bytes per env-step): uint8 actions [K, N] in; uint16 obs_done [K, N] (bits 0-13 observation,
+        14 terminated, 15 truncated) and float32 reward [K, N] out — CPU tensors / arrays in pinned memory (`host_buffer`).
+        wait=False submits and returns: the buffers belong to the library until `rollout_host_wait()`."""
+        self._ck(lib.amdp_rollout_host_compact(self._h, int(K), int(chunk), _hptr(actions_u8), _hptr(obs_done), _hptr(reward), 1 if wait else 0))
+
+    def rollout_host_wait(self, pending=0):
+        """Block until at most `pending` submitted rollouts are still in flight (0: all have landed in the host buffers)."""
+        self._ck(lib.amdp_rollout_host_wait(self._h, int(pending)))
 
     # ---- statistics / introspection -----------------------------------------------------------
     def stats_tensor(self, out=None):
@@ -501,3 +521,67 @@ def unpack_records(rec):
 
 def ceil_max_steps(x):
     return int(math.ceil(float(x)))
+
+
+def unpack_compact(obs_done, reward):
+    """Compact records (amdp_traj.obs_done + reward planes) -> dict(obs, terminated, truncated, reward)."""
+    od = obs_done.cpu().numpy() if isinstance(obs_done, torch.Tensor) else numpy.asarray(obs_done)
+    od = od.view(numpy.uint16)
+    rw = reward.cpu().numpy() if isinstance(reward, torch.Tensor) else numpy.asarray(reward)
+    return {"obs": (od & 0x3fff).astype(numpy.int32), "terminated": ((od >> 14) & 1).astype(bool),
+            "truncated": ((od >> 15) & 1).astype(bool), "reward": rw}
+
+
+class HostBuffer:
+    """Page-locked host memory from `amdp_host_alloc` (optionally write-combined), zero-filled by the calling thread — call
+    `bind_to_gpu_numa_node` first so that the pages land on the GPU's NUMA node.  `view(dtype, shape)` gives numpy arrays."""
+
+    def __init__(self, nbytes, write_combined=False):
+        p = ctypes.c_void_p()
+        rc = lib.amdp_host_alloc(int(nbytes), 1 if write_combined else 0, ctypes.byref(p))
+        if rc != _lib.OK:
+            raise AMDPError(f"amdp_host_alloc({nbytes}) failed: {lib.amdp_strerror(rc).decode()}")
+        self.ptr, self.nbytes = p.value, int(nbytes)
+        self._raw = (ctypes.c_ubyte * self.nbytes).from_address(self.ptr)
+
+    def view(self, dtype, shape, offset=0):
+        n = int(numpy.prod(shape))
+        return numpy.frombuffer(self._raw, dtype=dtype, count=n, offset=offset).reshape(shape)
+
+    def close(self):
+        if self.ptr:
+            self._raw = None
+            lib.amdp_host_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Restrict the calling process to the CPUs of the NUMA node the GPU hangs off (so that pinned buffers allocated next are
+    node-local and the copy threads run next to them).  Best effort: returns what it found; does nothing when the platform
+    exposes no NUMA information (numa_node = -1, e.g. a single-node VM)."""
+    import os
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read().strip())
+        info["numa_node"] = node
+        if node >= 0:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["cpus"], info["bound"] = len(cpus), True
+    except Exception as e:
+        info["error"] = str(e)[:100]
+    return info
