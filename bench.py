@@ -510,6 +510,31 @@ def measure_e2e(env, args, N, na, K, world, rank, local, dev):
     for st in sets:
         for hb in st[3:]:
             hb.close()
+    # what the box allows: every rank copies 64 MiB device -> pinned host in a loop for 0.25 s, all ranks at once.  One B200
+    # alone reaches ~56 GB/s; eight together ~106 GB/s on this pool's 8-GPU box (profiles/r2_d2h_ceiling_*.txt): the e2e
+    # path of N > 1 ranks is bounded by that aggregate, not by the engine.
+    src = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    dst = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0, n = time.perf_counter(), 0
+    while time.perf_counter() - w0 < 0.25:
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        n += 4
+    mine = n * (64 << 20) / (time.perf_counter() - w0) / 1e9
+    tot = torch.tensor([mine], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    agg = float(tot)
+    out["d2h_ceiling"] = {"aggregate_GBps": agg, "rank0_GBps": mine, "method": "64 MiB cudaMemcpyAsync device -> pinned host, all ranks at once, 0.25 s",
+                          "e2e_d2h_GBps_aggregate": out["d2h_GBps_per_gpu"] * world, "frac_of_ceiling": out["d2h_GBps_per_gpu"] * world / agg,
+                          "ceiling_env_steps_per_s_at_6_bytes": agg * 1e9 / 6}
     return out
 
 

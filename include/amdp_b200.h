@@ -366,6 +366,35 @@ int amdp_rollout_host(amdp_t* h, int32_t K, int32_t chunk, const int32_t* action
  * (see amdp_traj.packed).  actions_host uint8 [K][n_envs] or NULL; records_host uint64 [K][n_envs]. */
 int amdp_rollout_host_packed(amdp_t* h, int32_t K, int32_t chunk, const uint8_t* actions_host, uint64_t* records_host);
 
+/*
+ * Batched task sampling on the GPU.  Handle-free: plain device arrays in the amdp_upload_tasks layout
+ * (`ld` = the padded row length, a multiple of 4 >= n), so that sampled tasks go straight into amdp_upload_tasks.
+ *
+ * amdp_sample_mdp_batch: `count` CANDIDATE tasks with n states and na actions — the reference's sample_mdp
+ * (task_sampler_utils.py:177-256: sample_transition :65-175, the reward parts :10-63, and the <= 5 value-iteration rounds
+ * that place the terminal rewards :219-247), one thread block per candidate.  Draws come from Philox4x32-10 keyed by `seed`
+ * at the address (cand_base + i, stream, index): the reference's distribution, not its (numpy global MT19937) stream.
+ *   transition, reward, reward_noise  double [count][ld][na][ld] (zero padded)
+ *   is_terminal uint8 [count][ld];  s0_idx int32 [count][3], s0_prob double [count][3], n_s0 int32 [count]
+ *   final_goal  uint8 [count]  task["final_goal_terminate"];  status int32 [count]: 0 ok, 1 = sample_mdp returned None
+ *   sweeps      int32 [count] or NULL: value-iteration sweeps spent
+ *
+ * amdp_check_valuefunction_batch: the reference's task-quality filter (solver.check_valuefunction, solver.py:105-148) for
+ * `count` tasks: two value iterations at gamma = 2^(-1/n), the value gap of every start state, K = int(log2(max_steps)) + 1
+ * squarings of the greedy policy's transition matrix (hand-written batched float64 kernel), Gini impurity and entropy.
+ *   s0_ld row length of s0_idx / s0_prob;  max_steps double [count];  max_k = max over tasks of int(log2(max_steps)) + 1
+ *   work double [2 * count * n * n];  min_gap, gini, entropy double [count];  accept uint8 [count]
+ *   policy uint8 [count][ld] or NULL: the greedy policy (first argmax);  sweeps int32 [count] or NULL;  launches HOST int32 or NULL
+ */
+int amdp_sample_mdp_batch(int32_t device, int64_t count, int32_t n, int32_t na, int32_t ld, uint64_t seed, uint64_t cand_base,
+                          double* transition, double* reward, double* reward_noise, uint8_t* is_terminal, int32_t* s0_idx,
+                          double* s0_prob, int32_t* n_s0, uint8_t* final_goal, int32_t* status, int32_t* sweeps, void* stream);
+int amdp_check_valuefunction_batch(int32_t device, int64_t count, int32_t n, int32_t na, int32_t ld, const double* transition,
+                                   const double* reward, const uint8_t* is_terminal, const int32_t* s0_idx, const double* s0_prob,
+                                   const int32_t* n_s0, int32_t s0_ld, const double* max_steps, int32_t max_k, double* work,
+                                   double* min_gap, double* gini, double* entropy, uint8_t* accept, uint8_t* policy, int32_t* sweeps,
+                                   int32_t* launches, void* stream);
+
 /* Same, in the COMPACT wire format (see amdp_traj.obs_done): uint8 actions in, 6 bytes per env-step out as two planes —
  * obs_done_host uint16 [K][n_envs] (bits 0-13 observation, 14 terminated, 15 truncated) and reward_host float [K][n_envs].
  * wait != 0: synchronises like the calls above.  wait == 0: SUBMITS the rollout and returns; the host buffers belong to the

@@ -182,10 +182,10 @@ def test_task_quality_filter_matches_reference_check_valuefunction():
 
 
 def test_batch_task_sampler_gpu_filter():
-    """AnyMDPTaskSamplerBatch: CPU candidates, quality filter on the GPU; every returned task passes the filter again, has
+    """AnyMDPTaskSamplerBatch: candidates and quality filter on the GPU; every returned task passes the filter again, has
     the sampler's schema and runs in the engine."""
     from xenoverse_b200 import AnyMDPTaskSamplerBatch, AnyMDPVecEnv, check_valuefunction_batch
-    tasks = AnyMDPTaskSamplerBatch(12, state_space=16, action_space=5, seed=7, batch=48)
+    tasks = AnyMDPTaskSamplerBatch(12, state_space=16, action_space=5, seed=7, min_batch=48)
     assert len(tasks) == 12
     for t in tasks:
         assert t["transition"].shape == (16, 5, 16) and t["task_type"] == "MDP" and 100 <= t["max_steps"] <= 129
@@ -196,4 +196,4 @@ def test_batch_task_sampler_gpu_filter():
     env.reset()
     env.rollout(50)
     env.check()
-    assert tuple(AnyMDPTaskSamplerBatch(3, 16, 5, seed=7, batch=48)[0]["transition"].shape) == (16, 5, 16)
+    assert tuple(AnyMDPTaskSamplerBatch(3, 16, 5, seed=7, min_batch=48)[0]["transition"].shape) == (16, 5, 16)

@@ -38,6 +38,7 @@ def _rollout(t, steps=300):
     return env.stats()
 
 
+@pytest.mark.gpu
 def test_mdp_sampler_schema_and_quality():
     t0 = time.time()
     for seed, (ns, na) in enumerate([(16, 5), (32, 4), (64, 5)]):
@@ -57,6 +58,7 @@ def test_mdp_sampler_schema_and_quality():
     assert numpy.array_equal(a["transition"], b["transition"]) and a["max_steps"] == b["max_steps"]
 
 
+@pytest.mark.gpu
 def test_other_samplers():
     t = xb.AnyMDPTaskSampler(1, 4, seed=1)                         # bandit
     assert t["transition"].shape == (1, 4, 1) and t["max_steps"] == 1 and len(t["s_e"]) == 0
@@ -72,6 +74,19 @@ def test_other_samplers():
     t = xb.MultiTokensAnyPOMDPTaskSampler(16, 5, observation_space=8, observation_tokens=3, action_tokens=2, seed=4)
     assert t["task_type"] == "MTPOMDP" and len(t["observation_transition"]) == 3 and t["do"] == 3 and t["da"] == 2
     _rollout(t)
+    t = xb.GarnetTaskSampler(16, 4, b=2, seed=5)
+    _check_schema(t, 16, 4)
+    assert ((t["transition"] > 0).sum(-1) == 2).all()
+    _rollout(t)
+    with pytest.raises(AssertionError):
+        xb.AnyMDPTaskSampler(5, 3, seed=0)
+
+
+def test_host_side_samplers_bandit_and_garnet():
+    """The samplers that need no GPU: bandits (state_space == 1, sample_bandit) and Garnet tasks."""
+    t = xb.AnyMDPTaskSampler(1, 4, seed=1)
+    assert t["transition"].shape == (1, 4, 1) and t["max_steps"] == 1 and len(t["s_e"]) == 0
+    assert _rollout(t, 20)["episodes"] == 20
     t = xb.GarnetTaskSampler(16, 4, b=2, seed=5)
     _check_schema(t, 16, 4)
     assert ((t["transition"] > 0).sum(-1) == 2).all()

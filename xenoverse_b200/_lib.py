@@ -87,6 +87,10 @@ _SIGNATURES = {
     "amdp_rollout_host_packed": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P, _P]),
     "amdp_rollout_host_compact": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, ctypes.c_int32]),
     "amdp_rollout_host_wait": (ctypes.c_int, [_P, ctypes.c_int32]),
+    "amdp_sample_mdp_batch": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64,
+                                             ctypes.c_uint64] + [_P] * 11),
+    "amdp_check_valuefunction_batch": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32] + [_P] * 6 +
+                                       [ctypes.c_int32, _P, ctypes.c_int32] + [_P] * 7 + [ctypes.POINTER(ctypes.c_int32), _P]),
     "amdp_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int32, ctypes.POINTER(_P)]),
     "amdp_host_free": (ctypes.c_int, [_P]),
 }

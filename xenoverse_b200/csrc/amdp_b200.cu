@@ -618,10 +618,12 @@ __device__ __forceinline__ double* xg_data(void* base, unsigned long long seq, i
 }
 
 // combine iteration `g` from this rank's own buffer: sums in rank order, min / max; waits (bounded) for late peers
-__device__ void xg_combine(const Xchg& X, unsigned long long g, unsigned int* faults, double (*sh)[8]) {
+// (threads tbase .. tbase + world - 1 poll and load, so that in k_stats they overlap the posting threads of warp 0)
+__device__ void xg_combine(const Xchg& X, unsigned long long g, unsigned int* faults, double (*sh)[8], int tbase) {
     void* mine = X.peers[X.rank];
-    if ((int)threadIdx.x < X.world) {
-        const unsigned long long* f = xg_flag(mine, g, threadIdx.x);
+    const int tr = (int)threadIdx.x - tbase;
+    if (tr >= 0 && tr < X.world) {
+        const unsigned long long* f = xg_flag(mine, g, tr);
         unsigned long long v;
         const long long t0 = clock64();
         for (;;) {
@@ -630,9 +632,9 @@ __device__ void xg_combine(const Xchg& X, unsigned long long g, unsigned int* fa
             if (clock64() - t0 > 8000000000ll) { atomicOr(faults, AMDP_FAULT_PEER_TIMEOUT); break; }   // ~4 s: a peer died
             __nanosleep(200);
         }
-        const double* d = xg_data(mine, g, threadIdx.x);
+        const double* d = xg_data(mine, g, tr);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sh[threadIdx.x][i] = __ldcv(d + i);
+        for (int i = 0; i < 8; ++i) sh[tr][i] = __ldcv(d + i);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -652,7 +654,7 @@ __device__ void xg_combine(const Xchg& X, unsigned long long g, unsigned int* fa
 __global__ void __launch_bounds__(STAT_THREADS) k_stats(EnvArrays E, Stat6* __restrict__ part, unsigned int* __restrict__ ticket,
                                                         double total_steps, double* __restrict__ out8, Xchg X) {
     Stat6 v = {0, 0, 0, 0, INFINITY, -INFINITY};
-    for (long long e = (long long)blockIdx.x * STAT_THREADS + threadIdx.x; e < E.n_envs; e += (long long)STAT_BLOCKS * STAT_THREADS) {
+    for (long long e = (long long)blockIdx.x * STAT_THREADS + threadIdx.x; e < E.n_envs; e += (long long)gridDim.x * STAT_THREADS) {
         Stat6 w = {(double)E.ep_count[e], E.sum_ret[e], E.sum_ret_sq[e], (double)E.sum_len[e], E.min_ret[e], E.max_ret[e]};
         v = stat_merge(v, w);
     }
@@ -663,13 +665,13 @@ __global__ void __launch_bounds__(STAT_THREADS) k_stats(EnvArrays E, Stat6* __re
     if (threadIdx.x == 0) {
         part[blockIdx.x] = v;
         __threadfence();
-        last = (atomicAdd(ticket, 1u) == STAT_BLOCKS - 1);
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
     __syncthreads();
     if (!last) return;
     __threadfence();
     Stat6 f = {0, 0, 0, 0, INFINITY, -INFINITY};
-    if (threadIdx.x < STAT_BLOCKS) f = part[threadIdx.x];
+    if (threadIdx.x < gridDim.x) f = part[threadIdx.x];
     __syncthreads();
     f = stat_block_reduce(f);
     if (threadIdx.x == 0) {
@@ -688,13 +690,13 @@ __global__ void __launch_bounds__(STAT_THREADS) k_stats(EnvArrays E, Stat6* __re
         __threadfence_system();
         asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(xg_flag(peer, X.seq, X.rank)), "l"(X.seq) : "memory");
     }
-    if (X.seq > (unsigned long long)X.lag) xg_combine(X, X.seq - X.lag, E.faults, sh_x);
+    if (X.seq > (unsigned long long)X.lag) xg_combine(X, X.seq - X.lag, E.faults, sh_x, X.lag > 0 ? 32 : 0);
 }
 
 // combine the latest posted iteration without posting (the flush at the end of a job: lag 0)
 __global__ void __launch_bounds__(32) k_xchg_flush(Xchg X, unsigned int* faults) {
     __shared__ double sh_x[XG_MAX_RANKS][8];
-    xg_combine(X, X.seq, faults, sh_x);
+    xg_combine(X, X.seq, faults, sh_x, 0);
 }
 
 // ---- introspection -----------------------------------------------------------------------------
@@ -1177,6 +1179,13 @@ extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const 
     return AMDP_OK;
 }
 
+// blocks of the statistics reduction: one per 256 envs, at most one per SM (the partials are combined in index order by
+// the block that finishes last, so the result does not depend on the grid either way it is scheduled)
+static unsigned int stat_grid(const amdp* h) {
+    const long long b = (h->cfg.n_envs + STAT_THREADS - 1) / STAT_THREADS;
+    return (unsigned int)(b < 1 ? 1 : (b > STAT_BLOCKS ? STAT_BLOCKS : b));
+}
+
 extern "C" int amdp_stats(amdp_t* h, double* out8, void* stream) {
     if (!h || !out8) return AMDP_EINVAL;
     if (!h->assigned) return fail(h, AMDP_ESTATE, "stats before assign");
@@ -1184,7 +1193,7 @@ extern "C" int amdp_stats(amdp_t* h, double* out8, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     Xchg none;
     memset(&none, 0, sizeof(none));
-    k_stats<<<STAT_BLOCKS, STAT_THREADS, 0, st>>>(h->E, h->stat_part, h->stat_ticket, h->total_steps, out8, none);
+    k_stats<<<stat_grid(h), STAT_THREADS, 0, st>>>(h->E, h->stat_part, h->stat_ticket, h->total_steps, out8, none);
     h->launches += 1;
     CK(cudaGetLastError());
     mark_caller_stream(h, st);
@@ -1267,7 +1276,7 @@ extern "C" int amdp_stats_exchange(amdp_t* h, double* local_out8, double* global
     cudaStream_t st = (cudaStream_t)stream;
     Xchg X;
     X.peers = h->xg_peers_dev; X.world = h->xg_world; X.rank = h->xg_rank; X.lag = lag; X.seq = ++h->xg_seq; X.global_out8 = global_out8;
-    k_stats<<<STAT_BLOCKS, STAT_THREADS, 0, st>>>(h->E, h->stat_part, h->stat_ticket, h->total_steps, local_out8, X);
+    k_stats<<<stat_grid(h), STAT_THREADS, 0, st>>>(h->E, h->stat_part, h->stat_ticket, h->total_steps, local_out8, X);
     h->launches += 1;
     CK(cudaGetLastError());
     mark_caller_stream(h, st);

@@ -45,50 +45,26 @@ def optimal_policy(task, gamma=0.99):
     return greedy_policy(value_iteration(task, gamma))
 
 
-def check_valuefunction_batch(tasks, device=0, tol=1.0e-6, max_sweeps=20000):
+def check_valuefunction_batch(tasks, device=0):
     """The reference's task-quality filter (solver.check_valuefunction, solver.py:105-148) for a BATCH of MDP task dicts with
     the same number of states, on the GPU (the acceptance half of task sampling, 0.2-50 s per task on the
-    CPU).  Optimal and random-policy values come from two batched value iterations on the uploaded tables
-    (amdp_value_iteration, gamma = 2^(-1/n)); the long-run state distribution of the optimal policy is K = int(log2(max_steps))
-    + 1 squarings of its transition matrix (terminal states lead back to the start states), batched matmuls.
+    CPU): one thread block per task runs the two value iterations (optimal / uniform random policy, gamma = 2^(-1/n), the
+    reference's damped sweeps and stopping rule), takes the value gap of every start state and builds the greedy policy's
+    transition matrix (terminal states lead back to the start states); K = int(log2(max_steps)) + 1 squarings by a
+    hand-written batched float64 kernel; Gini impurity and entropy of the start states' rows (amdp_check_valuefunction_batch).
     Returns dict(accept bool[T], min_gap, gini, entropy float64[T]):
         accept = min_gap >= 2.0 and gini > 0.70 and entropy > 0.35        (solver.py:122-124,148)."""
     import torch
-    from .vec_env import AnyMDPVecEnv
-    T = len(tasks)
+    from .engine import pack_tasks, task_geometry
+    from .task_sampler import check_valuefunction_device
     n, na = numpy.asarray(tasks[0]["transition"]).shape[:2]
     if any(numpy.asarray(t["transition"]).shape != (n, na, n) for t in tasks):
         raise ValueError("check_valuefunction_batch needs tasks with the same number of states and actions")
-    env = AnyMDPVecEnv(1, device=device, search="warp")
-    env.set_task(list(tasks))                                    # uploads the tables; rejects malformed tasks like set_task
-    gamma = float(2.0 ** (-1.0 / n))
-    q_opt, pol, _ = env.engine.value_iteration(gamma, tol, max_sweeps, greedy=True)
-    q_rnd, _, _ = env.engine.value_iteration(gamma, tol, max_sweeps, greedy=False)
-    dev = env.device
-    max_steps = torch.tensor([float(t["max_steps"]) for t in tasks], dtype=torch.float64, device=dev)
-    scale = (1.0 - gamma) * max_steps
-    best = (q_opt[:, :n].max(dim=2).values - q_rnd[:, :n].max(dim=2).values) * scale[:, None]        # [T, n]
-    P = torch.as_tensor(numpy.stack([numpy.asarray(t["transition"], dtype=numpy.float64) for t in tasks]), device=dev)
-    ti = torch.arange(T, device=dev)[:, None]
-    M = P[ti, torch.arange(n, device=dev)[None, :], pol[:, :n].long()]                            # [T, n, n]: rows of the greedy actions
-    start = torch.zeros((T, n), dtype=torch.bool, device=dev)
-    for i, t in enumerate(tasks):
-        s0 = torch.as_tensor(numpy.atleast_1d(t["s_0"]).astype(numpy.int64), device=dev)
-        start[i, s0] = True
-        se = numpy.asarray(t["s_e"]).astype(numpy.int64)
-        if len(se):                                              # s_e directly lead to s_0 (solver.py:88-89)
-            M[i][torch.as_tensor(se, device=dev)[:, None], s0[None, :]] = torch.as_tensor(
-                numpy.asarray(t["s_0_prob"], dtype=numpy.float64), device=dev)[None, :]
-    K = (torch.log2(max_steps).floor().long() + 1)
-    for k in range(1, int(K.max()) + 1):
-        M = torch.where((K >= k)[:, None, None], torch.matmul(M, M), M)
-    p = M + 1.0e-12
-    gini = 1.0 - (p * p).sum(dim=2)
-    ent = -(p * torch.log(p)).sum(dim=2) / float(numpy.log(n))
-    inf = torch.full_like(gini, float("inf"))
-    out = {"min_gap": torch.where(start, best, inf).min(dim=1).values, "gini": torch.where(start, gini, inf).min(dim=1).values,
-           "entropy": torch.where(start, ent, inf).min(dim=1).values}
-    out = {k: v.cpu().numpy() for k, v in out.items()}
-    out["accept"] = (out["min_gap"] >= 2.0) & (out["gini"] > 0.70) & (out["entropy"] > 0.35)
-    env.close()
+    geo = task_geometry(list(tasks))
+    p = pack_tasks(list(tasks), geo)
+    dev = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+    batch = {k: torch.as_tensor(p[k]).to(dev) for k in ("transition", "reward", "is_terminal", "s0_idx", "s0_prob", "n_s0")}
+    res = check_valuefunction_device(batch, n, p["max_steps"])
+    out = {k: res[k].cpu().numpy() for k in ("min_gap", "gini", "entropy")}
+    out["accept"] = res["accept"].cpu().numpy().astype(bool)
     return out

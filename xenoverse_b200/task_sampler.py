@@ -4,9 +4,11 @@ Drop-in for `xenoverse.anymdp.{AnyMDPTaskSampler, AnyPOMDPTaskSampler, MultiToke
 GarnetTaskSampler}` (xenoverse/anymdp/task_sampler.py:15-159).  The CONTRACT is the dict they return — keys, dtypes
 and shapes consumed by `set_task` — and the family of tasks (banded state-to-state structure with
 Gaussian action kernels, pitfalls, an optional terminal goal, potential/position/state-action reward parts, a
-value-function quality filter).  The generator below is an independent, vectorised implementation of that recipe; it
-does not reproduce the reference's random stream (the reference reseeds numpy's global RNG and is not reproducible
-across numpy versions either).  Task sampling is host-side set-up work, outside the stepping hot path.
+value-function quality filter).  MDP candidates and the filter run on the GPU (csrc/amdp_sampler.cu: a step-by-step
+restatement of task_sampler_utils.py:65-256 and solver.py:57-148, one thread block per candidate): the reference's
+DISTRIBUTION of tasks, not its random stream (the reference draws from numpy's global MT19937, reseeded from the clock).
+tests/test_gpu_sampler.py compares the distributions with the live reference's (tests/golden/sampler_stats.npz).
+There is no CPU fallback for MDP tasks; bandits, Garnet tasks and the observation matrices are host-side numpy.
 """
 import numpy
 
@@ -37,7 +39,8 @@ def _state_subset(rng, state_space, min_state_space):
 
 
 def value_iteration(transition, reward, gamma, terminal, greedy=True, tol=1e-4, max_sweeps=5000):
-    """Q[s,a] of the greedy (or uniformly random) policy; terminal states have value 0.  Vectorised Jacobi sweeps."""
+    """Q[s,a] of the greedy (or uniformly random) policy; terminal states have value 0.  Vectorised Jacobi sweeps (host-side
+    helper for tests and small tools; the samplers run their value iterations on the GPU)."""
     n, na, _ = transition.shape
     exp_r = numpy.einsum("sat,sat->sa", transition, reward)
     q = numpy.zeros((n, na))
@@ -52,133 +55,73 @@ def value_iteration(transition, reward, gamma, terminal, greedy=True, tol=1e-4, 
     return q
 
 
-def _sample_structure(rng, n, na, s0_range=3):
-    # start states: a random non-negative weighting of the first s0_range states
-    w = numpy.clip(rng.normal(size=s0_range), 0.0, None)
-    while w.sum() < 1e-10:
-        w = numpy.clip(rng.normal(size=s0_range), 0.0, None)
-    s_0 = numpy.nonzero(w > 1e-10)[0]
-    s_0_prob = w[s_0] / w[s_0].sum()
-    # pitfalls: up to ~40 % of the states, never a start state; the last state is a terminal goal with probability 0.3
-    p_pit = max(float(rng.uniform(-0.20, 0.40)), 0.0)
-    pit = rng.random(n) < p_pit
-    while pit.sum() > n * p_pit + 1:
-        pit = rng.random(n) < p_pit
-    pit[s_0] = False
-    goal_terminates = bool(rng.random() < 0.3)
-    pit[n - 1] = goal_terminates
-    terminal = pit.copy()
-    # banded state-to-state kernel: state s reaches a window [lo, hi) around itself
-    back, fwd = n // 2 + 1, n // 4 + 1
-    idx = numpy.arange(n)
-    lo = numpy.clip(idx - rng.integers(1, back + 1, size=n), 0, None)
-    hi = numpy.clip(idx + 1 + rng.integers(1, max(fwd, 2) + 1, size=n), None, n)
-    hi = numpy.maximum(hi, numpy.minimum(lo + 3, n))
-    lo = numpy.minimum(lo, numpy.maximum(hi - 3, 0))
-    cols = idx[None, :]
-    window = (cols >= lo[:, None]) & (cols < hi[:, None])
-    base = numpy.clip(rng.normal(size=(n, n)), 0.10, 1.0) * window
-    base[idx, idx] *= 0.5                                          # discourage self loops
-    base[n - 1, n - 1] = 0.0
-    # a forward, non-pitfall successor must exist so that progress is possible
-    ahead = window & (cols > idx[:, None]) & ~terminal[None, :]
-    ahead[:, n - 1] |= window[:, n - 1] & goal_terminates
-    need = ~ahead.any(axis=1) & (idx < n - 1)
-    for s in numpy.nonzero(need)[0]:
-        cand = numpy.nonzero(~terminal[s + 1:])[0]
-        t = s + 1 + (int(cand[0]) if len(cand) else 0)
-        base[s, t] = max(base[s, t], 0.5)
-        hi[s] = max(hi[s], t + 1)
-        window[s, t] = True
-    base /= base.sum(axis=1, keepdims=True)
-    # actions: Gaussian kernels over the window, so that different actions favour different successors
-    centre = rng.uniform(lo[:, None] - 1.0, hi[:, None], size=(n, na))
-    sigma = numpy.clip(rng.exponential(1.0, size=(n, 1, 1)), 0.20, 1.6)
-    dist2 = (centre[:, :, None] - cols[None, :, :]) ** 2
-    kern = numpy.exp(-dist2 / sigma ** 2) * window[:, None, :]
-    tot = kern.sum(axis=1, keepdims=True)
-    nearest = dist2.argmin(axis=1)                                 # [n, n]: closest action for columns no kernel reaches
-    dead = (tot[:, 0, :] < 1e-10) & window
-    for s, t in zip(*numpy.nonzero(dead)):
-        kern[s, nearest[s, t], t] = 1.0
-    tot = kern.sum(axis=1, keepdims=True)
-    kern = numpy.divide(kern, tot, out=numpy.zeros_like(kern), where=tot > 0)
-    transition = kern * base[:, None, :]
-    row = transition.sum(axis=-1, keepdims=True)
-    # an action whose kernel misses the whole window falls back to the state-to-state kernel
-    transition = numpy.where(row > 1e-12, transition / numpy.where(row > 1e-12, row, 1.0), base[:, None, :])
-    transition[terminal] = 0.0                                     # terminal rows are all-zero (never sampled)
-    return s_0, s_0_prob, terminal, goal_terminates, transition
+# --------------------------------------------------------------------------------------------------
+# MDP tasks: candidates and quality filter on the GPU (csrc/amdp_sampler.cu)
+# --------------------------------------------------------------------------------------------------
+def sample_mdp_candidates(count, n, na, seed=0, cand_base=0, device=0, ld=None):
+    """`count` candidate tasks from the device-side restatement of the reference's `sample_mdp`
+    (task_sampler_utils.py:177-256; amdp_sample_mdp_batch): dict of CUDA tensors in the amdp_upload_tasks layout
+    (transition / reward / reward_noise float64 [count, ld, na, ld], is_terminal uint8 [count, ld], s0_idx int32 [count, 3],
+    s0_prob float64 [count, 3], n_s0 int32 [count]) plus final_goal uint8, status int32 (0 = ok, 1 = the reference would
+    have returned None) and sweeps int32."""
+    import ctypes
+    import torch
+    from ._lib import lib, OK
+    from .engine import round_up4, AMDPError, _ptr, _stream
+    if not torch.cuda.is_available():
+        raise AMDPError("xenoverse_b200 task sampling needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+    ld = round_up4(n) if ld is None else int(ld)
+    f64, i32, u8 = torch.float64, torch.int32, torch.uint8
+    with torch.cuda.device(dev):
+        out = {"transition": torch.empty((count, ld, na, ld), dtype=f64, device=dev),
+               "reward": torch.empty((count, ld, na, ld), dtype=f64, device=dev),
+               "reward_noise": torch.empty((count, ld, na, ld), dtype=f64, device=dev),
+               "is_terminal": torch.empty((count, ld), dtype=u8, device=dev),
+               "s0_idx": torch.empty((count, 3), dtype=i32, device=dev), "s0_prob": torch.empty((count, 3), dtype=f64, device=dev),
+               "n_s0": torch.empty(count, dtype=i32, device=dev), "final_goal": torch.empty(count, dtype=u8, device=dev),
+               "status": torch.empty(count, dtype=i32, device=dev), "sweeps": torch.empty(count, dtype=i32, device=dev)}
+        rc = lib.amdp_sample_mdp_batch(dev.index, int(count), int(n), int(na), ld, int(seed) & (2 ** 64 - 1), int(cand_base),
+                                       *[_ptr(out[k]) for k in ("transition", "reward", "reward_noise", "is_terminal", "s0_idx", "s0_prob",
+                                                                "n_s0", "final_goal", "status", "sweeps")], _stream())
+    if rc != OK:
+        raise AMDPError(f"amdp_sample_mdp_batch failed ({lib.amdp_strerror(rc).decode()}): n={n} na={na} count={count}")
+    return out
 
 
-def _fourier_potential(rng, n, scale):
-    x = numpy.arange(n) / max(2.0 * n, 1.0)
-    pot = numpy.zeros(n)
-    for _ in range(int(rng.integers(1, 4))):
-        order = int(rng.integers(1, 6))
-        pot += rng.normal() * numpy.cos(2 * numpy.pi * order * x + rng.uniform(0, 2 * numpy.pi))
-    return scale * pot
-
-
-def _sample_rewards(rng, n, na, terminal, goal_terminates, transition, s_0):
-    # potential-based shaping V(s) - V(s'), position reward, sparse state-action cost, step reward
-    scale = 0.0 if rng.random() < 0.5 else max(float(rng.uniform(-1, 1)) * float(numpy.clip(rng.exponential(1.0), 0.2, 5.0)), 0.0)
-    pot = _fourier_potential(rng, n, scale)
-    r_pot = pot[:, None, None] - pot[None, None, :]
-    pos_base = float(rng.exponential(0.2))
-    pdf = numpy.clip(rng.normal(size=n), 0.0, None)
-    pdf[-1] += 0.20
-    cdf = numpy.cumsum(pdf * pos_base)
-    r_pos = cdf - rng.uniform(0.1 * cdf[-1], 0.9 * cdf[-1])
-    n_pos = numpy.clip(rng.uniform(-0.30, 0.30, size=n), 0.0, None) * pos_base
-    r_pos[terminal], n_pos[terminal] = 0.0, 0.0
-    sa_base = float(numpy.clip(rng.exponential(0.05), 0.0, 0.10))
-    sparse = (rng.uniform(-0.7, 0.3, size=(n, na)) > 0).astype(float)
-    r_sa = sa_base * rng.normal(size=(n, na)) * sparse
-    n_sa = 0.30 * sa_base * numpy.clip(rng.normal(size=(n, na)), 0.0, None) * sparse
-    if goal_terminates:
-        r_step = min(float(rng.normal()), 0.0) * 0.01
-    elif terminal.any():
-        r_step = max(float(rng.normal()), 0.0) * 0.01
-    else:
-        r_step = 0.0
-    raw = r_pot + r_pos[None, None, :] + r_sa[:, :, None] + r_step
-    noise = numpy.broadcast_to(n_pos[None, None, :] + n_sa[:, :, None], (n, na, n)).copy()
-    # terminal rewards: the goal must be worth reaching, pitfalls must be worse than anything else
-    term_reward = numpy.zeros(n)
-    term_reward[-1] = 1.0
-    pit = terminal.copy()
-    pit[-1] = False
-    alive = ~terminal
-    last_valid = n - 2 if goal_terminates else n - 1
-    gamma = 0.99
-    for _ in range(5):
-        q = value_iteration(transition, raw + term_reward[None, None, :], gamma, terminal)
-        v = q.max(axis=1)
-        pit_gain = term_reward.min() - v[alive].min() + 1.0
-        goal_gap = v[s_0].max() - v[last_valid] + rng.uniform(2.0, 5.0)
-        if pit_gain <= 0 and goal_gap <= 0:
-            return raw + term_reward[None, None, :], noise
-        if pit_gain > 0:
-            term_reward[pit] -= pit_gain + rng.uniform(1.0, 10.0)
-        if goal_gap > 0:
-            dv = max(2.0 * goal_gap, rng.uniform(1.0, 10.0))
-            term_reward[-1] += dv if goal_terminates else (1.0 - gamma) * dv
-    return None
-
-
-def _good_enough(task):
-    """Quality filter in the spirit of solver.check_valuefunction (solver.py:105-148): the optimal policy must beat
-    the random policy by a clear margin from every start state."""
-    t, r = task["transition"], task["reward"]
-    n = t.shape[0]
-    terminal = numpy.zeros(n, dtype=bool)
-    terminal[numpy.asarray(task["s_e"], dtype=int)] = True
-    gamma = 2.0 ** (-1.0 / n)
-    scale = (1.0 - gamma) * task["max_steps"]
-    q_opt = value_iteration(t, r, gamma, terminal, greedy=True) * scale
-    q_rnd = value_iteration(t, r, gamma, terminal, greedy=False) * scale
-    return all(q_opt[s].max() - q_rnd[s].max() >= 2.0 for s in numpy.atleast_1d(task["s_0"]))
+def check_valuefunction_device(batch, n, max_steps, want_policy=False):
+    """The reference's quality filter (solver.check_valuefunction, solver.py:105-148) on a packed device batch
+    (amdp_check_valuefunction_batch): returns dict(accept uint8, min_gap, gini, entropy float64 [count], sweeps int32[, policy])."""
+    import ctypes
+    import math
+    import torch
+    from ._lib import lib, OK
+    from .engine import AMDPError, _ptr, _stream
+    tr = batch["transition"]
+    dev = tr.device
+    count, ld, na, _ = tr.shape
+    ms = torch.as_tensor(max_steps, dtype=torch.float64, device=dev).reshape(count).contiguous()
+    max_k = int(math.floor(math.log2(float(ms.max())))) + 1
+    with torch.cuda.device(dev):
+        work = torch.empty(2 * count * n * n, dtype=torch.float64, device=dev)
+        res = {"accept": torch.empty(count, dtype=torch.uint8, device=dev), "min_gap": torch.empty(count, dtype=torch.float64, device=dev),
+               "gini": torch.empty(count, dtype=torch.float64, device=dev), "entropy": torch.empty(count, dtype=torch.float64, device=dev),
+               "sweeps": torch.empty(count, dtype=torch.int32, device=dev)}
+        pol = torch.zeros((count, ld), dtype=torch.uint8, device=dev) if want_policy else None
+        launches = ctypes.c_int32(0)
+        s0 = batch["s0_idx"].contiguous()
+        rc = lib.amdp_check_valuefunction_batch(dev.index, int(count), int(n), int(na), int(ld), _ptr(tr), _ptr(batch["reward"]),
+                                                _ptr(batch["is_terminal"]), _ptr(s0), _ptr(batch["s0_prob"].contiguous()), _ptr(batch["n_s0"]),
+                                                int(s0.shape[1]), _ptr(ms), max_k, _ptr(work), _ptr(res["min_gap"]), _ptr(res["gini"]),
+                                                _ptr(res["entropy"]), _ptr(res["accept"]), _ptr(pol), _ptr(res["sweeps"]),
+                                                ctypes.byref(launches), _stream())
+        if rc != OK:
+            raise AMDPError(f"amdp_check_valuefunction_batch failed ({lib.amdp_strerror(rc).decode()})")
+        torch.cuda.current_stream().synchronize()       # `work` and `ms` may now be freed
+    res["launches"] = int(launches.value)
+    if want_policy:
+        res["policy"] = pol
+    return res
 
 
 def _bandit(rng, na):
@@ -191,69 +134,120 @@ def _bandit(rng, na):
             "s_0": numpy.array([0]), "s_e": numpy.array([]), "s_0_prob": numpy.array([1.0])}
 
 
+def sample_mdp_tasks_device(count, n, na, max_steps, seed=0, device=0, min_batch=64, max_rounds=400, verbose=False):
+    """`count` ACCEPTED tasks with n states, following the reference's rejection loop (task_sampler.py:52-63) slot by slot:
+    slot i keeps its `max_steps[i]` and draws candidates (amdp_sample_mdp_batch) until one passes the quality filter
+    (amdp_check_valuefunction_batch) — so, as in the reference, max_steps of the accepted tasks stays uniform.  All slots
+    are worked on at once; spare capacity of a round goes to the open slots as extra (speculative) candidates, and the
+    candidate with the lowest id wins a slot, so results depend only on (seed, count, n, na, max_steps).
+    Returns (packed batch of the accepted tasks (device tensors), info dict)."""
+    import torch
+    from .engine import round_up4
+    ld = round_up4(n)
+    dev = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+    ms_all = torch.as_tensor(numpy.asarray(max_steps, dtype=numpy.float64), device=dev)
+    keys = ("transition", "reward", "reward_noise", "is_terminal", "s0_idx", "s0_prob", "n_s0", "final_goal")
+    out = None
+    open_slots = numpy.arange(count)
+    tried = accepted_n = gave_up = 0
+    next_cand = 0
+    per_task = 3 * 8 * ld * na * ld
+    cap = max(min_batch, int((1 << 31) // per_task))                  # <= 2 GiB of candidate tensors per round
+    for rnd in range(max_rounds):
+        if len(open_slots) == 0:
+            break
+        B = int(min(cap, max(len(open_slots), min_batch)))
+        slot_of = open_slots[numpy.arange(B) % len(open_slots)]       # candidate j of the round works for slot slot_of[j]
+        cand = sample_mdp_candidates(B, n, na, seed=seed, cand_base=next_cand, device=dev.index, ld=ld)
+        next_cand += B
+        res = check_valuefunction_device(cand, n, ms_all[torch.as_tensor(slot_of, device=dev)])
+        good = ((cand["status"] == 0) & (res["accept"] != 0)).cpu().numpy()
+        tried += B
+        gave_up += int((cand["status"] != 0).sum())
+        accepted_n += int(good.sum())
+        if out is None:
+            out = {k: torch.zeros((count,) + tuple(cand[k].shape[1:]), dtype=cand[k].dtype, device=dev) for k in keys}
+        filled = {}
+        for j in numpy.nonzero(good)[0]:
+            filled.setdefault(int(slot_of[j]), int(j))                # first (lowest id) accepted candidate of a slot
+        if filled:
+            slots = torch.as_tensor(list(filled.keys()), device=dev)
+            src = torch.as_tensor(list(filled.values()), device=dev)
+            for k in keys:
+                out[k][slots] = cand[k][src]
+            open_slots = numpy.array([s for s in open_slots if s not in filled], dtype=numpy.int64)
+        if verbose:
+            print(f"round {rnd}: {int(good.sum())} of {B} candidates accepted, {count - len(open_slots)} / {count} slots filled")
+        del cand, res
+    if len(open_slots):
+        raise RuntimeError(f"{len(open_slots)} of {count} task slots still open after {max_rounds} rounds ({tried} candidates)")
+    info = {"candidates": tried, "accepted": accepted_n, "sample_mdp_gave_up": gave_up, "rounds": rnd}
+    return out, info
+
+
+def _batch_to_dicts(batch, n, ns, na, max_steps, state_mapping):
+    """Packed device batch -> list of reference-schema task dicts (numpy)."""
+    host = {k: v.cpu().numpy() for k, v in batch.items()}
+    tasks = []
+    for i in range(host["transition"].shape[0]):
+        k0 = int(host["n_s0"][i])
+        tasks.append({"ns": int(ns), "na": int(na), "max_steps": float(max_steps[i]), "state_mapping": numpy.asarray(state_mapping[i]),
+                      "task_type": "MDP", "s_0": host["s0_idx"][i, :k0].astype(numpy.int64), "s_0_prob": host["s0_prob"][i, :k0].copy(),
+                      "s_e": numpy.nonzero(host["is_terminal"][i, :n])[0].astype(numpy.int64),
+                      "transition": host["transition"][i, :n, :, :n].copy(), "reward": host["reward"][i, :n, :, :n].copy(),
+                      "reward_noise": host["reward_noise"][i, :n, :, :n].copy(), "final_goal_terminate": bool(host["final_goal"][i])})
+    return tasks
+
+
 def AnyMDPTaskSampler(state_space: int = 64, action_space: int = 5, min_state_space: int = None, seed=None,
-                      verbose=False, max_tries=50):
+                      verbose=False, device=0):
+    """One task, same signature / schema / task family as the reference's AnyMDPTaskSampler (task_sampler.py:15-65).  The
+    candidates and the quality filter run on the GPU (a small batch of candidates per round); bandits (state_space == 1) are
+    host-side like the reference's sample_bandit."""
     rng = _rng(seed)
     assert state_space >= 8 or state_space == 1, "State Space must be at least 8 or 1 (Multi-armed Bandit)!"
     max_steps = _max_steps(rng, state_space)
     state_mapping, n = _state_subset(rng, state_space, min_state_space)
-    task = {"ns": state_space, "na": action_space, "max_steps": max_steps, "state_mapping": state_mapping,
-            "task_type": "MDP"}
     if n == 1:
+        task = {"ns": state_space, "na": action_space, "max_steps": max_steps, "state_mapping": state_mapping, "task_type": "MDP"}
         task.update(_bandit(rng, action_space))
         return task
-    best = None
-    for attempt in range(max_tries):
-        s_0, s_0_prob, terminal, goal_terminates, transition = _sample_structure(rng, n, action_space)
-        rewards = _sample_rewards(rng, n, action_space, terminal, goal_terminates, transition, s_0)
-        if rewards is None:
-            continue
-        cand = dict(task)
-        cand.update({"s_0": s_0, "s_0_prob": s_0_prob, "s_e": numpy.nonzero(terminal)[0], "transition": transition,
-                     "reward": rewards[0], "reward_noise": rewards[1], "final_goal_terminate": goal_terminates})
-        best = cand
-        if _good_enough(cand):
-            return cand
-        if verbose:
-            print(f"task rejected by the value-function filter (attempt {attempt})")
-    if best is None:
-        raise RuntimeError("could not sample a valid MDP")
-    return best
+    dev_seed = int(rng.integers(0, 2 ** 63))
+    batch, info = sample_mdp_tasks_device(1, n, action_space, [max_steps], seed=dev_seed, device=device, min_batch=32, verbose=verbose)
+    return _batch_to_dicts(batch, n, state_space, action_space, [max_steps], [state_mapping])[0]
 
 
-def AnyMDPTaskSamplerBatch(count, state_space: int = 64, action_space: int = 5, seed=None, device=0, batch=None,
-                           max_rounds=50, verbose=False):
-    """`count` MDP tasks at once.  The reference samples one task at a time and runs two value iterations
-    per CANDIDATE on the CPU (task_sampler.py:52-63 -> solver.check_valuefunction), 0.2-50 s per accepted task.  Here
-    candidates are generated on the CPU without any value iteration and the whole quality filter (value gap of every start
-    state, Gini impurity and entropy of the optimal policy's long-run distribution; solver.py:105-148) runs for a batch of
-    candidates on the GPU (`solvers.check_valuefunction_batch`).  Returns a list of `count` task dicts (schema of
-    AnyMDPTaskSampler)."""
-    from .solvers import check_valuefunction_batch
+def AnyMDPTaskSamplerBatch(count, state_space: int = 64, action_space: int = 5, seed=None, device=0, packed=False,
+                           min_batch=256, verbose=False):
+    """`count` MDP tasks at once.  The reference samples one task at a time on the CPU: per CANDIDATE a
+    Python generator, up to 5 + 2 numba value iterations and K matrix squarings (task_sampler.py:52-63), 0.2-50 s per accepted
+    task.  Here every stage runs on the GPU, one thread block per candidate: amdp_sample_mdp_batch (generation + the
+    terminal-reward rounds) and amdp_check_valuefunction_batch (the filter, with a hand-written batched float64 squaring
+    kernel).  Returns a list of `count` task dicts (schema of AnyMDPTaskSampler), or with packed=True
+    (geometry dict, packed device batch) ready for `AnyMDPVecEnv.set_task(None, packed=(geo, count, [(0, batch)]))`."""
+    import torch
     assert state_space >= 8, "State Space must be at least 8"
     rng = _rng(seed)
-    batch = batch or max(16, min(1024, 2 * count))
-    out = []
-    for rnd in range(max_rounds):
-        cands = []
-        while len(cands) < batch:
-            max_steps = _max_steps(rng, state_space)
-            state_mapping, n = _state_subset(rng, state_space, None)
-            s_0, s_0_prob, terminal, goal_terminates, transition = _sample_structure(rng, n, action_space)
-            rewards = _sample_rewards(rng, n, action_space, terminal, goal_terminates, transition, s_0)
-            if rewards is None:
-                continue
-            cands.append({"ns": state_space, "na": action_space, "max_steps": max_steps, "state_mapping": state_mapping,
-                          "task_type": "MDP", "s_0": s_0, "s_0_prob": s_0_prob, "s_e": numpy.nonzero(terminal)[0],
-                          "transition": transition, "reward": rewards[0], "reward_noise": rewards[1],
-                          "final_goal_terminate": goal_terminates})
-        res = check_valuefunction_batch(cands, device=device)
-        out.extend(c for c, ok in zip(cands, res["accept"]) if ok)
-        if verbose:
-            print(f"round {rnd}: {int(res['accept'].sum())} of {batch} candidates accepted, {len(out)} / {count}")
-        if len(out) >= count:
-            return out[:count]
-    raise RuntimeError(f"only {len(out)} of {count} tasks passed the quality filter in {max_rounds} rounds")
+    max_steps = numpy.array([_max_steps(rng, state_space) for _ in range(count)])
+    mapping = numpy.stack([rng.permutation(state_space) for _ in range(count)])
+    dev_seed = int(rng.integers(0, 2 ** 63))
+    batch, info = sample_mdp_tasks_device(count, state_space, action_space, max_steps, seed=dev_seed, device=device,
+                                          min_batch=min_batch, verbose=verbose)
+    if not packed:
+        return _batch_to_dicts(batch, state_space, state_space, action_space, max_steps, mapping)
+    from .engine import round_up4
+    dev = batch["transition"].device
+    ld = round_up4(state_space)
+    sm = torch.zeros((count, ld), dtype=torch.int32, device=dev)
+    sm[:, :state_space] = torch.as_tensor(mapping, dtype=torch.int32, device=dev)
+    pb = {"transition": batch["transition"], "reward": batch["reward"], "reward_noise": batch["reward_noise"], "state_mapping": sm,
+          "n_real": torch.full((count,), state_space, dtype=torch.int32, device=dev), "is_terminal": batch["is_terminal"],
+          "s0_idx": batch["s0_idx"], "s0_prob": batch["s0_prob"], "n_s0": batch["n_s0"],
+          "max_steps": torch.as_tensor(max_steps, dtype=torch.float64, device=dev),
+          "ns": torch.full((count,), state_space, dtype=torch.int32, device=dev), "obs_transition": None}
+    geo = {"task_type": "MDP", "na": int(action_space), "da": 1, "do": 1, "n_pad": ld, "ns_max": int(state_space), "max_nnz": ld,
+           "max_obs_nnz": 0, "no_pad": 0, "s0_pad": 3}
+    return geo, pb, info
 
 
 def _observation_matrix(rng, n, observation_space, density, maximum_distribution):
