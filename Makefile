@@ -4,7 +4,7 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Iinclude --fmad=false $(EXTRA)
 SRC := xenoverse_b200/csrc
-OBJ := build/amdp_b200.o build/amdp_mdp.o build/amdp_w.o build/amdp_tp.o build/amdp_vi.o build/amdp_sampler.o
+OBJ := build/amdp_b200.o build/amdp_mdp.o build/amdp_w.o build/amdp_tp.o build/amdp_vi.o build/amdp_sampler.o build/amdp_mt.o
 LIB := xenoverse_b200/libamdp_b200.so
 
 all: $(LIB)

@@ -50,10 +50,12 @@ def sectors(n):
     return max(1, math.ceil(math.log2(n)) - 2)
 
 
-def b_alg(ns, no):
+def b_alg(ns, no, do=1, da=1):
     """Algorithmic bytes per env-step — the fixed yardstick of roofline.achieved."""
     if no is None:
         return 38 + 32 * (sectors(ns) + 2)
+    if do > 1 or da > 1:
+        return 38 + 4 * (do - 1) + 4 * (da - 1) + 32 * (da * (sectors(ns) + 1) + 1 + do * sectors(no))
     return 38 + 32 * (sectors(ns) + 2 + sectors(no))
 
 
@@ -427,6 +429,53 @@ def measure_garnet(local, dev, envs=65536, tasks=64, ns=128, na=5, b=3, ticks=12
     return out
 
 
+def measure_mtpomdp(local, dev, envs=65536, tasks=256, ns=128, na=5, no=32, do=4, da=2, ticks=64, steps=10):
+    """Multi-token POMDP rollouts on k_rollout_mt: the reference's own smoke configuration
+    (anymdp/test.py:38-45: state_space 128, action_space 5, observation_space 32, 4 observation tokens) with 2 action tokens."""
+    import torch
+    from xenoverse_b200 import AnyMDPVecEnv, synth_packed, synth_geometry
+    geo = synth_geometry(ns, na, no, do=do, da=da)
+    env = AnyMDPVecEnv(envs, device=local, seed=0)
+    per_task = 3 * 8 * geo["n_pad"] * na * geo["n_pad"]
+    chunk = max(1, min(tasks, (768 << 20) // per_task))
+    env.set_task(None, packed=(geo, tasks, ((t0, synth_packed(ns, na, min(chunk, tasks - t0), seed=1000 + t0, device=dev, no=no, do=do))
+                                            for t0 in range(0, tasks, chunk))))
+    env.reset()
+    traj = {"obs": torch.empty((ticks, envs, do), dtype=torch.int32, device=dev), "action": torch.empty((ticks, envs, da), dtype=torch.int32, device=dev),
+            "reward": torch.empty((ticks, envs), dtype=torch.float32, device=dev), "done": torch.empty((ticks, envs), dtype=torch.uint8, device=dev)}
+    ms, _, _ = timed_loop(lambda ev: env.rollout(ticks, out=traj), lambda: None, steps, 3, 1, dev)
+    env.check()
+    ms /= steps
+    out = {"workload": f"mtpomdp: AnyMDP MTPOMDP batch {envs} envs x ns={ns} na={na} no={no} do={do} da={da}, {tasks} synthetic tasks, uniform "
+                       f"random policy, {ticks} ticks per rollout launch (an env-step = one step() = {da} transitions + {do} observation draws)",
+           "value": envs * ticks / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "kernel": env.engine.rollout_kernel,
+           "table_bytes_per_gpu": env.engine.device_bytes, "algorithmic_bytes_per_env_step": b_alg(ns, no, do, da)}
+    env.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_sampler(local, dev, count=1024, ns=128, na=5):
+    """Batched task sampling on the GPU: `count` ACCEPTED tasks — candidates by amdp_sample_mdp_batch, filter
+    by amdp_check_valuefunction_batch.  Wall clock of the whole call, tasks left on the device (packed)."""
+    import torch
+    from xenoverse_b200 import AnyMDPTaskSamplerBatch
+    AnyMDPTaskSamplerBatch(8, 16, na, seed=0, device=local, packed=True)          # warm-up (module load)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    geo, batch, info = AnyMDPTaskSamplerBatch(count, ns, na, seed=1, device=local, packed=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {"workload": f"task sampler: AnyMDPTaskSamplerBatch({count}, {ns}, {na}) — accepted tasks of the reference's generator + quality filter",
+           "seconds": dt, "tasks_per_s": count / dt, "candidates": info["candidates"], "accepted": info["accepted"],
+           "sample_mdp_gave_up": info["sample_mdp_gave_up"], "rounds": info["rounds"],
+           "kernels": "k_sample_mdp, k_filter_values, k_square_batch, k_filter_finish",
+           "reference_cpu": "0.2-8 s per task at ns <= 64, 48 s for one ns=128 task (SURVEY.md §6, one core)"}
+    del batch
+    torch.cuda.empty_cache()
+    return out
+
+
 def measure_vi(name, tasks, ns, na, dev, local, sweeps=64):
     """Batched value iteration (amdp_value_iteration) over `tasks` resident synthetic tasks: a fixed
     number of sweeps (tol = 0), device time; HBM roofline = the float64 CDF rows streamed once per sweep."""
@@ -569,6 +618,8 @@ def other_workloads(world, rank, dev, local, args):
                 epsilon=0.1 if key.endswith("_table_policy") else None)
         run("cfg5_stats_every_32_ticks", quick_measure, "cfg5", 131072, 131072, 32, 5, None, 32, 20, dev, local, exchange="peer")
         run("garnet128_b3_sparse_rows", measure_garnet, local, dev)
+        run("mtpomdp_ns128_no32_do4_da2", measure_mtpomdp, local, dev)
+        run("task_sampler_batch_1024_ns128", measure_sampler, local, dev)
         run("cfg1_single_env_dropin", measure_dropin, local)
         for key, (wl, n_tasks) in {"value_iteration_cfg2": ("cfg2", 4096), "value_iteration_cfg5": ("cfg5", 131072)}.items():
             _, _, o_ns, o_na, _ = WORKLOADS[wl]

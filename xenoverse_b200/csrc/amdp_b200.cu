@@ -936,7 +936,8 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     h->two_level = (c.n_pad >= 256 && c.n_pad <= 1024) && !(c.reserved0 & 2) && ((c.reserved0 & 4) || c.n_pad >= 512 || c.n_envs >= 16384);
     if (h->two_level) { if ((rc = dalloc(h, &h->pivot, rows * 32))) return rc; }
     // thread-per-env tables: chosen for engines with enough envs to fill the GPU (or forced by flag 8; never with 16)
-    const bool tp_kind = mdp || (c.task_type == AMDP_POMDP && c.no_pad <= 128);      // POMDP: one observation token, <= 16 blocks
+    // POMDP: one observation token, <= 16 blocks; MTPOMDP: the same tables per observation token (k_rollout_mt)
+    const bool tp_kind = mdp || ((c.task_type == AMDP_POMDP || c.task_type == AMDP_MTPOMDP) && c.no_pad <= 128);
     // flags bits 8-12: bit_length(max ns - 1), the bits of state_mapping the thread-per-env tables carry in their code words
     // (0 = not stated: 15 is assumed and larger mappings are rejected at upload)
     const int obs_bits = ((c.reserved0 >> 8) & 31) ? ((c.reserved0 >> 8) & 31) : 15;
@@ -971,7 +972,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
             while ((1 << ob) < c.no_pad) ++ob;
             h->T.o_sparse_bits = (c.reserved0 & 128) ? (ob > 0 ? ob : 1) : 0;
             h->T.o_blocks = h->T.o_sparse_bits ? 0 : (c.no_pad + 7) / 8;
-            if ((rc = dalloc(h, &h->ofat, (size_t)c.n_tasks * c.n_pad * (8 + 8 * h->T.o_blocks)))) return rc;
+            if ((rc = dalloc(h, &h->ofat, (size_t)c.n_tasks * c.n_obs_tok * c.n_pad * (8 + 8 * h->T.o_blocks)))) return rc;
         }
     }
     // one warp per env, shortest dependent chain: rows of exactly 64 / 128 / 256 states (flag 32 keeps the older k_rollout_mdp)
@@ -1051,7 +1052,7 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
         const long long orows = (long long)cnt * c.n_obs_tok * c.n_pad;
         k_build_obs<<<nblk(orows, 128), 128, 0, st>>>(orows, c.n_pad, c.no_pad, obs_transition,
                                                       h->obs_cdf + (size_t)t0 * c.n_obs_tok * c.n_pad * c.no_pad,
-                                                      h->ofat ? h->ofat + (size_t)t0 * c.n_pad * (8 + 8 * h->T.o_blocks) : nullptr,
+                                                      h->ofat ? h->ofat + (size_t)t0 * c.n_obs_tok * c.n_pad * (8 + 8 * h->T.o_blocks) : nullptr,
                                                       h->T.o_blocks, h->T.o_sparse_bits, c.n_obs_tok * c.n_pad, status_out);
         h->launches += 1;
     }
@@ -1087,6 +1088,8 @@ extern "C" int amdp_reset(amdp_t* h, const uint8_t* mask, int32_t* obs_out, cons
     return AMDP_OK;
 }
 
+static inline bool c_not_mt(const amdp* h) { return h->cfg.task_type != AMDP_MTPOMDP; }
+
 template <int G>
 static void launch_step(amdp* h, const int32_t* actions, int32_t* obs, int32_t* final_obs, float* reward, float* reward_gt,
                         uint8_t* terminated, uint8_t* truncated, int32_t* actions_out, int32_t* steps_out, const double* u,
@@ -1103,7 +1106,7 @@ extern "C" int amdp_step(amdp_t* h, const int32_t* actions, int32_t* obs, int32_
     if (!h->assigned) return fail(h, AMDP_ESTATE, "Must \"set_task\" and \"reset\" before doing any actions");
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (h->tp && !u_inject && !h->force_generic) {               // (tp: MDP, or POMDP with one observation token)
+    if (h->tp && c_not_mt(h) && !u_inject && !h->force_generic) {   // (tp: MDP, or POMDP with one observation token)
         // engines that own the thread-per-env tables: one thread per env instead of G lanes streaming the float64 row
         amdp_launch_step_tp(h->T, h->E, h->cfg.n_envs, h->tp_coarse_bits, h->tick, actions, obs, final_obs, reward, reward_gt,
                             terminated, truncated, actions_out, steps_out, st);
@@ -1161,8 +1164,13 @@ extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const 
     cudaStream_t st = (cudaStream_t)stream;
     const bool policy_ok = !h->T.policy || actions || h->tp || h->wv2;   // (k_rollout_mdp has no table policy: the generic kernel runs)
     const bool fast = (h->cfg.task_type == AMDP_MDP || (h->tp && h->cfg.task_type == AMDP_POMDP)) && !u_inject && !h->force_generic && policy_ok;
+    // multi-token POMDP: the thread-per-env kernel k_rollout_mt (no table policy, separate record arrays)
+    const bool fast_mt = h->tp && h->cfg.task_type == AMDP_MTPOMDP && !u_inject && !h->force_generic && !(h->T.policy && !actions) &&
+                         !J.packed && !J.obs_done;
     if (fast) {
         launch_rollout_fast(h, K, actions, J, st);
+    } else if (fast_mt) {
+        amdp_launch_mt(h->T, h->E, h->cfg.n_envs, h->cfg.autoreset == AMDP_AUTORESET_NEXT_STEP, h->tp_coarse_bits, h->tick, K, actions, J, st);
     } else {
         switch (h->G) {
 #define CASE(g) case g: launch_rollout<g>(h, K, actions, J, u_inject, st); break;
@@ -1416,7 +1424,9 @@ extern "C" const char* amdp_rollout_kernel(amdp_t* h) {
     if (!h) return "";
     const amdp_config& c = h->cfg;
     const bool fast = (c.task_type == AMDP_MDP || (h->tp && c.task_type == AMDP_POMDP)) && !h->force_generic;
-    if (!fast) snprintf(h->kname, sizeof(h->kname), "k_rollout<G=%d>", h->G);
+    if (h->tp && c.task_type == AMDP_MTPOMDP && !h->force_generic)
+        snprintf(h->kname, sizeof(h->kname), "k_rollout_mt<levels=%d,do=%d,da=%d>", h->T.tp_levels, c.n_obs_tok, c.n_act_tok);
+    else if (!fast) snprintf(h->kname, sizeof(h->kname), "k_rollout<G=%d>", h->G);
     else if (h->tp) snprintf(h->kname, sizeof(h->kname), "k_rollout_tp<levels=%d,%s%s>", h->T.tp_levels, c.task_type == AMDP_POMDP ? "POMDP" : "MDP",
                              h->T.tp_nxt_bits ? ",sparse" : "");
     else if (h->two_level) snprintf(h->kname, sizeof(h->kname), "k_rollout_mdp<G=8,two-level>");

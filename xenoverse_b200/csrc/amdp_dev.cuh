@@ -1,7 +1,8 @@
 // amdp_dev.cuh — device-side definitions shared by the translation units of libamdp_b200.so: table / env-state structs,
 // Philox4x32-10 and the draw constructions, the monotone probability codes, streaming loads.  Kernels live in
 //   amdp_b200.cu (generic tick, task upload, statistics, C ABI), amdp_mdp.cu (k_rollout_mdp), amdp_w.cu (k_rollout_w),
-//   amdp_tp.cu (k_rollout_tp); each rollout kernel file exports one host launcher declared at the end of this header.
+//   amdp_tp.cu (k_rollout_tp), amdp_mt.cu (k_rollout_mt); each rollout kernel file exports one host launcher declared at the
+//   end of this header.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -265,6 +266,8 @@ void amdp_launch_step_tp(const Tables& T, const EnvArrays& E, long long n_envs, 
                          uint8_t* truncated, int32_t* actions_out, int32_t* steps_out, cudaStream_t st);
 void amdp_launch_w(const Tables& T, const EnvArrays& E, long long n_envs, unsigned long long tick, int K, const int32_t* actions,
                    const amdp_traj& J, cudaStream_t st);
+void amdp_launch_mt(const Tables& T, const EnvArrays& E, long long n_envs, bool next, int coarse_bits, unsigned long long tick, int K,
+                    const int32_t* actions, const amdp_traj& J, cudaStream_t st);
 int amdp_vi_run(const Tables& T, long long n_tasks, int greedy, double gamma, double tol, int max_sweeps, double* Q, double* V, double* er,
                 unsigned long long* maxdiff, uint8_t* policy_out, int* sweeps_out, long long* launches, cudaStream_t st);
 static inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }

@@ -56,6 +56,8 @@ def task_geometry(tasks):
         nnz_max = max(nnz_max, int((numpy.asarray(t["transition"]) != 0).sum(axis=-1).max()))
         if tt == "POMDP":
             onnz_max = max(onnz_max, int((numpy.asarray(t["observation_transition"]) != 0).sum(axis=-1).max()))
+        elif tt == "MTPOMDP":
+            onnz_max = max(onnz_max, max(int((numpy.asarray(m) != 0).sum(axis=-1).max()) for m in t["observation_transition"]))
         if t["task_type"] != tt or int(t["na"]) != na:
             raise ValueError("all tasks of one engine must share task_type and na")
         if tt == "MTPOMDP" and (int(t["da"]) != da or int(t["do"]) != do):
@@ -150,7 +152,7 @@ class Engine:
         sparse = (geo["task_type"] == "MDP" and search in ("auto", "sparse") and 0 < int(geo.get("max_nnz", 0)) <= 8
                   and geo["n_pad"] > 8) or (search == "sparse" and geo["task_type"] == "MDP")
         # sparse observation rows (POMDP tasks whose states observe at most 8 different observations)
-        osparse = geo["task_type"] == "POMDP" and 0 < int(geo.get("max_obs_nnz", 0)) <= 8 and search != "warp_v1"
+        osparse = geo["task_type"] in ("POMDP", "MTPOMDP") and 0 < int(geo.get("max_obs_nnz", 0)) <= 8 and search != "warp_v1"
         cfg = _lib.Config(device=self.device.index, task_type=_lib.TASK_TYPES[geo["task_type"]],
                           autoreset=_lib.AUTORESET[autoreset], na=geo["na"], n_pad=geo["n_pad"], no_pad=geo["no_pad"],
                           n_obs_tok=geo["do"], n_act_tok=geo["da"], s0_pad=geo["s0_pad"],

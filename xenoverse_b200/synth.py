@@ -70,13 +70,15 @@ def synth_task(ns, na, seed, term_frac=0.10, no=None, task_type=None, do=1, da=1
     return task
 
 
-def synth_geometry(ns, na, no=None):
-    return {"task_type": "MDP" if no is None else "POMDP", "na": int(na), "da": 1, "do": 1, "n_pad": round_up4(ns), "ns_max": int(ns), "max_obs_nnz": 0 if no is None else min(4, int(no)),
+def synth_geometry(ns, na, no=None, do=1, da=1):
+    """Engine geometry of `synth_packed` batches; do / da > 1 (or both given explicitly with `no`) make multi-token tasks."""
+    tt = "MDP" if no is None else ("MTPOMDP" if (do > 1 or da > 1) else "POMDP")
+    return {"task_type": tt, "na": int(na), "da": int(da), "do": int(do), "n_pad": round_up4(ns), "ns_max": int(ns), "max_obs_nnz": 0 if no is None else min(4, int(no)),
             "no_pad": round_up4(no) if no is not None else 0, "s0_pad": min(3, int(ns))}
 
 
 @torch.no_grad()
-def synth_packed(ns, na, count, seed, device, no=None, term_frac=0.10):
+def synth_packed(ns, na, count, seed, device, no=None, term_frac=0.10, do=1):
     """`count` synthetic tasks as device tensors in the amdp_upload_tasks layout (see engine.pack_tasks)."""
     n, n_pad = int(ns), round_up4(ns)
     g = torch.Generator(device=device)
@@ -125,17 +127,17 @@ def synth_packed(ns, na, count, seed, device, no=None, term_frac=0.10):
     }
     if no is not None:
         no_pad = round_up4(no)
-        sc = torch.rand((count, 1, n_pad, no_pad), generator=g, device=device)
+        sc = torch.rand((count, do, n_pad, no_pad), generator=g, device=device)
         sc[..., no:] = -1.0
         top = sc.topk(min(4, no), dim=-1).indices
-        m = torch.zeros((count, 1, n_pad, no_pad), dtype=f64, device=device)
+        m = torch.zeros((count, do, n_pad, no_pad), dtype=f64, device=device)
         m.scatter_(-1, top, torch.rand(top.shape, generator=g, device=device, dtype=f64) + 0.05)
         m /= m.sum(dim=-1, keepdim=True)
         batch["obs_transition"] = m
     return batch
 
 
-def packed_to_task(batch, i, no=None):
+def packed_to_task(batch, i, no=None, da=1):
     """Task `i` of a packed device batch as a reference-schema dict of numpy arrays (for the CPU oracle)."""
     n = int(batch["n_real"][i])
     g = lambda k: batch[k][i].cpu().numpy()
@@ -148,7 +150,13 @@ def packed_to_task(batch, i, no=None):
             "s_0_prob": g("s0_prob")[:k0].copy(), "s_e": numpy.nonzero(term)[0].astype(numpy.int64),
             "final_goal_terminate": True}
     if batch.get("obs_transition") is not None:
-        task["task_type"] = "POMDP"
+        ot = batch["obs_transition"][i].cpu().numpy()[:, :n, :no]
         task["no"] = int(no)
-        task["observation_transition"] = batch["obs_transition"][i, 0].cpu().numpy()[:n, :no].copy()
+        if ot.shape[0] == 1 and da == 1:
+            task["task_type"] = "POMDP"
+            task["observation_transition"] = ot[0].copy()
+        else:
+            task["task_type"] = "MTPOMDP"
+            task["do"], task["da"] = int(ot.shape[0]), int(da)
+            task["observation_transition"] = [m.copy() for m in ot]
     return task
