@@ -455,6 +455,26 @@ def measure_mtpomdp(local, dev, envs=65536, tasks=256, ns=128, na=5, no=32, do=4
     return out
 
 
+def measure_learner(local, dev, kind, envs, tasks, ns, na, ticks, steps=5):
+    """Device-side learning behaviour policy: policy -> step -> learner update for every env inside one
+    rollout kernel (amdp_rollout_learn), the loop the reference runs in Python around one env (test_utils.py:42-60)."""
+    import torch
+    env, geo = build_env("learner", envs, tasks, ns, na, None, dev, local)
+    env.attach_learner(kind)
+    env.reset()
+    traj = traj_buffers(ticks, envs, dev)
+    ms, _, _ = timed_loop(lambda ev: env.rollout_learn(ticks, out=traj), lambda: None, steps, 3, 1, dev)
+    env.check()
+    ms /= steps
+    out = {"workload": f"{kind} learner: {envs} envs x ns={ns} na={na}, {tasks} synthetic tasks, one "
+                       f"{'AnyMDPSolverQ' if kind == 'q' else 'AnyMDPSolverMBRL'} per env updated on the device, {ticks} ticks per launch",
+           "value": envs * ticks / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "kernel": f"k_rollout_learn<G={min(32, max(1, geo['n_pad'] // 4))},{kind}>",
+           "bound": "latency (per-env learner tables in HBM, float64 in the reference's operation order)"}
+    env.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def measure_sampler(local, dev, count=1024, ns=128, na=5):
     """Batched task sampling on the GPU: `count` ACCEPTED tasks — candidates by amdp_sample_mdp_batch, filter
     by amdp_check_valuefunction_batch.  Wall clock of the whole call, tasks left on the device (packed)."""
@@ -545,13 +565,13 @@ def measure_e2e(env, args, N, na, K, world, rank, local, dev):
     acts_h = torch.from_numpy(sets[0][0].copy()).pin_memory()
     rec_h = torch.empty((eK, N), dtype=torch.int64).pin_memory()
     for _ in range(3):
-        eng.rollout_host_packed(eK, args.e2e_chunk, acts_h, rec_h)
+        eng.rollout_host_packed(eK, min(args.e2e_chunk, 128), acts_h, rec_h)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     w0 = time.perf_counter()
     for _ in range(reps):
-        eng.rollout_host_packed(eK, args.e2e_chunk, acts_h, rec_h)   # synchronous
+        eng.rollout_host_packed(eK, min(args.e2e_chunk, 128), acts_h, rec_h)   # synchronous
     w = max_over_ranks(time.perf_counter() - w0, world, dev)
     out["packed8_synchronous"] = {"value": world * N * eK * reps / w, "ms_per_step": 1e3 * w / reps,
                                   "d2h_bytes_per_step": int(eK * N * 8), "d2h_GBps_per_gpu": eK * N * 8 * reps / w / 1e9}
@@ -620,6 +640,8 @@ def other_workloads(world, rank, dev, local, args):
         run("garnet128_b3_sparse_rows", measure_garnet, local, dev)
         run("mtpomdp_ns128_no32_do4_da2", measure_mtpomdp, local, dev)
         run("task_sampler_batch_1024_ns128", measure_sampler, local, dev)
+        run("q_learner_cfg2_tables", measure_learner, local, dev, "q", 4096, 4096, 128, 5, 256)
+        run("mbrl_learner_ns32", measure_learner, local, dev, "mbrl", 4096, 256, 32, 5, 128)
         run("cfg1_single_env_dropin", measure_dropin, local)
         for key, (wl, n_tasks) in {"value_iteration_cfg2": ("cfg2", 4096), "value_iteration_cfg5": ("cfg5", 131072)}.items():
             _, _, o_ns, o_na, _ = WORKLOADS[wl]

@@ -304,6 +304,28 @@ int amdp_poll_errors(amdp_t* h, uint32_t* faults, void* stream);
  * AMDP_EINVAL; the handle keeps a copy.  NULL switches back to the uniform random policy.  Synchronises `stream`. */
 int amdp_set_policy(amdp_t* h, const uint8_t* policy, float epsilon, void* stream);
 
+/*
+ * Device-side LEARNING behaviour policies: every env carries its own learner and the whole data-collection
+ * loop of the reference (test_utils.py:42-60: action = solver.policy(state); env.step; solver.learner(...)) runs inside
+ * one rollout kernel.  MDP engines with one action token (both solvers assume task_type == "MDP"); tables are indexed by the
+ * OBSERVED state, `ns_obs` = size of the observable state space (task["ns"]).
+ *   kind 0  AnyMDPSolverQ (anymdp_solver_q.py:8-59): tabular Q-learning, alpha_or_c = alpha (0.50), max_steps (4000) the
+ *           scale of its learning-rate / stiffness schedules; softmax exploration.
+ *   kind 1  AnyMDPSolverMBRL (anymdp_solver_mbrl.py:13-81): optimistic Thompson sampling on the estimated model, re-planned by
+ *           one in-place value-iteration sweep at every episode end; alpha_or_c = c (1.0); max_steps unused.
+ * amdp_rollout_learn: K ticks; greedy != 0 plays argmax of the value matrix (policy(state, is_test=True)); the learner is
+ * still updated, as in the reference's epoch_run.  Policy draws: Philox block 16 + j / 2 of the tick (amdp_dump_policy_draws:
+ * out double [K][n_envs][count], draw j < count of every (tick, env)).
+ * amdp_learner_get copies a table to `out` (device): which = 0 value_matrix [n_envs][ns_obs][na]; kind 0: 1 sa_visited,
+ * 2 s_visited [n_envs][ns_obs], 3 (avg_r, avg_r2, r_cnt, r_std) [n_envs][4]; kind 1: 1 vis_cnt_sa, 2 b_mat,
+ * 3 est_r [n_envs][ns_obs][na][ns_obs], 4 vis_cnt.
+ */
+int amdp_learner_create(amdp_t* h, int32_t kind, int32_t ns_obs, double gamma, double alpha_or_c, double max_steps, void* stream);
+int amdp_learner_destroy(amdp_t* h);
+int amdp_rollout_learn(amdp_t* h, int32_t K, int32_t greedy, const amdp_traj* traj, void* stream);
+int amdp_learner_get(amdp_t* h, int32_t which, double* out, void* stream);
+int amdp_dump_policy_draws(amdp_t* h, uint64_t tick0, int32_t K, int32_t count, double* out, void* stream);
+
 /* Batched value iteration over the resident tables (the reference's update_value_matrix(is_greedy=True),
  * solver.py:57-80, as used by AnyMDPSolverOpt, anymdp_solver_opt.py:32-36 — here as synchronous sweeps over ALL tasks of
  * the handle at once, stopped when max |dQ| <= tol or after max_sweeps):  q_out double [n_tasks][n_pad][na] (device, or NULL),

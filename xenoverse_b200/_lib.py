@@ -65,6 +65,11 @@ _SIGNATURES = {
     "amdp_get_tick": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),
     "amdp_set_tick": (ctypes.c_int, [_P, ctypes.c_uint64]),
     "amdp_set_seed": (ctypes.c_int, [_P, ctypes.c_uint64]),
+    "amdp_learner_create": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_double, _P]),
+    "amdp_learner_destroy": (ctypes.c_int, [_P]),
+    "amdp_rollout_learn": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(Traj), _P]),
+    "amdp_learner_get": (ctypes.c_int, [_P, ctypes.c_int32, _P, _P]),
+    "amdp_dump_policy_draws": (ctypes.c_int, [_P, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int32, _P, _P]),
     "amdp_set_policy": (ctypes.c_int, [_P, _P, ctypes.c_float, _P]),
     "amdp_value_iteration": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_double, ctypes.c_double, ctypes.c_int32, _P, _P,
                                             ctypes.POINTER(ctypes.c_int32), _P]),

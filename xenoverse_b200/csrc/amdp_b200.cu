@@ -58,6 +58,8 @@ struct EnvRegs {
 
 struct TickOut {
     float reward, reward_gt;
+    double reward_d;      // the reward in float64, as the device-side learners consume it
+    int ok;               // the tick stepped (no fault, not a pending-reset tick)
     int term, trunc;
     int steps;            // info["steps"] of this tick (before any same-step reset)
     int finished;         // an episode was closed in this tick
@@ -91,6 +93,7 @@ template <int G>
 __device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, long long t, bool active, int lane,
                                          const Draws& D, const int32_t* act_in /* [d_a] or null */,
                                          EnvRegs& R, TickOut& O, int* obs, int* final_obs, int* act_used) {
+    O.reward_d = 0.0; O.ok = 0;
     O.reward = 0.f; O.reward_gt = 0.f; O.term = 0; O.trunc = 0; O.steps = 0; O.finished = 0; O.fin_return = 0.0; O.fin_steps = 0;
     const int da = T.d_a;
     // draws of block 0: transition (token 0) and reset uniforms
@@ -147,6 +150,7 @@ __device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, lo
         R.state = s;
         O.term = term;
         O.reward = (float)rew;
+        O.reward_d = rew; O.ok = 1;
         O.reward_gt = (float)rew_gt;
         R.ep_return += rew;
     }
@@ -293,6 +297,8 @@ __global__ void __launch_bounds__(256) k_rollout(Tables T, EnvArrays E, unsigned
     if (active && lane == 0) { store_regs(E, e, R); store_stats(E, e, R); }
 }
 
+
+#include "amdp_learn.inc"
 
 __global__ void k_reset(Tables T, EnvArrays E, unsigned long long tick, int n_slots, const uint8_t* __restrict__ mask,
                         int32_t* __restrict__ obs_out, const double* __restrict__ u_inject) {
@@ -810,6 +816,10 @@ struct amdp {
     int xg_world, xg_rank;
     unsigned long long xg_seq;
     bool xg_ready;
+    // device-side learners (amdp_learner_*): kind -1 none, 0 Q-learning, 1 MBRL; tables indexed by observed state
+    int learn_kind, learn_ns;
+    LearnQ lq;
+    LearnM lm;
 };
 
 static int fail(amdp* h, int code, const char* fmt, const char* a = "") {
@@ -895,6 +905,10 @@ extern "C" int amdp_destroy(amdp_t* h) {
     if (h->hs_stream) cudaStreamDestroy(h->hs_stream);
     if (h->ev_caller) cudaEventDestroy(h->ev_caller);
     for (int r = 0; r < XG_MAX_RANKS; ++r) if (h->xg_opened[r] && h->xg_peer[r]) cudaIpcCloseMemHandle(h->xg_peer[r]);
+    {
+        void* lp[] = {h->lq.q, h->lq.sa_vis, h->lq.s_vis, h->lq.scal, h->lm.est_r, h->lm.vis_cnt, h->lm.vis_sa, h->lm.vm, h->lm.b_mat};
+        for (void* p : lp) if (p) cudaFree(p);
+    }
     if (h->xg_buf) cudaFree(h->xg_buf);
     if (h->xg_peers_dev) cudaFree(h->xg_peers_dev);
     if (h->st_ready) {
@@ -913,6 +927,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     if (!h) return AMDP_ENOMEM;
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
+    h->learn_kind = -1;
     const amdp_config& c = h->cfg;
     const bool mdp = c.task_type == AMDP_MDP;
     if (c.task_type < AMDP_MDP || c.task_type > AMDP_MTPOMDP || c.autoreset < 0 || c.autoreset > 2 || c.na < 1 ||
@@ -1403,6 +1418,118 @@ extern "C" int amdp_value_iteration(amdp_t* h, int32_t greedy, double gamma, dou
     h->launches += launches;
     if (q_out) CK(cudaMemcpyAsync(q_out, h->vi_q, sizeof(double) * rows, cudaMemcpyDeviceToDevice, st));
     if (sweeps_out) *sweeps_out = sweeps;
+    return AMDP_OK;
+}
+
+// ---- device-side learners ----------------------------------------------------------------------------
+static void learner_free(amdp* h) {
+    void** lp[] = {(void**)&h->lq.q, (void**)&h->lq.sa_vis, (void**)&h->lq.s_vis, (void**)&h->lq.scal, (void**)&h->lm.est_r,
+                   (void**)&h->lm.vis_cnt, (void**)&h->lm.vis_sa, (void**)&h->lm.vm, (void**)&h->lm.b_mat};
+    for (void** p : lp) if (*p) { cudaFree(*p); *p = nullptr; }
+    h->learn_kind = -1;
+}
+
+extern "C" int amdp_learner_create(amdp_t* h, int32_t kind, int32_t ns_obs, double gamma, double alpha_or_c, double max_steps, void* stream) {
+    if (!h || kind < 0 || kind > 1 || ns_obs < 1 || !(gamma >= 0.0 && gamma < 1.0)) return AMDP_EINVAL;
+    const amdp_config& c = h->cfg;
+    if (c.task_type != AMDP_MDP || c.n_act_tok != 1) return fail(h, AMDP_EINVAL, "The solver only works for MDP");   // anymdp_solver_q.py:17
+    if (c.na > LEARN_MAX_NA) return fail(h, AMDP_EINVAL, "device-side learners need na <= 32");
+    CK(cudaSetDevice(c.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    learner_free(h);
+    const size_t N = (size_t)c.n_envs, sa = N * ns_obs * c.na;
+    int rc;
+    if (kind == 0) {
+        LearnQ& L = h->lq;
+        if ((rc = dalloc(h, &L.q, sa))) return rc;
+        if ((rc = dalloc(h, &L.sa_vis, sa))) return rc;
+        if ((rc = dalloc(h, &L.s_vis, N * ns_obs))) return rc;
+        if ((rc = dalloc(h, &L.scal, N * 4))) return rc;
+        L.gamma = gamma; L.alpha = alpha_or_c; L.max_steps = max_steps;
+        k_learn_init_q<<<nblk((long long)sa, 256), 256, 0, st>>>(L, (long long)sa, (long long)(N * ns_obs), (long long)N);
+    } else {
+        LearnM& L = h->lm;
+        if ((rc = dalloc(h, &L.est_r, sa * ns_obs))) return rc;
+        if ((rc = dalloc(h, &L.vis_cnt, sa * ns_obs))) return rc;
+        if ((rc = dalloc(h, &L.vis_sa, sa))) return rc;
+        if ((rc = dalloc(h, &L.vm, sa))) return rc;
+        if ((rc = dalloc(h, &L.b_mat, sa))) return rc;
+        L.gamma = gamma; L.c = alpha_or_c / (1.0 - gamma);                                  // anymdp_solver_mbrl.py:28
+        k_learn_init_m<<<nblk((long long)(sa * ns_obs), 256), 256, 0, st>>>(L, (long long)(sa * ns_obs), (long long)sa);
+    }
+    h->launches += 1;
+    CK(cudaGetLastError());
+    h->learn_kind = kind;
+    h->learn_ns = ns_obs;
+    return AMDP_OK;
+}
+
+extern "C" int amdp_learner_destroy(amdp_t* h) {
+    if (!h) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaDeviceSynchronize());
+    learner_free(h);
+    return AMDP_OK;
+}
+
+template <int G>
+static void launch_learn(amdp* h, int K, int greedy, const amdp_traj& J, cudaStream_t st) {
+    const long long threads = h->cfg.n_envs * G;
+    if (h->learn_kind == 0) k_rollout_learn<G, 0><<<nblk(threads, 256), 256, 0, st>>>(h->T, h->E, h->tick, K, h->n_slots, h->learn_ns, h->lq, h->lm, greedy, J);
+    else k_rollout_learn<G, 1><<<nblk(threads, 256), 256, 0, st>>>(h->T, h->E, h->tick, K, h->n_slots, h->learn_ns, h->lq, h->lm, greedy, J);
+}
+
+extern "C" int amdp_rollout_learn(amdp_t* h, int32_t K, int32_t greedy, const amdp_traj* traj, void* stream) {
+    if (!h || K < 1) return AMDP_EINVAL;
+    if (h->learn_kind < 0) return fail(h, AMDP_ESTATE, "rollout_learn before learner_create");
+    if (!h->assigned) return fail(h, AMDP_ESTATE, "Must \"set_task\" and \"reset\" before doing any actions");
+    if (h->cfg.autoreset == AMDP_AUTORESET_DISABLED) return fail(h, AMDP_EINVAL, "rollout needs an auto-reset mode");
+    CK(cudaSetDevice(h->cfg.device));
+    amdp_traj J;
+    memset(&J, 0, sizeof(J));
+    if (traj) J = *traj;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (h->G) {
+#define CASE(g) case g: launch_learn<g>(h, K, greedy, J, st); break;
+        CASE(1) CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)
+#undef CASE
+        default: return fail(h, AMDP_EINVAL, "bad group size");
+    }
+    h->launches += 1;
+    h->tick += (unsigned long long)K;
+    h->total_steps += (double)h->cfg.n_envs * K;
+    CK(cudaGetLastError());
+    mark_caller_stream(h, st);
+    return AMDP_OK;
+}
+
+extern "C" int amdp_learner_get(amdp_t* h, int32_t which, double* out, void* stream) {
+    if (!h || !out) return AMDP_EINVAL;
+    if (h->learn_kind < 0) return fail(h, AMDP_ESTATE, "learner_get before learner_create");
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)h->cfg.n_envs, sa = N * h->learn_ns * h->cfg.na;
+    const double* src = nullptr;
+    size_t n = 0;
+    if (h->learn_kind == 0) {
+        if (which == 0) { src = h->lq.q; n = sa; } else if (which == 1) { src = h->lq.sa_vis; n = sa; }
+        else if (which == 2) { src = h->lq.s_vis; n = N * h->learn_ns; } else if (which == 3) { src = h->lq.scal; n = N * 4; }
+    } else {
+        if (which == 0) { src = h->lm.vm; n = sa; } else if (which == 1) { src = h->lm.vis_sa; n = sa; }
+        else if (which == 2) { src = h->lm.b_mat; n = sa; } else if (which == 3) { src = h->lm.est_r; n = sa * h->learn_ns; }
+        else if (which == 4) { src = h->lm.vis_cnt; n = sa * h->learn_ns; }
+    }
+    if (!src) return fail(h, AMDP_EINVAL, "learner_get: no such table");
+    CK(cudaMemcpyAsync(out, src, n * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return AMDP_OK;
+}
+
+extern "C" int amdp_dump_policy_draws(amdp_t* h, uint64_t tick0, int32_t K, int32_t count, double* out, void* stream) {
+    if (!h || !out || K < 1 || count < 1) return AMDP_EINVAL;
+    CK(cudaSetDevice(h->cfg.device));
+    const long long total = (long long)K * h->cfg.n_envs * count;
+    k_dump_policy_draws<<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(h->E, tick0, K, count, out);
+    h->launches += 1;
+    CK(cudaGetLastError());
     return AMDP_OK;
 }
 

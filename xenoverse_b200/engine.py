@@ -264,6 +264,52 @@ class Engine:
             torch.cuda.current_stream().synchronize()
         return q, pol, int(sweeps.value)
 
+    # ---- device-side learners -----------------------------------------------------------------------------
+    LEARNERS = {"q": 0, "mbrl": 1}
+
+    def learner_create(self, kind, ns_obs, gamma=0.99, alpha=0.50, c=1.0, max_steps=4000):
+        """Attach one learner per env: kind "q" = AnyMDPSolverQ (anymdp_solver_q.py), "mbrl" = AnyMDPSolverMBRL
+        (anymdp_solver_mbrl.py); tables indexed by observed state (ns_obs = task["ns"])."""
+        k = self.LEARNERS[kind]
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_learner_create(self._h, k, int(ns_obs), float(gamma), float(alpha if k == 0 else c), float(max_steps), _stream()))
+        self.learner = (kind, int(ns_obs))
+
+    def learner_destroy(self):
+        self._ck(lib.amdp_learner_destroy(self._h))
+        self.learner = None
+
+    def rollout_learn(self, K, traj=None, greedy=False):
+        """K ticks of policy -> step -> learner update inside one kernel (amdp_rollout_learn); traj as `rollout`."""
+        J = _lib.Traj()
+        traj = traj or {}
+        J.obs, J.actions_out = _ptr(traj.get("obs")), _ptr(traj.get("action"))
+        J.reward, J.reward_gt, J.done = _ptr(traj.get("reward")), _ptr(traj.get("reward_gt")), _ptr(traj.get("done"))
+        J.packed = _ptr(traj.get("packed"))
+        J.step_stride, J.env_stride = self.N, 1
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_rollout_learn(self._h, int(K), 1 if greedy else 0, ctypes.byref(J), _stream()))
+
+    def learner_table(self, which):
+        """Learner tables as float64 device tensors: "value_matrix" [N, ns, na]; Q: "sa_visited", "s_visited" [N, ns], "scalars"
+        [N, 4]; MBRL: "vis_cnt_sa", "b_mat", "est_r" [N, ns, na, ns], "vis_cnt"."""
+        kind, ns = self.learner
+        na, N = self.geo["na"], self.N
+        shapes = {"q": {"value_matrix": (0, (N, ns, na)), "sa_visited": (1, (N, ns, na)), "s_visited": (2, (N, ns)), "scalars": (3, (N, 4))},
+                  "mbrl": {"value_matrix": (0, (N, ns, na)), "vis_cnt_sa": (1, (N, ns, na)), "b_mat": (2, (N, ns, na)),
+                           "est_r": (3, (N, ns, na, ns)), "vis_cnt": (4, (N, ns, na, ns))}}[kind]
+        idx, shape = shapes[which]
+        out = torch.empty(shape, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_learner_get(self._h, idx, _ptr(out), _stream()))
+        return out
+
+    def dump_policy_draws(self, tick0, K, count):
+        out = torch.empty((K, self.N, count), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(lib.amdp_dump_policy_draws(self._h, int(tick0), int(K), int(count), _ptr(out), _stream()))
+        return out
+
     def set_seed(self, seed):
         self._ck(lib.amdp_set_seed(self._h, int(seed) & (2 ** 64 - 1)))
 

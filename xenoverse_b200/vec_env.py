@@ -163,6 +163,36 @@ class AnyMDPVecEnv:
             self.engine.set_policy(pol, epsilon)
         return q, pol, sweeps
 
+    # ---- device-side LEARNING behaviour policies ---------------------------------
+    def attach_learner(self, kind="q", gamma=0.99, alpha=0.50, c=1.0, max_steps=4000):
+        """One learner per env, updated inside the rollout kernel: kind "q" = the reference's AnyMDPSolverQ(env, gamma, alpha,
+        max_steps) (anymdp_solver_q.py), "mbrl" = AnyMDPSolverMBRL(env, gamma, c) (anymdp_solver_mbrl.py).  MDP tasks only,
+        as in the reference.  `rollout_learn` then replaces the loop of test_utils.py:42-60."""
+        self._require_task()
+        if self.task_type != "MDP":
+            raise AssertionError("The solver only works for MDP")            # anymdp_solver_q.py:17
+        self.engine.learner_create(kind, int(self.geo.get("ns_max") or self.geo["n_pad"]), gamma=gamma, alpha=alpha, c=c, max_steps=max_steps)
+
+    def rollout_learn(self, K, record=("obs", "action", "reward", "done"), greedy=False, out=None):
+        """K ticks of `action = learner.policy(state); step; learner.learner(...)` for every env in one launch; `greedy` is the
+        reference's is_test=True (argmax of the value matrix).  Returns the trajectory like `rollout`."""
+        self._require_task()
+        N, d = self.num_envs, self.device
+        traj = out if out is not None else {}
+        if out is None:
+            if "obs" in record:
+                traj["obs"] = torch.empty((K, N, 1), dtype=torch.int32, device=d)
+            if "action" in record:
+                traj["action"] = torch.empty((K, N, 1), dtype=torch.int32, device=d)
+            if "reward" in record:
+                traj["reward"] = torch.empty((K, N), dtype=torch.float32, device=d)
+            if "reward_gt" in record:
+                traj["reward_gt"] = torch.empty((K, N), dtype=torch.float32, device=d)
+            if "done" in record:
+                traj["done"] = torch.empty((K, N), dtype=torch.uint8, device=d)
+        self.engine.rollout_learn(K, traj=traj, greedy=greedy)
+        return traj
+
     # ---- K steps per launch ---------------------------------------------------------------------
     def rollout(self, K, actions=None, policy="uniform", record=("obs", "action", "reward", "done"), u_inject=None,
                 out=None):
