@@ -5,7 +5,9 @@
 // as synchronous (Jacobi) sweeps over all tasks at once instead of the reference's in-place per-task sweeps; both iterate to
 // the same fixed point, and the sweeps stop when max |dQ| over all tasks <= tol (the reference: RMS of a task <= 1e-4).
 // P is recovered from the CDF rows (p_j = cdf_j - cdf_{j-1}), R is the fp32 payload: nothing beyond the stepping tables is
-// kept.  One warp per (task, s, a) row; a sweep streams the float64 CDF rows once (8 B per table entry): HBM-bound.
+// kept.  Two drivers: k_vi_task (one block per task, all sweeps inside the kernel, rows re-read from L2 / shared memory) for
+// tasks of up to 1 MiB of CDF rows; k_vi_sweep (one warp per (task, s, a) row, one launch per sweep over ALL tasks, a sweep
+// streams the float64 CDF rows once — 8 B per table entry, HBM-bound) for larger rows.
 #include "amdp_dev.cuh"
 
 template <int G>
@@ -116,8 +118,181 @@ __global__ void k_vi_max(Tables T, long long states, const double* __restrict__ 
     if (policy) policy[i] = (uint8_t)arg;
 }
 
+// ------------------------------------------------------------------------------------------------
+// One thread block per TASK, iterated to convergence inside the kernel (tasks whose tables fit the block's share of L2 / its
+// shared memory: rows of up to 256 states).  The sweeps of a task re-read the SAME float64 CDF rows: with one resident block per
+// SM the rows in flight (148 x 640 KB at ns=128 na=5) stay in L2 after the first sweep, and tasks of <= ~150 KB (ns <= 64) keep
+// their rows in SHARED memory — HBM is touched once per task instead of once per sweep, no launch or host round trip per sweep,
+// and every task stops on its OWN max |dQ| <= tol (the reference iterates task by task as well).  G lanes per row as above.
+// ------------------------------------------------------------------------------------------------
+// U rows of a group at once (their loads in flight together); V[4 lane .. 4 lane + 3] is the same for every row of a sweep
+template <int G, int U>
+__device__ __forceinline__ void rows_dot4(const double* P, int n_pad, int lane, const int (&rc)[U], const double2 v01, const double2 v23,
+                                          double (&ev)[U]) {
+    double2 c01[U], c23[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        c01[u] = *reinterpret_cast<const double2*>(P + (size_t)rc[u] * n_pad + 4 * lane);
+        c23[u] = *reinterpret_cast<const double2*>(P + (size_t)rc[u] * n_pad + 4 * lane + 2);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        double prev = __shfl_up_sync(0xffffffffu, c23[u].y, 1, G);
+        if (lane == 0) prev = 0.0;
+        double acc = (c01[u].x - prev) * v01.x;
+        acc += (c01[u].y - c01[u].x) * v01.y;
+        acc += (c23[u].x - c01[u].y) * v23.x;
+        acc += (c23[u].y - c23[u].x) * v23.y;
+        ev[u] = group_sum_f64<G>(acc);
+    }
+}
+
+template <int G, bool LOOP>
+__device__ __forceinline__ double row_dot_plain(const double* cdf, const double* V, int n_pad, int lane) {
+    double acc = 0.0;
+    double carry = 0.0;
+    for (int base = 0; base < n_pad; base += 32) {
+        const int j = base + lane;
+        const double c = (j < n_pad) ? cdf[j] : 1.0;
+        double prev = __shfl_up_sync(0xffffffffu, c, 1);
+        if (lane == 0) prev = carry;
+        carry = __shfl_sync(0xffffffffu, c, 31);
+        if (j < n_pad) acc += (c - prev) * V[j];
+    }
+    return group_sum_f64<G>(acc);
+}
+
+template <int G, bool LOOP, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_vi_task(Tables T, long long n_tasks, int greedy, double gamma, double tol, int max_sweeps,
+                                                      int cache_rows, double* __restrict__ Qg, uint8_t* __restrict__ policy,
+                                                      int* __restrict__ sweeps_max) {
+    extern __shared__ double vsm[];
+    constexpr int U = 4;
+    const int n_pad = T.n_pad, na = T.na, rows = n_pad * na;
+    double* er = vsm; double* q = er + rows; double* V = q + rows; double* cache = V + n_pad;       // cache: rows x n_pad when cache_rows
+    __shared__ unsigned long long sh_max;
+    const int lane = threadIdx.x & (G - 1), grp = threadIdx.x / G, groups = NT / G;
+    const int iters = (rows + groups - 1) / groups;                          // the same trip count for every group: whole warps shuffle
+    for (long long t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+        const double* cdf_t = T.cdf + (size_t)t * rows * n_pad;
+        const float2* pay_t = T.payload + (size_t)t * rows * n_pad;
+        const int32_t* sinfo_t = T.sinfo + t * n_pad;
+        const int n_real = T.n_real[t];
+        // expected immediate reward of every row; rows into shared memory when they fit
+        for (int it = 0; it < iters; ++it) {
+            const int r = grp + it * groups;
+            const int rc = r < rows ? r : rows - 1;
+            const int s = rc / na;
+            const bool live = s < n_real && sinfo_t[s] >= 0;
+            const double v = row_dot<G, LOOP, true>(cdf_t + (size_t)rc * n_pad, pay_t + (size_t)rc * n_pad, nullptr, n_pad, lane);
+            if (lane == 0 && r < rows) { er[r] = live ? v : 0.0; q[r] = 0.0; }
+        }
+        if (cache_rows)
+            for (int i = threadIdx.x; i < rows * n_pad; i += NT) cache[i] = cdf_t[i];
+        for (int s = threadIdx.x; s < n_pad; s += NT) V[s] = 0.0;
+        __syncthreads();
+        const double* P = cache_rows ? cache : cdf_t;
+        double alpha = 1.0;
+        int sweep = 0;
+        while (sweep < max_sweeps) {
+            if (threadIdx.x == 0) sh_max = 0ull;
+            __syncthreads();
+            double dmax = 0.0;
+            auto commit = [&](int r, double ev) {
+                const int s = r / na;
+                if (lane == 0 && r < rows && s < n_real && sinfo_t[s] >= 0) {     // else Q stays 0 (an all-zero transition row)
+                    const double d = alpha * (er[r] + gamma * ev - q[r]);
+                    q[r] += d;
+                    dmax = fmax(dmax, fabs(d));
+                }
+            };
+            if (!LOOP) {
+                const double2 v01 = *reinterpret_cast<const double2*>(V + 4 * lane);
+                const double2 v23 = *reinterpret_cast<const double2*>(V + 4 * lane + 2);
+                for (int it = 0; it < iters; it += U) {
+                    int rr[U], rc[U];
+                    double ev[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) { rr[u] = grp + (it + u) * groups; rc[u] = rr[u] < rows ? rr[u] : rows - 1; }
+                    rows_dot4<G, U>(P, n_pad, lane, rc, v01, v23, ev);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) if (it + u < iters) commit(rr[u], ev[u]);
+                }
+            } else {
+                for (int it = 0; it < iters; ++it) {
+                    const int r = grp + it * groups;
+                    commit(r, row_dot_plain<G, LOOP>(P + (size_t)(r < rows ? r : rows - 1) * n_pad, V, n_pad, lane));
+                }
+            }
+            if (lane == 0 && dmax > 0.0) atomicMax(&sh_max, (unsigned long long)__double_as_longlong(dmax));
+            __syncthreads();
+            for (int s = threadIdx.x; s < n_pad; s += NT) {
+                double best = q[s * na], sum = best;
+                for (int a = 1; a < na; ++a) { const double x = q[s * na + a]; sum += x; best = fmax(best, x); }
+                V[s] = greedy ? best : sum / (double)na;
+            }
+            const double d = __longlong_as_double((long long)sh_max);
+            __syncthreads();
+            ++sweep;
+            alpha = fmax(0.80 * alpha, 0.50);
+            if (d <= tol) break;
+        }
+        for (int r = threadIdx.x; r < rows; r += NT) Qg[(size_t)t * rows + r] = q[r];
+        if (policy)
+            for (int s = threadIdx.x; s < n_pad; s += NT) {
+                int arg = 0;
+                double best = q[s * na];
+                for (int a = 1; a < na; ++a) if (q[s * na + a] > best) { best = q[s * na + a]; arg = a; }
+                policy[t * n_pad + s] = (uint8_t)arg;
+            }
+        if (threadIdx.x == 0) atomicMax(sweeps_max, sweep);
+        __syncthreads();
+    }
+}
+
+static int vi_run_per_task(const Tables& T, long long n_tasks, int greedy, double gamma, double tol, int max_sweeps, double* Q,
+                           unsigned long long* scratch, uint8_t* policy_out, int* sweeps_out, long long* launches, cudaStream_t st) {
+    const int rows = T.n_pad * T.na;
+    const int G = (T.n_pad == 16) ? 4 : (T.n_pad == 32) ? 8 : (T.n_pad == 64) ? 16 : 32;
+    const bool loop = T.n_pad != 4 * G;
+    const size_t base = sizeof(double) * (2 * (size_t)rows + T.n_pad);
+    const size_t with_cache = base + sizeof(double) * (size_t)rows * T.n_pad;
+    const int cache_rows = with_cache <= 200 * 1024 ? 1 : 0;
+    const size_t smem = cache_rows ? with_cache : base;
+    // small tasks (rows in shared memory): 128-thread blocks, several per SM; larger ones: one 512-thread block per SM, whose
+    // rows (<= 1 MiB) stay in L2 between the sweeps
+    const bool small = cache_rows && rows <= 512;
+    int per_sm = small ? (int)((200 * 1024) / smem) : 1;
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (long long)sms * per_sm;
+    const unsigned grid = (unsigned)(n_tasks < want ? n_tasks : want);
+    int* sw = reinterpret_cast<int*>(scratch);
+    cudaMemsetAsync(sw, 0, sizeof(int), st);
+#define VT_LAUNCH1(GG, LL, NT, MB) { cudaFuncSetAttribute(k_vi_task<GG, LL, NT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                                     k_vi_task<GG, LL, NT, MB><<<grid, NT, smem, st>>>(T, n_tasks, greedy, gamma, tol, max_sweeps, cache_rows, Q, policy_out, sw); }
+#define VT_LAUNCH(GG, LL) { if (small) VT_LAUNCH1(GG, LL, 128, 4) else VT_LAUNCH1(GG, LL, 512, 1) }
+    if (G == 4) VT_LAUNCH(4, false) else if (G == 8) VT_LAUNCH(8, false) else if (G == 16) VT_LAUNCH(16, false)
+    else if (!loop) VT_LAUNCH(32, false) else VT_LAUNCH(32, true)
+#undef VT_LAUNCH
+#undef VT_LAUNCH1
+    *launches += 1;
+    int sweeps = 0;
+    if (cudaMemcpyAsync(&sweeps, sw, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    if (sweeps_out) *sweeps_out = sweeps;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 int amdp_vi_run(const Tables& T, long long n_tasks, int greedy, double gamma, double tol, int max_sweeps, double* Q, double* V, double* er,
                 unsigned long long* maxdiff, uint8_t* policy_out, int* sweeps_out, long long* launches, cudaStream_t st) {
+    // tasks whose rows fit the per-SM share of L2 (<= 1 MiB of float64 CDF per task): one block per task, all sweeps in one launch
+    if ((size_t)T.n_pad * T.na * T.n_pad * sizeof(double) <= (1u << 20) && (size_t)T.n_pad * T.na * 16 + T.n_pad * 8 <= 64 * 1024 &&
+        !getenv("AMDP_VI_STREAMING"))
+        return vi_run_per_task(T, n_tasks, greedy, gamma, tol, max_sweeps, Q, maxdiff, policy_out, sweeps_out, launches, st);
     const long long states = n_tasks * T.n_pad, rows = states * T.na;
     cudaMemsetAsync(Q, 0, sizeof(double) * rows, st);
     cudaMemsetAsync(V, 0, sizeof(double) * states, st);
