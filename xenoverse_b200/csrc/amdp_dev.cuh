@@ -252,6 +252,7 @@ __device__ __forceinline__ int h2_count_lt_pos(unsigned w, unsigned v2, int acc)
 #endif
 #define TP_MINB_LO (640 / TP_TPB)
 #define TP_MINB_HI (896 / TP_TPB)
+#define TP_MINB_WIDE (448 / TP_TPB)
 // TP_TPB threads (= envs) per block: small blocks keep the last wave of a launch balanced over the 148 SMs
 // MINB = resident blocks per SM the register budget is sized for: 10 (96 registers, 640 envs per SM) or 14 (72 registers,
 // 896 envs per SM, chosen when that is what it takes to keep every env of the engine resident at once)

@@ -359,13 +359,22 @@ static void launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, boo
     // cfg5 at 65536-131072 envs the small budget wins everywhere (+3 .. +50 %, most where it turns 1.4 waves into one);
     // AMDP_TP_MINB=lo selects the large one for experiments.  The POMDP variant carries the observation search as well.
     bool hi = !pomdp;                                 // (the POMDP variant spills at 72 registers)
-    if (const char* o = getenv("AMDP_TP_MINB")) hi = (o[0] == 'h');
+    // POMDP engines that fit one wave at 7 blocks per SM (<= 448 envs per SM: cfg3's 65536 envs) get the whole register file:
+    // 144 registers, no spills (the 96-register build spills 182 B per thread: the observation search in flight next to the
+    // transition search)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    bool wide = pomdp && n_envs <= (long long)sms * TP_MINB_WIDE * TP_TPB;
+    if (const char* o = getenv("AMDP_TP_MINB")) { hi = (o[0] == 'h'); wide = (o[0] == 'w') && pomdp; }
 #define TP_LAUNCH(MINB, ACT, POMDP) k_rollout_tp<LEVELS, MINB, ACT, POMDP><<<blocks, TP_TPB, 0, st>>>(T, E, tick, K, actions, J, next, cmask)
     if (!actions && T.policy) {                       // table policy: one register budget per task type
         if (pomdp) TP_LAUNCH(TP_MINB_LO, 2, true); else TP_LAUNCH(TP_MINB_HI, 2, false);
         return;
     }
-    if (pomdp) {
+    if (pomdp && wide) {
+        if (actions) TP_LAUNCH(TP_MINB_WIDE, 1, true); else TP_LAUNCH(TP_MINB_WIDE, 0, true);
+    } else if (pomdp) {
         if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, 1, true); else TP_LAUNCH(TP_MINB_LO, 1, true); }
         else { if (hi) TP_LAUNCH(TP_MINB_HI, 0, true); else TP_LAUNCH(TP_MINB_LO, 0, true); }
     } else if (actions) { if (hi) TP_LAUNCH(TP_MINB_HI, 1, false); else TP_LAUNCH(TP_MINB_LO, 1, false); }

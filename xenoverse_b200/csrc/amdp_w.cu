@@ -66,7 +66,10 @@ __device__ __forceinline__ float2 ldg_f32x2_hint(const float2* p, uint64_t pol) 
 // table of amdp_set_policy.  The table costs the chain one select and one IMAD: the lane that owns the next state also owns
 // its table action (a register with the actions of the lane's own entries) and sends it along in the REDUX operand; the
 // action after a reset and the explore / exploit choice are made with the draws.
-template <int EPL, int ACT>
+// MAPREG: the observation (state_mapping of the next state) comes from a per-lane REGISTER holding the mapping of the lane's
+// own entries (8 bits each; observable spaces of up to 256 states), fetched from the owning lane with one SHFL, instead of a
+// global load of the task's state word: one load less in flight per tick.
+template <int EPL, int ACT, bool MAPREG>
 __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
                                                       const int32_t* __restrict__ actions, const amdp_traj J) {
     constexpr bool GIVEN = ACT == 1, TABLE = ACT == 2;
@@ -103,6 +106,12 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
     if (TABLE) {
 #pragma unroll
         for (int i = 0; i < EPL; ++i) mypol |= (unsigned long long)pol_t[lane * EPL + i] << (8 * i);
+    }
+
+    unsigned long long mymap = 0;                                 // state_mapping of this lane's own entries, 8 bits each
+    if (MAPREG) {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) mymap |= (unsigned long long)(sinfo_t[lane * EPL + i] & 0xff) << (8 * i);
     }
 
     int s = E.state[e], steps = E.steps[e];
@@ -307,7 +316,14 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
 #else
             nxf.q = ldg_row<NW>(nbase + roff);
 #endif
-            nxf.si = __ldg(sinfo_t + s_next);
+            if (MAPREG) {
+                // (one or two SHFLs off the chain; EPL <= 4: the low word holds all of a lane's entries)
+                const unsigned owner = s_next / EPL, sh = 8u * (s_next % EPL);
+                if (EPL <= 4) nxf.si = (int)((__shfl_sync(FULL, (unsigned)mymap, owner) >> sh) & 0xffu);
+                else nxf.si = (int)((__shfl_sync(FULL, mymap, owner) >> sh) & 0xffu);
+            } else {
+                nxf.si = __ldg(sinfo_t + s_next);
+            }
         };
         advance();
         if (r & 15u) {
@@ -371,9 +387,17 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
 void amdp_launch_w(const Tables& T, const EnvArrays& E, long long n_envs, unsigned long long tick, int K, const int32_t* actions,
                    const amdp_traj& J, cudaStream_t st) {
     const unsigned int blocks = nblk(n_envs, 4);
-#define WV2(epl) { if (actions) k_rollout_w<epl, 1><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); \
-                   else if (T.policy) k_rollout_w<epl, 2><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); \
-                   else k_rollout_w<epl, 0><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); }
+    // MAPREG (observation from a per-lane register + SHFL instead of the state-word load) is an EXPERIMENT, off by default:
+    // measured on cfg2 it LOSES 2 % (0.3522 vs 0.3444 ms per 512 ticks; table policy 0.3737 vs 0.3704): the load it removes
+    // was an L2 hit consumed a tick later, the SHFL it adds sits in the instruction stream of the chain.  What the chain
+    // waits for is the row, not the number of loads in flight.  AMDP_W_MAPREG=1 selects it.
+    bool mapreg = false;
+    if (const char* o = getenv("AMDP_W_MAPREG")) mapreg = T.tp_obs_bits <= 8 && o[0] == '1';
+#define WV3(epl, m) { if (actions) k_rollout_w<epl, 1, m><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); \
+                      else if (T.policy) k_rollout_w<epl, 2, m><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); \
+                      else k_rollout_w<epl, 0, m><<<blocks, 128, 0, st>>>(T, E, tick, K, actions, J); }
+#define WV2(epl) { if (mapreg) WV3(epl, true) else WV3(epl, false) }
     if (T.n_pad == 64) WV2(2) else if (T.n_pad == 128) WV2(4) else WV2(8)
 #undef WV2
+#undef WV3
 }
