@@ -798,6 +798,9 @@ def run_b200(args, name, envs, tasks, ns, na, no):
                 if "value" in o and "algorithmic_bytes_per_env_step" in o:
                     o["roofline_frac"] = o["algorithmic_bytes_per_env_step"] * o["value"] / o.get("n_gpus", 1) / 1e9 / peak
                     o.setdefault("bound", "hbm")
+                    if o["roofline_frac"] > 1.0 and o["bound"] != "l2":
+                        o["roofline_note"] = ("above 1: the yardstick B_alg (SURVEY.md 8d: a float64 bisection, one 32-byte sector per probe) is more "
+                                              "than this kernel's layout moves per step (16-bit filter rows / one 128-byte line + pivots, partly from L2)")
                     if o["bound"] == "l2":
                         o["roofline_note"] = ("tables are L2 resident: the HBM fraction is NOT a utilisation (it can exceed 1); see achieved_l2_GBps")
                     if "k_rollout_w" in o.get("kernel", ""):

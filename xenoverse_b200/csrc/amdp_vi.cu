@@ -135,15 +135,33 @@ __device__ __forceinline__ void rows_dot4(const double* P, int n_pad, int lane, 
         c01[u] = *reinterpret_cast<const double2*>(P + (size_t)rc[u] * n_pad + 4 * lane);
         c23[u] = *reinterpret_cast<const double2*>(P + (size_t)rc[u] * n_pad + 4 * lane + 2);
     }
+    double acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         double prev = __shfl_up_sync(0xffffffffu, c23[u].y, 1, G);
         if (lane == 0) prev = 0.0;
-        double acc = (c01[u].x - prev) * v01.x;
-        acc += (c01[u].y - c01[u].x) * v01.y;
-        acc += (c23[u].x - c01[u].y) * v23.x;
-        acc += (c23[u].y - c23[u].x) * v23.y;
-        ev[u] = group_sum_f64<G>(acc);
+        acc[u] = (c01[u].x - prev) * v01.x;
+        acc[u] += (c01[u].y - c01[u].x) * v01.y;
+        acc[u] += (c23[u].x - c01[u].y) * v23.x;
+        acc[u] += (c23[u].y - c23[u].x) * v23.y;
+    }
+    if (G >= 4 && U == 4) {
+        // four row sums over the G lanes of a group with 2 + 1 + log2(G / 4) double shuffles instead of 4 x log2(G) (SHFL issues
+        // one warp instruction per clock per SM: it was ~20 % of the sweep): exchange halves so that every lane keeps fewer
+        // rows — after xor G/2 the lower half holds rows 0,1 and the upper half rows 2,3; after xor G/4 every lane holds ONE
+        // row (row = sub-lane / (G/4)); then the remaining butterfly steps.
+        constexpr int H = G / 2, Q = G / 4;
+        const bool upH = (lane & H) != 0, upQ = (lane & Q) != 0;
+        const double a0 = (upH ? acc[2] : acc[0]) + __shfl_xor_sync(0xffffffffu, upH ? acc[0] : acc[2], H);
+        const double a1 = (upH ? acc[3] : acc[1]) + __shfl_xor_sync(0xffffffffu, upH ? acc[1] : acc[3], H);
+        double b = (upQ ? a1 : a0) + __shfl_xor_sync(0xffffffffu, upQ ? a0 : a1, Q);
+#pragma unroll
+        for (int o = Q >> 1; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+#pragma unroll
+        for (int u = 0; u < U; ++u) ev[u] = b;                     // valid for row u on sub-lanes u G/4 .. (u + 1) G/4 - 1
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) ev[u] = group_sum_f64<G>(acc[u]);
     }
 }
 
@@ -198,9 +216,9 @@ __global__ void __launch_bounds__(NT, MINB) k_vi_task(Tables T, long long n_task
             if (threadIdx.x == 0) sh_max = 0ull;
             __syncthreads();
             double dmax = 0.0;
-            auto commit = [&](int r, double ev) {
+            auto commit = [&](int r, double ev, int owner) {         // owner: the lane of the group that holds the row's sum
                 const int s = r / na;
-                if (lane == 0 && r < rows && s < n_real && sinfo_t[s] >= 0) {     // else Q stays 0 (an all-zero transition row)
+                if (lane == owner && r < rows && s < n_real && sinfo_t[s] >= 0) {     // else Q stays 0 (an all-zero transition row)
                     const double d = alpha * (er[r] + gamma * ev - q[r]);
                     q[r] += d;
                     dmax = fmax(dmax, fabs(d));
@@ -216,15 +234,15 @@ __global__ void __launch_bounds__(NT, MINB) k_vi_task(Tables T, long long n_task
                     for (int u = 0; u < U; ++u) { rr[u] = grp + (it + u) * groups; rc[u] = rr[u] < rows ? rr[u] : rows - 1; }
                     rows_dot4<G, U>(P, n_pad, lane, rc, v01, v23, ev);
 #pragma unroll
-                    for (int u = 0; u < U; ++u) if (it + u < iters) commit(rr[u], ev[u]);
+                    for (int u = 0; u < U; ++u) if (it + u < iters) commit(rr[u], ev[u], (G >= 4 && U == 4) ? (G / 4) * u : 0);
                 }
             } else {
                 for (int it = 0; it < iters; ++it) {
                     const int r = grp + it * groups;
-                    commit(r, row_dot_plain<G, LOOP>(P + (size_t)(r < rows ? r : rows - 1) * n_pad, V, n_pad, lane));
+                    commit(r, row_dot_plain<G, LOOP>(P + (size_t)(r < rows ? r : rows - 1) * n_pad, V, n_pad, lane), 0);
                 }
             }
-            if (lane == 0 && dmax > 0.0) atomicMax(&sh_max, (unsigned long long)__double_as_longlong(dmax));
+            if (dmax > 0.0) atomicMax(&sh_max, (unsigned long long)__double_as_longlong(dmax));
             __syncthreads();
             for (int s = threadIdx.x; s < n_pad; s += NT) {
                 double best = q[s * na], sum = best;
@@ -265,6 +283,7 @@ static int vi_run_per_task(const Tables& T, long long n_tasks, int greedy, doubl
     int per_sm = small ? (int)((200 * 1024) / smem) : 1;
     if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
+    if (!small) { if (const char* o = getenv("AMDP_VI_BLOCKS")) per_sm = (o[0] == '2') ? 2 : 1; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -274,7 +293,7 @@ static int vi_run_per_task(const Tables& T, long long n_tasks, int greedy, doubl
     cudaMemsetAsync(sw, 0, sizeof(int), st);
 #define VT_LAUNCH1(GG, LL, NT, MB) { cudaFuncSetAttribute(k_vi_task<GG, LL, NT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
                                      k_vi_task<GG, LL, NT, MB><<<grid, NT, smem, st>>>(T, n_tasks, greedy, gamma, tol, max_sweeps, cache_rows, Q, policy_out, sw); }
-#define VT_LAUNCH(GG, LL) { if (small) VT_LAUNCH1(GG, LL, 128, 4) else VT_LAUNCH1(GG, LL, 512, 1) }
+#define VT_LAUNCH(GG, LL) { if (small) VT_LAUNCH1(GG, LL, 128, 4) else if (per_sm == 2) VT_LAUNCH1(GG, LL, 256, 2) else VT_LAUNCH1(GG, LL, 512, 1) }
     if (G == 4) VT_LAUNCH(4, false) else if (G == 8) VT_LAUNCH(8, false) else if (G == 16) VT_LAUNCH(16, false)
     else if (!loop) VT_LAUNCH(32, false) else VT_LAUNCH(32, true)
 #undef VT_LAUNCH
