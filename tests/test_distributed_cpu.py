@@ -58,3 +58,56 @@ def test_allreduce_stats_gloo_world2(tmp_path):
     assert abs(d["sum_return"] - allr.sum()) < 1e-9 and abs(d["sum_return_sq"] - (allr ** 2).sum()) < 1e-9
     assert d["min_return"] == allr.min() and d["max_return"] == allr.max()
     assert abs(d["mean_return"] - allr.mean()) < 1e-12
+
+
+class _FakeEngine:
+    """Stands in for `Engine` in the host-side wiring of PeerStatsExchange (the CUDA part is tested on the GPU)."""
+
+    def __init__(self, rank):
+        self.rank, self.calls, self.device = rank, [], torch.device("cpu")
+
+    def xchg_create(self, world, rank):
+        self.calls.append(("create", world, rank))
+        return bytes([rank]) * 64, 0x1000 + rank
+
+    def xchg_open_ipc(self, handles):
+        self.calls.append(("open", [h[0] for h in handles], [len(h) for h in handles]))
+
+    def xchg_close(self):
+        self.calls.append(("close",))
+
+    def stats_exchange(self, g, l, lag):
+        self.calls.append(("step", lag))
+
+    def stats_exchange_flush(self, g):
+        self.calls.append(("flush",))
+
+
+def _xchg_worker(rank, world, port, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xenoverse_b200.distributed import PeerStatsExchange
+    eng = _FakeEngine(rank)
+    ex = PeerStatsExchange(eng, lag=2)
+    for _ in range(3):
+        ex.step()
+    ex.flush()
+    ex.close()
+    torch.save({"calls": eng.calls, "world": ex.world, "rank": ex.rank}, os.path.join(outdir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_peer_stats_exchange_wiring_gloo_world2(tmp_path):
+    """One process per rank: every rank creates its buffer, the 64-byte handles are gathered in RANK order and opened by every
+    rank, every rank makes the same calls (the kernels' protocol needs that), close() is followed by a barrier."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_xchg_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        d = torch.load(str(tmp_path / f"r{r}.pt"))
+        assert d["world"] == 2 and d["rank"] == r
+        assert d["calls"][0] == ("create", 2, r)
+        assert d["calls"][1] == ("open", [0, 1], [64, 64])
+        assert d["calls"][2:] == [("step", 2)] * 3 + [("flush",), ("close",)]
