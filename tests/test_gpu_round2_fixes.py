@@ -274,3 +274,38 @@ def test_compact_host_records_equal_device_rollout(search, N):
     env.engine.rollout(K, actions=acts[0].cuda(), traj={"packed": rec, "reward_gt": rgt})
     assert numpy.array_equal(rgt.cpu().numpy(), want[0]["reward_gt"])
     assert numpy.array_equal(unpack_records(rec)["reward"], want[0]["reward"])
+
+
+@pytest.mark.parametrize("N,K,dtype,off", [(131, 100, torch.uint8, 0), (131, 97, torch.uint8, 1), (33, 70, torch.uint8, 3), (50, 33, torch.uint8, 2),
+                                           (64, 200, torch.int32, 0), (37, 65, torch.int32, 1), (129, 31, torch.uint8, 0)])
+def test_warp_kernel_given_actions_prefetched_by_cp_async(N, K, dtype, off):
+    """k_rollout_w with caller actions copies the actions of a 32-tick batch global -> shared with cp.async a batch ahead (uint8
+    actions as the aligned 4-byte word that holds them).  Odd env counts, K off the batch size and action buffers that start at
+    any byte offset (a slice of a larger tensor, so words stick out at both ends) must give the generic kernel's records,
+    including the raw value of a bad action."""
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    tasks = [synth_task(64, 5, 2600 + t) for t in range(4)]
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    flat = torch.randint(0, 5, (off + K * N,), dtype=dtype, generator=g)
+    flat[off + (K - 1) * N + N - 1] = 7                     # a bad action in the very last slot (its word sticks out of the buffer)
+    flat[off + 40 * N % (K * N)] = 200 if dtype == torch.uint8 else 1000   # (fast kernels record 28 bits of a raw action)
+    acts = flat.cuda()[off:].view(K, N)
+    assert acts.data_ptr() % 4 == (off * acts.element_size()) % 4
+    outs = []
+    for generic in (False, True):
+        env = AnyMDPVecEnv(N, seed=61)
+        env.set_task(tasks)
+        assert env.engine.rollout_kernel.startswith("k_rollout_w<")
+        env.engine.force_generic(generic)
+        env.reset()
+        tr = {"obs": torch.zeros((K, N, 1), dtype=torch.int32, device="cuda"), "action": torch.zeros((K, N, 1), dtype=torch.int32, device="cuda"),
+              "reward": torch.zeros((K, N), dtype=torch.float32, device="cuda"), "done": torch.zeros((K, N), dtype=torch.uint8, device="cuda")}
+        env.engine.rollout(K, actions=acts, traj=tr)
+        with pytest.raises(AssertionError):
+            env.check()                                        # AMDP_FAULT_BAD_ACTION (anymdp_env.py:97)
+        outs.append((tr, env.engine.get_state()))
+    for key in ("obs", "action", "reward", "done"):
+        assert torch.equal(outs[0][0][key], outs[1][0][key]), key
+    for key in ("state", "steps", "flags", "ep_return"):
+        assert torch.equal(outs[0][1][key], outs[1][1][key]), key
+    assert int(outs[0][0]["action"][K - 1, N - 1, 0]) == 7

@@ -28,7 +28,7 @@
 // table of amdp_set_policy (policy[task][inner state], epsilon-greedy; one L1-resident byte load at the top of a tick).
 template <int LEVELS, int MINB, int ACT, bool POMDP>
 __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, const EnvArrays E, unsigned long long tick0, int K,
-                                                       const int32_t* __restrict__ actions, const amdp_traj J, int next, unsigned cmask) {
+                                                       const int32_t* __restrict__ actions, const amdp_traj J, int next, unsigned cmask, int lpw) {
     // GIVEN is a template parameter on purpose: with a runtime flag the (predicated-off) action load still owns a
     // scoreboard slot, which ptxas shares with the deferred payload / state-word loads, and the first use of the action at
     // the top of a tick then waits for those loads BEFORE the tick's first search load is issued (ncu: +15 % time).
@@ -39,7 +39,10 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
     __shared__ int sh_s0i[TP_S0][TP_TPB];                            // a reset costs no global-memory round trip
     __shared__ int sh_s0o[TP_S0][TP_TPB];                            // state_mapping of the start states (the observation of a reset)
     const int tx = threadIdx.x;
-    const long long e = (long long)blockIdx.x * TP_TPB + tx;
+    // `lpw` lanes of every warp carry an env (32 unless the engine is small): a warp instruction waits for the SLOWEST of its
+    // lanes' requests, so with fewer chains per warp a tick waits for the maximum of fewer DRAM latencies (launch_tp)
+    if ((tx & 31) >= lpw) return;
+    const long long e = ((long long)blockIdx.x * (TP_TPB / 32) + (tx >> 5)) * lpw + (tx & 31);
     if (e >= E.n_envs) return;
     const int n_pad = T.n_pad, na = T.na;
     const long long N = E.n_envs;
@@ -224,7 +227,11 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
         if (k > 0) { settle(k - 1); if (POMDP) obs_stage1(); }
         // the next tick's draws: in the shadow of the block load, or (small register budget) here, before the search data
         // occupies registers
-        constexpr bool DRAW_EARLY = (MINB == TP_MINB_HI);
+#ifndef AMDP_TP_DRAW_PV
+#define AMDP_TP_DRAW_PV 0   // experiment: three-level rows draw the next tick in the shadow of the second-level (pv) load
+#endif
+        constexpr bool DRAW_PV = AMDP_TP_DRAW_PV && LEVELS == 3 && MINB == TP_MINB_HI;
+        constexpr bool DRAW_EARLY = (MINB == TP_MINB_HI) && !DRAW_PV;
         Draw nx;
         if (DRAW_EARLY) nx = draw(k + 1);
         int done_bits = 0;
@@ -248,6 +255,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
                 // second level: the 16 block pivots of group g
                 const int g = min(count16(), n_groups - 1);
                 ldg_words_keep<2>(T.pv + (row * (unsigned)n_groups + (unsigned)g) * 16u, lv, pol_keep);
+                if (DRAW_PV) nx = draw(k + 1);
                 blk = min(g * 16 + count16(), n_blocks - 1);
             }
             if (LEVELS == 2) blk = min(count16(), n_blocks - 1);
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
             for (bool first = true;; first = false) {
                 uint4 bw[2];
                 ldg_words<2>(frow + blk * 8, bw);
-                if (first && !DRAW_EARLY) nx = draw(k + 1);        // in the shadow of the block load: the next tick's draws
+                if (first && !DRAW_EARLY && !DRAW_PV) nx = draw(k + 1);   // in the shadow of the block load: the next tick's draws
                 lt = 0; le = 0; mn = 0xffffffffu;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
@@ -353,7 +361,14 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
 template <int LEVELS>
 static void launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, bool pomdp, int next, unsigned cmask, unsigned long long tick, int K,
                       const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
-    const unsigned int blocks = nblk(n_envs, TP_TPB);
+    // Lanes per warp that carry an env.  Small engines are bound by the latency of the dependent chain, and a warp waits for
+    // the slowest of its lanes' requests: spreading the envs over up to 1024 warps (16 / 8 lanes each) measured +5 % at 16384
+    // envs and +11 % at 8192 (cfg4 tables; profiles/r2_tp_lanes_per_warp.txt); from 32768 envs on, full warps win.
+    // AMDP_TP_LPW = 32 / 16 / 8 / 4 / 2 / 1 overrides (experiments).
+    int lpw = 32;
+    while (lpw > 8 && (n_envs + lpw / 2 - 1) / (lpw / 2) <= 1024) lpw /= 2;
+    if (const char* o = getenv("AMDP_TP_LPW")) { const int v = atoi(o); if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) lpw = v; }
+    const unsigned int blocks = nblk(n_envs, (TP_TPB / 32) * lpw);
     // Two register budgets: 72 registers (896 envs resident per SM, the next tick's draws generated before the search
     // loads are issued) and 96 (640 per SM, draws generated in the shadow of the block load).  Measured on cfg2 / cfg4 /
     // cfg5 at 65536-131072 envs the small budget wins everywhere (+3 .. +50 %, most where it turns 1.4 waves into one);
@@ -367,7 +382,7 @@ static void launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, boo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     bool wide = pomdp && n_envs <= (long long)sms * TP_MINB_WIDE * TP_TPB;
     if (const char* o = getenv("AMDP_TP_MINB")) { hi = (o[0] == 'h'); wide = (o[0] == 'w') && pomdp; }
-#define TP_LAUNCH(MINB, ACT, POMDP) k_rollout_tp<LEVELS, MINB, ACT, POMDP><<<blocks, TP_TPB, 0, st>>>(T, E, tick, K, actions, J, next, cmask)
+#define TP_LAUNCH(MINB, ACT, POMDP) k_rollout_tp<LEVELS, MINB, ACT, POMDP><<<blocks, TP_TPB, 0, st>>>(T, E, tick, K, actions, J, next, cmask, lpw)
     if (!actions && T.policy) {                       // table policy: one register budget per task type
         if (pomdp) TP_LAUNCH(TP_MINB_LO, 2, true); else TP_LAUNCH(TP_MINB_HI, 2, false);
         return;

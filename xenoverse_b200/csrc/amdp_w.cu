@@ -34,15 +34,47 @@
 //     and written once per 32 ticks.
 // Undecided (code15(cdf[j]) == code15(u), ~n/30720 of the ticks): the float64 row decides, as everywhere else.
 // ------------------------------------------------------------------------------------------------
+// cache qualifiers of the row / payload loads (experiments: tools/gather2.cu measured 16-byte `nc.L1::no_allocate` requests
+// that miss L2 at 23 G/s against 37-41 G/s for L1-allocating ones)
+#ifndef AMDP_W_ROWQ
+#define AMDP_W_ROWQ 0      // 0 L1::no_allocate, 1 L1 allocate, 2 L1::evict_last, 3 L1::evict_first
+#endif
+#ifndef AMDP_W_PAYQ
+#define AMDP_W_PAYQ 0
+#endif
+#if AMDP_W_ROWQ == 0
+#define AMDP_W_ROWQS ".L1::no_allocate"
+#elif AMDP_W_ROWQ == 1
+#define AMDP_W_ROWQS ""
+#elif AMDP_W_ROWQ == 2
+#define AMDP_W_ROWQS ".L1::evict_last"
+#else
+#define AMDP_W_ROWQS ".L1::evict_first"
+#endif
+#if AMDP_W_PAYQ == 0
+#define AMDP_W_PAYQS ".L1::no_allocate"
+#elif AMDP_W_PAYQ == 1
+#define AMDP_W_PAYQS ""
+#elif AMDP_W_PAYQ == 2
+#define AMDP_W_PAYQS ".L1::evict_last"
+#else
+#define AMDP_W_PAYQS ".L1::evict_first"
+#endif
 template <int NW> struct RowW { unsigned w[NW]; };
 
 template <int NW>
 __device__ __forceinline__ RowW<NW> ldg_row(const char* p) {
     RowW<NW> r;
-    if constexpr (NW == 1) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r.w[0]) : "l"(p));
-    else if constexpr (NW == 2) asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[1]) : "l"(p));
-    else asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(p));
+    if constexpr (NW == 1) asm volatile("ld.global.nc" AMDP_W_ROWQS ".u32 %0, [%1];" : "=r"(r.w[0]) : "l"(p));
+    else if constexpr (NW == 2) asm volatile("ld.global.nc" AMDP_W_ROWQS ".v2.u32 {%0, %1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[1]) : "l"(p));
+    else asm volatile("ld.global.nc" AMDP_W_ROWQS ".v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(p));
     return r;
+}
+
+__device__ __forceinline__ float2 ldg_pay(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc" AMDP_W_PAYQS ".v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
 }
 
 // the same with an L2 eviction policy (createpolicy): rows of start states are re-read after every reset and are kept
@@ -82,6 +114,7 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
     __shared__ unsigned long long sh_cnt[2][4];                   // ep_count, sum_len
     __shared__ double sh_s0c[TP_S0][4];                           // start-state CDF / states of the warp's env
     __shared__ int sh_s0i[TP_S0][4];
+    __shared__ unsigned sh_act[4][32];                            // GIVEN: raw actions of the batch after the next one (cp.async)
     const int lane = threadIdx.x & 31, gi = threadIdx.x >> 5;
     const long long e = (long long)blockIdx.x * 4 + gi;
     if (e >= E.n_envs) return;                                    // whole warps leave: one env per warp
@@ -190,6 +223,38 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
     float b_z = 0.f;
     int b_act = 0;
     unsigned n_fallback = 0;
+    // given actions: the raw action of tick kt (lane-parallel: one byte / word per lane, K x N layout)
+    auto fetch_act = [&](int kt) { return (GIVEN && kt < K) ? load_action(actions, (long long)kt * N + e, J.actions_u8) : 0; };
+    // Inside the loop the actions of a batch are 32 different lines (tick-major layout, one byte / word per lane): an ordinary
+    // load of them shares the scoreboard barrier of the row load, and the chain then waits once per batch for the slowest of 32
+    // L2 / DRAM accesses.  They are copied global -> shared with cp.async instead (LDGSTS: no register, no scoreboard) a whole
+    // batch ahead and read back when the batch is drawn.  uint8 actions travel as the aligned 4-byte word that holds them.
+    auto act_prefetch = [&](int kt) {
+        unsigned* dst = &sh_act[gi][lane];
+        if (kt < K) {
+            const long long i = (long long)kt * N + e;
+            const char* src = reinterpret_cast<const char*>(actions) + (J.actions_u8 ? i : 4 * i);
+            const char* base = reinterpret_cast<const char*>(actions);
+            const char* end = base + (J.actions_u8 ? (long long)K * N : 4ll * K * N);
+            const char* w = reinterpret_cast<const char*>(reinterpret_cast<unsigned long long>(src) & ~3ull);
+            if (w >= base && w + 4 <= end) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(w) : "memory");
+            } else {                                              // the word sticks out of the caller's buffer: its bytes one by one
+                const int sh = (int)(reinterpret_cast<unsigned long long>(src) & 3ull) * 8;
+                *dst = (unsigned)*reinterpret_cast<const uint8_t*>(src) << sh;
+            }
+        } else *dst = 0u;
+    };
+    auto act_take = [&](int kt) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        unsigned v = sh_act[gi][lane];
+        if (J.actions_u8) {
+            const unsigned long long a = reinterpret_cast<unsigned long long>(actions) + (unsigned long long)((long long)kt * N + e);
+            v = (v >> ((unsigned)(a & 3ull) * 8u)) & 0xffu;
+        }
+        return (kt < K) ? (int)v : 0;
+    };
+    // GIVEN: `act` holds the raw action of tick kt on entry (fetch_act before the loop, act_take inside)
     auto make = [&](int kt, unsigned& pk, float& z, int& act) {
         const unsigned long long tk = tick0 + (unsigned long long)kt;
         const uint4 w0 = philox_block(env_id, 0u, tk, E.key);
@@ -197,8 +262,10 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
         z = box_muller(w2.x, w2.y);
         pk = code15_from_m21(w0.x >> 11) | ((unsigned)reset_state(u53(w0.z, w0.w)) << 23);
         if (GIVEN) {
-            act = (kt < K) ? load_action(actions, (long long)kt * N + e, J.actions_u8) : 0;
+            // a valid given action rides in the draw word like the engine policy's (bits 15-22), so that the hot path of a
+            // tick is the one of ACT == 0; only a bad action (bit 31) needs the raw value, fetched by a SHFL on its rare path
             if ((unsigned)act >= (unsigned)na) pk |= 0x80000000u;
+            else pk |= (unsigned)act << 15;
         } else {
             act = 0;
             pk |= __umulhi(w2.z, (uint32_t)na) << 15;
@@ -207,8 +274,9 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
     };
     unsigned pk;
     float z;
-    int a_raw;
+    int a_raw = fetch_act(0);
     make(0, pk, z, a_raw);
+    b_act = fetch_act(lane + 1);
     make(lane + 1, b_pk, b_z, b_act);
     if (GIVEN && (pk >> 31)) fault |= AMDP_FAULT_BAD_ACTION;                                  // :97
     int a = GIVEN ? ((pk >> 31) ? 0 : a_raw) : (int)((pk >> 15) & 0xffu);
@@ -258,14 +326,19 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
     asm volatile("" : "+r"(lane_base32), "+r"(myterm16));
     const float2* pay_row = pay_t + (unsigned long long)sa * N_PAD;   // payload row of (s, a)
 
+    // The once-per-batch / rare paths (draw the next batch, flush records, prefetch actions, float64 fallback) take the tick
+    // index through an opaque copy made INSIDE their branch: otherwise the optimiser strength-reduces their addresses and
+    // Philox counters into ~10-20 loop-carried induction variables that are updated every tick, and every warp instruction
+    // of a tick costs ~6 cycles here (7 warps per scheduler; ncu: 105 vs 141 instructions per tick = 0.342 vs 0.394 ms).
+    auto opaque = [](int v) { asm volatile("" : "+r"(v)); return v; };
     auto tick = [&](const int k, const Flight& cur, Flight& nxf) {
         const int j = k & 31;
         // (A) inputs of the NEXT tick: independent of the row in flight
         const unsigned npk = __shfl_sync(FULL, b_pk, j);
         const float nz = __shfl_sync(FULL, b_z, j);
         int na_raw = 0;
-        if (GIVEN || TABLE) na_raw = __shfl_sync(FULL, b_act, j);
-        int n_a = GIVEN ? ((npk >> 31) ? 0 : na_raw) : (int)((npk >> 15) & 0xffu);
+        if (TABLE) na_raw = __shfl_sync(FULL, b_act, j);
+        int n_a = (int)((npk >> 15) & 0xffu);                     // GIVEN: 0 for a bad action
         // table policy: the next action if this tick ends the episode (the table action of the reset state, or the random one)
         const int n_a_reset = (na_raw & 0x100) ? n_a : (a_raw & 0xff);
         const char* nbase = TABLE ? sk_lane : sk_lane + (unsigned)n_a * ROW_BYTES;
@@ -296,6 +369,9 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
             nxt = r >> ISH;
             const bool done = ((r | trunc16) & 16u) != 0;         // anymdp_env.py:108,114
             s_next = done ? sreset : nxt;                         // same-step auto-reset (anymdp_env.py:81-90)
+            // a tick with a bad action does not step.  One SEL on the chain; re-issuing the loads on a rare path instead gets
+            // if-converted by ptxas into predicated loads that overwrite the registers of the row in flight, and a predicated-off
+            // load still waits for the scoreboard of its destination: every tick then waited for the row before settle() (+35 %)
             if (GIVEN && !valid) s_next = (unsigned)s;
             if (TABLE) {
                 const int a_table = (na_raw & 0x100) ? (int)((npk >> 15) & 0xffu) : (int)((r >> 5) & 0xffu);
@@ -309,7 +385,7 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
 #if AMDP_W_HINT & 1
             nxf.pay = ldg_f32x2_hint(pay_row + nxt, pol_first);
 #else
-            nxf.pay = ldg_stream_f32x2(pay_row + nxt);
+            nxf.pay = ldg_pay(pay_row + nxt);
 #endif
 #if AMDP_W_HINT & 2
             nxf.q = ldg_row_hint<NW>(nbase + roff, done ? pol_keep : pol_norm);
@@ -326,9 +402,10 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
             }
         };
         advance();
+        if (GIVEN && j == 0) act_prefetch(opaque(k) + 33 + lane);         // once per 32 ticks: the actions of the batch after the next one
         if (r & 15u) {
             // undecided: exact float64 entries (numpy choice: searchsorted(cdf, u, 'right'))   anymdp_env.py:100
-            const uint4 w0 = philox_block(env_id, 0u, tick0 + (unsigned long long)k, E.key);
+            const uint4 w0 = philox_block(env_id, 0u, tick0 + (unsigned long long)opaque(k), E.key);
             const double u = u53(w0.x, w0.y);
             const double* cr = cdf_lane + (unsigned long long)sa * N_PAD;
             int cnt = 0;
@@ -348,7 +425,7 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
 
         // (C) settle the previous tick; once per 32 ticks write the finished batch of records, lane-parallel
         settle(k - 1, cur.pay, cur.si);
-        if (j == 0 && k > 0) flush(k - 32, 32);
+        if (j == 0 && k > 0) flush(opaque(k) - 32, 32);
         // (D) this tick becomes the previous one
         z_p = z; valid_p = valid;
         ad_p = GIVEN ? (a_raw & 0x0fffffff) : a;
@@ -358,8 +435,10 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
             if ((r | trunc16) & 16u) { close_p = true; steps_p = steps; steps = 0; }
             s = (int)s_next;
         }
+        // GIVEN: the raw value of a bad action, for its record (warp-uniform, rare; after the chain, before b_act is redrawn)
+        if (GIVEN) { na_raw = n_a; if (npk >> 31) na_raw = __shfl_sync(FULL, b_act, j); }
         // once per 32 ticks: draw the next batch
-        if (j == 31) make(k + 2 + lane, b_pk, b_z, b_act);
+        if (j == 31) { const int kn = opaque(k) + 2 + lane; if (GIVEN) b_act = act_take(kn); make(kn, b_pk, b_z, b_act); }
         // rotate to the next tick
         if (GIVEN && (npk >> 31) && k + 1 < K) fault |= AMDP_FAULT_BAD_ACTION;               // :97
         pk = npk; z = nz; a = n_a; a_raw = na_raw; v2 = nv2;
