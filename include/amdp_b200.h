@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define AMDP_ABI_VERSION 2
+#define AMDP_ABI_VERSION 3
 
 /* status codes */
 #define AMDP_OK       0
@@ -218,6 +218,13 @@ typedef struct amdp_traj {
     uint16_t* obs_done;     /* or NULL.  COMPACT records: with `reward` (and `packed` NULL) 6 bytes per (tick, env): bits 0-13 the
                                observation, 14 terminated, 15 truncated.  Needs do == 1 and at most 2^14 observations.  The action is
                                not echoed: this format is for rollouts whose actions the caller supplied (or does not need). */
+    double*  transition_gt; /* or NULL.  info["transition_gt"] of every step (anymdp_env.py:130: transition_obs[state, action], the
+                               row of the state the step LED TO — before any auto-reset — indexed by mapped state) as a label plane:
+                               width da * ns_out doubles per (tick, env), zeros for a tick that did not step.  Needs an engine
+                               created with keep_transition.  Rollouts with this plane run on the generic kernel: a label row is
+                               ns_out * 8 bytes per step (1 KiB at ns = 128) and bounds the launch whatever steps the envs. */
+    int32_t  ns_out;        /* width of a label row: the task's ns (observable state space) */
+    int32_t  reserved2;
 } amdp_traj;
 
 int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const amdp_traj* traj,

@@ -311,6 +311,8 @@ class OracleVecEnv:
             "terminated": numpy.zeros(N, dtype=bool), "truncated": numpy.zeros(N, dtype=bool),
             "state": numpy.zeros(N, dtype=numpy.int64), "steps": numpy.zeros(N, dtype=numpy.int64),
             "action": numpy.zeros((N, self.da), dtype=numpy.int64),
+            # info["transition_gt"] of the step (anymdp_env.py:130), before any auto-reset; zeros for a tick that did not step
+            "transition_gt": numpy.zeros((N, self.da, self.tasks[0].ns)),
         }
         for i, e in enumerate(self.envs):
             if actions is None and self.policy is not None and not U[i, SLOT_EXPLORE] < self.epsilon:
@@ -337,6 +339,7 @@ class OracleVecEnv:
             out["obs"][i] = o
             out["reward"][i] = r
             out["reward_gt"][i] = info["reward_gt"]
+            out["transition_gt"][i] = numpy.asarray(e.transition_gt(a)).reshape(self.da, -1)
             out["terminated"][i] = term
             out["truncated"][i] = trunc
             self.ep_return[i] += r

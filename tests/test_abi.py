@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 def test_config_struct_layout_matches_header():
     from xenoverse_b200 import _lib
     assert ctypes.sizeof(_lib.Config) == 10 * 4 + 4 * 8
-    assert ctypes.sizeof(_lib.Traj) == 5 * 8 + 2 * 8 + 8 + 2 * 4 + 8
+    assert ctypes.sizeof(_lib.Traj) == 5 * 8 + 2 * 8 + 8 + 2 * 4 + 8 + 8 + 2 * 4      # ABI 3: + transition_gt, ns_out, reserved2
 
 
 def test_no_cpu_fallback():

@@ -309,3 +309,37 @@ def test_warp_kernel_given_actions_prefetched_by_cp_async(N, K, dtype, off):
     for key in ("state", "steps", "flags", "ep_return"):
         assert torch.equal(outs[0][1][key], outs[1][1][key]), key
     assert int(outs[0][0]["action"][K - 1, N - 1, 0]) == 7
+
+
+@pytest.mark.parametrize("fixture,N,K,mode", [("tasks_mdp64", 40, 60, "same_step"), ("tasks_minss64", 24, 50, "next_step"),
+                                              ("tasks_mtpomdp32", 20, 40, "same_step")])
+def test_rollout_records_carry_transition_gt_labels(fixture, N, K, mode):
+    """Rollout records with the `transition_gt` label plane (info["transition_gt"], anymdp_env.py:130: the observation-indexed
+    transition row of the state the step led to, one row per action token) equal the oracle's, which is pinned to the live
+    reference's info dict (tests/test_oracle_vs_reference.py); ticks that only reset carry zeros.  Tasks of the live samplers,
+    incl. `min_state_space` (mapped states beyond n_pad) and multi-token actions."""
+    from xenoverse_b200 import AnyMDPVecEnv
+    tasks = _tasks(fixture)
+    env = AnyMDPVecEnv(N, seed=9, autoreset=mode, keep_transition=True)
+    env.set_task(tasks)
+    obs0, _ = env.reset()
+    tr = env.rollout(K, record=("obs", "action", "reward_gt", "done", "transition_gt"))
+    env.check()
+    lab = tr["transition_gt"].cpu().numpy()
+    assert lab.shape == (K, N, env.da, tasks[0]["ns"])
+    draws = env.engine.dump_draws(0, K + 1).cpu().numpy()
+    orc = ao.OracleVecEnv(tasks, env_task=numpy.arange(N) % len(tasks), autoreset=mode)
+    orc.reset(draws[0])
+    stepped = 0
+    for k in range(K):
+        o = orc.step(None, draws[k + 1])
+        assert numpy.array_equal(tr["obs"][k].cpu().numpy().reshape(N, -1), o["obs"]), k
+        assert numpy.array_equal(lab[k], o["transition_gt"]), k            # raw float64 rows: bit-exact
+        stepped += int((o["transition_gt"].sum(axis=(1, 2)) > 0).sum())
+    assert stepped > K * N // 2
+    # the plane needs the raw tables
+    env2 = AnyMDPVecEnv(N, seed=9)
+    env2.set_task(tasks)
+    env2.reset()
+    with pytest.raises(Exception, match="keep_transition"):
+        env2.rollout(4, record=("obs", "transition_gt"))

@@ -19,7 +19,7 @@ FAULT_NEED_RESET, FAULT_TERMINAL_STATE, FAULT_BAD_ACTION, FAULT_PEER_TIMEOUT = 1
 TASK_OK, TASK_BAD_ROW_SUM, TASK_NOT_NORMALISED, TASK_NEGATIVE_P, TASK_S0_IN_SE, TASK_OBS_RANGE, TASK_NOT_SPARSE = 0, 1, 2, 3, 4, 5, 6
 SLOTS_PER_TOKEN = 8
 SLOT_TRANS, SLOT_RESET, SLOT_OBS, SLOT_RESET_OBS, SLOT_Z, SLOT_ACTION = 0, 1, 2, 3, 4, 5
-ABI_VERSION = 2
+ABI_VERSION = 3
 NO_ACTION = -2 ** 31      # AMDP_NO_ACTION: tokens after the first of a multi-token step that ends early
 
 
@@ -35,7 +35,8 @@ class Traj(ctypes.Structure):
     _fields_ = [("obs", ctypes.c_void_p), ("actions_out", ctypes.c_void_p), ("reward", ctypes.c_void_p),
                 ("reward_gt", ctypes.c_void_p), ("done", ctypes.c_void_p),
                 ("step_stride", ctypes.c_int64), ("env_stride", ctypes.c_int64), ("packed", ctypes.c_void_p),
-                ("actions_u8", ctypes.c_int32), ("reserved", ctypes.c_int32), ("obs_done", ctypes.c_void_p)]
+                ("actions_u8", ctypes.c_int32), ("reserved", ctypes.c_int32), ("obs_done", ctypes.c_void_p),
+                ("transition_gt", ctypes.c_void_p), ("ns_out", ctypes.c_int32), ("reserved2", ctypes.c_int32)]
 
 
 _P = ctypes.c_void_p

@@ -62,6 +62,7 @@ struct TickOut {
     int ok;               // the tick stepped (no fault, not a pending-reset tick)
     int term, trunc;
     int steps;            // info["steps"] of this tick (before any same-step reset)
+    int state_after;      // inner state the step led to, before any auto-reset (the row of info["transition_gt"])
     int finished;         // an episode was closed in this tick
     double fin_return;    // its return
     int fin_steps;        // its length
@@ -155,6 +156,7 @@ __device__ __forceinline__ void env_tick(const Tables& T, const EnvArrays& E, lo
         R.ep_return += rew;
     }
     O.steps = R.steps;
+    O.state_after = s;
     // observation of the step (drawn after the transition, from the new state; :132,145-159)
     observe<G>(T, t, s, D, AMDP_SLOT_OBS, lane, ok, obs);
     for (int k = 0; k < T.d_o; ++k) final_obs[k] = obs[k];
@@ -292,6 +294,26 @@ __global__ void __launch_bounds__(256) k_rollout(Tables T, EnvArrays E, unsigned
             if (J.reward_gt) J.reward_gt[o] = O.reward_gt;
             if (J.done) J.done[o] = (uint8_t)(O.term | (O.trunc << 1));
             if (J.obs_done) J.obs_done[o] = (uint16_t)(((unsigned)obs[0] & 0x3fffu) | ((unsigned)(O.term | (O.trunc << 1)) << 14));
+        }
+        if (J.transition_gt) {
+            // info["transition_gt"] = transition_obs[state, action] (anymdp_env.py:130): the raw row of the state the step led
+            // to, scattered by state_mapping (anymdp_env.py:12-20), one row per action token; the G lanes of the env share it
+            const int ns_out = J.ns_out;
+            double* lab = J.transition_gt + ((long long)k * J.step_stride + ec * J.env_stride) * (long long)(T.d_a * ns_out);
+            if (active) for (int j = lane; j < T.d_a * ns_out; j += G) lab[j] = 0.0;
+            __syncwarp();
+            if (active && O.ok) {
+                const int n = T.n_real[t];
+                for (int q = 0; q < T.d_a; ++q) {
+                    const int a = act[q];
+                    if (a < 0 || a >= T.na) continue;
+                    const double* row = T.raw_t + ((t * T.n_pad + O.state_after) * T.na + a) * (long long)T.n_pad;
+                    for (int j = lane; j < n; j += G) {
+                        const int m = T.sinfo[t * T.n_pad + j] & 0x7fffffff;
+                        if (m < ns_out) lab[q * ns_out + m] = row[j];
+                    }
+                }
+            }
         }
     }
     if (active && lane == 0) { store_regs(E, e, R); store_stats(E, e, R); }
@@ -1176,12 +1198,17 @@ extern "C" int amdp_rollout(amdp_t* h, int32_t K, const int32_t* actions, const 
         if (h->cfg.n_obs_tok != 1 || (h->cfg.task_type == AMDP_MDP ? (ob == 0 || ob > 14) : h->cfg.no_pad > (1 << 14)))
             return fail(h, AMDP_EINVAL, "compact records (obs_done) need do == 1 and at most 2^14 observations (state the observation bits in amdp_config.reserved0)");
     }
+    if (J.transition_gt) {
+        if (!h->raw_t) return fail(h, AMDP_ESTATE, "transition_gt labels need an engine created with keep_transition");
+        if (J.ns_out < 1) return fail(h, AMDP_EINVAL, "transition_gt labels need ns_out (the task's ns)");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const bool policy_ok = !h->T.policy || actions || h->tp || h->wv2;   // (k_rollout_mdp has no table policy: the generic kernel runs)
-    const bool fast = (h->cfg.task_type == AMDP_MDP || (h->tp && h->cfg.task_type == AMDP_POMDP)) && !u_inject && !h->force_generic && policy_ok;
+    const bool fast = (h->cfg.task_type == AMDP_MDP || (h->tp && h->cfg.task_type == AMDP_POMDP)) && !u_inject && !h->force_generic && policy_ok &&
+                      !J.transition_gt;
     // multi-token POMDP: the thread-per-env kernel k_rollout_mt (no table policy, separate record arrays)
     const bool fast_mt = h->tp && h->cfg.task_type == AMDP_MTPOMDP && !u_inject && !h->force_generic && !(h->T.policy && !actions) &&
-                         !J.packed && !J.obs_done;
+                         !J.packed && !J.obs_done && !J.transition_gt;
     if (fast) {
         launch_rollout_fast(h, K, actions, J, st);
     } else if (fast_mt) {

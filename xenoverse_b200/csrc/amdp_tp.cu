@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
         // the next tick's draws: in the shadow of the block load, or (small register budget) here, before the search data
         // occupies registers
 #ifndef AMDP_TP_DRAW_PV
-#define AMDP_TP_DRAW_PV 0   // experiment: three-level rows draw the next tick in the shadow of the second-level (pv) load
+#define AMDP_TP_DRAW_PV 1   // three-level rows draw the next tick in the shadow of the second-level (pv) load, a DRAM access (cfg4 x 65536 envs: 0.644 -> 0.701 of the yardstick); 0: before the search, in the shadow of the L2-resident top level
 #endif
         constexpr bool DRAW_PV = AMDP_TP_DRAW_PV && LEVELS == 3 && MINB == TP_MINB_HI;
         constexpr bool DRAW_EARLY = (MINB == TP_MINB_HI) && !DRAW_PV;

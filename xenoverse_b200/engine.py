@@ -405,6 +405,11 @@ class Engine:
         J.reward, J.reward_gt, J.done = _ptr(traj.get("reward")), _ptr(traj.get("reward_gt")), _ptr(traj.get("done"))
         J.packed = _ptr(traj.get("packed"))
         J.obs_done = _ptr(traj.get("obs_done"))          # compact records: uint16 [K, N] (with "reward")
+        lab = traj.get("transition_gt")                  # label plane: float64 [K, N, da, ns] (anymdp_env.py:130)
+        if lab is not None:
+            if lab.dtype != torch.float64 or lab.dim() != 4 or env_major:
+                raise ValueError("transition_gt labels: float64 [K, N, da, ns], tick-major")
+            J.transition_gt, J.ns_out = _ptr(lab), int(lab.shape[-1])
         J.actions_u8 = 1 if (actions is not None and actions.dtype == torch.uint8) else 0
         if env_major:
             J.step_stride, J.env_stride = 1, int(K)

@@ -198,7 +198,9 @@ class AnyMDPVecEnv:
                 out=None):
         """The data-collection loop around env.step() (test_utils.py:42-60) as one kernel launch.
         actions int tensor [K, N(, da)] or None with policy="uniform".  Returns a dict of [K, N(, w)]
-        tensors for the requested fields (`done`: bit0 terminated, bit1 truncated)."""
+        tensors for the requested fields (`done`: bit0 terminated, bit1 truncated).  "transition_gt" in `record` adds the
+        label plane info["transition_gt"] (anymdp_env.py:130) as float64 [K, N, da, ns] (needs keep_transition=True; such a
+        rollout runs on the generic kernel: a label row is ns * 8 bytes per step)."""
         self._require_task()
         if actions is None and policy not in ("uniform", "device"):
             raise ValueError("without actions the policy is 'uniform' or the table given to set_policy ('device')")
@@ -221,6 +223,11 @@ class AnyMDPVecEnv:
                 traj["done"] = torch.empty((K, N), dtype=torch.uint8, device=d)
             if "packed" in record:
                 traj = {"packed": torch.empty((K, N), dtype=torch.int64, device=d)}
+                if "reward_gt" in record:
+                    traj["reward_gt"] = torch.empty((K, N), dtype=torch.float32, device=d)
+            if "transition_gt" in record:
+                ns = int(self.geo.get("ns_max") or self.geo["n_pad"])
+                traj["transition_gt"] = torch.empty((K, N, self.da, ns), dtype=torch.float64, device=d)
         self.engine.rollout(K, actions=a, traj=traj, u_inject=u_inject)
         return traj
 
