@@ -61,6 +61,8 @@
 #define AMDP_W_PAYQS ".L1::evict_first"
 #endif
 template <int NW> struct RowW { unsigned w[NW]; };
+struct Chk { static constexpr bool value = true; };             // tags of the two copies of a tick (k_rollout_w, given actions)
+struct NoChk { static constexpr bool value = false; };
 
 template <int NW>
 __device__ __forceinline__ RowW<NW> ldg_row(const char* p) {
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
     make(0, pk, z, a_raw);
     b_act = fetch_act(lane + 1);
     make(lane + 1, b_pk, b_z, b_act);
+    bool b_anybad = GIVEN && __any_sync(FULL, (int)(b_pk >> 31)); // GIVEN: the batch in b_pk holds an out-of-range action
     if (GIVEN && (pk >> 31)) fault |= AMDP_FAULT_BAD_ACTION;                                  // :97
     int a = GIVEN ? ((pk >> 31) ? 0 : a_raw) : (int)((pk >> 15) & 0xffu);
     if (TABLE && !(a_raw & 0x100)) a = (int)pol_t[s];
@@ -331,7 +334,11 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
     // Philox counters into ~10-20 loop-carried induction variables that are updated every tick, and every warp instruction
     // of a tick costs ~6 cycles here (7 warps per scheduler; ncu: 105 vs 141 instructions per tick = 0.342 vs 0.394 ms).
     auto opaque = [](int v) { asm volatile("" : "+r"(v)); return v; };
-    auto tick = [&](const int k, const Flight& cur, Flight& nxf) {
+    // CHK (given actions only): the tick checks its action (anymdp_env.py:97).  The main loop runs a 32-tick period through the
+    // unchecked copy of the tick when none of the period's actions is out of range — known from the batch's draw words, one
+    // VOTE per batch — so that the validity logic (~15 instructions per tick) exists only where a bad action does.
+    auto tick = [&](auto chk_tag, const int k, const Flight& cur, Flight& nxf) {
+        constexpr bool CHK = GIVEN && decltype(chk_tag)::value;
         const int j = k & 31;
         // (A) inputs of the NEXT tick: independent of the row in flight
         const unsigned npk = __shfl_sync(FULL, b_pk, j);
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
         const char* nbase = TABLE ? sk_lane : sk_lane + (unsigned)n_a * ROW_BYTES;
         asm volatile("" : "+l"(nbase));                           // one IMAD.WIDE from the next row address
         const unsigned nv2 = (npk & 0x7fffu) * 0x00010001u;
-        const bool valid = !GIVEN || !(pk >> 31);                 // a tick with a bad action does not step
+        const bool valid = !CHK || !(pk >> 31);                   // a tick with a bad action does not step
         const unsigned sreset = (pk >> 23) & 0xffu;
         const bool trunc = steps + 1 >= max_ceil;                 // anymdp_env.py:113-114
         const unsigned trunc16 = trunc ? 16u : 0u;
@@ -372,7 +379,7 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
             // a tick with a bad action does not step.  One SEL on the chain; re-issuing the loads on a rare path instead gets
             // if-converted by ptxas into predicated loads that overwrite the registers of the row in flight, and a predicated-off
             // load still waits for the scoreboard of its destination: every tick then waited for the row before settle() (+35 %)
-            if (GIVEN && !valid) s_next = (unsigned)s;
+            if (CHK && !valid) s_next = (unsigned)s;
             if (TABLE) {
                 const int a_table = (na_raw & 0x100) ? (int)((npk >> 15) & 0xffu) : (int)((r >> 5) & 0xffu);
                 n_a = done ? n_a_reset : a_table;
@@ -428,7 +435,7 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
         if (j == 0 && k > 0) flush(opaque(k) - 32, 32);
         // (D) this tick becomes the previous one
         z_p = z; valid_p = valid;
-        ad_p = GIVEN ? (a_raw & 0x0fffffff) : a;
+        ad_p = CHK ? (a_raw & 0x0fffffff) : a;
         if (valid) {
             ad_p |= (int)((((r >> 4) & 1u) | (trunc ? 2u : 0u)) << 28);
             steps += 1;
@@ -436,18 +443,29 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
             s = (int)s_next;
         }
         // GIVEN: the raw value of a bad action, for its record (warp-uniform, rare; after the chain, before b_act is redrawn)
-        if (GIVEN) { na_raw = n_a; if (npk >> 31) na_raw = __shfl_sync(FULL, b_act, j); }
+        if (GIVEN) { na_raw = n_a; if (CHK && (npk >> 31)) na_raw = __shfl_sync(FULL, b_act, j); }
         // once per 32 ticks: draw the next batch
-        if (j == 31) { const int kn = opaque(k) + 2 + lane; if (GIVEN) b_act = act_take(kn); make(kn, b_pk, b_z, b_act); }
+        if (j == 31) {
+            const int kn = opaque(k) + 2 + lane;
+            if (GIVEN) b_act = act_take(kn);
+            make(kn, b_pk, b_z, b_act);
+            if (GIVEN) b_anybad = __any_sync(FULL, (int)(b_pk >> 31));
+        }
         // rotate to the next tick
-        if (GIVEN && (npk >> 31) && k + 1 < K) fault |= AMDP_FAULT_BAD_ACTION;               // :97
+        if (CHK && (npk >> 31) && k + 1 < K) fault |= AMDP_FAULT_BAD_ACTION;                 // :97
         pk = npk; z = nz; a = n_a; a_raw = na_raw; v2 = nv2;
         sa = (unsigned)(s * na + n_a);
         pay_row = pay_t + (unsigned long long)sa * N_PAD;
     };
     int k = 0;
-    for (; k + 1 < K; k += 2) { tick(k, fa, fb); tick(k + 1, fb, fa); }
-    if (k < K) { tick(k, fa, fb); settle(K - 1, fb.pay, fb.si); }
+    while (k + 1 < K) {
+        const int kend = min(K, (k | 31) + 1);                    // one 32-tick period (= the batch in b_pk); periods are even
+        // all actions of the period in range: the tick at its start (drawn with the previous batch) and the batch's 32
+        const bool clean = !GIVEN || !(b_anybad || (pk >> 31));
+        if (clean) for (; k + 1 < kend; k += 2) { tick(NoChk{}, k, fa, fb); tick(NoChk{}, k + 1, fb, fa); }
+        else for (; k + 1 < kend; k += 2) { tick(Chk{}, k, fa, fb); tick(Chk{}, k + 1, fb, fa); }
+    }
+    if (k < K) { tick(Chk{}, k, fa, fb); settle(K - 1, fb.pay, fb.si); }
     else settle(K - 1, fa.pay, fa.si);
     {
         const int kb = ((K - 1) / 32) * 32;
