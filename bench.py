@@ -631,7 +631,7 @@ def other_workloads(world, rank, dev, local, args):
         for key, (wl, n_envs, n_tasks, tk) in {"cfg2_x65536_envs": ("cfg2", 65536, 4096, 128), "cfg3": ("cfg3", 65536, 4096, 64),
                                                "cfg4_32_tasks": ("cfg4", 65536, 32, 64), "cfg4_32_tasks_x131072_envs": ("cfg4", 131072, 32, 64),
                                                "cfg4_32_tasks_x8192_envs": ("cfg4", 8192, 32, 64),
-                                               "cfg5": ("cfg5", 131072, 131072, 128),
+                                               "cfg5": ("cfg5", 131072, 131072, 128), "cfg5_4096_shared_tasks": ("cfg5", 131072, 4096, 128),
                                                "cfg2_table_policy": ("cfg2", 4096, 4096, 512), "cfg5_table_policy": ("cfg5", 131072, 131072, 128)}.items():
             _, _, o_ns, o_na, o_no = WORKLOADS[wl]
             run(key, quick_measure, wl, n_envs, n_tasks, o_ns, o_na, o_no, tk, 10, dev, local,

@@ -84,13 +84,16 @@ CASES = {
     "cfg2": (128,  5,  None, 4096,   4096,  96,  "k_rollout_w<EPL=4>",               256),
     "cfg3": (64,   8,  64,   65536,  4096,  48,  "k_rollout_tp<levels=2,POMDP>",     256),
     "cfg4": (1024, 16, None, 8192,   4,     40,  "k_rollout_tp<levels=3,MDP>",       96),
+    "cfg4_wide_rows": (1024, 16, None, 8192, 4, 40, "k_rollout_tp<levels=3,MDP,wide>", 96),   # AMDP_TP_WIDE=1 (experiment)
     "cfg5": (32,   5,  None, 131072, 131072, 64, "k_rollout_tp<levels=2,MDP>",       384),
 }
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_bench_workload_kernel_replays_through_oracle(name):
+def test_bench_workload_kernel_replays_through_oracle(name, monkeypatch):
     ns, na, no, envs, tasks, K, kernel, n_sel = CASES[name]
+    if name == "cfg4_wide_rows":
+        monkeypatch.setenv("AMDP_TP_WIDE", "1")
     env, chunk = _build(ns, na, no, envs, tasks, seed=17)
     assert env.engine.rollout_kernel == kernel, env.engine.rollout_kernel
     obs0, _ = env.reset()
@@ -99,13 +102,13 @@ def test_bench_workload_kernel_replays_through_oracle(name):
     env.check()
     st_dev = env.episode_stats()
     rng = numpy.random.default_rng(5)
-    if name == "cfg4":
+    if name.startswith("cfg4"):
         # two of the four 400 MB tasks (host memory): envs of tasks 1 and 2
         pool = numpy.nonzero(numpy.isin(numpy.arange(envs) % tasks, (1, 2)))[0]
         sel = numpy.sort(rng.choice(pool, n_sel, replace=False))
     else:
         sel = numpy.sort(rng.choice(envs, n_sel, replace=False))
-    if name != "cfg4":
+    if not name.startswith("cfg4"):
         sel[0] = 0                                                 # always include the first env of the engine
     env_task = sel % tasks
     task_dicts = _oracle_tasks(ns, na, no, tasks, chunk, sorted(set(int(t) for t in env_task)))

@@ -440,16 +440,22 @@ def test_two_level_search_equals_generic_kernel(ns, na, N, mode, given, search):
     assert ca["exact_fallbacks"] > 0            # n/65536 of the ticks are undecided on the filter
 
 
-@pytest.mark.parametrize("ns,na,N,mode,given,coarse", [
+@pytest.mark.parametrize("ns,na,N,mode,given,coarse,wide", [c if len(c) == 7 else c + (None,) for c in [
     (8, 3, 70, "same_step", False, 0), (16, 5, 300, "next_step", True, 0), (30, 5, 200, "same_step", True, 0),
     (64, 8, 130, "same_step", False, 0), (128, 5, 257, "same_step", False, 0), (128, 5, 100, "next_step", True, 18),
     (200, 3, 60, "same_step", True, 0), (256, 3, 40, "next_step", False, 16), (520, 2, 33, "same_step", False, 0),
-    (1000, 2, 12, "same_step", True, 14), (1024, 2, 40, "next_step", False, 0), (32, 5, 500, "same_step", False, 20)])
-def test_thread_per_env_kernel_equals_generic_kernel(ns, na, N, mode, given, coarse):
+    (1000, 2, 12, "same_step", True, 14), (1024, 2, 40, "next_step", False, 0), (32, 5, 500, "same_step", False, 20),
+    (200, 3, 60, "same_step", True, 0, "0"), (520, 2, 33, "same_step", False, 12, "0"), (1024, 2, 40, "next_step", False, 0, "0"),
+    (1000, 3, 33, "same_step", False, 16, "1"), (1152, 2, 20, "same_step", True, 0, "1"), (136, 4, 70, "next_step", True, 17, "1")]])
+def test_thread_per_env_kernel_equals_generic_kernel(ns, na, N, mode, given, coarse, wide, monkeypatch):
     """k_rollout_tp (one thread per env; pivots + one block of 31-bit codes, is_terminal in bit 0) vs the generic per-tick
     kernel: identical records, env state and statistics.  `coarse` > 0 drops low code bits so that the float64
-    fallback (code31(cdf) == code31(u)) runs often; with 0 the production path is compared."""
+    fallback (code31(cdf) == code31(u)) runs often; with 0 the production path is compared.  Three-level rows (more than
+    128 states) of up to 1152 states run as WIDE rows (24-entry blocks: first level -> index sector -> entry sector) by
+    default; `wide` = "0" keeps them on the 8-entry block lines (top -> pivots -> block), "1" forces wide rows."""
     from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    if wide is not None:
+        monkeypatch.setenv("AMDP_TP_WIDE", wide)
     tasks = [synth_task(ns, na, 1200 + t) for t in range(5)]
     if ns >= 200:
         for t in tasks:
@@ -462,6 +468,8 @@ def test_thread_per_env_kernel_equals_generic_kernel(ns, na, N, mode, given, coa
     for generic in (False, True):
         env = AnyMDPVecEnv(N, seed=43, autoreset=mode, search="thread")
         env.set_task(tasks)
+        if ns > 128 and ns <= 1152:
+            assert env.engine.rollout_kernel.endswith(",wide>") == (wide == "1"), env.engine.rollout_kernel
         env.engine.force_generic(generic)
         env.engine.tp_coarse_bits(coarse)
         env.reset()

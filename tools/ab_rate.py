@@ -10,16 +10,18 @@ sys.path.insert(0, ".")
 import bench  # noqa: E402
 
 name, envs, tasks, K = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-var, vals, given = None, [None], False
+var, vals, given, search = None, [None], False, "auto"
 for a in sys.argv[5:]:
     if a == "given":
         given = True
+    elif a.startswith("search="):
+        search = a.split("=")[1]
     else:
         var, v = a.split("=")
         vals = v.split(",")
 _, _, ns, na, no = bench.WORKLOADS[name]
 dev = torch.device("cuda", 0)
-env, geo = bench.build_env(name, envs, tasks, ns, na, no, dev, 0)
+env, geo = bench.build_env(name, envs, tasks, ns, na, no, dev, 0, search=search)
 env.reset()
 tr = bench.traj_buffers(K, envs, dev)
 cases = [("uniform policy", None, tr)]

@@ -502,6 +502,34 @@ __global__ void k_build_rows(int64_t cnt, int n_pad, int na, const double* __res
     }
 }
 
+// WIDE rows (Tables::wfat / wtop), re-packed from the thread-per-env block lines k_build_rows just wrote (the code words, with
+// their is_terminal / state_mapping bits and run handling, are taken as they are): one thread per (row, 24-entry block)
+__global__ void k_build_wide(long long rows, int n_pad, int tp_blocks, int w_blocks, const uint4* __restrict__ fat,
+                             const double* __restrict__ cdf, uint4* __restrict__ wfat, uint16_t* __restrict__ wtop) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * w_blocks) return;
+    const long long r = i / w_blocks;
+    const int wb = (int)(i % w_blocks);
+    uint4* line = wfat + (r * w_blocks + wb) * 8;
+    // (blocks beyond the row: the last code word of the row — the code of 1.0 with the low bits of its run — repeated)
+    const uint4 last4 = fat[(r * tp_blocks + (tp_blocks - 1)) * 8 + 1];
+    const uint4 pad = make_uint4(last4.w, last4.w, last4.w, last4.w);
+    unsigned idx[3];
+    for (int q = 0; q < 3; ++q) {
+        const int b8 = 3 * wb + q;
+        const uint4 lo = b8 < tp_blocks ? fat[(r * tp_blocks + b8) * 8] : pad;
+        const uint4 hi = b8 < tp_blocks ? fat[(r * tp_blocks + b8) * 8 + 1] : pad;
+        line[2 + 2 * q] = lo;
+        line[3 + 2 * q] = hi;
+        idx[q] = hi.w;
+    }
+    line[0] = make_uint4(idx[0], idx[1], idx[2], 0u);
+    line[1] = make_uint4(0u, 0u, 0u, 0u);
+    const int last = min(24 * wb + 23, n_pad - 1);
+    wtop[r * 48 + wb] = (uint16_t)code15(cdf[r * n_pad + last]);
+    if (wb == 0) for (int b = w_blocks; b < 48; ++b) wtop[r * 48 + b] = (uint16_t)0x7bff;
+}
+
 // per-task small tables; one thread per task
 __global__ void k_build_small(int64_t cnt, int n_pad, int s0_pad, const int32_t* __restrict__ state_mapping,
                               const int32_t* __restrict__ n_real, const uint8_t* __restrict__ is_terminal,
@@ -813,6 +841,7 @@ struct amdp {
     int n_sm;              // multiprocessors of the device
     int tp_coarse_bits;    // debug: low bits of the 31-bit codes ignored by k_rollout_tp (0 in production)
     uint4* fat; uint16_t* pv; uint16_t* top; uint32_t* ofat;   // its tables (see Tables)
+    uint4* wfat; uint16_t* wtop;                               // wide rows (k_rollout_tp<4>)
     char err[512];
     char kname[64];
     // rollout_host staging
@@ -914,7 +943,7 @@ static int pick_group(int n_pad) {
 extern "C" int amdp_destroy(amdp_t* h) {
     if (!h) return AMDP_OK;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits, h->policy, h->vi_q, h->vi_v, h->vi_er, h->vi_diff,
+    void* ptrs[] = {h->wfat, h->wtop, h->ofat, h->fat, h->pv, h->top, h->cdf, h->payload, h->sketch, h->pivot, h->sinfo, h->s0_cdf, h->s0_idx, h->obs_cdf, h->max_ceil, h->tflags, h->raw_t, h->tbits, h->policy, h->vi_q, h->vi_v, h->vi_er, h->vi_diff,
                     h->hs_act, h->hs_obs, h->hs_rew, h->hs_rgt, h->hs_term, h->hs_trunc, h->hs_steps, h->hs_out,
                     h->n_real, h->env_task, h->stat_part, h->stat_ticket, h->faults, h->counters, h->E.state, h->E.steps, h->E.flags, h->E.ep_return,
                     h->E.ep_count, h->E.sum_ret, h->E.sum_ret_sq, h->E.sum_len, h->E.min_ret, h->E.max_ret,
@@ -1003,6 +1032,19 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
         // rows of 64 / 128 states lose 5 / 16 %: their pivot table stays L2-resident, the lines do not)
         if (h->T.tp_levels == 3 || (h->T.tp_levels == 2 && nb > 4)) { if ((rc = dalloc(h, &h->pv, rows * h->T.tp_groups * 16))) return rc; }
         if (h->T.tp_levels == 3) { if ((rc = dalloc(h, &h->top, rows * 16))) return rc; }
+        // WIDE rows for rollouts (k_rollout_tp<4>, see Tables::wfat): three-level MDP rows of at most 48 x 24 states whose
+        // first level (96 bytes per row) stays L2-resident — then a transition has ONE dependent DRAM access instead of two.
+        // AMDP_TP_WIDE=0 / 1 switches them off / forces them (experiments).  k_step_tp / k_rollout_mt keep the block lines.
+        // MEASURED (profiles/r2_tp_wide_rows_experiment.txt): they LOSE everywhere — cfg4 x 65536 envs 0.55 vs 0.70 of the yardstick,
+        // 8192 envs 0.164 vs 0.186, and still 0.84 vs 0.90 with 4 tasks (every first level L2-resident): a step then moves two
+        // DRAM lines (codes; payload) instead of 1-1.6 and issues 6 requests instead of 4.  Off unless AMDP_TP_WIDE=1.
+        bool wide = false;
+        if (const char* o = getenv("AMDP_TP_WIDE")) wide = mdp && !sparse && h->T.tp_levels == 3 && c.n_pad <= 48 * 24 && o[0] == '1';
+        if (wide) {
+            h->T.w_blocks = (c.n_pad + 23) / 24;
+            if ((rc = dalloc(h, &h->wfat, rows * h->T.w_blocks * 8))) return rc;
+            if ((rc = dalloc(h, &h->wtop, rows * 48))) return rc;
+        }
         if (!mdp) {
             // flag 128: sparse observation rows (at most 8 non-zero observations per state)
             int ob = 0;
@@ -1046,7 +1088,7 @@ extern "C" int amdp_create(amdp_t** out, const amdp_config* cfg) {
     E.task = h->env_task; E.faults = h->faults; E.counters = h->counters; E.n_envs = c.n_envs; E.env_id_base = c.env_id_base;
     E.key = make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32));
     Tables& T = h->T;
-    T.fat = h->fat; T.pv = h->pv; T.top = h->top; T.ofat = h->ofat;
+    T.fat = h->fat; T.pv = h->pv; T.top = h->top; T.ofat = h->ofat; T.wfat = h->wfat; T.wtop = h->wtop;
     T.cdf = h->cdf; T.payload = h->payload; T.sketch = h->sketch; T.pivot = h->pivot; T.sinfo = h->sinfo; T.s0_cdf = h->s0_cdf; T.s0_idx = h->s0_idx;
     T.obs_cdf = h->obs_cdf; T.max_ceil = h->max_ceil; T.tflags = h->tflags; T.raw_t = h->raw_t; T.n_real = h->n_real; T.tbits = h->tbits;
     T.n_pad = c.n_pad; T.na = c.na; T.no_pad = c.no_pad; T.d_o = c.n_obs_tok; T.d_a = c.n_act_tok; T.s0_pad = c.s0_pad;
@@ -1080,6 +1122,14 @@ extern "C" int amdp_upload_tasks(amdp_t* h, int64_t t0, int64_t cnt, const doubl
                                                   h->pv ? h->pv + (size_t)t0 * c.n_pad * c.na * h->T.tp_groups * 16 : nullptr,
                                                   h->top ? h->top + (size_t)t0 * c.n_pad * c.na * 16 : nullptr,
                                                   h->T.tp_blocks, h->T.tp_groups, h->T.tp_obs_bits, h->T.tp_nxt_bits, status_out);
+    if (h->wfat) {
+        k_build_wide<<<nblk(rows * h->T.w_blocks, 128), 128, 0, st>>>(rows, c.n_pad, h->T.tp_blocks, h->T.w_blocks,
+                                                                     h->fat + (size_t)t0 * c.n_pad * c.na * h->T.tp_blocks * 8,
+                                                                     h->cdf + t0 * per_task,
+                                                                     h->wfat + (size_t)t0 * c.n_pad * c.na * h->T.w_blocks * 8,
+                                                                     h->wtop + (size_t)t0 * c.n_pad * c.na * 48);
+        h->launches += 1;
+    }
     k_build_small<<<nblk(cnt, 128), 128, 0, st>>>(cnt, c.n_pad, c.s0_pad, state_mapping, n_real, is_terminal, s0_idx, s0_prob,
                                                   n_s0, max_steps, ns, h->sinfo + t0 * c.n_pad, h->s0_cdf + t0 * c.s0_pad,
                                                   h->s0_idx + t0 * c.s0_pad, h->max_ceil + t0, h->tflags + t0,
@@ -1581,8 +1631,8 @@ extern "C" const char* amdp_rollout_kernel(amdp_t* h) {
     if (h->tp && c.task_type == AMDP_MTPOMDP && !h->force_generic)
         snprintf(h->kname, sizeof(h->kname), "k_rollout_mt<levels=%d,do=%d,da=%d>", h->T.tp_levels, c.n_obs_tok, c.n_act_tok);
     else if (!fast) snprintf(h->kname, sizeof(h->kname), "k_rollout<G=%d>", h->G);
-    else if (h->tp) snprintf(h->kname, sizeof(h->kname), "k_rollout_tp<levels=%d,%s%s>", h->T.tp_levels, c.task_type == AMDP_POMDP ? "POMDP" : "MDP",
-                             h->T.tp_nxt_bits ? ",sparse" : "");
+    else if (h->tp) snprintf(h->kname, sizeof(h->kname), "k_rollout_tp<levels=%d,%s%s%s>", h->T.tp_levels, c.task_type == AMDP_POMDP ? "POMDP" : "MDP",
+                             h->T.tp_nxt_bits ? ",sparse" : "", h->T.wfat ? ",wide" : "");
     else if (h->two_level) snprintf(h->kname, sizeof(h->kname), "k_rollout_mdp<G=8,two-level>");
     else if (h->wv2) snprintf(h->kname, sizeof(h->kname), "k_rollout_w<EPL=%d>", c.n_pad / 32);
     else snprintf(h->kname, sizeof(h->kname), "k_rollout_mdp<G=%d>", h->G);

@@ -46,6 +46,14 @@ struct Tables {
                               // bytes 96-127 of the row's first block line instead (pv == null)
     const uint16_t* top;      // [T][n_pad][na][16] code15 of the last entry of each group (three-level rows only)
     int tp_levels, tp_groups, tp_blocks;
+    // WIDE rows (k_rollout_tp<4>; three-level MDP rows whose first level fits L2): a row is cut into 24-entry blocks, ONE
+    // 128-byte line per block = [sector 0: the code words of entries 7, 15, 23 (the index)] [sectors 1-3: the 24 code words], and
+    // ONE first level of up to 48 pivots per row (2 bytes per 24 entries: 50 MB for 32 tasks of 1024 x 16 x 1024).  A transition is
+    // first level (L2) -> index sector (DRAM) -> entry sector (same line: L2 hit); its payload comes from `payload` (a second
+    // DRAM line, off the chain).  One DEPENDENT DRAM access per step instead of two (pv node -> block line).
+    const uint4*    wfat;     // [T][n_pad][na][w_blocks] 128-byte lines (null: no wide rows)
+    const uint16_t* wtop;     // [T][n_pad][na][48] code15 of the last entry of every 24-entry block; pad 0x7bff
+    int w_blocks;
     int tp_obs_bits;          // bits of state_mapping carried in the code words (bit_length(max ns - 1) <= 15)
     int tp_nxt_bits;          // > 0: SPARSE rows (every (s, a) has at most 8 non-zero successors, e.g. Garnet tasks): a row is ONE
                               // line whose 8 entries are its non-zero successors; their state indices sit above the mapping bits

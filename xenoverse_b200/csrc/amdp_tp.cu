@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
     const bool always_term = (T.tflags[t] & 1) != 0;
     const unsigned long long env_id = E.env_id_base + (unsigned long long)e;
     const int n_blocks = T.tp_blocks, n_groups = T.tp_groups;
+    const int w_blocks = T.w_blocks;                              // LEVELS == 4: WIDE rows (24-entry blocks, see Tables::wfat)
     const uint64_t pol_keep = l2_policy_evict_last();
 
     int s = E.state[e], steps = E.steps[e], flags = E.flags[e];
@@ -217,11 +218,14 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
         if (given && !pend && !a_ok) fault |= AMDP_FAULT_BAD_ACTION;                          // :97
         const unsigned long long row = rbase + (unsigned long long)(s * na + (valid ? cur.a : 0));
         // (1) first level of the search tree of row (s, a)                                      anymdp_env.py:99
-        uint4 lv[2];                                               // 16 pivots (15-bit codes)
-        if (LEVELS == 3 && valid) ldg_words_keep<2>(T.top + row * 16u, lv, pol_keep);
-        if (LEVELS == 2 && valid) {
-            if (T.pv) ldg_words_keep<2>(T.pv + row * 16u, lv, pol_keep);
-            else ldg_words<2>(T.fat + row * (unsigned)n_blocks * 8u + 6, lv);      // rows of <= 4 blocks: spare sector of the first block line
+        uint4 lv[LEVELS == 4 ? 6 : 2];                             // 16 pivots (15-bit codes); wide rows: 48
+        if constexpr (LEVELS == 4) { if (valid) ldg_words_keep<6>(T.wtop + row * 48u, lv, pol_keep); }
+        if constexpr (LEVELS == 3) { if (valid) ldg_words_keep<2>(T.top + row * 16u, lv, pol_keep); }
+        if constexpr (LEVELS == 2) {
+            if (valid) {
+                if (T.pv) ldg_words_keep<2>(T.pv + row * 16u, lv, pol_keep);
+                else ldg_words<2>(T.fat + row * (unsigned)n_blocks * 8u + 6, lv);      // rows of <= 4 blocks: spare sector of the first block line
+            }
         }
         // (2) in the shadow of that load: the previous tick's reward / record
         if (k > 0) { settle(k - 1); if (POMDP) obs_stage1(); }
@@ -230,8 +234,11 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
 #ifndef AMDP_TP_DRAW_PV
 #define AMDP_TP_DRAW_PV 1   // three-level rows draw the next tick in the shadow of the second-level (pv) load, a DRAM access (cfg4 x 65536 envs: 0.644 -> 0.701 of the yardstick); 0: before the search, in the shadow of the L2-resident top level
 #endif
+#ifndef AMDP_TP_DRAW_BLK
+#define AMDP_TP_DRAW_BLK 0  // experiment: two-level rows at the small register budget draw in the shadow of the block load too
+#endif
         constexpr bool DRAW_PV = AMDP_TP_DRAW_PV && LEVELS == 3 && MINB == TP_MINB_HI;
-        constexpr bool DRAW_EARLY = (MINB == TP_MINB_HI) && !DRAW_PV;
+        constexpr bool DRAW_EARLY = (MINB == TP_MINB_HI) && !DRAW_PV && !(AMDP_TP_DRAW_BLK && LEVELS == 2 && !POMDP) && LEVELS != 4;
         Draw nx;
         if (DRAW_EARLY) nx = draw(k + 1);
         int done_bits = 0;
@@ -251,7 +258,16 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
                 return -acc;
             };
             int blk = 0;
-            if (LEVELS == 3) {
+            if constexpr (LEVELS == 4) {
+                int acc = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    acc = h2_count_lt(lv[i].x, v2, acc); acc = h2_count_lt(lv[i].y, v2, acc);
+                    acc = h2_count_lt(lv[i].z, v2, acc); acc = h2_count_lt(lv[i].w, v2, acc);
+                }
+                blk = min(-acc, w_blocks - 1);
+            }
+            if constexpr (LEVELS == 3) {
                 // second level: the 16 block pivots of group g
                 const int g = min(count16(), n_groups - 1);
                 ldg_words_keep<2>(T.pv + (row * (unsigned)n_groups + (unsigned)g) * 16u, lv, pol_keep);
@@ -262,13 +278,24 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
             // code31(u) << 1; cmask = 0xfffffffe drops the is_terminal bit of the entries (tests coarsen it further to
             // exercise the float64 fallback)
             const unsigned ve = ((((cur.wx >> 5) << 4) | (cur.wy >> 28)) << 1) & cmask;
-            const uint4* frow = T.fat + row * (unsigned)n_blocks * 8u;                  // 8 x 16 bytes per block line
+            const uint4* frow = LEVELS == 4 ? T.wfat + row * (unsigned)w_blocks * 8u    // wide rows: index + 3 entry sectors per line
+                                            : T.fat + row * (unsigned)n_blocks * 8u;    // 8 x 16 bytes per block line
             int lt, le;
             unsigned mn;
+            int sec = 0;                                           // wide rows: the entry sector of the block (0..2)
             for (bool first = true;; first = false) {
                 uint4 bw[2];
+                if (LEVELS == 4) {
+                    // the index sector (the block's DRAM access): code words of entries 7, 15, 23 -> the sector of the transition
+                    ldg_words<2>(frow + blk * 8, bw);
+                    if (first) nx = draw(k + 1);                   // in the shadow of that load: the next tick's draws
+                    const int lt3 = ((bw[0].x & cmask) < ve) + ((bw[0].y & cmask) < ve) + ((bw[0].z & cmask) < ve);
+                    if (lt3 == 3 && blk < w_blocks - 1) { ++blk; continue; }   // the whole block is below u (its pivot shared u's cell)
+                    sec = min(lt3, 2);
+                    ldg_words<2>(frow + blk * 8 + 2 + 2 * sec, bw);   // the entry sector: same line, an L2 hit
+                } else
                 ldg_words<2>(frow + blk * 8, bw);
-                if (first && !DRAW_EARLY && !DRAW_PV) nx = draw(k + 1);   // in the shadow of the block load: the next tick's draws
+                if (first && !DRAW_EARLY && !DRAW_PV && LEVELS != 4) nx = draw(k + 1);   // in the shadow of the block load: the next tick's draws
                 lt = 0; le = 0; mn = 0xffffffffu;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
@@ -281,10 +308,10 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
                         mn = min(mn, xm >= ve ? x[j] : 0xffffffffu);
                     }
                 }
-                if (lt < 8 || blk >= n_blocks - 1) break;
+                if (LEVELS == 4 || lt < 8 || blk >= n_blocks - 1) break;
                 ++blk;                                             // the whole block is below u (its pivot shared u's 15-bit cell)
             }
-            int nxt = blk * 8 + lt;
+            int nxt = LEVELS == 4 ? min(blk * 24 + sec * 8 + lt, n_pad - 1) : blk * 8 + lt;
             // sparse rows (one line per row, LEVELS == 1): the state index of the entry sits above its mapping bits
             const bool sparse = LEVELS == 1 && T.tp_nxt_bits > 0;
             if (sparse) nxt = (le != lt) ? 0 : (int)((mn >> (1 + T.tp_obs_bits)) & ((1u << T.tp_nxt_bits) - 1u));
@@ -300,6 +327,9 @@ __global__ void __launch_bounds__(TP_TPB, MINB) k_rollout_tp(const Tables T, con
                 n_fallback += 1;
                 // (4) payload (reward, noise) of (s, a, s')  (anymdp_env.py:103-104): consumed by settle() of the next tick
                 pay_p = ldg_stream_f32x2(T.payload + (row * (unsigned)n_pad + (unsigned)nxt));
+            } else if (LEVELS == 4) {
+                pay_p = ldg_stream_f32x2(T.payload + (row * (unsigned)n_pad + (unsigned)nxt));   // wide rows: the payload table
+                if (!POMDP) ob_p = (int)((mn >> 1) & omask);
             } else {
                 const char* line = reinterpret_cast<const char*>(frow + blk * 8);
                 pay_p = ldg_stream_f32x2(reinterpret_cast<const float2*>(line + 32) + lt);
@@ -401,7 +431,8 @@ void amdp_launch_tp(const Tables& T, const EnvArrays& E, long long n_envs, bool 
                     const int32_t* actions, const amdp_traj& J, cudaStream_t st) {
     const int low = 1 + T.tp_obs_bits + T.tp_nxt_bits + coarse_bits;   // is_terminal + state_mapping (+ sparse: state index) bits (+ bits the tests drop)
     const unsigned cmask = 0xffffffffu << (low < 30 ? low : 30);
-    if (T.tp_levels == 1) launch_tp<1>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
+    if (T.wfat && !pomdp) launch_tp<4>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
+    else if (T.tp_levels == 1) launch_tp<1>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
     else if (T.tp_levels == 2) launch_tp<2>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
     else launch_tp<3>(T, E, n_envs, pomdp, next ? 1 : 0, cmask, tick, K, actions, J, st);
 }
