@@ -82,6 +82,34 @@ def main():
     env.engine.rollout_host_compact(16, 4, a, ho.view(numpy.uint16, (16, 64)), hr.view(numpy.float32, (16, 64)))
     env.check()
     env.close()
+    # round 2, second half: given actions of k_rollout_w (cp.async prefetch of a batch; uint8 words that stick out of the buffer at
+    # both ends; int32), the transition_gt label plane, wide rows (AMDP_TP_WIDE=1), thread-per-env with 8 env lanes per warp
+    for N, K, dt, off in ((33, 70, torch.uint8, 3), (37, 65, torch.int32, 1)):
+        env = xb.AnyMDPVecEnv(N, seed=7)
+        env.set_task(tasks)
+        assert env.engine.rollout_kernel.startswith("k_rollout_w<")
+        env.reset()
+        flat = torch.randint(0, 4, (off + K * N,), dtype=dt).cuda()
+        env.rollout(K, actions=flat[off:].view(K, N))
+        env.check()
+        env.close()
+    env = xb.AnyMDPVecEnv(24, seed=8, keep_transition=True)
+    env.set_task(tasks)
+    env.reset()
+    env.rollout(20, record=("obs", "transition_gt"))
+    env.check()
+    env.close()
+    big = [xb.synth_task(200, 2, 60 + t) for t in range(2)]
+    for wide in ("0", "1"):
+        os.environ["AMDP_TP_WIDE"] = wide
+        env = xb.AnyMDPVecEnv(48, seed=9, search="thread")
+        env.set_task(big)
+        assert env.engine.rollout_kernel.endswith(",wide>") == (wide == "1")
+        env.reset()
+        env.rollout(40)
+        env.check()
+        env.close()
+    os.environ.pop("AMDP_TP_WIDE")
     print("all ok")
 
 
