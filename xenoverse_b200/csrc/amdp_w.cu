@@ -412,7 +412,11 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
         if (GIVEN && j == 0) act_prefetch(opaque(k) + 33 + lane);         // once per 32 ticks: the actions of the batch after the next one
         if (r & 15u) {
             // undecided: exact float64 entries (numpy choice: searchsorted(cdf, u, 'right'))   anymdp_env.py:100
-            const uint4 w0 = philox_block(env_id, 0u, tick0 + (unsigned long long)opaque(k), E.key);
+            // (the env id through an opaque copy as well: its Philox counter words are otherwise hoisted above this branch and
+            // recomputed every tick)
+            const unsigned long long eid = E.env_id_base + (unsigned long long)(unsigned)opaque((int)(unsigned)e) +
+                                           ((unsigned long long)(e >> 32) << 32);
+            const uint4 w0 = philox_block(eid, 0u, tick0 + (unsigned long long)opaque(k), E.key);
             const double u = u53(w0.x, w0.y);
             const double* cr = cdf_lane + (unsigned long long)sa * N_PAD;
             int cnt = 0;
@@ -459,11 +463,13 @@ __global__ void __launch_bounds__(128, AMDP_W_MINB) k_rollout_w(const Tables T, 
     };
     int k = 0;
     while (k + 1 < K) {
-        const int kend = min(K, (k | 31) + 1);                    // one 32-tick period (= the batch in b_pk); periods are even
-        // all actions of the period in range: the tick at its start (drawn with the previous batch) and the batch's 32
-        const bool clean = !GIVEN || !(b_anybad || (pk >> 31));
-        if (clean) for (; k + 1 < kend; k += 2) { tick(NoChk{}, k, fa, fb); tick(NoChk{}, k + 1, fb, fa); }
-        else for (; k + 1 < kend; k += 2) { tick(Chk{}, k, fa, fb); tick(Chk{}, k + 1, fb, fa); }
+        // one 32-tick period (= the batch in b_pk; k is a multiple of 32 here): 16 double ticks unless K ends it.
+        // All actions of the period in range: the tick at its start (drawn with the previous batch) and the batch's 32.  (A VOTE,
+        // although both operands are warp-uniform: the compiler cannot see that, and guards every SHFL of a loop behind a
+        // possibly divergent branch with BRA.DIV / BSSY / BSYNC.)
+        const bool clean = !GIVEN || !__any_sync(FULL, (int)(b_anybad || (pk >> 31)));
+        if (clean) for (int i = 0; i < 16 && k + 1 < K; ++i, k += 2) { tick(NoChk{}, k, fa, fb); tick(NoChk{}, k + 1, fb, fa); }
+        else for (int i = 0; i < 16 && k + 1 < K; ++i, k += 2) { tick(Chk{}, k, fa, fb); tick(Chk{}, k + 1, fb, fa); }
     }
     if (k < K) { tick(Chk{}, k, fa, fb); settle(K - 1, fb.pay, fb.si); }
     else settle(K - 1, fa.pay, fa.si);
