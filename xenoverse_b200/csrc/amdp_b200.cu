@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(256) k_step(Tables T, EnvArrays E, unsigned lo
                                               int32_t* __restrict__ final_obs_out, float* __restrict__ reward,
                                               float* __restrict__ reward_gt, uint8_t* __restrict__ terminated,
                                               uint8_t* __restrict__ truncated, int32_t* __restrict__ actions_out,
-                                              int32_t* __restrict__ steps_out, const double* __restrict__ u_inject) {
+                                              int32_t* __restrict__ steps_out, const double* __restrict__ u_inject,
+                                              int32_t* host_rec, int host_seq) {
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long e = gtid / G;
     const int lane = (int)(gtid % G);
@@ -252,6 +253,16 @@ __global__ void __launch_bounds__(256) k_step(Tables T, EnvArrays E, unsigned lo
         truncated[e] = (uint8_t)O.trunc;
         if (actions_out) for (int k = 0; k < T.d_a; ++k) actions_out[e * T.d_a + k] = act[k];
         if (steps_out) steps_out[e] = O.steps;
+        if (host_rec) {
+            // single-env engines (amdp_step_host, zero-copy): the 16-word result record of k_pack_result written straight into
+            // mapped host memory, then the sequence word the host polls — the whole step() of the drop-in is ONE launch
+            for (int k = 0; k < 8; ++k) host_rec[k] = k < T.d_o ? obs[k] : 0;
+            host_rec[8] = __float_as_int(O.reward); host_rec[9] = __float_as_int(O.reward_gt);
+            host_rec[10] = O.term; host_rec[11] = O.trunc; host_rec[12] = O.steps;
+            host_rec[13] = R.state; host_rec[14] = (int32_t)*reinterpret_cast<volatile unsigned int*>(E.faults); host_rec[15] = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile int32_t*>(host_rec + 16) = host_seq;
+        }
     }
 }
 
@@ -824,6 +835,11 @@ struct amdp {
     // amdp_step_host / amdp_reset_host: device staging and the handle's own stream
     int32_t* hs_act; int32_t* hs_obs; float* hs_rew; float* hs_rgt; uint8_t* hs_term; uint8_t* hs_trunc; int32_t* hs_steps; int32_t* hs_out;
     cudaStream_t hs_stream;
+    // zero-copy variant of the single-call host step (engines of at most 128 envs: the single-env drop-in): actions and result
+    // records live in MAPPED pinned host memory that the kernels read / write over PCIe, and the host polls a sequence word the
+    // result kernel writes last — no cudaMemcpyAsync, no cudaStreamSynchronize on the path of a step
+    int32_t* hs_act_h; int32_t* hs_out_h; bool hs_zc; int hs_seq;
+    int32_t* fuse_rec; int fuse_seq;                           // set around the amdp_step of a fused single-env host step
     int32_t* env_task;
     Stat6* stat_part;
     unsigned int* stat_ticket;
@@ -954,6 +970,8 @@ extern "C" int amdp_destroy(amdp_t* h) {
         for (void* p : st) if (p) cudaFree(p);
     }
     if (h->hs_stream) cudaStreamDestroy(h->hs_stream);
+    if (h->hs_act_h) cudaFreeHost(h->hs_act_h);
+    if (h->hs_out_h) cudaFreeHost(h->hs_out_h);
     if (h->ev_caller) cudaEventDestroy(h->ev_caller);
     for (int r = 0; r < XG_MAX_RANKS; ++r) if (h->xg_opened[r] && h->xg_peer[r]) cudaIpcCloseMemHandle(h->xg_peer[r]);
     {
@@ -1183,7 +1201,7 @@ static void launch_step(amdp* h, const int32_t* actions, int32_t* obs, int32_t* 
                         cudaStream_t st) {
     const long long threads = h->cfg.n_envs * G;
     k_step<G><<<nblk(threads, 256), 256, 0, st>>>(h->T, h->E, h->tick, h->n_slots, actions, obs, final_obs, reward, reward_gt,
-                                                  terminated, truncated, actions_out, steps_out, u);
+                                                  terminated, truncated, actions_out, steps_out, u, h->fuse_rec, h->fuse_seq);
 }
 
 extern "C" int amdp_step(amdp_t* h, const int32_t* actions, int32_t* obs, int32_t* final_obs, float* reward,
@@ -1744,14 +1762,22 @@ extern "C" int amdp_poll_errors(amdp_t* h, uint32_t* faults, void* stream) {
 // 13 inner state, 14 sticky fault word of the engine, 15 zero
 __global__ void k_pack_result(EnvArrays E, int d_o, const int32_t* __restrict__ obs, const float* __restrict__ rew,
                               const float* __restrict__ rgt, const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc,
-                              const int32_t* __restrict__ steps, int with_step, int32_t* __restrict__ out) {
+                              const int32_t* __restrict__ steps, int with_step, int32_t* __restrict__ out, int seq) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E.n_envs) return;
-    int32_t* o = out + e * 16;
-    for (int k = 0; k < 8; ++k) o[k] = k < d_o ? obs[e * d_o + k] : 0;
-    o[8] = with_step ? __float_as_int(rew[e]) : 0; o[9] = with_step ? __float_as_int(rgt[e]) : 0;
-    o[10] = with_step ? term[e] : 0; o[11] = with_step ? trunc[e] : 0; o[12] = with_step ? steps[e] : 0;
-    o[13] = E.state[e]; o[14] = (int32_t)*E.faults; o[15] = 0;
+    if (e < E.n_envs) {
+        int32_t* o = out + e * 16;
+        for (int k = 0; k < 8; ++k) o[k] = k < d_o ? obs[e * d_o + k] : 0;
+        o[8] = with_step ? __float_as_int(rew[e]) : 0; o[9] = with_step ? __float_as_int(rgt[e]) : 0;
+        o[10] = with_step ? term[e] : 0; o[11] = with_step ? trunc[e] : 0; o[12] = with_step ? steps[e] : 0;
+        o[13] = E.state[e]; o[14] = (int32_t)*E.faults; o[15] = 0;
+    }
+    if (seq) {
+        // zero-copy variant (one block): `out` is mapped host memory; the sequence word behind the records tells the polling
+        // host that all of them have landed
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) { *reinterpret_cast<volatile int32_t*>(out + E.n_envs * 16) = seq; __threadfence_system(); }
+    }
 }
 
 static int host_step_init(amdp* h) {
@@ -1767,14 +1793,45 @@ static int host_step_init(amdp* h) {
     if ((rc = dalloc(h, &h->hs_trunc, n))) return rc;
     if ((rc = dalloc(h, &h->hs_steps, n))) return rc;
     if ((rc = dalloc(h, &h->hs_out, n * 16))) return rc;
+    const char* zc = getenv("AMDP_HOST_ZEROCOPY");
+    if (n <= 128 && !(zc && zc[0] == '0')) {
+        if (cudaHostAlloc((void**)&h->hs_act_h, sizeof(int32_t) * n * c.n_act_tok, cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostAlloc((void**)&h->hs_out_h, sizeof(int32_t) * (n * 16 + 16), cudaHostAllocMapped) == cudaSuccess) {
+            memset(h->hs_out_h, 0, sizeof(int32_t) * (n * 16 + 16));
+            h->hs_zc = true;
+        } else {
+            cudaGetLastError();
+            if (h->hs_act_h) { cudaFreeHost(h->hs_act_h); h->hs_act_h = nullptr; }
+        }
+    }
     CK(cudaStreamCreateWithFlags(&h->hs_stream, cudaStreamNonBlocking));
+    return AMDP_OK;
+}
+
+// zero-copy host step: wait for the sequence word behind the result records in mapped host memory, hand the records over
+static int host_poll(amdp* h, int seq, int32_t* result_host) {
+    const amdp_config& c = h->cfg;
+    volatile int32_t* flag = h->hs_out_h + (size_t)c.n_envs * 16;
+    long long spins = 0;
+    while (*flag != seq && ++spins < 20000000ll) { }               // ~10 ms of polling, then the stream decides (and reports errors)
+    if (*flag != seq) CK(cudaStreamSynchronize(h->hs_stream));
+    memcpy(result_host, h->hs_out_h, sizeof(int32_t) * 16 * (size_t)c.n_envs);
+    if (result_host[14]) CK(cudaMemsetAsync(h->faults, 0, sizeof(unsigned int), h->hs_stream));
     return AMDP_OK;
 }
 
 static int host_result(amdp* h, int with_step, int32_t* result_host) {
     const amdp_config& c = h->cfg;
+    if (h->hs_zc) {
+        const int seq = h->hs_seq = (h->hs_seq % 0x3fffffff) + 1;
+        k_pack_result<<<1, 128, 0, h->hs_stream>>>(h->E, c.n_obs_tok, h->hs_obs, h->hs_rew, h->hs_rgt, h->hs_term, h->hs_trunc,
+                                                   h->hs_steps, with_step, h->hs_out_h, seq);
+        h->launches += 1;
+        CK(cudaGetLastError());
+        return host_poll(h, seq, result_host);
+    }
     k_pack_result<<<nblk(c.n_envs, 128), 128, 0, h->hs_stream>>>(h->E, c.n_obs_tok, h->hs_obs, h->hs_rew, h->hs_rgt, h->hs_term, h->hs_trunc,
-                                                                 h->hs_steps, with_step, h->hs_out);
+                                                                 h->hs_steps, with_step, h->hs_out, 0);
     h->launches += 1;
     CK(cudaMemcpyAsync(result_host, h->hs_out, sizeof(int32_t) * 16 * (size_t)c.n_envs, cudaMemcpyDeviceToHost, h->hs_stream));
     CK(cudaStreamSynchronize(h->hs_stream));
@@ -1797,9 +1854,19 @@ extern "C" int amdp_step_host(amdp_t* h, const int32_t* actions_host, int32_t* r
     if (rc) return rc;
     const amdp_config& c = h->cfg;
     wait_caller_stream(h, h->hs_stream);
+    const int32_t* acts = h->hs_act;
+    if (h->hs_zc) {                                                // the step kernel reads the actions from mapped host memory
+        memcpy(h->hs_act_h, actions_host, sizeof(int32_t) * (size_t)c.n_envs * c.n_act_tok);
+        acts = h->hs_act_h;
+    } else
     CK(cudaMemcpyAsync(h->hs_act, actions_host, sizeof(int32_t) * (size_t)c.n_envs * c.n_act_tok, cudaMemcpyHostToDevice, h->hs_stream));
-    if ((rc = amdp_step(h, h->hs_act, h->hs_obs, nullptr, h->hs_rew, h->hs_rgt, h->hs_term, h->hs_trunc, nullptr, h->hs_steps, nullptr, h->hs_stream)))
-        return rc;
+    // one env on the generic step kernel: the kernel writes the result record itself (no k_pack_result launch)
+    const bool fused = h->hs_zc && c.n_envs == 1 && !(h->tp && c_not_mt(h) && !h->force_generic);
+    if (fused) { h->fuse_seq = h->hs_seq = (h->hs_seq % 0x3fffffff) + 1; h->fuse_rec = h->hs_out_h; }
+    rc = amdp_step(h, acts, h->hs_obs, nullptr, h->hs_rew, h->hs_rgt, h->hs_term, h->hs_trunc, nullptr, h->hs_steps, nullptr, h->hs_stream);
+    h->fuse_rec = nullptr;
+    if (rc) return rc;
+    if (fused) return host_poll(h, h->fuse_seq, result_host);
     return host_result(h, 1, result_host);
 }
 
