@@ -346,7 +346,10 @@ int amdp_value_iteration(amdp_t* h, int32_t greedy, double gamma, double tol, in
  * gymnasium drop-in: anymdp_env.py:81-90 / :112-132 become one library call each).  Both run on a stream owned by the
  * handle and synchronise.  actions_host: int32 [n_envs][da].  result_host: int32 [n_envs][16] (pinned memory preferred):
  * words 0-7 observation tokens, 8 reward (fp32 bits), 9 reward_gt (fp32 bits), 10 terminated, 11 truncated, 12 info["steps"],
- * 13 inner state, 14 the engine's sticky fault word (AMDP_FAULT_*; cleared once reported), 15 zero; reset fills 0-7, 13, 14. */
+ * 13 inner state, 14 the engine's sticky fault word (AMDP_FAULT_*; cleared once reported), 15 zero; reset fills 0-7, 13, 14.
+ * Engines of at most 128 envs take a zero-copy path: actions and records in mapped pinned host memory owned by the handle, a
+ * sequence word behind the records that the call polls (a single-env engine's step is ONE kernel launch, no copy, no stream
+ * synchronise); AMDP_HOST_ZEROCOPY=0 in the environment keeps the copy-based path. */
 int amdp_reset_host(amdp_t* h, int32_t* result_host);
 int amdp_step_host(amdp_t* h, const int32_t* actions_host, int32_t* result_host);
 
