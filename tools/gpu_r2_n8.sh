@@ -1,5 +1,5 @@
 #!/bin/bash
-# 2-GPU bench exactly as the driver launches it (round-2 final build)
+# 8-GPU bench exactly as the driver launches it (round-2 final build)
 mkdir -p gpurun_out
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
 echo "rc=$?"; tail -3 gpurun_out/bench_n8.err
