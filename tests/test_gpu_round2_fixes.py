@@ -343,3 +343,46 @@ def test_rollout_records_carry_transition_gt_labels(fixture, N, K, mode):
     env2.reset()
     with pytest.raises(Exception, match="keep_transition"):
         env2.rollout(4, record=("obs", "transition_gt"))
+
+
+@pytest.mark.parametrize("N,zc", [(1, "1"), (1, "0"), (5, "1"), (128, "1"), (129, "1"), (40, "0")])
+def test_host_step_paths_equal_device_step(N, zc, monkeypatch):
+    """amdp_reset_host / amdp_step_host (one library call per reset / step from host memory — the single-env drop-in's path) on
+    their three code paths: one env (the step kernel writes the result record and its sequence word into mapped host memory
+    itself), 2..128 envs (k_pack_result writes them), more envs or AMDP_HOST_ZEROCOPY=0 (device buffers + copies).  Every path
+    must return exactly what the device API returns for a twin engine with the same seed."""
+    import ctypes
+    from xenoverse_b200 import synth_task, AnyMDPVecEnv
+    from xenoverse_b200._lib import lib
+    monkeypatch.setenv("AMDP_HOST_ZEROCOPY", zc)
+    tasks = [synth_task(24, 4, 2700 + t) for t in range(3)]
+    a = AnyMDPVecEnv(N, seed=77)
+    b = AnyMDPVecEnv(N, seed=77)
+    for e in (a, b):
+        e.set_task(tasks)
+    obs_b, _ = b.reset()
+    res = numpy.zeros((N, 16), dtype=numpy.int32)
+    acts = numpy.zeros((N, 1), dtype=numpy.int32)
+    p_res, p_act = ctypes.c_void_p(res.ctypes.data), ctypes.c_void_p(acts.ctypes.data)
+    a.engine._ck(lib.amdp_reset_host(a.engine._h, p_res))
+    assert numpy.array_equal(res[:, 0], obs_b.cpu().numpy().reshape(N))
+    rng = numpy.random.default_rng(N)
+    for k in range(60):
+        acts[:, 0] = rng.integers(0, 4, N)
+        a.engine._ck(lib.amdp_step_host(a.engine._h, p_act, p_res))
+        o, r, term, trunc, info = b.step(torch.as_tensor(acts[:, 0].copy()))
+        assert numpy.array_equal(res[:, 0], o.cpu().numpy().reshape(N)), k
+        assert numpy.array_equal(res[:, 8].view(numpy.float32), r.cpu().numpy()), k
+        assert numpy.array_equal(res[:, 9].view(numpy.float32), info["reward_gt"].cpu().numpy()), k
+        assert numpy.array_equal(res[:, 10] != 0, term.cpu().numpy()) and numpy.array_equal(res[:, 11] != 0, trunc.cpu().numpy()), k
+        assert numpy.array_equal(res[:, 12], info["steps"].cpu().numpy()), k
+        assert numpy.array_equal(res[:, 13], b.engine.get_state()["state"].cpu().numpy()), k
+        assert not res[:, 14].any()
+    # a bad action is reported in the record's fault word and cleared once reported (anymdp_env.py:97)
+    acts[:, 0] = 0
+    acts[0, 0] = 9
+    a.engine._ck(lib.amdp_step_host(a.engine._h, p_act, p_res))
+    assert res[0, 14] != 0
+    acts[0, 0] = 1
+    a.engine._ck(lib.amdp_step_host(a.engine._h, p_act, p_res))
+    assert not res[:, 14].any()
