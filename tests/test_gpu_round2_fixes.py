@@ -312,7 +312,7 @@ def test_warp_kernel_given_actions_prefetched_by_cp_async(N, K, dtype, off):
 
 
 @pytest.mark.parametrize("fixture,N,K,mode", [("tasks_mdp64", 40, 60, "same_step"), ("tasks_minss64", 24, 50, "next_step"),
-                                              ("tasks_mtpomdp32", 20, 40, "same_step")])
+                                              ("tasks_mtpomdp32", 20, 40, "same_step"), ("tasks_pomdp64", 16, 40, "next_step")])
 def test_rollout_records_carry_transition_gt_labels(fixture, N, K, mode):
     """Rollout records with the `transition_gt` label plane (info["transition_gt"], anymdp_env.py:130: the observation-indexed
     transition row of the state the step led to, one row per action token) equal the oracle's, which is pinned to the live
